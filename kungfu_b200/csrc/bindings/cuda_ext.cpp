@@ -1,0 +1,162 @@
+// kungfu_b200 — Python bindings of the CUDA kernel library + PeerMesh (`kungfu_b200._kfcuda`).
+//
+// Counterpart of the reference's pybind module `kungfu_torch_ops` (srcs/cpp/src/torch/
+// module_cuda.cpp:28-40). Tensors are passed as raw device pointers and streams as integers
+// (`tensor.data_ptr()`, `torch.cuda.current_stream().cuda_stream`), which keeps this extension
+// independent of libtorch's ABI and lets it build in seconds.
+#include <pybind11/functional.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "../kernels/kernels.h"
+#include "../mesh/peer_mesh.h"
+
+namespace py = pybind11;
+using namespace kf;
+
+static inline cudaStream_t S(uintptr_t s) { return reinterpret_cast<cudaStream_t>(s); }
+template <typename T> static inline T* P(uintptr_t p) { return reinterpret_cast<T*>(p); }
+
+PYBIND11_MODULE(_kfcuda, m) {
+    m.doc() = "kungfu_b200 sm_100a kernels and peer mesh";
+    m.attr("MAX_RANKS") = kMaxRanks;
+    m.attr("MAX_BLOCKS") = kMaxBlocks;
+    m.attr("NUM_CHANNELS") = kNumChannels;
+    m.attr("ALGO_AUTO") = (int)kAlgoAuto;
+    m.attr("ALGO_ONESHOT") = (int)kAlgoOneShot;
+    m.attr("ALGO_TWOSHOT") = (int)kAlgoTwoShot;
+    m.attr("ALGO_NVLS") = (int)kAlgoNvls;
+    m.attr("FLAG_SCALE") = (int)kArScale;
+    m.attr("FLAG_SUMSQ") = (int)kArSumSq;
+    m.attr("OPT_SGD") = (int)kOptSgd;
+    m.attr("OPT_ADAM") = (int)kOptAdam;
+    m.attr("HYPER_COUNT") = (int)kHpCount;
+
+    py::class_<PeerMesh>(m, "PeerMesh")
+        .def(py::init<int, size_t, const std::string&>(), py::arg("device"), py::arg("arena_bytes"), py::arg("mode") = "auto")
+        .def("connect",
+             [](PeerMesh& self, int rank, int nranks, py::object oob, bool want_multicast) {
+                 OobAllGather fn = [oob](const std::string& mine) {
+                     py::object res = oob(py::bytes(mine));
+                     std::vector<std::string> out;
+                     for (auto item : res) out.push_back(py::cast<std::string>(py::bytes(py::reinterpret_borrow<py::object>(item))));
+                     return out;
+                 };
+                 self.connect(rank, nranks, fn, want_multicast);
+             },
+             py::arg("rank"), py::arg("nranks"), py::arg("oob"), py::arg("want_multicast") = true)
+        .def("disconnect", &PeerMesh::disconnect)
+        .def_property_readonly("rank", &PeerMesh::rank)
+        .def_property_readonly("nranks", &PeerMesh::nranks)
+        .def_property_readonly("device", &PeerMesh::device)
+        .def_property_readonly("epoch", &PeerMesh::epoch)
+        .def_property_readonly("arena_bytes", &PeerMesh::arena_bytes)
+        .def_property_readonly("alloc_bytes", &PeerMesh::alloc_bytes)
+        .def_property_readonly("local_ptr", &PeerMesh::local_ptr)
+        .def_property_readonly("mc_ptr", &PeerMesh::mc_ptr)
+        .def_property_readonly("has_multicast", &PeerMesh::has_multicast)
+        .def_property_readonly("mode", &PeerMesh::mode)
+        .def_property_readonly("multicast_note", &PeerMesh::multicast_note)
+        .def("peer_ptr", &PeerMesh::peer_ptr)
+        .def("status", &PeerMesh::status)
+        .def("clear_status", &PeerMesh::clear_status)
+        .def("set_timeout_ms", &PeerMesh::set_timeout_ms)
+        .def("reset_signals", [](PeerMesh& self, uintptr_t st) { self.reset_signals(S(st)); })
+        .def("topology", [](const PeerMesh& self) {
+            MeshTopology t = self.topology();
+            py::dict d;
+            d["device"] = t.device;
+            d["device_count"] = t.device_count;
+            d["can_access"] = t.can_access;
+            d["perf_rank"] = t.perf_rank;
+            d["native_atomic"] = t.native_atomic;
+            d["multicast_supported"] = t.multicast_supported;
+            d["sm_count"] = t.sm_count;
+            d["total_mem"] = t.total_mem;
+            d["name"] = t.name;
+            return d;
+        });
+
+    m.def("launch_count", &launch_count);
+    m.def("nvls_supported", &nvls_supported);
+
+    m.def("allreduce",
+          [](const PeerMesh& mesh, int channel, int algo, size_t off, uintptr_t out, size_t nbytes, int dtype, int op,
+             float scale, uintptr_t sumsq, int flags, int blocks, int threads, uintptr_t st) {
+              launch_allreduce(algo, mesh.args(channel), off, P<void>(out), nbytes, dtype, op, scale, P<float>(sumsq), flags,
+                               blocks, threads, S(st));
+          });
+    m.def("ssgd_fused",
+          [](const PeerMesh& mesh, int channel, int algo, size_t grad_off, size_t param_off, int dtype, size_t nbytes,
+             uintptr_t master, uintptr_t s1, uintptr_t s2, uintptr_t hyper, int opt_kind, uintptr_t sumsq, int flags,
+             int blocks, int threads, uintptr_t st) {
+              launch_ssgd_fused(algo, mesh.args(channel), grad_off, param_off, dtype, nbytes, P<float>(master), P<float>(s1),
+                                P<float>(s2), P<const float>(hyper), opt_kind, P<float>(sumsq), flags, blocks, threads, S(st));
+          });
+    m.def("sma_fused",
+          [](const PeerMesh& mesh, int channel, int algo, size_t param_off, size_t avg_off, int dtype, size_t nbytes,
+             uintptr_t grads, int grad_dtype, uintptr_t s1, uintptr_t s2, uintptr_t model_out, int model_dtype,
+             uintptr_t hyper, int opt_kind, int blocks, int threads, uintptr_t st) {
+              launch_sma_fused(algo, mesh.args(channel), param_off, avg_off, dtype, nbytes, P<const void>(grads), grad_dtype,
+                               P<float>(s1), P<float>(s2), P<void>(model_out), model_dtype, P<const float>(hyper), opt_kind,
+                               blocks, threads, S(st));
+          });
+    m.def("pair_avg",
+          [](const PeerMesh& mesh, int channel, int target, size_t pub0, size_t pub1, size_t ver_off, uintptr_t params,
+             int dtype, size_t nbytes, uintptr_t grads, int grad_dtype, uintptr_t s1, uintptr_t s2, uintptr_t hyper,
+             int opt_kind, int do_step, uintptr_t done_counter, int blocks, int threads, uintptr_t st) {
+              launch_pair_avg(mesh.args(channel), target, pub0, pub1, ver_off, P<void>(params), dtype, nbytes,
+                              P<const void>(grads), grad_dtype, P<float>(s1), P<float>(s2), P<const float>(hyper), opt_kind,
+                              do_step, P<uint32_t>(done_counter), blocks, threads, S(st));
+          });
+    m.def("publish",
+          [](const PeerMesh& mesh, int channel, size_t pub0, size_t pub1, size_t ver_off, uintptr_t src, size_t nbytes,
+             uintptr_t done_counter, int blocks, int threads, uintptr_t st) {
+              launch_publish(mesh.args(channel), pub0, pub1, ver_off, P<const void>(src), nbytes, P<uint32_t>(done_counter),
+                             blocks, threads, S(st));
+          });
+    m.def("pull",
+          [](const PeerMesh& mesh, int channel, int target, size_t pub0, size_t pub1, size_t ver_off, uintptr_t dst,
+             size_t nbytes, uintptr_t ok, int blocks, int threads, uintptr_t st) {
+              launch_pull(mesh.args(channel), target, pub0, pub1, ver_off, P<void>(dst), nbytes, P<uint32_t>(ok), blocks,
+                          threads, S(st));
+          });
+    m.def("broadcast",
+          [](const PeerMesh& mesh, int channel, int algo, size_t off, size_t nbytes, int root, int blocks, int threads,
+             uintptr_t st) { launch_broadcast(algo, mesh.args(channel), off, nbytes, root, blocks, threads, S(st)); });
+    m.def("allgather",
+          [](const PeerMesh& mesh, int channel, int algo, size_t in_off, size_t out_off, size_t nbytes_per_rank, int blocks,
+             int threads, uintptr_t st) {
+              launch_allgather(algo, mesh.args(channel), in_off, out_off, nbytes_per_rank, blocks, threads, S(st));
+          });
+    m.def("barrier", [](const PeerMesh& mesh, int channel, uintptr_t st) { launch_barrier(mesh.args(channel), S(st)); });
+
+    m.def("hyper_tick", [](uintptr_t hyper, uintptr_t st) { launch_hyper_tick(P<float>(hyper), S(st)); });
+    m.def("flat_opt",
+          [](uintptr_t params, int dtype, uintptr_t grads, int grad_dtype, uintptr_t master, uintptr_t s1, uintptr_t s2,
+             uintptr_t hyper, int opt_kind, size_t nelem, uintptr_t st) {
+              launch_flat_opt(P<void>(params), dtype, P<const void>(grads), grad_dtype, P<float>(master), P<float>(s1),
+                              P<float>(s2), P<const float>(hyper), opt_kind, nelem, S(st));
+          });
+    m.def("cast", [](uintptr_t src, int sdt, uintptr_t dst, int ddt, size_t nelem, float scale, uintptr_t st) {
+        launch_cast(P<const void>(src), sdt, P<void>(dst), ddt, nelem, scale, S(st));
+    });
+    m.def("sumsq", [](uintptr_t src, int dt, size_t nelem, uintptr_t out, uintptr_t st) {
+        launch_sumsq(P<const void>(src), dt, nelem, P<float>(out), S(st));
+    });
+    m.def("sumsq_diff", [](uintptr_t a, uintptr_t b, int dt, size_t nelem, uintptr_t out, uintptr_t st) {
+        launch_sumsq_diff(P<const void>(a), P<const void>(b), dt, nelem, P<float>(out), S(st));
+    });
+    m.def("axpby", [](uintptr_t y, uintptr_t x, int dt, size_t nelem, float a, float b, uintptr_t st) {
+        launch_axpby(P<void>(y), P<const void>(x), dt, nelem, a, b, S(st));
+    });
+    m.def("gns_finalize",
+          [](uintptr_t sums, uintptr_t state, uintptr_t out, float b_small, float b_big, float alpha, float nranks,
+             uintptr_t st) {
+              launch_gns_finalize(P<const float>(sums), P<float>(state), P<float>(out), b_small, b_big, alpha, nranks, S(st));
+          });
+    m.def("u8_normalize", [](uintptr_t src, uintptr_t dst, int ddt, size_t npix, uintptr_t mean3, uintptr_t invstd3, uintptr_t st) {
+        launch_u8_normalize(P<const uint8_t>(src), P<void>(dst), ddt, npix, P<const float>(mean3), P<const float>(invstd3), S(st));
+    });
+    m.def("fill_u32", [](uintptr_t p, uint32_t v, size_t n, uintptr_t st) { launch_fill_u32(P<uint32_t>(p), v, n, S(st)); });
+}

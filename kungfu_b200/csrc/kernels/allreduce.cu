@@ -1,0 +1,289 @@
+// kungfu_b200 — K1/K6/K10/K11: all-reduce kernels over peer-mapped HBM (NVLink 5 / NVSwitch).
+//
+// Three algorithms, picked per message size by the host-side dispatcher (see ops/allreduce.py):
+//   one-shot  : every rank loads the message from all peers and reduces locally. Latency path.
+//   two-shot  : reduce-scatter by P2P loads into the slice owner, then all-gather by P2P stores.
+//               In place on the symmetric arena; no barrier between the two phases is needed because
+//               slice r of every buffer is read only by rank r and written only by rank r.
+//   NVLS      : `multimem.ld_reduce` (switch fan-in) + `multimem.st` (switch fan-out) on the slice.
+// Fused epilogues: scale (1/np averaging, TF S-SGD `g / np`, optimizers/sync_sgd.py:103-104) and
+// squared-norm side reductions (gradient noise scale / variance monitors, optimizers/
+// grad_noise_scale.py:11-88, ops/monitor.py:6-17) without an extra pass over the gradients.
+//
+// Reference call sites replaced: ncclAllReduce (srcs/cpp/src/nccl/gpu_collective.cpp:146-166) and the
+// D2H → CPU all-reduce → H2D staging of the torch binding (srcs/cpp/src/torch/ops/cuda/
+// collective.cpp:31-54).
+#include "multimem.cuh"
+#include "signal.cuh"
+#include "kernels.h"
+
+#include <atomic>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+
+namespace kf {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+struct ArArgs {
+    size_t off;      // byte offset of the message inside every rank's arena
+    size_t nvec;     // number of 16-byte vectors
+    void* out;       // one-shot: local output (may be any device memory); others: unused
+    float scale;     // applied to float-accumulated types when flags & kArScale
+    float* sumsq;    // [0] += sum_r |x_r[slice]|^2 (or |x_local|^2 for NVLS), [1] += |result[slice]|^2
+    int flags;
+};
+
+template <typename T> struct IsFloatAcc { static constexpr bool value = std::is_floating_point<typename Elem<T>::Acc>::value; };
+
+template <typename T> __device__ __forceinline__ float vec_sumsq(const AccVec<T>& x) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < Elem<T>::kLanes; ++i) {
+        const float f = (float)x.a[i];
+        s = fmaf(f, f, s);
+    }
+    return s;
+}
+
+template <typename T> __device__ __forceinline__ void apply_scale(AccVec<T>& x, float scale) {
+    if constexpr (IsFloatAcc<T>::value) {
+#pragma unroll
+        for (int i = 0; i < Elem<T>::kLanes; ++i) x.a[i] = (typename Elem<T>::Acc)(x.a[i] * scale);
+    }
+}
+
+// Load vector `v` of the message from every peer (all loads issued before any use so that
+// nranks NVLink requests are in flight per thread) and reduce. `pre` accumulates sum_r |x_r|^2.
+template <typename T, int OP, bool SUMSQ>
+__device__ __forceinline__ AccVec<T> gather_reduce(const MeshArgs& m, size_t byte_off, float& pre) {
+    Vec16 buf[kMaxRanks];
+#pragma unroll
+    for (int i = 0; i < kMaxRanks; ++i) {
+        if (i < m.nranks) {
+            int r = m.rank + i;
+            if (r >= m.nranks) r -= m.nranks;
+            buf[i] = ld_stream(reinterpret_cast<const char*>(m.data[r]) + byte_off);
+        }
+    }
+    AccVec<T> acc = unpack<T>(buf[0]);
+    if constexpr (SUMSQ) pre += vec_sumsq<T>(acc);
+#pragma unroll
+    for (int i = 1; i < kMaxRanks; ++i) {
+        if (i < m.nranks) {
+            AccVec<T> x = unpack<T>(buf[i]);
+            if constexpr (SUMSQ) pre += vec_sumsq<T>(x);
+            red_into<OP, T>(acc, x);
+        }
+    }
+    return acc;
+}
+
+__device__ __forceinline__ void slice_bounds(size_t nvec, int nranks, int rank, size_t& s0, size_t& s1) {
+    const size_t per = (nvec + nranks - 1) / nranks;
+    s0 = (size_t)rank * per;
+    if (s0 > nvec) s0 = nvec;
+    s1 = s0 + per;
+    if (s1 > nvec) s1 = nvec;
+}
+
+template <bool SUMSQ> __device__ __forceinline__ void flush_sumsq(const ArArgs& a, float pre, float post) {
+    if constexpr (SUMSQ) {
+        __shared__ float red[32];
+        const float p0 = block_sum(pre, red);
+        const float p1 = block_sum(post, red);
+        if (threadIdx.x == 0) {
+            atomicAdd(&a.sumsq[0], p0);
+            atomicAdd(&a.sumsq[1], p1);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// one-shot
+// --------------------------------------------------------------------------------------------
+template <typename T, int OP, bool SUMSQ>
+__global__ void __launch_bounds__(512) allreduce_oneshot_kernel(const __grid_constant__ MeshArgs m,
+                                                                const __grid_constant__ ArArgs a) {
+    uint32_t seq = load_seq(m);
+    block_barrier<false>(m, seq);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    float pre = 0.f, post = 0.f;
+    for (size_t v = tid; v < a.nvec; v += stride) {
+        AccVec<T> acc = gather_reduce<T, OP, SUMSQ>(m, a.off + v * 16, pre);
+        if (a.flags & kArScale) apply_scale<T>(acc, a.scale);
+        if constexpr (SUMSQ) post += vec_sumsq<T>(acc);
+        st_plain(reinterpret_cast<char*>(a.out) + v * 16, pack<T>(acc));
+    }
+    // one-shot computes the full result on every rank: scale the side sums so that summing them over
+    // ranks gives the same totals as the sliced algorithms.
+    if constexpr (SUMSQ) {
+        pre /= (float)m.nranks;
+        post /= (float)m.nranks;
+    }
+    flush_sumsq<SUMSQ>(a, pre, post);
+    block_barrier<false>(m, seq); // peers are done reading my staging slot
+    store_seq(m, seq);
+}
+
+// --------------------------------------------------------------------------------------------
+// two-shot, P2P loads (reduce-scatter) + P2P stores (all-gather), in place
+// --------------------------------------------------------------------------------------------
+template <typename T, int OP, bool SUMSQ>
+__global__ void __launch_bounds__(512) allreduce_twoshot_kernel(const __grid_constant__ MeshArgs m,
+                                                                const __grid_constant__ ArArgs a) {
+    uint32_t seq = load_seq(m);
+    block_barrier<false>(m, seq);
+    size_t s0, s1;
+    slice_bounds(a.nvec, m.nranks, m.rank, s0, s1);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    float pre = 0.f, post = 0.f;
+    for (size_t v = s0 + tid; v < s1; v += stride) {
+        const size_t bo = a.off + v * 16;
+        AccVec<T> acc = gather_reduce<T, OP, SUMSQ>(m, bo, pre);
+        if (a.flags & kArScale) apply_scale<T>(acc, a.scale);
+        if constexpr (SUMSQ) post += vec_sumsq<T>(acc);
+        const Vec16 res = pack<T>(acc);
+#pragma unroll
+        for (int i = 0; i < kMaxRanks; ++i) {
+            if (i < m.nranks) {
+                int r = m.rank + i;
+                if (r >= m.nranks) r -= m.nranks;
+                st_stream(reinterpret_cast<char*>(m.data[r]) + bo, res);
+            }
+        }
+    }
+    flush_sumsq<SUMSQ>(a, pre, post);
+    block_barrier<true>(m, seq); // all slices have landed in my buffer / my stores are visible
+    store_seq(m, seq);
+}
+
+// --------------------------------------------------------------------------------------------
+// NVLS: switch-side reduction and multicast
+// --------------------------------------------------------------------------------------------
+template <typename T, int OP, bool SUMSQ>
+__global__ void __launch_bounds__(512) allreduce_nvls_kernel(const __grid_constant__ MeshArgs m,
+                                                             const __grid_constant__ ArArgs a) {
+    uint32_t seq = load_seq(m);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    float pre = 0.f, post = 0.f;
+    if constexpr (SUMSQ) {
+        // |x_local|^2 over the whole local message. Block b touches exactly the vectors that the
+        // peers' block b will later overwrite, and does so before it signals — no race with the
+        // in-place multicast stores.
+        for (int r = 0; r < m.nranks; ++r) {
+            size_t q0, q1;
+            slice_bounds(a.nvec, m.nranks, r, q0, q1);
+            for (size_t v = q0 + tid; v < q1; v += stride) {
+                const Vec16 x = ld_stream(reinterpret_cast<const char*>(m.data[m.rank]) + a.off + v * 16);
+                pre += vec_sumsq<T>(unpack<T>(x));
+            }
+        }
+    }
+    block_barrier<false>(m, seq);
+    size_t s0, s1;
+    slice_bounds(a.nvec, m.nranks, m.rank, s0, s1);
+    char* mc = reinterpret_cast<char*>(m.mc) + a.off;
+    for (size_t v = s0 + tid; v < s1; v += stride) {
+        Vec16 x = Multimem<T, OP>::ld_reduce(mc + v * 16);
+        if ((a.flags & kArScale) || SUMSQ) {
+            AccVec<T> acc = unpack<T>(x);
+            if (a.flags & kArScale) apply_scale<T>(acc, a.scale);
+            if constexpr (SUMSQ) post += vec_sumsq<T>(acc);
+            x = pack<T>(acc);
+        }
+        multimem_st(mc + v * 16, x);
+    }
+    flush_sumsq<SUMSQ>(a, pre, post);
+    block_barrier<true>(m, seq);
+    store_seq(m, seq);
+}
+
+// --------------------------------------------------------------------------------------------
+// host dispatch
+// --------------------------------------------------------------------------------------------
+template <typename T, int OP, bool SUMSQ>
+static void launch_typed(int algo, const MeshArgs& m, const ArArgs& a, int blocks, int threads, cudaStream_t st) {
+    if (algo == kAlgoOneShot) {
+        allreduce_oneshot_kernel<T, OP, SUMSQ><<<blocks, threads, 0, st>>>(m, a);
+    } else if (algo == kAlgoTwoShot) {
+        allreduce_twoshot_kernel<T, OP, SUMSQ><<<blocks, threads, 0, st>>>(m, a);
+    } else if (algo == kAlgoNvls) {
+        if constexpr (Multimem<T, OP>::kSupported) {
+            allreduce_nvls_kernel<T, OP, SUMSQ><<<blocks, threads, 0, st>>>(m, a);
+        } else {
+            throw std::runtime_error("kungfu_b200: NVLS all-reduce unsupported for this dtype/op");
+        }
+    } else {
+        throw std::runtime_error("kungfu_b200: unknown all-reduce algorithm");
+    }
+    count_launch();
+    KF_CUDA_CHECK(cudaGetLastError());
+}
+
+template <typename T, bool SUMSQ>
+static void launch_op(int op, int algo, const MeshArgs& m, const ArArgs& a, int blocks, int threads, cudaStream_t st) {
+    switch (op) {
+    case kSum: launch_typed<T, kSum, SUMSQ>(algo, m, a, blocks, threads, st); break;
+    case kMin: launch_typed<T, kMin, false>(algo, m, a, blocks, threads, st); break;
+    case kMax: launch_typed<T, kMax, false>(algo, m, a, blocks, threads, st); break;
+    case kProd: launch_typed<T, kProd, false>(algo, m, a, blocks, threads, st); break;
+    default: throw std::runtime_error("kungfu_b200: bad reduce op");
+    }
+}
+
+bool nvls_supported(int dtype, int op) {
+    switch (dtype) {
+    case kF32: return op == kSum;
+    case kBF16: case kF16: return op == kSum || op == kMin || op == kMax;
+    default: return false;
+    }
+}
+
+void launch_allreduce(int algo, const MeshArgs& m, size_t off, void* out, size_t nbytes, int dtype, int op, float scale,
+                      float* sumsq, int flags, int blocks, int threads, cudaStream_t st) {
+    if (nbytes % 16 != 0) throw std::runtime_error("kungfu_b200: all-reduce message must be padded to 16 bytes");
+    if (off % 16 != 0) throw std::runtime_error("kungfu_b200: all-reduce offset must be 16-byte aligned");
+    if (blocks < 1 || blocks > kMaxBlocks) throw std::runtime_error("kungfu_b200: bad block count");
+    if (threads < m.nranks || threads > 512) throw std::runtime_error("kungfu_b200: bad thread count");
+    if (algo == kAlgoNvls && m.mc == nullptr) throw std::runtime_error("kungfu_b200: NVLS requested but no multicast mapping");
+    if (algo == kAlgoOneShot && out == nullptr) throw std::runtime_error("kungfu_b200: one-shot needs an output buffer");
+    ArArgs a;
+    a.off = off;
+    a.nvec = nbytes / 16;
+    a.out = out;
+    a.scale = scale;
+    a.sumsq = sumsq;
+    a.flags = flags;
+    const bool sq = (flags & kArSumSq) != 0;
+    if (sq && (sumsq == nullptr || op != kSum)) throw std::runtime_error("kungfu_b200: sumsq epilogue needs op=sum and an output");
+#define KF_DISPATCH(T)                                                                                                  \
+    do {                                                                                                                \
+        if (sq) launch_op<T, true>(op, algo, m, a, blocks, threads, st);                                                \
+        else launch_op<T, false>(op, algo, m, a, blocks, threads, st);                                                  \
+    } while (0)
+    switch (dtype) {
+    case kF32: KF_DISPATCH(float); break;
+    case kBF16: KF_DISPATCH(__nv_bfloat16); break;
+    case kF16: KF_DISPATCH(__half); break;
+    case kF64: KF_DISPATCH(double); break;
+    case kI32: KF_DISPATCH(int32_t); break;
+    case kI64: KF_DISPATCH(int64_t); break;
+    case kU8: KF_DISPATCH(uint8_t); break;
+    case kI8: KF_DISPATCH(int8_t); break;
+    case kU32: KF_DISPATCH(uint32_t); break;
+    case kU64: KF_DISPATCH(uint64_t); break;
+    case kI16: KF_DISPATCH(int16_t); break;
+    case kU16: KF_DISPATCH(uint16_t); break;
+    default: throw std::runtime_error("kungfu_b200: unsupported dtype");
+    }
+#undef KF_DISPATCH
+}
+
+} // namespace kf

@@ -1,0 +1,133 @@
+// kungfu_b200 — shared device-side building blocks for the sm_100a collective kernels.
+//
+// Everything that the reference does on the CPU in `std_transform_2` / `float16_sum`
+// (srcs/go/kungfu/base/op.cpp:57-93, f16.c:16-50) happens here on 16-byte vectors with
+// fp32 accumulation for the 16-bit float types.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "mesh_args.h"
+
+namespace kf {
+
+// ---------------------------------------------------------------------------------------------
+// 16-byte vector access. Peer (NVLink) and local accesses use the same instructions; the address
+// aperture routes them. Streaming hints keep one-touch collective data out of L1.
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) Vec16 {
+    uint32_t w[4];
+};
+
+__device__ __forceinline__ Vec16 ld_stream(const void* p) {
+    Vec16 v;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3])
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_stream(void* p, const Vec16& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]),
+                 "r"(v.w[3])
+                 : "memory");
+}
+__device__ __forceinline__ Vec16 ld_plain(const void* p) { return *reinterpret_cast<const Vec16*>(p); }
+__device__ __forceinline__ void st_plain(void* p, const Vec16& v) { *reinterpret_cast<Vec16*>(p) = v; }
+
+// ---------------------------------------------------------------------------------------------
+// Element traits: storage type T, accumulator type A, lanes per 16-byte vector.
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Elem {
+    using Acc = T;
+    static constexpr int kLanes = 16 / sizeof(T);
+    __device__ static __forceinline__ Acc up(T x) { return x; }
+    __device__ static __forceinline__ T down(Acc x) { return x; }
+};
+template <> struct Elem<__nv_bfloat16> {
+    using Acc = float;
+    static constexpr int kLanes = 8;
+    __device__ static __forceinline__ float up(__nv_bfloat16 x) { return __bfloat162float(x); }
+    __device__ static __forceinline__ __nv_bfloat16 down(float x) { return __float2bfloat16_rn(x); }
+};
+template <> struct Elem<__half> {
+    using Acc = float;
+    static constexpr int kLanes = 8;
+    __device__ static __forceinline__ float up(__half x) { return __half2float(x); }
+    __device__ static __forceinline__ __half down(float x) { return __float2half_rn(x); }
+};
+
+template <typename T> struct AccVec {
+    typename Elem<T>::Acc a[Elem<T>::kLanes];
+};
+
+template <typename T> __device__ __forceinline__ AccVec<T> unpack(const Vec16& v) {
+    AccVec<T> r;
+    const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+    for (int i = 0; i < Elem<T>::kLanes; ++i) r.a[i] = Elem<T>::up(e[i]);
+    return r;
+}
+template <typename T> __device__ __forceinline__ Vec16 pack(const AccVec<T>& r) {
+    Vec16 v;
+    T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+    for (int i = 0; i < Elem<T>::kLanes; ++i) e[i] = Elem<T>::down(r.a[i]);
+    return v;
+}
+
+template <int OP, typename A> __device__ __forceinline__ A red_apply(A x, A y) {
+    if constexpr (OP == kSum) return x + y;
+    else if constexpr (OP == kMin) return x < y ? x : y;
+    else if constexpr (OP == kMax) return x > y ? x : y;
+    else return x * y;
+}
+template <int OP, typename T> __device__ __forceinline__ void red_into(AccVec<T>& acc, const AccVec<T>& x) {
+#pragma unroll
+    for (int i = 0; i < Elem<T>::kLanes; ++i) acc.a[i] = red_apply<OP>(acc.a[i], x.a[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block-wide sum of a float (used by the fused squared-norm side reductions).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// returns the block total in thread 0 (other threads: undefined). `smem` needs 32 floats.
+__device__ __forceinline__ float block_sum(float v, float* smem) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        t = lane < nw ? smem[lane] : 0.f;
+        t = warp_sum(t);
+    }
+    __syncthreads();
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side launch bookkeeping: every launch of one of OUR kernels is counted so bench.py can
+// report `gpu_launches` truthfully.
+// ---------------------------------------------------------------------------------------------
+
+#define KF_CUDA_CHECK(expr)                                                                                             \
+    do {                                                                                                                \
+        cudaError_t _e = (expr);                                                                                        \
+        if (_e != cudaSuccess) {                                                                                        \
+            throw std::runtime_error(std::string("CUDA error ") + cudaGetErrorString(_e) + " at " + __FILE__ + ":" +    \
+                                     std::to_string(__LINE__) + " in " #expr);                                          \
+        }                                                                                                               \
+    } while (0)
+
+} // namespace kf

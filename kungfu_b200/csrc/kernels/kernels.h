@@ -1,0 +1,82 @@
+// kungfu_b200 — host-callable launch API of the sm_100a kernel library (torch-free: raw pointers
+// and cudaStream_t only, so the library builds in seconds and has no ABI coupling to libtorch).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "mesh_args.h"
+
+namespace kf {
+
+enum Algo : int { kAlgoAuto = 0, kAlgoOneShot = 1, kAlgoTwoShot = 2, kAlgoNvls = 3 };
+enum ArFlags : int { kArScale = 1, kArSumSq = 2 };
+enum OptKind : int { kOptSgd = 0, kOptAdam = 1 };
+
+// Device-resident optimizer hyper-parameters (16 floats). Kept in device memory so that a captured
+// CUDA graph picks up learning-rate changes and the step counter without re-capture.
+enum HyperSlot : int {
+    kHpLr = 0, kHpMomentum = 1, kHpDampening = 2, kHpWeightDecay = 3, kHpNesterov = 4, kHpGradScale = 5,
+    kHpFirstStep = 6, kHpBeta1 = 7, kHpBeta2 = 8, kHpEps = 9, kHpBiasC1 = 10, kHpBiasC2 = 11, kHpStep = 12,
+    kHpAlpha = 13, kHpDecoupledWd = 14, kHpReserved = 15, kHpCount = 16
+};
+
+// ---- allreduce.cu
+void launch_allreduce(int algo, const MeshArgs& m, size_t off, void* out, size_t nbytes, int dtype, int op, float scale,
+                      float* sumsq, int flags, int blocks, int threads, cudaStream_t st);
+bool nvls_supported(int dtype, int op);
+
+// ---- fused_step.cu
+// S-SGD: reduce-scatter(grads) -> optimizer on the owned shard (fp32 master/state) -> all-gather(params).
+void launch_ssgd_fused(int algo, const MeshArgs& m, size_t grad_off, size_t param_off, int dtype, size_t nbytes,
+                       float* master_shard, float* s1_shard, float* s2_shard, const float* hyper, int opt_kind,
+                       float* sumsq, int flags, int blocks, int threads, cudaStream_t st);
+// SMA: all-reduce(params)/np -> alpha blend -> local optimizer step with LOCAL gradients.
+void launch_sma_fused(int algo, const MeshArgs& m, size_t param_off, size_t avg_off, int dtype, size_t nbytes,
+                      const void* grads, int grad_dtype, float* s1, float* s2, void* model_out, int model_dtype,
+                      const float* hyper, int opt_kind, int blocks, int threads, cudaStream_t st);
+// PairAveraging: pull the peer's published model over NVLink, v <- 0.5 (v + other), local optimizer step,
+// publish the new model (double buffer + version words).
+void launch_pair_avg(const MeshArgs& m, int target, size_t pub_off0, size_t pub_off1, size_t ver_off, void* params,
+                     int dtype, size_t nbytes, const void* grads, int grad_dtype, float* s1, float* s2,
+                     const float* hyper, int opt_kind, int do_step, uint32_t* done_counter, int blocks, int threads,
+                     cudaStream_t st);
+// publish(params) without averaging (step 0 of PairAveraging; `save_variable` on device)
+void launch_publish(const MeshArgs& m, size_t pub_off0, size_t pub_off1, size_t ver_off, const void* src, size_t nbytes,
+                    uint32_t* done_counter, int blocks, int threads, cudaStream_t st);
+// request(peer): copy the peer's latest published blob into dst; ok[0] = version read (0 = nothing published)
+void launch_pull(const MeshArgs& m, int target, size_t pub_off0, size_t pub_off1, size_t ver_off, void* dst,
+                 size_t nbytes, uint32_t* ok, int blocks, int threads, cudaStream_t st);
+
+// ---- misc.cu
+void launch_broadcast(int algo, const MeshArgs& m, size_t off, size_t nbytes, int root, int blocks, int threads,
+                      cudaStream_t st);
+void launch_allgather(int algo, const MeshArgs& m, size_t in_off, size_t out_off, size_t nbytes_per_rank, int blocks,
+                      int threads, cudaStream_t st);
+void launch_barrier(const MeshArgs& m, cudaStream_t st);
+
+// ---- optim.cu (single-GPU building blocks)
+void launch_hyper_tick(float* hyper, cudaStream_t st);
+void launch_flat_opt(void* params, int dtype, const void* grads, int grad_dtype, float* master, float* s1, float* s2,
+                     const float* hyper, int opt_kind, size_t nelem, cudaStream_t st);
+void launch_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t nelem, float scale, cudaStream_t st);
+void launch_sumsq(const void* src, int dtype, size_t nelem, float* out, cudaStream_t st); // out[0] += |x|^2
+void launch_sumsq_diff(const void* a, const void* b, int dtype, size_t nelem, float* out, cudaStream_t st);
+void launch_axpby(void* y, const void* x, int dtype, size_t nelem, float a, float b, cudaStream_t st); // y = a*x + b*y
+// gradient-noise-scale finalisation on device (reference: cpu/collective.cpp:212-258, ops/monitor.py:6-17)
+//   in : sums[0] = sum_r |g_r|^2 (over ranks), sums[1] = |g_avg|^2
+//   state: [0]=G_ema [1]=S_ema [2]=initialised flag; out[0]=noise scale, out[1]=G_biased, out[2]=S_biased
+void launch_gns_finalize(const float* sums, float* state, float* out, float batch_small, float batch_big, float alpha,
+                         float nranks, cudaStream_t st);
+// uint8 NHWC image -> normalised bf16/fp32 NHWC (channels_last) tensor, fused cast+normalise
+void launch_u8_normalize(const uint8_t* src, void* dst, int dst_dtype, size_t npix, const float* mean3,
+                         const float* invstd3, cudaStream_t st);
+void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t st);
+
+void count_launch(int n = 1);
+uint64_t launch_count();
+
+} // namespace kf

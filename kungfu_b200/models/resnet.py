@@ -1,0 +1,129 @@
+"""ResNet family (ImageNet), architecture-identical to torchvision's `resnet50` (25,557,032 parameters, 161
+trainable tensors) — the model of the reference's headline benchmark (benchmarks/system/benchmark_kungfu_torch.py:58
+`getattr(models, args.model)()`; README.md:201-219).
+
+B200 specifics: built for channels_last + bf16 from the start; BatchNorm+ReLU(+residual add) are expressed as one
+module (`BNAct`) so that a fused sm_100a kernel can replace the three memory-bound element-wise passes.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Type
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class BNAct(nn.BatchNorm2d):
+    """BatchNorm2d followed by an optional residual add and ReLU."""
+
+    def __init__(self, ch: int, relu: bool = True, zero_init: bool = False) -> None:
+        super().__init__(ch)
+        self.relu = relu
+        if zero_init:
+            nn.init.zeros_(self.weight)
+
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:  # type: ignore[override]
+        y = super().forward(x)
+        if residual is not None:
+            y = y + residual
+        return F.relu(y, inplace=True) if self.relu else y
+
+
+def conv3x3(i: int, o: int, stride: int = 1) -> nn.Conv2d:
+    return nn.Conv2d(i, o, 3, stride, 1, bias=False)
+
+
+def conv1x1(i: int, o: int, stride: int = 1) -> nn.Conv2d:
+    return nn.Conv2d(i, o, 1, stride, 0, bias=False)
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes: int, planes: int, stride: int = 1, downsample: Optional[nn.Module] = None) -> None:
+        super().__init__()
+        self.conv1 = conv1x1(inplanes, planes)
+        self.bn1 = BNAct(planes)
+        self.conv2 = conv3x3(planes, planes, stride)
+        self.bn2 = BNAct(planes)
+        self.conv3 = conv1x1(planes, planes * 4)
+        self.bn3 = BNAct(planes * 4)
+        self.downsample = downsample
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        identity = x if self.downsample is None else self.downsample(x)
+        out = self.bn1(self.conv1(x))
+        out = self.bn2(self.conv2(out))
+        return self.bn3(self.conv3(out), identity)
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, inplanes: int, planes: int, stride: int = 1, downsample: Optional[nn.Module] = None) -> None:
+        super().__init__()
+        self.conv1 = conv3x3(inplanes, planes, stride)
+        self.bn1 = BNAct(planes)
+        self.conv2 = conv3x3(planes, planes)
+        self.bn2 = BNAct(planes)
+        self.downsample = downsample
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        identity = x if self.downsample is None else self.downsample(x)
+        out = self.bn1(self.conv1(x))
+        return self.bn2(self.conv2(out), identity)
+
+
+class _Down(nn.Sequential):
+    def __init__(self, i: int, o: int, stride: int) -> None:
+        super().__init__(conv1x1(i, o, stride), BNAct(o, relu=False))
+
+
+class ResNet(nn.Module):
+    def __init__(self, block: Type[nn.Module], layers: List[int], num_classes: int = 1000) -> None:
+        super().__init__()
+        self.inplanes = 64
+        self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
+        self.bn1 = BNAct(64)
+        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        self.layer1 = self._make_layer(block, 64, layers[0], 1)
+        self.layer2 = self._make_layer(block, 128, layers[1], 2)
+        self.layer3 = self._make_layer(block, 256, layers[2], 2)
+        self.layer4 = self._make_layer(block, 512, layers[3], 2)
+        self.avgpool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Linear(512 * block.expansion, num_classes)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+    def _make_layer(self, block, planes: int, blocks: int, stride: int) -> nn.Sequential:
+        down = None
+        if stride != 1 or self.inplanes != planes * block.expansion:
+            down = _Down(self.inplanes, planes * block.expansion, stride)
+        layers = [block(self.inplanes, planes, stride, down)]
+        self.inplanes = planes * block.expansion
+        layers += [block(self.inplanes, planes) for _ in range(1, blocks)]
+        return nn.Sequential(*layers)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = self.maxpool(self.bn1(self.conv1(x)))
+        x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
+        return self.fc(torch.flatten(self.avgpool(x), 1))
+
+
+def resnet18(num_classes: int = 1000) -> ResNet:
+    return ResNet(BasicBlock, [2, 2, 2, 2], num_classes)
+
+
+def resnet50(num_classes: int = 1000) -> ResNet:
+    return ResNet(Bottleneck, [3, 4, 6, 3], num_classes)
+
+
+def resnet101(num_classes: int = 1000) -> ResNet:
+    return ResNet(Bottleneck, [3, 4, 23, 3], num_classes)
+
+
+def to_b200(model: nn.Module, dtype: torch.dtype = torch.bfloat16, device="cuda") -> nn.Module:
+    """channels_last + low-precision weights; the fused optimizers keep the fp32 master copy."""
+    return model.to(device=device, dtype=dtype, memory_format=torch.channels_last)

@@ -1,0 +1,293 @@
+"""Collective operations: GPU tensors go through our sm_100a kernels over peer-mapped HBM, CPU tensors
+through the native CPU runtime (graph strategies over sockets).
+
+API parity: `kungfu.torch.ops.{all_reduce_fn,inplace_all_reduce_op,inplace_all_reduce_async_op,wait_handle,
+wait_all_handles,all_gather,broadcast_parameters}` (srcs/python/kungfu/torch/ops/collective.py:8-55) and the TF
+ops `barrier/consensus/broadcast/all_reduce/all_gather` (srcs/python/kungfu/tensorflow/ops/collective.py:8-133).
+
+Algorithm table (KUNGFU_CONFIG_ALGO = auto | oneshot | twoshot | nvls):
+  <= oneshot_max bytes  : one-shot (every rank reduces the whole message; latency path)
+  larger                : NVLS multimem reduce+multicast when the mesh has a multicast mapping and the
+                          dtype/op is switch-reducible, else two-shot P2P.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from ..runtime import get_runtime
+from ..utils import dtypes
+
+
+@dataclass
+class AlgoConfig:
+    algo: str = os.environ.get("KUNGFU_CONFIG_ALGO", "auto").lower()
+    oneshot_max: int = int(os.environ.get("KUNGFU_ONESHOT_MAX", str(256 << 10)))
+    threads: int = int(os.environ.get("KUNGFU_COMM_THREADS", "512"))
+    max_blocks: int = int(os.environ.get("KUNGFU_COMM_BLOCKS", "32"))
+    vec_per_thread: int = 2
+
+
+CONFIG = AlgoConfig()
+
+_ALGO_CODE = {"auto": 0, "oneshot": 1, "twoshot": 2, "nvls": 3}
+
+
+def pick_algo(arena, nbytes: int, dtype_code: int, op_code: int, inplace: bool, force: Optional[str] = None) -> int:
+    """Returns the kernel algorithm code for a message."""
+    ext = arena.ext
+    name = (force or CONFIG.algo).lower()
+    if name == "nccl":
+        name = "auto"
+    if name != "auto":
+        code = _ALGO_CODE[name]
+        if code == ext.ALGO_NVLS and not (arena.has_multicast and ext.nvls_supported(dtype_code, op_code)):
+            code = ext.ALGO_TWOSHOT
+        if code == ext.ALGO_ONESHOT and inplace:
+            code = ext.ALGO_TWOSHOT
+        return code
+    if not inplace and nbytes <= CONFIG.oneshot_max:
+        return ext.ALGO_ONESHOT
+    if arena.has_multicast and ext.nvls_supported(dtype_code, op_code):
+        return ext.ALGO_NVLS
+    return ext.ALGO_TWOSHOT
+
+
+def pick_blocks(nbytes: int, nranks: int, sliced: bool, max_blocks: Optional[int] = None) -> int:
+    """Grid size: enough CTAs to keep NVLink busy, few enough to leave the SMs to backward."""
+    mb = max_blocks or CONFIG.max_blocks
+    nvec = (nbytes + 15) // 16
+    work = (nvec + nranks - 1) // nranks if sliced else nvec
+    per_block = CONFIG.threads * CONFIG.vec_per_thread
+    return max(1, min(mb, (work + per_block - 1) // per_block))
+
+
+class Handle:
+    """Completion handle of an asynchronous collective (reference: `HandleManager`,
+    srcs/cpp/include/kungfu/utils/handler_manager.hpp:40-83 — busy-waiting there, a CUDA event here)."""
+
+    __slots__ = ("event", "post", "arena")
+
+    def __init__(self, event=None, post=None, arena=None):
+        self.event = event
+        self.post = post
+        self.arena = arena
+
+    def wait(self) -> None:
+        if self.event is not None:
+            torch.cuda.current_stream().wait_event(self.event)
+            self.event = None
+        if self.post is not None:
+            self.post()
+            self.post = None
+
+
+def _run_on_comm(plane, fn, tensors=(), wait: bool = True):
+    """Run `fn(stream)` on the plane's comm stream, ordered after the caller's stream. All staged
+    collectives share the staging slot and signal channel 0, so they are serialised on ONE stream."""
+    cur = torch.cuda.current_stream()
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    plane.comm_stream.wait_event(ev)
+    with torch.cuda.stream(plane.comm_stream):
+        fn(plane.comm_stream)
+    for t in tensors:
+        t.record_stream(plane.comm_stream)
+    done = torch.cuda.Event()
+    done.record(plane.comm_stream)
+    if wait:
+        cur.wait_event(done)
+    return done
+
+
+def _gpu_all_reduce_(x: torch.Tensor, op_code: int, average: bool, stream: Optional[torch.cuda.Stream] = None,
+                     algo: Optional[str] = None) -> None:
+    """In-place all-reduce of an arbitrary contiguous CUDA tensor, staged through the symmetric arena.
+    Must be called with `stream` = the plane's comm stream (see `_run_on_comm`)."""
+    rt = get_runtime()
+    plane = rt.gpu
+    arena, off, cap = plane.staging()
+    ext = plane.ext
+    dt = dtypes.dtype_code(x.dtype)
+    flat = x.view(-1)
+    esize = x.element_size()
+    st = stream or torch.cuda.current_stream()
+    scale = 1.0 / rt.size if average else 1.0
+    flags = ext.FLAG_SCALE if average else 0
+    if average and not x.dtype.is_floating_point:
+        raise TypeError("kungfu_b200: averaging all-reduce needs a floating point tensor")
+    chunk_elems = (cap // esize) // 8 * 8
+    n = flat.numel()
+    with torch.cuda.stream(st):
+        for lo in range(0, n, chunk_elems):
+            hi = min(n, lo + chunk_elems)
+            nb = (hi - lo) * esize
+            nb_pad = (nb + 15) // 16 * 16
+            stage = arena.bytes_view(off, nb_pad)
+            stage[:nb].copy_(flat[lo:hi].view(torch.uint8), non_blocking=True)
+            if nb_pad != nb:
+                stage[nb:].zero_()
+            a = pick_algo(arena, nb_pad, dt, op_code, inplace=False, force=algo)
+            if a == ext.ALGO_ONESHOT and nb_pad == nb and flat[lo:hi].data_ptr() % 16 == 0:
+                # results go straight into the user tensor
+                blocks = pick_blocks(nb_pad, rt.size, sliced=False)
+                ext.allreduce(arena.mesh, 0, a, off, flat[lo:hi].data_ptr(), nb_pad, dt, op_code, scale, 0, flags, blocks,
+                              CONFIG.threads, st.cuda_stream)
+            else:
+                if a == ext.ALGO_ONESHOT:
+                    a = ext.ALGO_TWOSHOT
+                blocks = pick_blocks(nb_pad, rt.size, sliced=True)
+                ext.allreduce(arena.mesh, 0, a, off, 0, nb_pad, dt, op_code, scale, 0, flags, blocks, CONFIG.threads,
+                              st.cuda_stream)
+                flat[lo:hi].view(torch.uint8).copy_(stage[:nb], non_blocking=True)
+
+
+def all_reduce_(x: torch.Tensor, op=None, name: str = "") -> torch.Tensor:
+    """In-place all-reduce. `op`: sum (default) | min | max | prod | avg."""
+    code, avg = dtypes.op_code(op)
+    rt = get_runtime()
+    if rt.size == 1:
+        return x
+    if x.is_cuda:
+        plane = rt.gpu
+        if not x.is_contiguous():
+            y = x.contiguous()
+            _run_on_comm(plane, lambda s: _gpu_all_reduce_(y, code, avg, stream=s), (y,))
+            x.copy_(y)
+        else:
+            _run_on_comm(plane, lambda s: _gpu_all_reduce_(x, code, avg, stream=s), (x,))
+        return x
+    opname = {0: "sum", 1: "min", 2: "max", 3: "prod"}[code]
+    if x.is_contiguous():
+        rt.control.all_reduce_cpu_(x, opname, name)
+        if avg:
+            x.div_(rt.size)
+    else:
+        y = x.contiguous()
+        rt.control.all_reduce_cpu_(y, opname, name)
+        if avg:
+            y.div_(rt.size)
+        x.copy_(y)
+    return x
+
+
+def all_reduce(x: torch.Tensor, op=None, name: str = "") -> torch.Tensor:
+    return all_reduce_(x.clone(), op, name)
+
+
+def all_reduce_async_(x: torch.Tensor, name: str = "", op=None) -> Handle:
+    """Asynchronous in-place all-reduce on the comm stream; `Handle.wait()` makes the current stream
+    wait for it (no host blocking)."""
+    code, avg = dtypes.op_code(op)
+    rt = get_runtime()
+    if rt.size == 1:
+        return Handle()
+    if not x.is_cuda:
+        all_reduce_(x, op, name)
+        return Handle()
+    plane = rt.gpu
+    done = _run_on_comm(plane, lambda s: _gpu_all_reduce_(x, code, avg, stream=s), (x,), wait=False)
+    return Handle(event=done)
+
+
+def wait_handle(h: Handle) -> None:
+    h.wait()
+
+
+def wait_all_handles(hs: List[Handle]) -> None:
+    for h in hs:
+        h.wait()
+
+
+def broadcast_(x: torch.Tensor, root: int = 0, name: str = "") -> torch.Tensor:
+    rt = get_runtime()
+    if rt.size == 1:
+        return x
+    if x.is_cuda:
+        plane = rt.gpu
+        arena, off, cap = plane.staging()
+        ext = plane.ext
+        flat = x.contiguous().view(-1).view(torch.uint8)
+        n = flat.numel()
+
+        def run(st):
+            for lo in range(0, n, cap):
+                hi = min(n, lo + cap)
+                nb = hi - lo
+                nb_pad = (nb + 15) // 16 * 16
+                stage = arena.bytes_view(off, nb_pad)
+                if rt.rank == root:
+                    stage[:nb].copy_(flat[lo:hi], non_blocking=True)
+                algo = ext.ALGO_NVLS if (arena.has_multicast and CONFIG.algo in ("auto", "nvls")) else ext.ALGO_TWOSHOT
+                blocks = pick_blocks(nb_pad, 1, sliced=False)
+                ext.broadcast(arena.mesh, 0, algo, off, nb_pad, root, blocks, CONFIG.threads, st.cuda_stream)
+                if rt.rank != root:
+                    flat[lo:hi].copy_(stage[:nb], non_blocking=True)
+
+        _run_on_comm(plane, run, (flat,))
+        if not x.is_contiguous():
+            x.copy_(flat.view(x.dtype).view(x.shape))
+        return x
+    data = x.contiguous().view(-1).view(torch.uint8).numpy().tobytes() if rt.rank == root else b""
+    got = rt.control.broadcast_bytes(data, root)
+    if rt.rank != root:
+        x.copy_(torch.frombuffer(bytearray(got), dtype=x.dtype).view(x.shape))
+    return x
+
+
+def all_gather(x: torch.Tensor, name: str = "") -> torch.Tensor:
+    """Returns a tensor of shape [np, *x.shape] (reference: torch/ops/collective.py:50-55)."""
+    rt = get_runtime()
+    n = rt.size
+    out = x.new_empty((n,) + tuple(x.shape))
+    if n == 1:
+        out[0].copy_(x)
+        return out
+    if x.is_cuda:
+        plane = rt.gpu
+        arena, off, cap = plane.staging()
+        ext = plane.ext
+        flat = x.contiguous().view(-1).view(torch.uint8)
+        nb = flat.numel()
+        nb_pad = (nb + 15) // 16 * 16
+        if nb_pad * (n + 1) > cap:
+            raise ValueError("kungfu_b200: all_gather message exceeds the staging arena (raise KUNGFU_STAGING_MB)")
+        in_off, out_off = off, off + nb_pad
+
+        def run(st):
+            arena.bytes_view(in_off, nb_pad)[:nb].copy_(flat, non_blocking=True)
+            algo = ext.ALGO_NVLS if (arena.has_multicast and CONFIG.algo in ("auto", "nvls")) else ext.ALGO_TWOSHOT
+            ext.allgather(arena.mesh, 0, algo, in_off, out_off, nb_pad, pick_blocks(nb_pad, 1, False), CONFIG.threads,
+                          st.cuda_stream)
+            res = arena.bytes_view(out_off, nb_pad * n).view(n, nb_pad)[:, :nb]
+            out.view(n, -1).view(torch.uint8).copy_(res, non_blocking=True)
+
+        _run_on_comm(plane, run, (flat, out))
+        return out
+    parts = rt.control.all_gather_bytes(x.contiguous().view(-1).view(torch.uint8).numpy().tobytes())
+    for i, p in enumerate(parts):
+        out[i].copy_(torch.frombuffer(bytearray(p), dtype=x.dtype).view(x.shape))
+    return out
+
+
+def barrier() -> None:
+    """Host barrier over the control plane (+ device flag barrier when a GPU plane exists)."""
+    rt = get_runtime()
+    if rt.size > 1 and rt._gpu is not None and rt._gpu._staging is not None:
+        a, _, _ = rt.gpu.staging()
+        _run_on_comm(rt.gpu, lambda s: rt.gpu.ext.barrier(a.mesh, 0, s.cuda_stream))
+        torch.cuda.current_stream().synchronize()
+        a.check()
+    rt.control.barrier()
+
+
+def consensus(x) -> bool:
+    rt = get_runtime()
+    if isinstance(x, torch.Tensor):
+        b = x.detach().cpu().contiguous().view(-1).view(torch.uint8).numpy().tobytes()
+    else:
+        b = bytes(x)
+    return rt.control.consensus(b)

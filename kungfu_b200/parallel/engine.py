@@ -1,0 +1,436 @@
+"""FlatEngine — the GPU execution engine behind the distributed optimizers.
+
+One engine owns a symmetric arena holding the flat gradient region (and, depending on the mode, the flat
+parameter region, an averaging scratch region or the published-model double buffer), re-points
+`param.data` / `param.grad` into it, and launches ONE fused kernel per bucket on a high-priority comm
+stream as soon as backward has produced the bucket (post-accumulate-grad hooks), so communication +
+optimizer math overlap the rest of backward. Everything is stream-ordered: no host synchronisation, no
+per-step negotiation, CUDA-graph capturable (sequence numbers and hyper-parameters live on the device).
+
+Replaces: `NCCLScheduler` / `LinearExecutor` / `NCCLThread` order agreement + blocking per-op stream sync
+(srcs/cpp/src/nccl/scheduler.cpp:8-130, gpu_collective.cpp:146-155), the TF-stream spin-wait
+(srcs/cpp/src/tensorflow/ops/gpu/collective.cpp:11-34), and the torch path's "all comm after backward"
+(srcs/python/kungfu/torch/optimizers/sync_sgd.py:12-26).
+
+Modes
+  ssgd    fused reduce-scatter -> optimizer(shard) -> all-gather(params)       [K1b]
+  grads   bucketed in-place all-reduce(avg) of gradients, then any torch optimizer  [K1]
+  sma     all-reduce(model)/np -> blend -> local step                               [K8]
+  pair    pull one peer's published model -> average -> local step -> publish       [K9]
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional
+
+import torch
+
+from ..ops import collective as coll
+from ..runtime import get_runtime
+from ..utils import dtypes
+from .flat import Bucket, FlatLayout, group_params
+
+HP = dict(lr=0, momentum=1, dampening=2, weight_decay=3, nesterov=4, grad_scale=5, first_step=6, beta1=7, beta2=8, eps=9,
+          bias_c1=10, bias_c2=11, step=12, alpha=13, decoupled_wd=14)
+
+
+def _view_like(flat: torch.Tensor, offset: int, p: torch.Tensor) -> torch.Tensor:
+    """View of `flat[offset : offset + p.numel()]` with p's shape AND memory format (channels_last conv
+    weights keep their NHWC strides, so cuDNN sees the layout it was given and autograd's gradient
+    layout contract holds without extra copies)."""
+    if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
+        return flat.as_strided(p.shape, p.stride(), flat.storage_offset() + offset)
+    if p.dim() == 5 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last_3d):
+        return flat.as_strided(p.shape, p.stride(), flat.storage_offset() + offset)
+    return flat[offset:offset + p.numel()].view(p.shape)
+
+
+class _Set:
+    """One homogeneous (param group, dtype) set with its regions and state."""
+
+    def __init__(self, group_index: int, layout: FlatLayout) -> None:
+        self.group_index = group_index
+        self.layout = layout
+        self.g_off = 0
+        self.p_off = 0
+        self.x_off = 0  # sma: avg scratch; pair: pub buffer 0
+        self.x_off2 = 0  # pair: pub buffer 1
+        self.ver_off = 0
+        self.grads: Optional[torch.Tensor] = None
+        self.params: Optional[torch.Tensor] = None
+        self.hyper: Optional[torch.Tensor] = None
+        self.hyper_cache: Optional[List[float]] = None
+        self.master: List[Optional[torch.Tensor]] = []
+        self.s1: List[Optional[torch.Tensor]] = []
+        self.s2: List[Optional[torch.Tensor]] = []
+        self.ready: List[int] = []
+        self.done_counter: Optional[torch.Tensor] = None
+        self.state_ready = False
+
+
+class FlatEngine:
+    def __init__(self, param_groups, named_parameters=None, mode: str = "ssgd", opt_kind: Optional[str] = None,
+                 average: bool = True, overlap: bool = True, bucket_mb: Optional[float] = None, monitor: bool = False,
+                 alpha: float = 0.1, algo: Optional[str] = None, name: str = "engine") -> None:
+        self.rt = get_runtime()
+        self.plane = self.rt.gpu
+        self.ext = self.plane.ext
+        self.mode = mode
+        self.opt_kind = opt_kind  # "sgd" | "adam" | None (grads mode)
+        self.average = average
+        self.overlap = overlap and mode in ("ssgd", "grads")
+        self.monitor = monitor
+        self.alpha = alpha
+        self.algo = algo
+        self.param_groups = param_groups
+        self.nranks = self.rt.size
+        self.rank = self.rt.rank
+        mb = bucket_mb if bucket_mb is not None else float(os.environ.get("KUNGFU_BUCKET_MB", "8"))
+        self.bucket_bytes = int(mb * (1 << 20))
+        self.max_blocks = int(os.environ.get("KUNGFU_COMM_BLOCKS", "32"))
+        self.threads = coll.CONFIG.threads
+        named = list(named_parameters) if named_parameters is not None else None
+        self.sets: List[_Set] = []
+        whole = mode in ("pair",)  # pair averaging works on the whole model at once
+        for s in group_params(param_groups, named):
+            bb = (1 << 62) if whole else self.bucket_bytes
+            self.sets.append(_Set(s["group"], FlatLayout(s["items"], s["dtype"], bb)))
+        if not self.sets:
+            raise ValueError("kungfu_b200: optimizer has no trainable parameters")
+        self._check_consensus()
+        self._build_arena(name)
+        self._adopt_tensors()
+        self.sumsq = torch.zeros(4, dtype=torch.float32, device=self.plane.device)
+        self._step_open = False  # a step's first kernel has been launched
+        self._launched = [0 for _ in self.sets]  # next bucket to launch per set
+        self._hooks = []
+        self._pending_event: Optional[torch.cuda.Event] = None
+        self.steps = 0
+        self.kernel_launches = 0
+        if self.overlap:
+            self._install_hooks()
+
+    # ---------------------------------------------------------------------------------------------
+    def _check_consensus(self) -> None:
+        if self.nranks == 1:
+            return
+        import hashlib
+
+        h = hashlib.sha1()
+        for s in self.sets:
+            h.update(s.layout.digest())
+        h.update(f"{self.mode}:{self.opt_kind}:{self.bucket_bytes}".encode())
+        if not self.rt.control.consensus(h.digest()):
+            raise RuntimeError("kungfu_b200: ranks disagree on the parameter/bucket plan")
+
+    def _build_arena(self, name: str) -> None:
+        total = 1 << 20
+        for s in self.sets:
+            nb = (s.layout.nbytes + 4095) // 4096 * 4096
+            n_regions = {"ssgd": 2, "grads": 1, "sma": 3, "pair": 4}[self.mode]
+            total += n_regions * (nb + 4096) + 8192
+        self.arena = self.plane.new_arena(total, name)
+        for s in self.sets:
+            nb = s.layout.nbytes
+            s.g_off = self.arena.alloc(nb, align=4096)
+            if self.mode in ("ssgd", "sma", "pair"):
+                s.p_off = self.arena.alloc(nb, align=4096)
+            if self.mode == "sma":
+                s.x_off = self.arena.alloc(nb, align=4096)
+            if self.mode == "pair":
+                s.x_off = self.arena.alloc(nb, align=4096)
+                s.x_off2 = self.arena.alloc(nb, align=4096)
+                s.ver_off = self.arena.alloc(256, align=256)
+                s.done_counter = torch.zeros(4, dtype=torch.int32, device=self.plane.device)
+            s.hyper = torch.zeros(16, dtype=torch.float32, device=self.plane.device)
+
+    def _adopt_tensors(self) -> None:
+        """Re-point param.grad (and param.data where the mode needs it) into the arena."""
+        for s in self.sets:
+            lay = s.layout
+            s.grads = self.arena.view(s.g_off, lay.total, lay.dtype)
+            s.grads.zero_()
+            if self.mode in ("ssgd", "sma", "pair"):
+                s.params = self.arena.view(s.p_off, lay.total, lay.dtype)
+                s.params.zero_()
+            for e in lay.entries:
+                p = e.param
+                if s.params is not None:
+                    pv = _view_like(s.params, e.offset, p)
+                    pv.copy_(p.data)
+                    p.data = pv
+                gv = _view_like(s.grads, e.offset, p)
+                if p.grad is not None:
+                    gv.copy_(p.grad)
+                p.grad = gv
+            nb = len(lay.buckets)
+            s.master = [None] * nb
+            s.s1 = [None] * nb
+            s.s2 = [None] * nb
+            s.ready = [0] * nb
+        torch.cuda.current_stream().synchronize()
+
+    # ---------------------------------------------------------------------------------------------
+    def _sync_hyper(self) -> None:
+        """Mirror the torch optimizer's param_group hyper-parameters into device memory (only when changed)."""
+        for s in self.sets:
+            g = self.param_groups[s.group_index]
+            v = [0.0] * 16
+            v[HP["lr"]] = float(g.get("lr", 0.0))
+            v[HP["weight_decay"]] = float(g.get("weight_decay", 0.0))
+            v[HP["grad_scale"]] = (1.0 / self.nranks) if (self.average and self.mode in ("ssgd",)) else 1.0
+            v[HP["alpha"]] = float(self.alpha)
+            if self.opt_kind == "adam":
+                b1, b2 = g.get("betas", (0.9, 0.999))
+                v[HP["beta1"]], v[HP["beta2"]] = float(b1), float(b2)
+                v[HP["eps"]] = float(g.get("eps", 1e-8))
+                v[HP["decoupled_wd"]] = 1.0 if g.get("decoupled_weight_decay", g.get("_adamw", False)) else 0.0
+            else:
+                v[HP["momentum"]] = float(g.get("momentum", 0.0))
+                v[HP["dampening"]] = float(g.get("dampening", 0.0))
+                v[HP["nesterov"]] = 1.0 if g.get("nesterov", False) else 0.0
+            if s.hyper_cache is None:
+                s.hyper.copy_(torch.tensor(v, dtype=torch.float32))
+                s.hyper_cache = v
+            elif any(v[i] != s.hyper_cache[i] for i in (0, 1, 2, 3, 4, 5, 7, 8, 9, 13, 14)):
+                # keep the device-side step counter / bias corrections
+                idx = [0, 1, 2, 3, 4, 5, 7, 8, 9, 13, 14]
+                s.hyper[idx] = torch.tensor([v[i] for i in idx], dtype=torch.float32, device=s.hyper.device)
+                s.hyper_cache = v
+
+    def _needs_state(self, s: _Set):
+        g = self.param_groups[s.group_index]
+        if self.opt_kind == "adam":
+            return True, True
+        return float(g.get("momentum", 0.0)) != 0.0, False
+
+    def _ensure_state(self) -> None:
+        """Lazily create fp32 master weights + optimizer state (after any user-side broadcast)."""
+        for s in self.sets:
+            if s.state_ready or self.mode == "grads":
+                s.state_ready = True
+                continue
+            lay = s.layout
+            need1, need2 = self._needs_state(s)
+            dev = self.plane.device
+            for b in lay.buckets:
+                if self.mode == "ssgd" and self.nranks > 1:
+                    n = lay.shard_elems(b, self.nranks)
+                    lo, hi = lay.shard_range(b, self.nranks, self.rank)
+                else:
+                    n = b.numel
+                    lo, hi = b.start, b.start + b.numel
+                if lay.dtype != torch.float32 and self.mode == "ssgd":
+                    m = torch.zeros(n, dtype=torch.float32, device=dev)
+                    m[:hi - lo].copy_(s.params[lo:hi])
+                    s.master[b.index] = m
+                if need1:
+                    s.s1[b.index] = torch.zeros(n, dtype=torch.float32, device=dev)
+                if need2:
+                    s.s2[b.index] = torch.zeros(n, dtype=torch.float32, device=dev)
+            s.state_ready = True
+
+    # ---------------------------------------------------------------------------------------------
+    def _install_hooks(self) -> None:
+        for si, s in enumerate(self.sets):
+            for e in s.layout.entries:
+                gv = _view_like(s.grads, e.offset, e.param)
+
+                def hook(p, si=si, bi=e.bucket, gv=gv):
+                    g = p.grad
+                    if g is not None and g.data_ptr() != gv.data_ptr():
+                        # somebody replaced .grad (e.g. zero_grad(set_to_none=True)): move it back into the arena
+                        gv.copy_(g)
+                        p.grad = gv
+                    self._on_grad_ready(si, bi)
+                self._hooks.append(e.param.register_post_accumulate_grad_hook(hook))
+
+    def remove_hooks(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks.clear()
+
+    def _on_grad_ready(self, si: int, bi: int) -> None:
+        s = self.sets[si]
+        s.ready[bi] += 1
+        # launch strictly in bucket order so that every rank issues the same kernel sequence
+        while self._launched[si] < len(s.layout.buckets):
+            b = s.layout.buckets[self._launched[si]]
+            if s.ready[b.index] < len(b.entries):
+                break
+            self._launch_bucket(si, b, after_current=True)
+            self._launched[si] += 1
+
+    def _open_step(self) -> None:
+        if self._step_open:
+            return
+        self._step_open = True
+        self._sync_hyper()
+        self._ensure_state()
+        cs = self.plane.comm_stream
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        cs.wait_event(ev)
+        if self.opt_kind is not None:
+            for s in self.sets:
+                self.ext.hyper_tick(s.hyper.data_ptr(), cs.cuda_stream)
+                self.kernel_launches += 1
+
+    def _algo_for(self, s: _Set, nbytes: int) -> int:
+        dt = dtypes.dtype_code(s.layout.dtype)
+        return coll.pick_algo(self.arena, nbytes, dt, dtypes.SUM, inplace=True, force=self.algo)
+
+    def _launch_bucket(self, si: int, b: Bucket, after_current: bool) -> None:
+        s = self.sets[si]
+        lay = s.layout
+        self._open_step()
+        cs = self.plane.comm_stream
+        if after_current:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            cs.wait_event(ev)
+        nbytes = b.nbytes(lay.esize)
+        boff = b.start * lay.esize
+        dt = dtypes.dtype_code(lay.dtype)
+        flags = self.ext.FLAG_SUMSQ if self.monitor else 0
+        sumsq = self.sumsq.data_ptr() if self.monitor else 0
+        kind = self.ext.OPT_ADAM if self.opt_kind == "adam" else self.ext.OPT_SGD
+        ptr = lambda t: t.data_ptr() if t is not None else 0
+        if self.mode == "ssgd":
+            if self.nranks == 1:
+                self.ext.flat_opt(s.params.data_ptr() + boff, dt, s.grads.data_ptr() + boff, dt, ptr(s.master[b.index]),
+                                  ptr(s.s1[b.index]), ptr(s.s2[b.index]), s.hyper.data_ptr(), kind, b.numel, cs.cuda_stream)
+                if self.monitor:
+                    self.ext.sumsq(s.grads.data_ptr() + boff, dt, b.numel, self.sumsq.data_ptr(), cs.cuda_stream)
+                    self.ext.sumsq(s.grads.data_ptr() + boff, dt, b.numel, self.sumsq.data_ptr() + 4, cs.cuda_stream)
+                    self.kernel_launches += 2
+            else:
+                algo = self._algo_for(s, nbytes)
+                blocks = coll.pick_blocks(nbytes, self.nranks, True, self.max_blocks)
+                self.ext.ssgd_fused(self.arena.mesh, 0, algo, s.g_off + boff, s.p_off + boff, dt, nbytes,
+                                    ptr(s.master[b.index]), ptr(s.s1[b.index]), ptr(s.s2[b.index]), s.hyper.data_ptr(), kind,
+                                    sumsq, flags, blocks, self.threads, cs.cuda_stream)
+        elif self.mode == "grads":
+            if self.nranks > 1:
+                algo = self._algo_for(s, nbytes)
+                blocks = coll.pick_blocks(nbytes, self.nranks, True, self.max_blocks)
+                scale = 1.0 / self.nranks if self.average else 1.0
+                f = flags | (self.ext.FLAG_SCALE if self.average else 0)
+                self.ext.allreduce(self.arena.mesh, 0, algo, s.g_off + boff, 0, nbytes, dt, dtypes.SUM, scale, sumsq, f, blocks,
+                                   self.threads, cs.cuda_stream)
+            elif self.monitor:
+                self.ext.sumsq(s.grads.data_ptr() + boff, dt, b.numel, self.sumsq.data_ptr(), cs.cuda_stream)
+                self.ext.sumsq(s.grads.data_ptr() + boff, dt, b.numel, self.sumsq.data_ptr() + 4, cs.cuda_stream)
+                self.kernel_launches += 1
+            else:
+                self.kernel_launches -= 1
+        elif self.mode == "sma":
+            if self.nranks == 1:
+                self.ext.flat_opt(s.params.data_ptr() + boff, dt, s.grads.data_ptr() + boff, dt, 0, ptr(s.s1[b.index]),
+                                  ptr(s.s2[b.index]), s.hyper.data_ptr(), kind, b.numel, cs.cuda_stream)
+            else:
+                algo = self._algo_for(s, nbytes)
+                blocks = coll.pick_blocks(nbytes, self.nranks, True, self.max_blocks)
+                grads = (s.grads.data_ptr() + boff) if self.opt_kind is not None else 0
+                self.ext.sma_fused(self.arena.mesh, 0, algo, s.p_off + boff, s.x_off + boff, dt, nbytes, grads, dt,
+                                   ptr(s.s1[b.index]), ptr(s.s2[b.index]), 0, dt, s.hyper.data_ptr(), kind, blocks,
+                                   self.threads, cs.cuda_stream)
+        else:
+            raise AssertionError(self.mode)
+        self.kernel_launches += 1
+
+    # ---------------------------------------------------------------------------------------------
+    def pair_step(self, target: int, do_step: bool) -> None:
+        """PairAveraging: one kernel per set on the side stream (whole model)."""
+        self._open_step()
+        cs = self.plane.comm_stream
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        cs.wait_event(ev)
+        kind = self.ext.OPT_ADAM if self.opt_kind == "adam" else self.ext.OPT_SGD
+        ptr = lambda t: t.data_ptr() if t is not None else 0
+        for s in self.sets:
+            lay = s.layout
+            dt = dtypes.dtype_code(lay.dtype)
+            blocks = coll.pick_blocks(lay.nbytes, 1, False, max(self.max_blocks, 64))
+            self.ext.pair_avg(self.arena.mesh, 1, target, s.x_off, s.x_off2, s.ver_off, s.params.data_ptr(), dt, lay.nbytes,
+                              s.grads.data_ptr(), dt, ptr(s.s1[0]), ptr(s.s2[0]), s.hyper.data_ptr(), kind, 1 if do_step else 0,
+                              s.done_counter.data_ptr(), blocks, self.threads, cs.cuda_stream)
+            self.kernel_launches += 1
+
+    def publish(self) -> None:
+        cs = self.plane.comm_stream
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        cs.wait_event(ev)
+        for s in self.sets:
+            lay = s.layout
+            blocks = coll.pick_blocks(lay.nbytes, 1, False, max(self.max_blocks, 64))
+            self.ext.publish(self.arena.mesh, 1, s.x_off, s.x_off2, s.ver_off, s.params.data_ptr(), lay.nbytes,
+                             s.done_counter.data_ptr(), blocks, self.threads, cs.cuda_stream)
+            self.kernel_launches += 1
+        self.finish()
+
+    # ---------------------------------------------------------------------------------------------
+    def flush(self) -> None:
+        """Launch every bucket that the hooks have not launched yet (unused params, overlap disabled)."""
+        for si, s in enumerate(self.sets):
+            first = True
+            while self._launched[si] < len(s.layout.buckets):
+                b = s.layout.buckets[self._launched[si]]
+                self._launch_bucket(si, b, after_current=first)
+                first = False
+                self._launched[si] += 1
+
+    def finish(self) -> None:
+        """Make the current stream wait for the comm stream and reset the per-step bookkeeping."""
+        done = torch.cuda.Event()
+        done.record(self.plane.comm_stream)
+        torch.cuda.current_stream().wait_event(done)
+        self._step_open = False
+        for si, s in enumerate(self.sets):
+            self._launched[si] = 0
+            for i in range(len(s.ready)):
+                s.ready[i] = 0
+        self.steps += 1
+
+    def step_buckets(self) -> None:
+        self.flush()
+        self.finish()
+
+    def zero_grad(self) -> None:
+        for s in self.sets:
+            s.grads.zero_()
+
+    def check(self) -> None:
+        self.arena.check()
+
+    # ---- monitoring --------------------------------------------------------------------------------
+    def read_sumsq(self, reset: bool = True) -> torch.Tensor:
+        """[sum_r |g_r|^2, |g_avg|^2] summed over ranks (device tensor, stream-ordered)."""
+        out = self.sumsq[:2].clone()
+        if self.nranks > 1:
+            coll.all_reduce_(out, "sum")
+        if reset:
+            self.sumsq.zero_()
+        return out
+
+    def gather_state(self) -> Dict[str, torch.Tensor]:
+        """Full (un-sharded) fp32 optimizer state for checkpointing: {master, s1, s2} flat per set."""
+        out: Dict[str, torch.Tensor] = {}
+        for si, s in enumerate(self.sets):
+            for key, shards in (("master", s.master), ("s1", s.s1), ("s2", s.s2)):
+                if not any(t is not None for t in shards):
+                    continue
+                parts = []
+                for b in s.layout.buckets:
+                    t = shards[b.index]
+                    if t is None:
+                        continue
+                    if self.mode == "ssgd" and self.nranks > 1:
+                        g = coll.all_gather(t).view(-1)[:b.numel]
+                    else:
+                        g = t[:b.numel]
+                    parts.append(g)
+                out[f"set{si}.{key}"] = torch.cat(parts)
+        return out

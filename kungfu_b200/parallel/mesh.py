@@ -1,0 +1,180 @@
+"""Device plane: symmetric, peer-mapped HBM arenas on every rank.
+
+`SymmetricArena` wraps the native `PeerMesh` (csrc/mesh/peer_mesh.cpp). Every rank creates arenas in the
+same order with the same sizes, so a byte offset names the same logical buffer on all ranks — that
+offset is all a kernel needs to address its peers (`MeshArgs.data[r] + off`).
+
+Replaces the reference's `NCCLHelper` / `NCCLController` pair (srcs/cpp/include/kungfu/nccl/helper.hpp:14-27,
+controller.hpp:9-33): there is no communicator object, only mapped memory + signal pads.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from ..utils import dtypes
+
+
+def _load_ext():
+    try:
+        from .. import _kfcuda  # type: ignore[attr-defined]
+
+        return _kfcuda
+    except ImportError as e:  # fail loudly: a silent PyTorch fallback would hide a missing native build
+        raise ImportError(
+            "kungfu_b200: the CUDA extension `_kfcuda` is not built. Run `python -m kungfu_b200._build` "
+            "(or `__graft_entry__.build()`) first.") from e
+
+
+class _CudaView:
+    """Zero-copy torch view of raw device memory via the CUDA array interface."""
+
+    def __init__(self, ptr: int, nbytes: int, owner) -> None:
+        self._owner = owner  # keeps the arena alive while tensors view it
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes,),
+            "typestr": "|u1",
+            "data": (ptr, False),
+            "version": 3,
+            "strides": None,
+        }
+
+
+class SymmetricArena:
+    """One symmetric allocation + signal pads + (optional) NVLS multicast alias."""
+
+    def __init__(self, plane: "GpuPlane", nbytes: int, name: str = "arena", want_multicast: bool = True) -> None:
+        ext = _load_ext()
+        self.plane = plane
+        self.name = name
+        self.ext = ext
+        rt = plane.runtime
+        mode = os.environ.get("KUNGFU_MESH_MODE", "auto" if rt.size > 1 else "local")
+        if rt.size == 1 and mode == "auto":
+            mode = "local"
+        self.mesh = ext.PeerMesh(plane.device_index, int(nbytes), mode)
+        self.mesh.set_timeout_ms(float(os.environ.get("KUNGFU_DEVICE_TIMEOUT_MS", "20000")))
+        self._cursor = 0
+        self._regions: Dict[str, Tuple[int, int]] = {}
+        self._connect(want_multicast)
+        base = _CudaView(self.mesh.local_ptr, self.mesh.arena_bytes, self)
+        with torch.cuda.device(plane.device_index):
+            self._bytes = torch.as_tensor(base, device=torch.device("cuda", plane.device_index))
+
+    def _connect(self, want_multicast: bool) -> None:
+        rt = self.plane.runtime
+        want_mc = want_multicast and os.environ.get("KUNGFU_DISABLE_NVLS", "0") != "1"
+        self.mesh.connect(rt.rank, rt.size, rt.control.all_gather_bytes, want_mc)
+
+    def reconnect(self, want_multicast: bool = True) -> None:
+        """Rebuild peer mappings after a membership change (local memory and views survive)."""
+        torch.cuda.synchronize(self.plane.device_index)
+        self._connect(want_multicast)
+
+    # ---- allocation -------------------------------------------------------------------------------
+    @property
+    def nbytes(self) -> int:
+        return self.mesh.arena_bytes
+
+    @property
+    def has_multicast(self) -> bool:
+        return bool(self.mesh.has_multicast)
+
+    def alloc(self, nbytes: int, align: int = 256, name: Optional[str] = None) -> int:
+        """Bump-allocate `nbytes`; returns the byte offset (identical on every rank)."""
+        if name is not None and name in self._regions:
+            off, size = self._regions[name]
+            if size < nbytes:
+                raise ValueError(f"region {name!r} exists with {size} < {nbytes} bytes")
+            return off
+        off = (self._cursor + align - 1) // align * align
+        end = off + (nbytes + 15) // 16 * 16
+        if end > self.nbytes:
+            raise MemoryError(f"kungfu_b200: arena {self.name!r} exhausted ({end} > {self.nbytes} bytes)")
+        self._cursor = end
+        if name is not None:
+            self._regions[name] = (off, end - off)
+        return off
+
+    def view(self, off: int, numel: int, dtype: torch.dtype) -> torch.Tensor:
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        return self._bytes[off:off + nbytes].view(dtype)
+
+    def bytes_view(self, off: int, nbytes: int) -> torch.Tensor:
+        return self._bytes[off:off + nbytes]
+
+    def check(self) -> None:
+        """Raise if a device-side wait timed out (dead / diverged peer)."""
+        st = self.mesh.status()
+        if st[0] != 0:
+            info = (f"code={st[0]} rank={st[1] >> 16} waiting_for_peer={st[1] & 0xffff} timeouts={st[2]} "
+                    f"want_seq={st[3]} seen_seq={st[4]}")
+            self.mesh.clear_status()
+            raise RuntimeError("kungfu_b200: device-side barrier timed out: " + info)
+
+    def close(self) -> None:
+        self._bytes = None  # type: ignore[assignment]
+        try:
+            self.mesh.disconnect()
+        except Exception:
+            pass
+
+
+class GpuPlane:
+    """Per-process GPU context: device selection, comm streams, the default staging arena."""
+
+    def __init__(self, runtime) -> None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("kungfu_b200: no CUDA device available")
+        self.runtime = runtime
+        self.ext = _load_ext()
+        self.device_index = runtime.cuda_index()
+        if self.device_index < 0:
+            raise RuntimeError("kungfu_b200: this worker has no GPU assigned")
+        torch.cuda.set_device(self.device_index)
+        self.device = torch.device("cuda", self.device_index)
+        # high-priority streams so that comm CTAs are scheduled as soon as SMs drain
+        self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.side_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self._arenas: List[SymmetricArena] = []
+        self._staging: Optional[SymmetricArena] = None
+        self._staging_off = 0
+        self._staging_bytes = 0
+        self.sm_count = torch.cuda.get_device_properties(self.device_index).multi_processor_count
+
+    def new_arena(self, nbytes: int, name: str, want_multicast: bool = True) -> SymmetricArena:
+        a = SymmetricArena(self, nbytes, name, want_multicast)
+        self._arenas.append(a)
+        return a
+
+    def staging(self) -> Tuple[SymmetricArena, int, int]:
+        """Default arena used to stage arbitrary tensors for the generic collectives."""
+        if self._staging is None:
+            mb = int(os.environ.get("KUNGFU_STAGING_MB", "64"))
+            self._staging = self.new_arena((mb + 2) << 20, "staging")
+            self._staging_bytes = mb << 20
+            self._staging_off = self._staging.alloc(self._staging_bytes, name="stage")
+        return self._staging, self._staging_off, self._staging_bytes
+
+    def reconnect_all(self) -> None:
+        for a in self._arenas:
+            a.reconnect()
+
+    def topology(self) -> dict:
+        st, _, _ = self.staging()
+        return st.mesh.topology()
+
+    def close(self) -> None:
+        try:
+            torch.cuda.synchronize(self.device_index)
+        except Exception:
+            pass
+        for a in self._arenas:
+            a.close()
+        self._arenas.clear()
+        self._staging = None
+
+
+_DT = dtypes

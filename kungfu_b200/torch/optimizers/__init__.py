@@ -1,0 +1,5 @@
+"""Distributed optimizers (reference: srcs/python/kungfu/tensorflow/optimizers/__init__.py and
+srcs/python/kungfu/torch/optimizers/__init__.py)."""
+from .sync_sgd import SynchronousSGDOptimizer
+
+__all__ = ["SynchronousSGDOptimizer"]

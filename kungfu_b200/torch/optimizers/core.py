@@ -1,0 +1,121 @@
+"""Shared machinery of the distributed optimizers.
+
+Reference: `_KungFuAlgorithm` strategy objects wrapping a user optimizer (srcs/python/kungfu/tensorflow/optimizers/
+core.py:6-72) and the dynamic-subclass trick of the torch binding (torch/optimizers/sync_sgd.py:29-32): the
+returned object *is an instance of the user's optimizer class* (so LR schedulers, `isinstance` checks and
+`state_dict` keep working) with `step()` / `zero_grad()` overridden.
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, List, Optional, Tuple
+
+import torch
+
+from ...ops import collective as coll
+from ...runtime import get_runtime
+
+
+def fusable_kind(optimizer: torch.optim.Optimizer) -> Optional[str]:
+    """Returns "sgd"/"adam" if our fused kernels implement exactly this optimizer, else None."""
+    cls = optimizer.__class__
+    base = [c.__name__ for c in cls.__mro__]
+    for g in optimizer.param_groups:
+        if g.get("maximize", False) or g.get("amsgrad", False) or g.get("capturable", False):
+            return None
+        if g.get("differentiable", False):
+            return None
+    if "SGD" in base:
+        for g in optimizer.param_groups:
+            if g.get("nesterov", False) and (g.get("momentum", 0) <= 0 or g.get("dampening", 0) != 0):
+                return None
+        return "sgd"
+    if "AdamW" in base:
+        for g in optimizer.param_groups:
+            g["_adamw"] = True
+        return "adam"
+    if "Adam" in base:
+        return "adam"
+    return None
+
+
+def named_trainable(optimizer: torch.optim.Optimizer, named_parameters) -> List[Tuple[str, torch.nn.Parameter]]:
+    """Stable (name, param) list covering every trainable parameter of the optimizer."""
+    ids = set()
+    for g in optimizer.param_groups:
+        for p in g["params"]:
+            ids.add(id(p))
+    out = []
+    if named_parameters is not None:
+        for n, p in named_parameters:
+            if id(p) in ids and p.requires_grad:
+                out.append((n, p))
+    if len(out) == 0:
+        k = 0
+        for gi, g in enumerate(optimizer.param_groups):
+            for pi, p in enumerate(g["params"]):
+                if p.requires_grad:
+                    out.append((f"group{gi}.param{pi}", p))
+                    k += 1
+    return out
+
+
+def all_cuda(params: Iterable[torch.nn.Parameter]) -> bool:
+    ps = list(params)
+    return len(ps) > 0 and all(p.is_cuda for p in ps)
+
+
+def wrap_optimizer(optimizer: torch.optim.Optimizer, mixin: type, init: Callable) -> torch.optim.Optimizer:
+    """Create an instance of a dynamic subclass of `optimizer.__class__` that shares the optimizer's state."""
+    if getattr(optimizer, "_kf_wrapped", False):
+        raise ValueError("kungfu_b200: optimizer is already wrapped")
+    cls = type(optimizer.__class__.__name__, (mixin, optimizer.__class__), {})
+    obj = cls.__new__(cls)
+    obj.__dict__.update(optimizer.__dict__)
+    obj._kf_wrapped = True
+    obj._kf_inner_cls = optimizer.__class__
+    init(obj)
+    return obj
+
+
+class KungFuMixin:
+    """Common helpers; concrete optimizers add `step`."""
+
+    def _kf_setup(self, named_parameters, use_gpu_engine: bool) -> None:
+        self._kf_rt = get_runtime()
+        self._kf_named = named_trainable(self, named_parameters)
+        self._kf_gpu = use_gpu_engine and all_cuda(p for _, p in self._kf_named)
+        self._kf_engine = None
+        self._kf_step_count = 0
+
+    def _kf_inner_step(self, closure=None):
+        return self._kf_inner_cls.step(self, closure)
+
+    def zero_grad(self, set_to_none: bool = False):  # noqa: D401 - torch API
+        eng = getattr(self, "_kf_engine", None)
+        if eng is not None:
+            eng.zero_grad()
+            return
+        return self._kf_inner_cls.zero_grad(self, set_to_none=set_to_none)
+
+    @property
+    def engine(self):
+        return getattr(self, "_kf_engine", None)
+
+    def cluster_size(self) -> int:
+        return self._kf_rt.size
+
+
+def cpu_all_reduce_grads(named, op: str, average: bool) -> None:
+    """Reference torch path: one named all-reduce per gradient (torch/optimizers/sync_sgd.py:12-22)."""
+    rt = get_runtime()
+    if rt.size == 1:
+        return
+    handles = []
+    for name, p in named:
+        if p.grad is None:
+            continue
+        if p.grad.is_cuda:
+            handles.append(coll.all_reduce_async_(p.grad, name, "avg" if average else op))
+        else:
+            coll.all_reduce_(p.grad, "avg" if average else op, name)
+    coll.wait_all_handles(handles)

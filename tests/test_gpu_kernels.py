@@ -1,0 +1,282 @@
+"""Numerics of the sm_100a kernels on ONE GPU against plain PyTorch fp32 references.
+
+Reference test model: C++ unit tests of `std_transform_2` / dtype sizes (tests/cpp/unit/test_operations.cpp) and the
+NCCL `simple_test` sweep (tests/cpp/integration/fake_nccl_trainer.cpp:34-63).
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def plane():
+    from kungfu_b200.runtime import get_runtime
+
+    rt = get_runtime()
+    return rt.gpu
+
+
+def _ptr(t):
+    return t.data_ptr()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16, torch.int32, torch.int64, torch.uint8, torch.float64])
+@pytest.mark.parametrize("algo", ["oneshot", "twoshot"])
+def test_allreduce_single_rank_identity(plane, dtype, algo):
+    """np=1: all-reduce must be the identity for every dtype/algorithm (≙ test_kungfu.cpp AllReduce with np=1)."""
+    from kungfu_b200.utils import dtypes
+
+    ext = plane.ext
+    arena, off, cap = plane.staging()
+    n = 4096 + 8
+    if dtype.is_floating_point:
+        x = torch.randn(n, device="cuda").to(dtype)
+    else:
+        x = torch.randint(0, 100, (n,), device="cuda").to(dtype)
+    nb = x.numel() * x.element_size()
+    nb_pad = (nb + 15) // 16 * 16
+    stage = arena.bytes_view(off, nb_pad)
+    stage.zero_()
+    stage[:nb].copy_(x.view(torch.uint8))
+    out = torch.zeros(nb_pad, dtype=torch.uint8, device="cuda")
+    code = {"oneshot": ext.ALGO_ONESHOT, "twoshot": ext.ALGO_TWOSHOT}[algo]
+    ext.allreduce(arena.mesh, 0, code, off, _ptr(out), nb_pad, dtypes.dtype_code(dtype), 0, 1.0, 0, 0, 4, 256, _st())
+    torch.cuda.synchronize()
+    arena.check()
+    got = (out if algo == "oneshot" else stage)[:nb].view(dtype)
+    assert torch.equal(got, x)
+
+
+def test_allreduce_scale_and_sumsq(plane):
+    from kungfu_b200.utils import dtypes
+
+    ext = plane.ext
+    arena, off, cap = plane.staging()
+    n = 1 << 16
+    x = torch.randn(n, device="cuda", dtype=torch.bfloat16)
+    stage = arena.view(off, n, torch.bfloat16)
+    stage.copy_(x)
+    acc = torch.zeros(2, device="cuda")
+    ext.allreduce(arena.mesh, 0, ext.ALGO_TWOSHOT, off, 0, n * 2, dtypes.BF16, 0, 0.5, _ptr(acc), ext.FLAG_SCALE | ext.FLAG_SUMSQ,
+                  8, 512, _st())
+    torch.cuda.synchronize()
+    ref = (x.float() * 0.5).to(torch.bfloat16)
+    assert torch.equal(stage, ref)
+    pre = (x.float() ** 2).sum().item()
+    post = ((x.float() * 0.5) ** 2).sum().item()
+    assert math.isclose(acc[0].item(), pre, rel_tol=1e-3)
+    assert math.isclose(acc[1].item(), post, rel_tol=1e-3)
+
+
+@pytest.mark.parametrize("pdtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("kind", ["sgd", "sgd_nesterov", "adam", "adamw"])
+def test_flat_opt_matches_torch(plane, pdtype, kind):
+    """The device update rule == torch.optim on an fp32 reference (3 steps)."""
+    from kungfu_b200.utils import dtypes
+
+    ext = plane.ext
+    torch.manual_seed(0)
+    n = 10007
+    w0 = torch.randn(n, device="cuda")
+    ref = torch.nn.Parameter(w0.clone())
+    if kind == "sgd":
+        opt = torch.optim.SGD([ref], lr=0.1, momentum=0.9, weight_decay=1e-2, dampening=0.1)
+    elif kind == "sgd_nesterov":
+        opt = torch.optim.SGD([ref], lr=0.1, momentum=0.9, nesterov=True)
+    elif kind == "adam":
+        opt = torch.optim.Adam([ref], lr=1e-2, weight_decay=1e-2)
+    else:
+        opt = torch.optim.AdamW([ref], lr=1e-2, weight_decay=1e-1)
+    g = opt.param_groups[0]
+    hp = torch.zeros(16)
+    hp[0] = g["lr"]
+    hp[3] = g["weight_decay"]
+    hp[5] = 1.0
+    if kind.startswith("sgd"):
+        hp[1], hp[2], hp[4] = g["momentum"], g["dampening"], float(g["nesterov"])
+        k = ext.OPT_SGD
+    else:
+        hp[7], hp[8], hp[9] = g["betas"][0], g["betas"][1], g["eps"]
+        hp[14] = 1.0 if kind == "adamw" else 0.0
+        k = ext.OPT_ADAM
+    hyper = hp.cuda()
+    params = w0.to(pdtype).clone()
+    master = w0.clone() if pdtype != torch.float32 else None
+    s1 = torch.zeros(n, device="cuda")
+    s2 = torch.zeros(n, device="cuda")
+    for step in range(3):
+        grad = torch.randn(n, device="cuda")
+        gd = grad.to(pdtype)
+        ref.grad = gd.float()  # the reference sees the same (rounded) gradient
+        opt.step()
+        ext.hyper_tick(_ptr(hyper), _st())
+        ext.flat_opt(_ptr(params), dtypes.dtype_code(pdtype), _ptr(gd), dtypes.dtype_code(pdtype), _ptr(master) if master is not None else 0,
+                     _ptr(s1), _ptr(s2), _ptr(hyper), k, n, _st())
+    torch.cuda.synchronize()
+    got = master if master is not None else params
+    tol = 2e-5
+    assert torch.allclose(got, ref.data, atol=tol, rtol=tol), (got - ref.data).abs().max()
+    if pdtype != torch.float32:
+        assert torch.equal(params, master.to(pdtype))
+
+
+def test_cast_sumsq_axpby(plane):
+    from kungfu_b200.utils import dtypes
+
+    ext = plane.ext
+    n = 123457
+    x = torch.randn(n, device="cuda")
+    y = torch.empty(n, device="cuda", dtype=torch.bfloat16)
+    ext.cast(_ptr(x), dtypes.F32, _ptr(y), dtypes.BF16, n, 2.0, _st())
+    assert torch.equal(y, (x * 2).to(torch.bfloat16))
+    acc = torch.zeros(1, device="cuda")
+    ext.sumsq(_ptr(x), dtypes.F32, n, _ptr(acc), _st())
+    assert math.isclose(acc.item(), (x.double() ** 2).sum().item(), rel_tol=1e-4)
+    z = torch.randn(n, device="cuda")
+    acc.zero_()
+    ext.sumsq_diff(_ptr(x), _ptr(z), dtypes.F32, n, _ptr(acc), _st())
+    assert math.isclose(acc.item(), ((x - z).double() ** 2).sum().item(), rel_tol=1e-4)
+    z0 = z.clone()
+    ext.axpby(_ptr(z), _ptr(x), dtypes.F32, n, 0.25, 0.75, _st())
+    assert torch.allclose(z, 0.25 * x + 0.75 * z0, atol=1e-6)
+
+
+def test_u8_normalize(plane):
+    from kungfu_b200.utils import dtypes
+
+    ext = plane.ext
+    B, H, W = 3, 17, 19
+    img = torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, device="cuda")
+    mean = torch.tensor([120.0, 110.0, 100.0], device="cuda")
+    inv = torch.tensor([1 / 58.0, 1 / 57.0, 1 / 56.0], device="cuda")
+    out = torch.empty((B, 3, H, W), dtype=torch.bfloat16, device="cuda").contiguous(memory_format=torch.channels_last)
+    ext.u8_normalize(_ptr(img), _ptr(out), dtypes.BF16, B * H * W, _ptr(mean), _ptr(inv), _st())
+    ref = ((img.float() - mean) * inv).permute(0, 3, 1, 2)
+    assert torch.allclose(out.float(), ref, atol=2e-2, rtol=1e-2)
+
+
+def test_gns_finalize(plane):
+    """Device finalisation == the reference formulas (ops/monitor.py:6-17, cpu/collective.cpp:245-257)."""
+    ext = plane.ext
+    state = torch.zeros(4, device="cuda")
+    out = torch.zeros(4, device="cuda")
+    bs, bb, alpha, nr = 32.0, 128.0, 0.9, 4.0
+    ge = se = None
+    for gs_sum, gb in [(40.0, 6.0), (36.0, 5.0), (44.0, 7.5)]:
+        sums = torch.tensor([gs_sum, gb], device="cuda")
+        ext.gns_finalize(_ptr(sums), _ptr(state), _ptr(out), bs, bb, alpha, nr, _st())
+        g_small = gs_sum / nr
+        G = (bb * gb - bs * g_small) / (bb - bs)
+        S = (g_small - gb) / (1 / bs - 1 / bb)
+        ge = G if ge is None else alpha * ge + (1 - alpha) * G
+        se = S if se is None else alpha * se + (1 - alpha) * S
+        torch.cuda.synchronize()
+        assert math.isclose(out[0].item(), se / ge, rel_tol=1e-4)
+        assert math.isclose(out[1].item(), G, rel_tol=1e-4)
+        assert math.isclose(out[2].item(), S, rel_tol=1e-4)
+
+
+def _mlp(dtype):
+    torch.manual_seed(1)
+    return torch.nn.Sequential(torch.nn.Linear(64, 128), torch.nn.ReLU(), torch.nn.Linear(128, 10)).cuda().to(dtype)
+
+
+@pytest.mark.parametrize("optname", ["sgd", "adam"])
+def test_ssgd_optimizer_fp32_matches_torch(plane, optname):
+    """np=1 fused path (flat arena + our optimizer kernel) == torch.optim, fp32, several steps."""
+    import kungfu_b200.torch as kf
+
+    m1, m2 = _mlp(torch.float32), _mlp(torch.float32)
+    m2.load_state_dict(m1.state_dict())
+    mk = (lambda p: torch.optim.SGD(p, lr=0.05, momentum=0.9, weight_decay=1e-3)) if optname == "sgd" else (
+        lambda p: torch.optim.Adam(p, lr=1e-2))
+    o1 = mk(m1.parameters())
+    o2 = kf.optimizers.SynchronousSGDOptimizer(mk(m2.parameters()), named_parameters=m2.named_parameters())
+    assert o2.engine is not None and o2.engine.mode == "ssgd"
+    x = torch.randn(32, 64, device="cuda")
+    y = torch.randint(0, 10, (32,), device="cuda")
+    for _ in range(5):
+        for m, o in ((m1, o1), (m2, o2)):
+            o.zero_grad()
+            torch.nn.functional.cross_entropy(m(x), y).backward()
+            o.step()
+    torch.cuda.synchronize()
+    o2.engine.check()
+    for a, b in zip(m1.parameters(), m2.parameters()):
+        assert torch.allclose(a, b, atol=1e-5, rtol=1e-4), (a - b).abs().max()
+
+
+def test_ssgd_optimizer_generic_path(plane):
+    """An optimizer without a fused kernel (RMSprop) goes through the bucketed grads mode."""
+    import kungfu_b200.torch as kf
+
+    m1, m2 = _mlp(torch.float32), _mlp(torch.float32)
+    m2.load_state_dict(m1.state_dict())
+    o1 = torch.optim.RMSprop(m1.parameters(), lr=1e-3)
+    o2 = kf.optimizers.SynchronousSGDOptimizer(torch.optim.RMSprop(m2.parameters(), lr=1e-3), named_parameters=m2.named_parameters())
+    assert o2.engine.mode == "grads"
+    x = torch.randn(16, 64, device="cuda")
+    y = torch.randint(0, 10, (16,), device="cuda")
+    for _ in range(3):
+        for m, o in ((m1, o1), (m2, o2)):
+            o.zero_grad()
+            torch.nn.functional.cross_entropy(m(x), y).backward()
+            o.step()
+    for a, b in zip(m1.parameters(), m2.parameters()):
+        assert torch.allclose(a, b, atol=1e-6)
+
+
+def test_ssgd_bf16_master_weights(plane):
+    """bf16 parameters + fp32 master shard: tracks an fp32 torch reference within bf16 resolution."""
+    import kungfu_b200.torch as kf
+
+    ref = _mlp(torch.float32)
+    m = _mlp(torch.bfloat16)
+    with torch.no_grad():
+        for a, b in zip(ref.parameters(), m.parameters()):
+            a.copy_(b.float())
+    o1 = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9)
+    o2 = kf.optimizers.SynchronousSGDOptimizer(torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9), named_parameters=m.named_parameters())
+    x = torch.randn(32, 64, device="cuda")
+    y = torch.randint(0, 10, (32,), device="cuda")
+    l0 = None
+    for i in range(10):
+        o1.zero_grad()
+        torch.nn.functional.cross_entropy(ref(x), y).backward()
+        o1.step()
+        o2.zero_grad()
+        loss = torch.nn.functional.cross_entropy(m(x.bfloat16()).float(), y)
+        loss.backward()
+        o2.step()
+        l0 = l0 or loss.item()
+    assert loss.item() < l0
+    for a, b in zip(ref.parameters(), m.parameters()):
+        assert torch.allclose(a, b.float(), atol=3e-2, rtol=3e-2)
+
+
+def test_image_trainer_cuda_graph(plane):
+    """Whole-step CUDA graph capture (fwd + bwd + hooks + fused optimizer on the comm stream) replays correctly."""
+    import kungfu_b200.torch as kf
+    from kungfu_b200.models import resnet
+    from kungfu_b200.trainer import ImageTrainer
+
+    torch.manual_seed(0)
+    model = resnet.to_b200(resnet.resnet18(num_classes=10), torch.bfloat16, "cuda")
+    opt = kf.optimizers.SynchronousSGDOptimizer(torch.optim.SGD(model.parameters(), lr=0.02, momentum=0.9),
+                                                named_parameters=model.named_parameters())
+    tr = ImageTrainer(model, opt, 16, 64, torch.bfloat16, use_graph=True)
+    assert tr.graph is not None, tr.graph_error
+    assert tr.launches_per_step > 0
+    imgs = torch.randint(0, 256, (16, 64, 64, 3), dtype=torch.uint8).pin_memory()
+    labels = torch.randint(0, 10, (16,), dtype=torch.int64).pin_memory()
+    losses = [tr.step(imgs, labels) for _ in range(12)]
+    opt.engine.check()
+    assert all(math.isfinite(l) for l in losses)
+    assert losses[-1] < losses[0]
