@@ -114,7 +114,7 @@ def test_flat_opt_matches_torch(plane, pdtype, kind):
     for step in range(3):
         grad = torch.randn(n, device="cuda")
         gd = grad.to(pdtype)
-        ref.grad = gd.float()  # the reference sees the same (rounded) gradient
+        ref.grad = gd.float().clone()  # same (rounded) gradient; clone: foreach-nesterov updates .grad in place
         opt.step()
         ext.hyper_tick(_ptr(hyper), _st())
         ext.flat_opt(_ptr(params), dtypes.dtype_code(pdtype), _ptr(gd), dtypes.dtype_code(pdtype), _ptr(master) if master is not None else 0,
