@@ -129,10 +129,19 @@ def main() -> int:
         rt.control.barrier()
 
     ext = rt.gpu.ext
+
+    def align_devices():
+        """Flag barrier ON THE DEVICE right before the first timed event, so rank skew after the host barrier
+        (python wake-up jitter) is not billed to the first step."""
+        if N > 1:
+            st_arena = rt.gpu.staging()[0]
+            ext.barrier(st_arena.mesh, 2, torch.cuda.current_stream().cuda_stream)
+
     # ---------------- kernel-only: resident device batch ----------------
     for _ in range(args.warmup):
         trainer.device_step()
     barrier()
+    align_devices()
     sampler = ClockSampler(dev_index).start() if rt.rank == 0 else None
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.time()
@@ -158,6 +167,7 @@ def main() -> int:
             fut = trainer.step_async(host_images[i & 1], host_labels[i & 1])
         fut.result()
         barrier()
+        align_devices()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         prev = None

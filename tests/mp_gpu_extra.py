@@ -1,0 +1,168 @@
+"""Multi-GPU checks of the SMA and PairAveraging kernels against in-process fp32 simulations of all N replicas."""
+import torch
+
+import kungfu_b200.torch as kf
+from kungfu_b200.ops import collective as coll
+
+
+def mlp(seed, dtype=torch.float32):
+    torch.manual_seed(seed)
+    return torch.nn.Sequential(torch.nn.Linear(48, 96), torch.nn.Tanh(), torch.nn.Linear(96, 7)).cuda().to(dtype)
+
+
+def batch(rank, step, n=16):
+    g = torch.Generator(device="cuda").manual_seed(991 * step + rank)
+    return torch.randn(n, 48, device="cuda", generator=g), torch.randint(0, 7, (n,), device="cuda", generator=g)
+
+
+def loss_of(m, rank, step):
+    x, y = batch(rank, step)
+    return torch.nn.functional.cross_entropy(m(x), y)
+
+
+def check_sma(rt, log, algo):
+    N, me = rt.size, rt.rank
+    alpha, lr, mom = 0.1, 0.05, 0.9
+    # replicas start DIFFERENT (seed = rank) so that averaging matters
+    sims = [mlp(100 + r) for r in range(N)]
+    sim_opts = [torch.optim.SGD(s.parameters(), lr=lr, momentum=mom) for s in sims]
+    m = mlp(100 + me)
+    opt = kf.optimizers.SynchronousAveragingOptimizer(torch.optim.SGD(m.parameters(), lr=lr, momentum=mom),
+                                                      named_parameters=m.named_parameters(), alpha=alpha, bucket_mb=0.01, algo=algo)
+    assert opt.engine is not None and opt.engine.mode == "sma"
+    fails = 0
+    for step in range(5):
+        # simulation: gradients at the pre-blend weights, blend with the mean model, then the local step
+        for r in range(N):
+            sim_opts[r].zero_grad()
+            loss_of(sims[r], r, step).backward()
+        with torch.no_grad():
+            means = [sum(ps) / N for ps in zip(*[[p.data.clone() for p in s.parameters()] for s in sims])]
+            for s in sims:
+                for p, mu in zip(s.parameters(), means):
+                    p.data.mul_(1 - alpha).add_(mu, alpha=alpha)
+        for r in range(N):
+            sim_opts[r].step()
+        opt.zero_grad()
+        loss_of(m, me, step).backward()
+        opt.step()
+        torch.cuda.synchronize()
+        opt.engine.check()
+    for a, b in zip(sims[me].parameters(), m.parameters()):
+        if not torch.allclose(a, b, atol=2e-5, rtol=2e-5):
+            fails += 1
+            log(f"FAIL sma algo={algo} maxdiff={(a - b).abs().max().item()}")
+            break
+    return fails
+
+
+def check_pair(rt, log):
+    N, me = rt.size, rt.rank
+    fails = 0
+    lr = 0.05
+    sims = [mlp(200 + r) for r in range(N)]
+    sim_opts = [torch.optim.SGD(s.parameters(), lr=lr) for s in sims]
+    published = [[p.data.clone() for p in s.parameters()] for s in sims]  # what each replica last published
+    m = mlp(200 + me)
+    opt = kf.optimizers.PairAveragingOptimizer(torch.optim.SGD(m.parameters(), lr=lr), named_parameters=m.named_parameters(),
+                                               peer_selection="roundrobin")
+    eng = opt.engine
+    assert eng is not None and eng.mode == "pair"
+    rr = [0] * N
+    # deterministic schedule: one rank steps at a time (what it pulls is then well defined)
+    for step in range(3):
+        for r in range(N):
+            rr[r] += 1
+            target = (r + 1 + (rr[r] - 1) % (N - 1)) % N
+            sim_opts[r].zero_grad()
+            loss_of(sims[r], r, step).backward()
+            with torch.no_grad():
+                for p, o in zip(sims[r].parameters(), published[target]):
+                    p.data.add_(o).mul_(0.5)
+            sim_opts[r].step()
+            published[r] = [p.data.clone() for p in sims[r].parameters()]
+            if r == me:
+                opt.zero_grad()
+                loss_of(m, me, step).backward()
+                opt.step()
+                torch.cuda.synchronize()
+            elif step == 0 and not opt._kf_published:
+                # every rank must take part in the first publish + barrier
+                eng._sync_hyper(); eng._ensure_state(); eng.publish(); coll.barrier(); opt._kf_published = True
+            coll.barrier()
+    for a, b in zip(sims[me].parameters(), m.parameters()):
+        if not torch.allclose(a, b, atol=2e-5, rtol=2e-5):
+            fails += 1
+            log(f"FAIL pair maxdiff={(a - b).abs().max().item()}")
+            break
+    # concurrent gossip stress with lr = 0: models must contract towards each other, nothing may hang or tear
+    for g in opt.param_groups:
+        g["lr"] = 0.0
+    opt._kf_selection = "random"
+
+    def spread():
+        flat = torch.cat([p.data.reshape(-1) for p in m.parameters()])
+        allf = coll.all_gather(flat)
+        return (allf - allf.mean(0, keepdim=True)).pow(2).mean().item()
+
+    s0 = spread()
+    for step in range(60):
+        opt.zero_grad()
+        loss_of(m, me, 1000 + step).backward()
+        opt.step()
+    torch.cuda.synchronize()
+    eng.check()
+    coll.barrier()
+    s1 = spread()
+    st = eng.arena.mesh.status()
+    if not (s1 < 0.05 * s0 + 1e-12):
+        fails += 1
+        log(f"FAIL pair gossip did not contract: {s0} -> {s1}")
+    log(f"pair gossip spread {s0:.3e} -> {s1:.3e}, torn={st[5]}")
+    return fails
+
+
+def check_pull_publish(rt, log):
+    """publish -> barrier -> pull(peer) returns the peer's bytes exactly; unknown versions report 0."""
+    N, me = rt.size, rt.rank
+    plane = rt.gpu
+    ext = plane.ext
+    arena = plane.new_arena(8 << 20, "pubtest")
+    n = 1 << 18
+    pub0, pub1, ver = arena.alloc(n * 4), arena.alloc(n * 4), arena.alloc(256)
+    done = torch.zeros(4, dtype=torch.int32, device="cuda")
+    ok = torch.zeros(4, dtype=torch.int32, device="cuda")
+    dst = torch.zeros(n, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    fails = 0
+    target = (me + 1) % N
+    ext.pull(arena.mesh, 1, target, pub0, pub1, ver, dst.data_ptr(), n * 4, ok.data_ptr(), 8, 512, st)
+    torch.cuda.synchronize()
+    if ok[0].item() != 0:
+        fails += 1
+        log("FAIL pull before publish reported a version")
+    for v in range(1, 4):
+        src = torch.full((n,), float(100 * me + v), device="cuda")
+        ext.publish(arena.mesh, 1, pub0, pub1, ver, src.data_ptr(), n * 4, done.data_ptr(), 8, 512, st)
+        torch.cuda.synchronize()
+        coll.barrier()
+        ext.pull(arena.mesh, 1, target, pub0, pub1, ver, dst.data_ptr(), n * 4, ok.data_ptr(), 8, 512, st)
+        torch.cuda.synchronize()
+        if ok[0].item() != v or not torch.all(dst == float(100 * target + v)):
+            fails += 1
+            log(f"FAIL pull v={v} got version {ok[0].item()} value {dst[0].item()}")
+        coll.barrier()
+    return fails
+
+
+def run(rt, log):
+    fails = 0
+    fails += check_pull_publish(rt, log)
+    log("pull/publish done, fails =", fails)
+    arena = rt.gpu.staging()[0]
+    for algo in ["twoshot"] + (["nvls"] if arena.has_multicast else []):
+        fails += check_sma(rt, log, algo)
+    log("sma done, fails =", fails)
+    fails += check_pair(rt, log)
+    log("pair done, fails =", fails)
+    return fails

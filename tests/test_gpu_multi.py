@@ -30,3 +30,8 @@ def test_collectives_all_gpus():
 def test_fused_optimizers_all_gpus():
     n = torch.cuda.device_count()
     _run(n if n in (2, 4, 8) else 2, ["ssgd"])
+
+
+def test_sma_pair_all_gpus():
+    n = torch.cuda.device_count()
+    _run(n if n in (2, 4, 8) else 2, ["extra"])
