@@ -195,7 +195,8 @@ def main():
             fails += check_ssgd(rt, algo, "sgd", torch.bfloat16, monitor=True)
         log("ssgd done, fails =", fails)
     if "extra" in what:
-        from tests import mp_gpu_extra
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        import mp_gpu_extra
 
         fails += mp_gpu_extra.run(rt, log)
     tot = torch.tensor([fails], dtype=torch.int64)

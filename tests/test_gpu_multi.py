@@ -18,6 +18,12 @@ def _run(n, what):
     env = dict(os.environ, KUNGFU_DEVICE_TIMEOUT_MS="15000")
     r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     print(r.stdout[-6000:])
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"mp_{n}_{'_'.join(what)}.log"), "w") as f:
+            f.write(r.stdout)
+    except OSError:
+        pass
     assert r.returncode == 0, r.stdout[-3000:]
     assert '"fails": 0' in r.stdout
 
