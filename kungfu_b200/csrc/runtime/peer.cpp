@@ -1,0 +1,260 @@
+#include "peer.hpp"
+
+#include <unistd.h>
+
+#include <cstdlib>
+
+#include "http.hpp"
+
+namespace kfrt {
+
+// ---- bootstrap --------------------------------------------------------------------------------------
+PeerConfig PeerConfig::from_env() {
+    PeerConfig c;
+    const std::string self = getenv_str(envkeys::kSelfSpec);
+    if (!self.empty()) { // launched by kungfu-run
+        c.launcher = "kungfu-run";
+        c.self = PeerID::parse(self);
+        c.init_peers = PeerList::parse(getenv_str(envkeys::kInitPeers));
+        c.init_runners = PeerList::parse(getenv_str(envkeys::kInitRunners));
+        const std::string parent = getenv_str(envkeys::kParentID);
+        if (!parent.empty()) c.parent = PeerID::parse(parent);
+        c.init_cluster_version = atoi(getenv_str(envkeys::kInitClusterVersion, "0").c_str());
+        c.strategy = parse_strategy(getenv_str(envkeys::kAllReduceStrategy, "AUTO"));
+        c.config_server = getenv_str(envkeys::kConfigServer);
+        return c;
+    }
+    const std::string rank = getenv_str("RANK"), world = getenv_str("WORLD_SIZE");
+    if (!rank.empty() && !world.empty() && atoi(world.c_str()) > 1) { // torchrun, one node
+        c.launcher = "torchrun";
+        const int r = atoi(rank.c_str()), n = atoi(world.c_str());
+        const uint32_t ip = resolve_ipv4(getenv_str("MASTER_ADDR", "127.0.0.1"));
+        const int master_port = atoi(getenv_str("MASTER_PORT", "29500").c_str());
+        int base = atoi(getenv_str("KUNGFU_PORT_BASE", "0").c_str());
+        if (base <= 0) base = 10000 + (master_port * 7 + 131) % 40000;
+        for (int i = 0; i < n; ++i) c.init_peers.push_back(PeerID{ip, (uint16_t)(base + i)});
+        c.self = c.init_peers[r];
+        c.strategy = parse_strategy(getenv_str(envkeys::kAllReduceStrategy, "AUTO"));
+        c.config_server = getenv_str(envkeys::kConfigServer);
+        return c;
+    }
+    c.single = true;
+    c.self = PeerID{parse_ipv4("127.0.0.1"), kDefaultPortBegin};
+    c.init_peers.push_back(c.self);
+    return c;
+}
+
+PeerConfig PeerConfig::single_machine(int rank, int size, uint16_t base_port) {
+    PeerConfig c;
+    c.launcher = "explicit";
+    const uint32_t ip = parse_ipv4("127.0.0.1");
+    if (base_port == 0) base_port = kDefaultPortBegin;
+    for (int i = 0; i < size; ++i) c.init_peers.push_back(PeerID{ip, (uint16_t)(base_port + i)});
+    c.self = c.init_peers.at(rank);
+    c.single = size == 1;
+    c.strategy = parse_strategy(getenv_str(envkeys::kAllReduceStrategy, "AUTO"));
+    return c;
+}
+
+// ---- lifecycle --------------------------------------------------------------------------------------
+Peer::Peer(const PeerConfig& cfg) : cfg_(cfg) {
+    client_.reset(new Client(cfg_.self));
+    p2p_.reset(new P2PEndpoint(client_.get(), cfg_.self));
+    server_.reset(new Server(cfg_.self, &coll_, p2p_.get(), Config::get().use_unix_sock));
+    cluster_.runners = cfg_.init_runners;
+    cluster_.workers = cfg_.init_peers;
+    cluster_version_ = cfg_.init_cluster_version;
+}
+
+Peer::~Peer() {
+    try {
+        close();
+    } catch (...) {
+    }
+}
+
+void Peer::start() {
+    if (started_) return;
+    started_ = true;
+    if (!cfg_.single) {
+        server_->set_control_handler([this](const PeerID& src, const std::string& name, const Bytes& payload) { on_control(src, name, payload); });
+        server_->start();
+        if (Config::get().enable_monitoring) {
+            metrics_.reset(new HttpServer());
+            try {
+                const int port = metrics_->start("0.0.0.0", cfg_.self.port + 10000, [](const HttpRequest& r) {
+                    HttpResponse resp;
+                    if (r.path == "/metrics") resp.body = NetMonitor::get().metrics_text();
+                    else resp.status = 404;
+                    return resp;
+                });
+                KF_LOGI("peer %s started, monitoring endpoint http://%s:%d/metrics", cfg_.self.str().c_str(), format_ipv4(cfg_.self.ipv4).c_str(), port);
+            } catch (const std::exception& e) {
+                KF_LOGW("metrics endpoint unavailable: %s", e.what());
+                metrics_.reset();
+            }
+        }
+    }
+    update();
+}
+
+void Peer::close() {
+    if (!started_) return;
+    started_ = false;
+    coll_.shutdown("peer closed");
+    p2p_->shutdown();
+    if (metrics_) metrics_->stop();
+    if (!cfg_.single) server_->stop();
+    client_->close_all();
+}
+
+void Peer::on_control(const PeerID& src, const std::string& name, const Bytes&) {
+    if (name == "exit") { // fault injection / orderly removal (reference: rchannel/handler/control.go:17-21)
+        KF_LOGW("exit requested by %s", src.str().c_str());
+        _exit(0);
+    }
+}
+
+uint64_t Peer::uid() const {
+    const uint64_t hi = cfg_.self.ipv4;
+    const uint64_t lo = ((uint64_t)cfg_.self.port << 16) | (uint64_t)(uint16_t)cfg_.init_cluster_version;
+    return (hi << 32) | lo;
+}
+
+Cluster Peer::current_cluster() {
+    std::lock_guard<std::mutex> g(mu_);
+    return cluster_;
+}
+
+std::shared_ptr<Session> Peer::session() {
+    std::lock_guard<std::mutex> g(mu_);
+    if (!session_) update_to(cluster_.workers);
+    if (!session_) fail("this peer is not part of the current cluster");
+    return session_;
+}
+
+bool Peer::update() {
+    std::lock_guard<std::mutex> g(mu_);
+    return update_to(cluster_.workers);
+}
+
+bool Peer::update_to(const PeerList& pl) {
+    StallGuard sg("updateTo(" + pl.str() + ")");
+    server_->set_token((uint32_t)cluster_version_);
+    if (updated_) return true;
+    KF_LOGD("updateTo v%d of %d peers: %s", cluster_version_, (int)pl.size(), pl.str().c_str());
+    client_->reset_connections(pl, (uint32_t)cluster_version_);
+    if (!pl.contains(cfg_.self)) return false;
+    coll_.reopen();
+    auto sess = std::make_shared<Session>(cfg_.strategy, cfg_.self, pl, client_.get(), &coll_);
+    sess->barrier(); // meets the barrier of every other member of the new cluster version
+    session_ = sess;
+    updated_ = true;
+    return true;
+}
+
+// ---- elastic ------------------------------------------------------------------------------------------
+bool Peer::fetch_cluster(Cluster& out) {
+    if (cfg_.config_server.empty()) return false;
+    std::string body;
+    const int st = http_request("GET", cfg_.config_server, "", &body);
+    if (st != 200) return false;
+    try {
+        out = Cluster::from_json(body);
+        return true;
+    } catch (const std::exception& e) {
+        KF_LOGW("bad cluster config from %s: %s", cfg_.config_server.c_str(), e.what());
+        return false;
+    }
+}
+
+void Peer::propose_new_size(int new_size) {
+    Cluster c;
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        c = cluster_.resized(new_size);
+    }
+    if (cfg_.config_server.empty()) fail("propose_new_size: no config server (KUNGFU_CONFIG_SERVER)");
+    std::string resp;
+    const int st = http_request("PUT", cfg_.config_server, c.to_json(), &resp);
+    if (st != 200) KF_LOGW("propose_new_size(%d): config server answered %d %s", new_size, st, resp.c_str());
+}
+
+std::pair<bool, bool> Peer::propose(const Cluster& c) {
+    StallGuard sg("propose");
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        if (cluster_ == c) return {false, false};
+    }
+    const std::string d = c.digest();
+    if (!session()->consensus(d.data(), d.size(), "kungfu::propose")) {
+        KF_LOGE("diverging proposal among peers; I proposed %s", c.workers.str().c_str());
+        return {false, false};
+    }
+    Stage st;
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        st.version = cluster_version_ + 1;
+    }
+    st.cluster = c;
+    const std::string payload = st.to_json();
+    const double wait_s = Config::get().wait_runner_timeout_s;
+    std::string err = parallel_for((int)c.runners.size(), [&](int i) {
+        const PeerID& r = c.runners[i];
+        if (!client_->wait_peer(r, wait_s)) fail("runner " + r.str() + " is not reachable");
+        client_->send(r, "update", payload.data(), payload.size(), kConnControl, kNoFlag);
+    });
+    if (!err.empty()) fail("propose: " + err);
+    std::lock_guard<std::mutex> g(mu_);
+    if (cluster_.workers.disjoint(c.workers)) KF_LOGE("full update detected: %s -> %s! State will be lost.", cluster_.workers.str().c_str(), c.workers.str().c_str());
+    else if (!c.workers.empty() && !cluster_.workers.contains(c.workers[0])) KF_LOGE("the new root is a new worker! State will be lost.");
+    cluster_ = c;
+    cluster_version_ += 1;
+    updated_ = false;
+    session_.reset();
+    const bool keep = c.workers.contains(cfg_.self);
+    return {true, !keep};
+}
+
+std::pair<bool, bool> Peer::resize_cluster(int new_size) {
+    if (session()->rank() == 0) {
+        try {
+            propose_new_size(new_size);
+        } catch (const std::exception& e) {
+            KF_LOGW("resize_cluster: %s", e.what());
+        }
+    }
+    return resize_cluster_from_url();
+}
+
+std::pair<bool, bool> Peer::resize_cluster_from_url() {
+    Cluster c;
+    for (int i = 0;; ++i) {
+        if (!fetch_cluster(c)) {
+            if (i == 0) KF_LOGD("no cluster config available, using the current one");
+            std::lock_guard<std::mutex> g(mu_);
+            c = cluster_;
+        }
+        const std::string d = c.digest();
+        if (session()->consensus(d.data(), d.size(), "kungfu::resize")) break;
+        KF_LOGW("peers read different cluster configs (attempt %d), retrying", i + 1);
+        sleep_ms(50);
+    }
+    auto res = propose(c);
+    if (res.second) detached_ = true;
+    else update();
+    return res;
+}
+
+// ---- p2p ----------------------------------------------------------------------------------------------
+void Peer::save(const std::string& name, const void* data, size_t len) { p2p_->save(name, data, len); }
+void Peer::save_version(const std::string& version, const std::string& name, const void* data, size_t len) {
+    p2p_->save_version(version, name, data, len);
+}
+bool Peer::request(int rank, const std::string& version, const std::string& name, void* buf, size_t len) {
+    auto sess = session();
+    if (rank < 0 || rank >= sess->size()) fail("request: rank out of range");
+    return p2p_->request(sess->peers()[rank], version, name, buf, len);
+}
+
+} // namespace kfrt
