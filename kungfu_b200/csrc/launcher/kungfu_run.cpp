@@ -1,0 +1,841 @@
+// kungfu-run — the launcher of kungfu_b200 (C++; the reference's is Go).
+//
+// Reference: srcs/go/cmd/kungfu-run/app/kungfu-run.go:18-124 (main flow), srcs/go/kungfu/runner/{flags.go:69-104,
+// simple.go:13-21, watch.go:23-150, monitored.go:18-75, handler.go:19-123, discovery.go:18-26},
+// srcs/go/kungfu/runner/monitorserver/monitor.go:17-198, srcs/go/kungfu/job/{job.go:17-102, gpu_resource.go:11-51},
+// srcs/go/utils/runner/local/local.go:18-92 (tee'd, colour-prefixed worker output; cancel all on first failure).
+//
+//   kungfu-run [-np N] [-H ip:slots,...|-hostfile f] [-self ip|-nic name] [-strategy S] [-port-range a-b] [-port p]
+//              [-w] [-k] [-config-server URL] [-builtin-config-port p] [-init-version v] [-timeout d] [-logdir d]
+//              [-logfile f] [-q] [-v] [-allow-nvlink] [-auto-recover d] [-delay d] [-debug-port p] prog args...
+//
+// Modes: static (spawn local workers, fail fast) | -w watch (elastic: a control server receives Stage updates from the
+// workers' resize protocol and spawns/reaps local workers by diff, GPUs from a smallest-free pool) | -auto-recover
+// (heartbeat failure detector on :7756; on a stalled batch: kill the local workers, patch --n-epochs/--num-epochs,
+// append `--restart 1`, relaunch).
+//
+// B200 default: every worker sees ALL GPUs (P2P / NVLS need that) and is told its device through
+// KUNGFU_CUDA_VISIBLE_DEVICES; `-allow-nvlink=false` restores the reference's one-visible-GPU isolation.
+#include <fcntl.h>
+#include <ifaddrs.h>
+#include <net/if.h>
+#include <netinet/in.h>
+#include <signal.h>
+#include <sys/stat.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <set>
+#include <sstream>
+
+#include "base.hpp"
+#include "config_server.hpp"
+#include "graph.hpp"
+#include "http.hpp"
+#include "plan.hpp"
+#include "transport.hpp"
+
+using namespace kfrt;
+
+extern char** environ;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------
+// flags
+// ---------------------------------------------------------------------------------------------------
+struct Flags {
+    int np = 1;
+    double auto_recover_s = 0;
+    std::string hosts = "127.0.0.1:" + std::to_string(std::max(1u, std::thread::hardware_concurrency()));
+    std::string hostfile;
+    std::string peer_list; // -P: parsed for parity, unused (as in the reference)
+    std::string user;
+    PortRange port_range;
+    std::string self;
+    double timeout_s = 0;
+    bool verbose = true;
+    std::string nic;
+    bool allow_nvlink = true;
+    std::string strategy = "BINARY_TREE_STAR";
+    int port = kDefaultRunnerPort;
+    int debug_port = 0;
+    bool watch = false;
+    bool keep = false;
+    int init_version = 0;
+    std::string config_server;
+    long t0 = (long)time(nullptr);
+    std::string logfile, logdir;
+    bool quiet = false;
+    double delay_s = 0;
+    int builtin_config_port = 0;
+    std::string prog;
+    std::vector<std::string> args;
+};
+
+[[noreturn]] void usage(const std::string& err) {
+    if (!err.empty()) fprintf(stderr, "kungfu-run: %s\n", err.c_str());
+    fprintf(stderr,
+            "usage: kungfu-run [-np N] [-H ip:slots,...] [-hostfile f] [-self ip] [-nic name] [-strategy S]\n"
+            "                  [-port-range a-b] [-port p] [-w] [-k] [-config-server URL] [-builtin-config-port p]\n"
+            "                  [-init-version v] [-timeout d] [-logdir d] [-logfile f] [-q] [-v] [-allow-nvlink]\n"
+            "                  [-auto-recover d] [-delay d] [-debug-port p] prog args...\n"
+            "strategies: ");
+    for (auto& s : strategy_names()) fprintf(stderr, "%s ", s.c_str());
+    fprintf(stderr, "\n");
+    exit(err.empty() ? 0 : 2);
+}
+
+bool parse_bool(const std::string& v) { return v == "1" || v == "true" || v == "True" || v == "yes" || v.empty(); }
+
+Flags parse_flags(int argc, char** argv) {
+    Flags f;
+    int i = 1;
+    auto is_bool_flag = [](const std::string& k) {
+        return k == "w" || k == "k" || k == "q" || k == "v" || k == "allow-nvlink" || k == "h" || k == "help";
+    };
+    for (; i < argc; ++i) {
+        std::string a = argv[i];
+        if (a == "--") {
+            ++i;
+            break;
+        }
+        if (a.size() < 2 || a[0] != '-') break;
+        std::string k = a.substr(a[1] == '-' ? 2 : 1), v;
+        bool has_v = false;
+        auto eq = k.find('=');
+        if (eq != std::string::npos) {
+            v = k.substr(eq + 1);
+            k = k.substr(0, eq);
+            has_v = true;
+        }
+        if (!has_v && !is_bool_flag(k)) {
+            if (i + 1 >= argc) usage("flag -" + k + " needs a value");
+            v = argv[++i];
+        }
+        if (k == "np") f.np = atoi(v.c_str());
+        else if (k == "auto-recover") f.auto_recover_s = parse_duration_s(v, 0);
+        else if (k == "H") f.hosts = v;
+        else if (k == "hostfile") f.hostfile = v;
+        else if (k == "P") f.peer_list = v;
+        else if (k == "u") f.user = v;
+        else if (k == "port-range") f.port_range = PortRange::parse(v);
+        else if (k == "self") f.self = v;
+        else if (k == "timeout") f.timeout_s = parse_duration_s(v, 0);
+        else if (k == "v") f.verbose = parse_bool(v);
+        else if (k == "nic") f.nic = v;
+        else if (k == "allow-nvlink") f.allow_nvlink = parse_bool(v);
+        else if (k == "strategy") f.strategy = v;
+        else if (k == "port") f.port = atoi(v.c_str());
+        else if (k == "debug-port") f.debug_port = atoi(v.c_str());
+        else if (k == "w") f.watch = parse_bool(v);
+        else if (k == "k") f.keep = parse_bool(v);
+        else if (k == "init-version") f.init_version = atoi(v.c_str());
+        else if (k == "config-server") f.config_server = v;
+        else if (k == "t0") f.t0 = atol(v.c_str());
+        else if (k == "logfile") f.logfile = v;
+        else if (k == "logdir") f.logdir = v;
+        else if (k == "q") f.quiet = parse_bool(v);
+        else if (k == "delay") f.delay_s = parse_duration_s(v, 0);
+        else if (k == "builtin-config-port") f.builtin_config_port = atoi(v.c_str());
+        else if (k == "h" || k == "help") usage("");
+        else usage("unknown flag -" + k);
+    }
+    if (i >= argc) usage("missing program name");
+    f.prog = argv[i++];
+    for (; i < argc; ++i) f.args.push_back(argv[i]);
+    parse_strategy(f.strategy); // validate early
+    return f;
+}
+
+uint32_t infer_self_ipv4(const std::string& self, const std::string& nic) {
+    if (!self.empty()) return resolve_ipv4(self);
+    if (!nic.empty()) {
+        ifaddrs* ifa = nullptr;
+        if (getifaddrs(&ifa) == 0) {
+            for (ifaddrs* p = ifa; p; p = p->ifa_next)
+                if (p->ifa_addr && p->ifa_addr->sa_family == AF_INET && nic == p->ifa_name) {
+                    uint32_t ip = ntohl(reinterpret_cast<sockaddr_in*>(p->ifa_addr)->sin_addr.s_addr);
+                    freeifaddrs(ifa);
+                    return ip;
+                }
+            freeifaddrs(ifa);
+        }
+        fail("network interface '" + nic + "' has no IPv4 address");
+    }
+    return parse_ipv4("127.0.0.1");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// job / proc
+// ---------------------------------------------------------------------------------------------------
+struct Proc {
+    std::string name; // ip.port
+    std::string prog;
+    std::vector<std::string> args;
+    std::map<std::string, std::string> envs;
+    std::string log_prefix;
+};
+
+// smallest-free GPU id pool (reference: job/gpu_resource.go:11-51)
+class GpuPool {
+public:
+    explicit GpuPool(int n) : used_(n > 0 ? n : 0, false) {}
+    int get() {
+        std::lock_guard<std::mutex> g(mu_);
+        for (size_t i = 0; i < used_.size(); ++i)
+            if (!used_[i]) {
+                used_[i] = true;
+                return (int)i;
+            }
+        return -1;
+    }
+    void put(int id) {
+        std::lock_guard<std::mutex> g(mu_);
+        if (id >= 0 && id < (int)used_.size()) used_[id] = false;
+    }
+
+private:
+    std::mutex mu_;
+    std::vector<bool> used_;
+};
+
+struct Job {
+    long start_time = 0;
+    std::string strategy;
+    PeerID parent;
+    HostList hosts;
+    PortRange port_range;
+    std::string prog;
+    std::vector<std::string> args;
+    std::string logdir;
+    std::string config_server;
+    bool allow_nvlink = true;
+
+    // maps a local GPU slot through the launcher's own CUDA_VISIBLE_DEVICES (reference: job/cuda_visible_device.go)
+    static std::string cuda_index(int slot) {
+        const char* v = getenv("CUDA_VISIBLE_DEVICES");
+        if (!v) return std::to_string(slot);
+        std::vector<std::string> ids;
+        std::stringstream ss(v);
+        std::string part;
+        while (std::getline(ss, part, ',')) ids.push_back(part);
+        if (slot >= 0 && slot < (int)ids.size()) return ids[slot];
+        return "-1";
+    }
+
+    Proc new_proc(const PeerID& peer, int gpu_slot, int version, const Cluster& cluster) const {
+        Proc p;
+        p.name = format_ipv4(peer.ipv4) + "." + std::to_string(peer.port);
+        p.prog = prog;
+        p.args = args;
+        p.log_prefix = p.name + "@" + std::to_string(version);
+        auto& e = p.envs;
+        e[envkeys::kSelfSpec] = peer.str();
+        e[envkeys::kInitPeers] = cluster.workers.str();
+        e[envkeys::kInitRunners] = cluster.runners.str();
+        e[envkeys::kParentID] = parent.str();
+        e[envkeys::kInitClusterVersion] = std::to_string(version);
+        e[envkeys::kAllReduceStrategy] = strategy;
+        e[envkeys::kJobStart] = std::to_string(start_time);
+        e[envkeys::kProcStart] = std::to_string((long)time(nullptr));
+        if (!config_server.empty()) e[envkeys::kConfigServer] = config_server;
+        const std::string idx = cuda_index(gpu_slot);
+        e[envkeys::kCudaVisibleDevices] = idx;
+        if (allow_nvlink) e[envkeys::kAllowNvlink] = "1";
+        else e["CUDA_VISIBLE_DEVICES"] = idx; // reference default: hide the other GPUs (kills P2P)
+        e["PYTHONUNBUFFERED"] = "1";
+        return p;
+    }
+
+    std::vector<Proc> create_procs(const Cluster& cluster, uint32_t host, int version) const {
+        std::vector<Proc> ps;
+        int slot = 0;
+        for (auto& w : cluster.workers)
+            if (w.ipv4 == host) ps.push_back(new_proc(w, slot++, version, cluster));
+        return ps;
+    }
+};
+
+// ---- running one process with tee'd, prefixed output ------------------------------------------------
+const char* kColors[] = {"\x1b[1;32m", "\x1b[1;34m", "\x1b[1;33m", "\x1b[1;35m", "\x1b[1;36m", "\x1b[1;31m"};
+
+struct Cancel {
+    std::atomic<bool> flag{false};
+    std::mutex mu;
+    std::set<pid_t> pids;
+    void add(pid_t p) {
+        std::lock_guard<std::mutex> g(mu);
+        pids.insert(p);
+    }
+    void remove(pid_t p) {
+        std::lock_guard<std::mutex> g(mu);
+        pids.erase(p);
+    }
+    void cancel(int sig = SIGTERM) {
+        flag = true;
+        std::lock_guard<std::mutex> g(mu);
+        for (pid_t p : pids) ::kill(p, sig); // exact PIDs we forked
+    }
+};
+
+void pump(int fd, const std::string& tag, const char* color, bool verbose, FILE* console, const std::string& logpath) {
+    FILE* lf = logpath.empty() ? nullptr : fopen(logpath.c_str(), "w");
+    FILE* in = fdopen(fd, "r");
+    if (!in) {
+        close(fd);
+        if (lf) fclose(lf);
+        return;
+    }
+    char* line = nullptr;
+    size_t cap = 0;
+    ssize_t n;
+    static std::mutex console_mu;
+    while ((n = getline(&line, &cap, in)) >= 0) {
+        if (lf) {
+            fwrite(line, 1, (size_t)n, lf);
+            fflush(lf);
+        }
+        if (verbose) {
+            std::lock_guard<std::mutex> g(console_mu);
+            fprintf(console, "%s[%s]\x1b[m %s", color, tag.c_str(), line);
+            if (n == 0 || line[n - 1] != '\n') fputc('\n', console);
+            fflush(console);
+        }
+    }
+    free(line);
+    fclose(in);
+    if (lf) fclose(lf);
+}
+
+// returns the exit code (128+signal when killed)
+int run_proc(const Proc& p, bool verbose, const std::string& logdir, Cancel* cancel, int color_idx) {
+    int out_pipe[2], err_pipe[2];
+    if (pipe(out_pipe) != 0 || pipe(err_pipe) != 0) fail("pipe() failed");
+    std::vector<std::string> envs;
+    for (char** e = environ; *e; ++e) {
+        std::string kv = *e;
+        std::string k = kv.substr(0, kv.find('='));
+        if (!p.envs.count(k)) envs.push_back(kv);
+    }
+    for (auto& kv : p.envs) envs.push_back(kv.first + "=" + kv.second);
+    std::vector<char*> envp, argv;
+    for (auto& s : envs) envp.push_back(const_cast<char*>(s.c_str()));
+    envp.push_back(nullptr);
+    argv.push_back(const_cast<char*>(p.prog.c_str()));
+    for (auto& a : p.args) argv.push_back(const_cast<char*>(a.c_str()));
+    argv.push_back(nullptr);
+    pid_t pid = fork();
+    if (pid < 0) fail("fork() failed");
+    if (pid == 0) {
+        dup2(out_pipe[1], 1);
+        dup2(err_pipe[1], 2);
+        close(out_pipe[0]);
+        close(out_pipe[1]);
+        close(err_pipe[0]);
+        close(err_pipe[1]);
+        execvpe(p.prog.c_str(), argv.data(), envp.data());
+        fprintf(stderr, "kungfu-run: cannot exec %s: %s\n", p.prog.c_str(), strerror(errno));
+        _exit(127);
+    }
+    close(out_pipe[1]);
+    close(err_pipe[1]);
+    if (cancel) cancel->add(pid);
+    if (!logdir.empty()) mkdir(logdir.c_str(), 0755);
+    const std::string base = logdir.empty() ? "" : logdir + "/" + p.log_prefix;
+    const char* color = kColors[color_idx % 6];
+    std::thread t1(pump, out_pipe[0], p.name + "::stdout", color, verbose, stdout, base.empty() ? "" : base + ".stdout.log");
+    std::thread t2(pump, err_pipe[0], p.name + "::stderr", color, verbose, stderr, base.empty() ? "" : base + ".stderr.log");
+    int status = 0;
+    while (waitpid(pid, &status, 0) < 0 && errno == EINTR) {
+    }
+    if (cancel) cancel->remove(pid);
+    t1.join();
+    t2.join();
+    if (WIFEXITED(status)) return WEXITSTATUS(status);
+    if (WIFSIGNALED(status)) return 128 + WTERMSIG(status);
+    return 1;
+}
+
+// run all procs concurrently; the first failure cancels the rest (fail-fast). Returns 0 iff all succeeded.
+int run_all(const std::vector<Proc>& procs, bool verbose, const std::string& logdir, Cancel& cancel) {
+    std::vector<int> codes(procs.size(), 0);
+    std::vector<std::thread> ts;
+    for (size_t i = 0; i < procs.size(); ++i)
+        ts.emplace_back([&, i] {
+            codes[i] = run_proc(procs[i], verbose, logdir, &cancel, (int)i);
+            if (codes[i] != 0 && !cancel.flag) {
+                KF_LOGE("%s exited with %d, cancelling the others", procs[i].name.c_str(), codes[i]);
+                cancel.cancel();
+            }
+        });
+    for (auto& t : ts) t.join();
+    for (int c : codes)
+        if (c != 0) return c;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// signal handling
+// ---------------------------------------------------------------------------------------------------
+Cancel* g_cancel = nullptr;
+std::atomic<bool> g_stop{false};
+void on_signal(int sig) {
+    g_stop = true;
+    if (g_cancel) {
+        g_cancel->flag = true;
+        // async-signal-safe enough: kill() on the pids we track (best effort without the lock)
+        for (pid_t p : g_cancel->pids) ::kill(p, sig == SIGINT ? SIGINT : SIGTERM);
+    }
+}
+
+void install_timeout(double timeout_s, Cancel& cancel) {
+    if (timeout_s <= 0) return;
+    std::thread([timeout_s, &cancel] {
+        const double t0 = now_s();
+        while (now_s() - t0 < timeout_s) {
+            if (g_stop) return;
+            sleep_ms(100);
+        }
+        KF_LOGE("timeout after %.1fs, killing workers", timeout_s);
+        g_stop = true;
+        cancel.cancel(SIGKILL);
+    }).detach();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// static mode
+// ---------------------------------------------------------------------------------------------------
+int simple_run(const Flags& f, const Job& job, const Cluster& cluster, uint32_t self_ip) {
+    Cancel cancel;
+    g_cancel = &cancel;
+    install_timeout(f.timeout_s, cancel);
+    auto procs = job.create_procs(cluster, self_ip, f.init_version);
+    KF_LOGI("will parallel run %d instances of %s", (int)procs.size(), job.prog.c_str());
+    const double t0 = now_s();
+    const int rc = run_all(procs, f.verbose, f.logdir, cancel);
+    KF_LOGI("all %d/%d local peers finished, took %.2fs", (int)procs.size(), (int)cluster.workers.size(), now_s() - t0);
+    return g_stop && rc == 0 ? 1 : rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// watch (elastic) mode
+// ---------------------------------------------------------------------------------------------------
+struct Watcher {
+    const Flags& f;
+    Job job;
+    PeerID self;
+    Cancel cancel;
+    GpuPool gpus;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Stage> stages;
+    std::vector<Stage> history;
+    std::map<uint64_t, std::thread> running; // peer key -> waiter thread
+    std::map<uint64_t, bool> finished;
+    int n_running = 0;
+    bool failed = false;
+    int fail_code = 0;
+    Cluster current;
+
+    Watcher(const Flags& fl, const Job& j, const PeerID& s) : f(fl), job(j), self(s), gpus(j.hosts.slots_of(s.ipv4)) {}
+
+    void push(const Stage& st) {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto& h : history)
+            if (h.version == st.version) {
+                if (h.cluster != st.cluster) KF_LOGE("inconsistent update for version %d ignored", st.version);
+                return; // duplicates arrive from every worker
+            }
+        history.push_back(st);
+        stages.push_back(st);
+        cv.notify_all();
+    }
+
+    void create(const PeerID& id, const Stage& st) {
+        const int gpu = gpus.get();
+        if (gpu < 0) KF_LOGW("no free GPU slot for %s", id.str().c_str());
+        Proc p = job.new_proc(id, gpu, st.version, st.cluster);
+        {
+            std::lock_guard<std::mutex> g(mu);
+            ++n_running;
+            finished[id.key()] = false;
+        }
+        const int color = (int)(id.port % 6);
+        std::thread t([this, p, gpu, id, color] {
+            const int rc = run_proc(p, true, job.logdir, &cancel, color);
+            gpus.put(gpu);
+            std::lock_guard<std::mutex> g(mu);
+            --n_running;
+            finished[id.key()] = true;
+            if (rc != 0 && !cancel.flag) {
+                KF_LOGE("%s finished with error %d", p.name.c_str(), rc);
+                failed = true;
+                fail_code = rc;
+            }
+            cv.notify_all();
+        });
+        std::lock_guard<std::mutex> g(mu);
+        running[id.key()] = std::move(t);
+    }
+
+    void remove(const PeerID& id) {
+        std::thread t;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto it = running.find(id.key());
+            if (it == running.end()) return;
+            t = std::move(it->second);
+            running.erase(it);
+        }
+        if (t.joinable()) t.join(); // detached workers stop themselves
+    }
+
+    void update(const Stage& st, Server& server) {
+        server.set_token((uint32_t)st.version);
+        if (!current.workers.empty() && current.workers.disjoint(st.cluster.workers)) KF_LOGE("full update detected");
+        PeerList del = current.workers.minus(st.cluster.workers).on_host(self.ipv4);
+        PeerList add = st.cluster.workers.minus(current.workers).on_host(self.ipv4);
+        KF_LOGI("arrived at v%d, new np=%d, local: +%d/-%d", st.version, (int)st.cluster.workers.size(), (int)add.size(), (int)del.size());
+        for (auto& id : del) remove(id);
+        for (auto& id : add) create(id, st);
+        current = st.cluster;
+    }
+
+    int loop(Server& server) {
+        bool started = false;
+        while (true) {
+            Stage st;
+            bool have = false;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait_for(lk, std::chrono::milliseconds(200), [&] { return !stages.empty() || failed || g_stop.load(); });
+                if (failed) {
+                    lk.unlock();
+                    cancel.cancel();
+                    join_all();
+                    return fail_code ? fail_code : 1;
+                }
+                if (g_stop) {
+                    lk.unlock();
+                    cancel.cancel();
+                    join_all();
+                    return 1;
+                }
+                if (!stages.empty()) {
+                    st = stages.front();
+                    stages.pop_front();
+                    have = true;
+                } else if (started && n_running == 0 && !f.keep) {
+                    lk.unlock();
+                    join_all();
+                    return 0;
+                }
+            }
+            if (have) {
+                update(st, server);
+                started = true;
+            }
+        }
+    }
+
+    void join_all() {
+        std::map<uint64_t, std::thread> ts;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            ts.swap(running);
+        }
+        for (auto& kv : ts)
+            if (kv.second.joinable()) kv.second.join();
+    }
+};
+
+int watch_run(const Flags& f, const Job& job, const Cluster& init, const PeerID& self) {
+    Watcher w(f, job, self);
+    g_cancel = &w.cancel;
+    install_timeout(f.timeout_s, w.cancel);
+    Server server(self, nullptr, nullptr, Config::get().use_unix_sock);
+    server.set_control_handler([&](const PeerID& src, const std::string& name, const Bytes& payload) {
+        if (name == "update") {
+            try {
+                w.push(Stage::from_json(std::string(payload.begin(), payload.end())));
+            } catch (const std::exception& e) {
+                KF_LOGE("bad stage from %s: %s", src.str().c_str(), e.what());
+            }
+        } else if (name == "exit") {
+            KF_LOGW("exit requested by %s", src.str().c_str());
+            g_stop = true;
+        }
+    });
+    server.start();
+    HttpServer debug;
+    if (f.debug_port > 0) {
+        debug.start("0.0.0.0", f.debug_port, [&](const HttpRequest&) {
+            HttpResponse r;
+            r.content_type = "application/json";
+            std::lock_guard<std::mutex> g(w.mu);
+            r.body = "[";
+            for (size_t i = 0; i < w.history.size(); ++i) r.body += (i ? "," : "") + w.history[i].to_json();
+            r.body += "]\n";
+            return r;
+        });
+        KF_LOGI("debug server: http://127.0.0.1:%d/", f.debug_port);
+    }
+    if (f.init_version < 0) {
+        KF_LOGI("waiting to be initialized");
+    } else {
+        Stage st;
+        st.version = f.init_version;
+        st.cluster = init;
+        w.push(st);
+    }
+    KF_LOGI("watching config server");
+    const int rc = w.loop(server);
+    KF_LOGI("stop watching");
+    server.stop();
+    debug.stop();
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// failure detector + auto recovery
+// ---------------------------------------------------------------------------------------------------
+struct MonitorResult {
+    bool down = false, finish = false;
+    int epochs = 0;
+};
+
+class MonitorServer {
+public:
+    MonitorServer(int cluster_size, double threshold_s) : n_(cluster_size), threshold_s_(threshold_s > 0 ? threshold_s : 10.0) {
+        trainend_.assign(n_, 0);
+        begin_.assign(n_, 0.0);
+        epochs_.assign(n_, 0);
+    }
+    // blocks until a worker stalls (down) or every rank reported train end (finish)
+    MonitorResult run(const std::string& self_ip, const HostList& hosts, int port = 7756) {
+        bool main_server = false;
+        std::vector<std::string> others;
+        if (hosts.size() != 1) {
+            int idx = 0;
+            for (auto& h : hosts) {
+                if (format_ipv4(h.ipv4) == self_ip) {
+                    if (idx == 0) main_server = true;
+                } else {
+                    others.push_back(format_ipv4(h.ipv4));
+                }
+                ++idx;
+            }
+        }
+        HttpServer http;
+        try {
+            http.start("0.0.0.0", port, [this](const HttpRequest& r) { return handle(r); });
+        } catch (const std::exception& e) {
+            KF_LOGE("monitor server: %s", e.what());
+        }
+        MonitorResult res;
+        auto relay = [&](const std::string& key) {
+            for (auto& ip : others) http_request("POST", "http://" + ip + ":" + std::to_string(port) + "/", "{\"key\":\"" + key + "\"}", nullptr);
+        };
+        while (!g_stop && !stop_) {
+            sleep_ms(100);
+            std::lock_guard<std::mutex> g(mu_);
+            int ended = 0;
+            const double t = now_s();
+            bool down = false;
+            for (int i = 0; i < n_; ++i) {
+                if (trainend_[i]) ++ended;
+                if (begin_[i] != 0 && t - begin_[i] > threshold_s_) down = true;
+            }
+            if (down) {
+                res.down = true;
+                res.epochs = *std::min_element(epochs_.begin(), epochs_.end());
+                if (main_server) relay("otherdown:" + std::to_string(res.epochs));
+                break;
+            }
+            if (other_down_) {
+                res.down = true;
+                res.epochs = other_epochs_;
+                break;
+            }
+            if (ended == n_ || other_finish_) {
+                if (main_server) relay("otherfinish:0");
+                res.finish = true;
+                break;
+            }
+        }
+        http.stop();
+        return res;
+    }
+    void stop() { stop_ = true; }
+
+private:
+    HttpResponse handle(const HttpRequest& r) {
+        HttpResponse resp;
+        std::string key;
+        try {
+            JsonValue v = JsonValue::parse(r.body);
+            const JsonValue* k = v.find("key");
+            if (k) key = k->str;
+        } catch (...) {
+        }
+        auto colon = key.find(':');
+        if (colon == std::string::npos) {
+            resp.status = 400;
+            return resp;
+        }
+        const std::string kind = key.substr(0, colon);
+        const int v = atoi(key.c_str() + colon + 1);
+        std::lock_guard<std::mutex> g(mu_);
+        const bool in_range = v >= 0 && v < n_;
+        if (kind == "trainend" && in_range) trainend_[v] = 1;
+        else if (kind == "begin" && in_range) begin_[v] = now_s();
+        else if (kind == "end" && in_range) begin_[v] = 0;
+        else if (kind == "epoch" && in_range) epochs_[v] += 1;
+        else if (kind == "otherfinish") other_finish_ = true;
+        else if (kind == "otherdown") {
+            other_epochs_ = v;
+            other_down_ = true;
+        }
+        return resp;
+    }
+    int n_;
+    double threshold_s_;
+    std::mutex mu_;
+    std::vector<int> trainend_, epochs_;
+    std::vector<double> begin_;
+    bool other_finish_ = false, other_down_ = false;
+    int other_epochs_ = 0;
+    std::atomic<bool> stop_{false};
+};
+
+int monitored_run(const Flags& f, Job job, const Cluster& cluster, uint32_t self_ip) {
+    const std::string self = f.self.empty() ? format_ipv4(self_ip) : f.self;
+    int restarts = 0;
+    while (!g_stop) {
+        Cancel cancel;
+        g_cancel = &cancel;
+        auto procs = job.create_procs(cluster, self_ip, f.init_version);
+        MonitorServer mon((int)cluster.workers.size(), f.auto_recover_s);
+        KF_LOGI("will parallel run %d instances of %s under the failure detector (threshold %.1fs)", (int)procs.size(), job.prog.c_str(),
+                f.auto_recover_s);
+        std::atomic<int> rc{-1};
+        std::thread runner([&] {
+            rc = run_all(procs, f.verbose, f.logdir, cancel);
+            if (rc != 0) mon.stop(); // a crashed worker ends the watch as well
+        });
+        MonitorResult res = mon.run(self, job.hosts);
+        if (res.down || (rc.load() > 0 && !res.finish && !g_stop)) {
+            KF_LOGW("worker failure detected (finished epochs: %d); restarting from the last checkpoint", res.epochs);
+            cancel.cancel(SIGKILL);
+            runner.join();
+            for (size_t i = 0; i + 1 < job.args.size(); ++i)
+                if (job.args[i] == "--n-epochs" || job.args[i] == "--num-epochs") {
+                    const int ini = atoi(job.args[i + 1].c_str());
+                    job.args[i + 1] = std::to_string(std::max(0, ini - res.epochs));
+                }
+            if (std::find(job.args.begin(), job.args.end(), "--restart") == job.args.end()) {
+                job.args.push_back("--restart");
+                job.args.push_back("1");
+            }
+            if (++restarts > 16) {
+                KF_LOGE("giving up after %d restarts", restarts);
+                return 1;
+            }
+            continue;
+        }
+        runner.join();
+        if (res.finish && rc == 0) {
+            KF_LOGI("success finish");
+            return 0;
+        }
+        return rc.load() ? rc.load() : 1;
+    }
+    return 1;
+}
+
+void log_env() {
+    for (char** e = environ; *e; ++e)
+        if (!strncmp(*e, "KUNGFU_", 7) || !strncmp(*e, "CUDA_", 5) || !strncmp(*e, "NCCL_", 5)) KF_LOGD("env %s", *e);
+}
+
+} // namespace
+
+int main(int argc, char** argv) {
+    try {
+        Flags f = parse_flags(argc, argv);
+        if (f.quiet) Logger::get().set_level(LogLevel::Warn);
+        Logger::get().set_prefix("[kungfu-run] ");
+        if (!f.logfile.empty()) {
+            std::string lf = f.logdir.empty() ? f.logfile : f.logdir + "/" + f.logfile;
+            auto slash = lf.rfind('/');
+            if (slash != std::string::npos) mkdir(lf.substr(0, slash).c_str(), 0755);
+            Logger::get().set_output(lf);
+        }
+        log_env();
+        if (f.delay_s > 0) {
+            KF_LOGW("delay start for %.1fs", f.delay_s);
+            sleep_ms((int)(f.delay_s * 1000));
+        }
+        signal(SIGPIPE, SIG_IGN);
+        struct sigaction sa {};
+        sa.sa_handler = on_signal;
+        sigaction(SIGINT, &sa, nullptr);
+        sigaction(SIGTERM, &sa, nullptr);
+
+        HostList hosts;
+        if (!f.hostfile.empty()) {
+            std::ifstream in(f.hostfile);
+            if (!in) fail("cannot read hostfile " + f.hostfile);
+            std::stringstream ss;
+            ss << in.rdbuf();
+            hosts = HostList::parse_hostfile(ss.str());
+        } else {
+            hosts = HostList::parse(f.hosts);
+        }
+        const uint32_t self_ip = infer_self_ipv4(f.self, f.nic);
+        const PeerID self{self_ip, (uint16_t)f.port};
+        PeerList runners = hosts.gen_runner_list((uint16_t)f.port);
+        if (!runners.contains(self)) fail(self.str() + " not in " + runners.str());
+        PeerList peers = hosts.gen_peer_list(f.np, f.port_range);
+        Cluster init{runners, peers};
+
+        ConfigServer builtin;
+        std::string config_server = f.config_server;
+        if (f.builtin_config_port > 0) {
+            builtin.start("0.0.0.0", f.builtin_config_port, &init);
+            if (config_server.empty()) config_server = "http://127.0.0.1:" + std::to_string(f.builtin_config_port) + "/config";
+            KF_LOGI("builtin config server at %s", config_server.c_str());
+        }
+
+        Job job;
+        job.start_time = f.t0;
+        job.strategy = f.strategy;
+        job.parent = self;
+        job.hosts = hosts;
+        job.port_range = f.port_range;
+        job.prog = f.prog;
+        job.args = f.args;
+        job.logdir = f.logdir;
+        job.allow_nvlink = f.allow_nvlink;
+        job.config_server = config_server;
+
+        const double t0 = now_s();
+        int rc;
+        if (f.watch) rc = watch_run(f, job, init, self);
+        else if (f.auto_recover_s > 0) rc = monitored_run(f, job, init, self_ip);
+        else rc = simple_run(f, job, init, self_ip);
+        if (f.builtin_config_port > 0) builtin.stop();
+        KF_LOGD("kungfu-run finished, took %.2fs", now_s() - t0);
+        return rc;
+    } catch (const std::exception& e) {
+        fprintf(stderr, "kungfu-run: %s\n", e.what());
+        return 1;
+    }
+}
