@@ -1,0 +1,15 @@
+"""`kungfu` — import-name compatibility with the reference (`import kungfu.torch as kf`, `kungfu.python`, `kungfu.cmd`).
+Everything lives in `kungfu_b200`; this package only aliases the modules."""
+import importlib
+import sys
+
+import kungfu_b200 as _impl
+
+__version__ = _impl.__version__
+
+for _name in ("python", "torch", "cmd", "ops", "elastic", "initializer", "checkpoint", "utils", "models", "parallel"):
+    _mod = importlib.import_module(f"kungfu_b200.{_name}")
+    sys.modules[f"kungfu.{_name}"] = _mod
+    globals()[_name] = _mod
+for _sub in ("torch.ops", "torch.optimizers"):
+    sys.modules[f"kungfu.{_sub}"] = importlib.import_module(f"kungfu_b200.{_sub}")

@@ -28,11 +28,14 @@ OBJ = PKG / "build"
 BIN = PKG / "bin"
 
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-CXX = os.environ.get("CXX") or shutil.which("g++") or "g++"
+# NB: $CXX in this image points at a wrapper that links libstdc++ statically; a second libstdc++ inside a process that
+# also hosts libtorch crashes in iostream/locale code. Always use the system compiler (dynamic libstdc++) unless
+# KUNGFU_CXX overrides it.
+CXX = os.environ.get("KUNGFU_CXX") or ("/usr/bin/g++" if os.path.exists("/usr/bin/g++") else (shutil.which("g++") or "g++"))
 CUDA_HOME = os.environ.get("CUDA_HOME") or str(Path(NVCC).resolve().parent.parent)
 
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ARCH_FLAGS + ["-lineinfo", "-O3", "-std=c++17", "--use_fast_math", "-Xcompiler", "-fPIC", "-Xcompiler",
+NVCC_FLAGS = ARCH_FLAGS + ["-ccbin", CXX, "-lineinfo", "-O3", "-std=c++17", "--use_fast_math", "-Xcompiler", "-fPIC", "-Xcompiler",
                            "-fvisibility=hidden", "--expt-relaxed-constexpr", "-diag-suppress", "177,550,2361"]
 CXX_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", "-pthread", "-fvisibility=hidden"]
 
@@ -107,7 +110,7 @@ def build_cuda(verbose: bool = False, force: bool = False) -> Path:
         for f in futs:
             changed |= bool(f.result())
     if changed or not out.exists():
-        _run([NVCC] + ARCH_FLAGS + ["-shared", "-o", str(out)] + [str(o) for o in objs] + ["-lpthread"])
+        _run([NVCC, "-ccbin", CXX] + ARCH_FLAGS + ["-shared", "-o", str(out)] + [str(o) for o in objs] + ["-lpthread"])
         if verbose:
             print(f"[kungfu_b200] linked {out.name}")
     return out

@@ -730,7 +730,7 @@ int monitored_run(const Flags& f, Job job, const Cluster& cluster, uint32_t self
             rc = run_all(procs, f.verbose, f.logdir, cancel);
             if (rc != 0) mon.stop(); // a crashed worker ends the watch as well
         });
-        MonitorResult res = mon.run(self, job.hosts);
+        MonitorResult res = mon.run(self, job.hosts, atoi(getenv_str("KUNGFU_MONITOR_PORT", "7756").c_str()));
         if (res.down || (rc.load() > 0 && !res.finish && !g_stop)) {
             KF_LOGW("worker failure detected (finished epochs: %d); restarting from the last checkpoint", res.epochs);
             cancel.cancel(SIGKILL);

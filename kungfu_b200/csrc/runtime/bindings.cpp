@@ -352,8 +352,7 @@ PYBIND11_MODULE(_kfrt, m) {
                 py::gil_scoped_release rel;
                 auto sess = p.session();
                 const int n = sess->size();
-                static std::atomic<uint64_t> seq{0};
-                const std::string tag = name + "#" + std::to_string(seq++);
+                const std::string tag = name + "#" + std::to_string(sess->next_seq());
                 std::vector<int64_t> lens(n, 0);
                 int64_t len = (int64_t)mine.size();
                 sess->all_gather(mk((uintptr_t)&len, (uintptr_t)lens.data(), 1, kI64, kSum, "kungfu::agb::len::" + tag));
@@ -372,8 +371,8 @@ PYBIND11_MODULE(_kfrt, m) {
         .def("all_reduce_int_max", [](Peer& p, int64_t x) {
             py::gil_scoped_release rel;
             int64_t y = x;
-            static std::atomic<uint64_t> seq{0};
-            p.session()->all_reduce(mk((uintptr_t)&x, (uintptr_t)&y, 1, kI64, kMax, "kungfu::int_max::" + std::to_string(seq++)));
+            auto sess = p.session();
+            sess->all_reduce(mk((uintptr_t)&x, (uintptr_t)&y, 1, kI64, kMax, "kungfu::int_max::" + std::to_string(sess->next_seq())));
             return y;
         })
         .def("set_tree", [](Peer& p, const std::vector<int32_t>& father) { p.session()->set_tree(father); }, py::call_guard<py::gil_scoped_release>())

@@ -76,6 +76,7 @@ public:
     void print_strategy_stats();
     bool check_interference();
     double last_throughput();
+    uint64_t next_seq() { return seq_++; } // session-scoped op numbering: identical on survivors and newcomers
 
 private:
     struct Strat {

@@ -1,0 +1,59 @@
+"""Initial state synchronisation.
+
+Reference: `kungfu.tensorflow.initializer` (srcs/python/kungfu/tensorflow/initializer/__init__.py:13-99):
+`BroadcastGlobalVariablesOp`, `broadcast_variables`, `BroadcastGlobalVariablesHook`, `BroadcastGlobalVariablesCallback`
+(fires after the first batch so optimizer slots exist). Torch: `broadcast_parameters(state_dict)`
+(srcs/python/kungfu/torch/ops/collective.py:42-47).
+"""
+from __future__ import annotations
+
+from typing import Iterable, Optional
+
+import torch
+
+from .ops import collective as coll
+
+
+def broadcast_variables(tensors: Iterable[torch.Tensor], root: int = 0) -> None:
+    for t in tensors:
+        coll.broadcast_(t, root)
+
+
+def broadcast_parameters(state_dict, root: int = 0) -> None:
+    for _, v in state_dict.items():
+        if isinstance(v, torch.Tensor):
+            coll.broadcast_(v, root)
+
+
+def broadcast_optimizer_state(optimizer: torch.optim.Optimizer, root: int = 0) -> None:
+    """Broadcast every tensor in the optimizer state (momentum buffers, Adam moments, step counters)."""
+    for group in optimizer.param_groups:
+        for p in group["params"]:
+            st = optimizer.state.get(p, {})
+            for k in sorted(st.keys()):
+                v = st[k]
+                if isinstance(v, torch.Tensor):
+                    coll.broadcast_(v, root)
+
+
+def BroadcastGlobalVariablesOp(model: torch.nn.Module, optimizer: Optional[torch.optim.Optimizer] = None, root: int = 0) -> None:
+    """Make every worker start from rank `root`'s model (parameters AND buffers) and optimizer state."""
+    broadcast_parameters(model.state_dict(), root)
+    if optimizer is not None:
+        broadcast_optimizer_state(optimizer, root)
+
+
+class BroadcastGlobalVariablesCallback:
+    """Training-loop callback: broadcasts once, after the first batch (so lazily created optimizer slots exist)."""
+
+    def __init__(self, model: torch.nn.Module, optimizer: Optional[torch.optim.Optimizer] = None, root: int = 0) -> None:
+        self.model, self.optimizer, self.root = model, optimizer, root
+        self.done = False
+
+    def on_batch_end(self, batch: int = 0) -> None:
+        if not self.done:
+            BroadcastGlobalVariablesOp(self.model, self.optimizer, self.root)
+            self.done = True
+
+
+BroadcastGlobalVariablesHook = BroadcastGlobalVariablesCallback

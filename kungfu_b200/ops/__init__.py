@@ -1,1 +1,57 @@
-"""kungfu_b200.ops"""
+"""Operator-level API (reference: srcs/python/kungfu/tensorflow/ops/__init__.py:29-83).
+
+GPU tensors run on our sm_100a kernels over peer-mapped HBM; CPU tensors on the native graph-collective runtime.
+"""
+from typing import List, Sequence
+
+import torch
+
+from .adapt import StepBasedSchedule, resize, resize_cluster, resize_cluster_from_url, set_tree, step_based_schedule
+from .collective import (Handle, all_gather, all_reduce, all_reduce_, all_reduce_async_, barrier, broadcast_, consensus,
+                         wait_all_handles, wait_handle)
+from .monitor import NoiseScale, egress_rates, global_noise_scale
+from .p2p import request_variable, request_variable_with_template, save_variable, save_variables
+from .state import Counter, ExponentialMovingAverage, counter, exponential_moving_average
+from .topology import (cluster_size, get_neighbour_mask, get_peer_latencies, global_minimum_spanning_tree,
+                       minimum_spanning_tree_father, peer_info, rank, round_robin)
+
+
+def broadcast(t: torch.Tensor, root: int = 0) -> torch.Tensor:
+    return broadcast_(t.clone(), root)
+
+
+def group_all_reduce(ts: Sequence[torch.Tensor], op="sum") -> List[torch.Tensor]:
+    """All-reduce a list of tensors (None entries pass through, as in the reference's group_all_reduce)."""
+    return [None if t is None else all_reduce(t, op) for t in ts]
+
+
+def monitored_all_reduce(t: torch.Tensor, tree=None, op="sum") -> torch.Tensor:
+    """All-reduce that also feeds the strategy throughput statistics (calc_stats / check_interference)."""
+    from ..runtime import get_runtime
+
+    rt = get_runtime()
+    f = getattr(rt.control, "monitored_all_reduce_cpu_", None)
+    if t.is_cuda or f is None or rt.size == 1:
+        return all_reduce(t, op)
+    out = t.detach().clone().contiguous()
+    f(out, None if tree is None else [int(x) for x in (tree.tolist() if isinstance(tree, torch.Tensor) else tree)], op)
+    return out
+
+
+def fuse(ts: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Flatten + concatenate (reference: ops/__init__.py:29-33)."""
+    return torch.cat([t.reshape(-1) for t in ts])
+
+
+def defuse(y: torch.Tensor, shapes) -> List[torch.Tensor]:
+    """Inverse of `fuse` (reference: ops/__init__.py:36-46)."""
+    out, off = [], 0
+    for s in shapes:
+        n = 1
+        for d in s:
+            n *= int(d)
+        out.append(y[off:off + n].view(tuple(s)))
+        off += n
+    if off != y.numel():
+        raise ValueError("defuse: shapes do not cover the fused tensor")
+    return out

@@ -231,6 +231,10 @@ def broadcast_(x: torch.Tensor, root: int = 0, name: str = "") -> torch.Tensor:
         if not x.is_contiguous():
             x.copy_(flat.view(x.dtype).view(x.shape))
         return x
+    native = getattr(rt.control, "broadcast_cpu_", None)
+    if native is not None and root == 0 and x.is_contiguous():
+        native(x, name)  # graph broadcast from rank 0, zero-copy on the tensor's memory
+        return x
     data = x.contiguous().view(-1).view(torch.uint8).numpy().tobytes() if rt.rank == root else b""
     got = rt.control.broadcast_bytes(data, root)
     if rt.rank != root:
@@ -267,6 +271,9 @@ def all_gather(x: torch.Tensor, name: str = "") -> torch.Tensor:
 
         _run_on_comm(plane, run, (flat, out))
         return out
+    native = getattr(rt.control, "all_gather_cpu", None)
+    if native is not None:
+        return native(x.contiguous(), name)
     parts = rt.control.all_gather_bytes(x.contiguous().view(-1).view(torch.uint8).numpy().tobytes())
     for i, p in enumerate(parts):
         out[i].copy_(torch.frombuffer(bytearray(p), dtype=x.dtype).view(x.shape))

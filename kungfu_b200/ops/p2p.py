@@ -1,0 +1,95 @@
+"""Peer-to-peer model store ops.
+
+Reference: `save_variable(s)` / `request_variable(_with_template)` (srcs/python/kungfu/tensorflow/ops/p2p.py:4-26,
+local.py; kernels cpu/local.cpp:29-43, cpu/p2p_new.cpp:39-57). A request for an unknown name/version reports failure
+instead of raising (rchannel/handler/p2p.go:102-120).
+CPU tensors use the native runtime's blob store; CUDA tensors use a published double buffer in the symmetric arena
+that peers read directly over NVLink (`publish` / `pull` kernels).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from ..runtime import get_runtime
+
+_gpu_slots: Dict[str, dict] = {}
+
+
+def _gpu_slot(name: str, nbytes: int) -> dict:
+    slot = _gpu_slots.get(name)
+    if slot is None:
+        rt = get_runtime()
+        plane = rt.gpu
+        pad = (nbytes + 15) // 16 * 16
+        arena = plane.new_arena(2 * pad + (1 << 16), f"p2p:{name}", want_multicast=False)
+        slot = {"arena": arena, "pub0": arena.alloc(pad, 4096), "pub1": arena.alloc(pad, 4096), "ver": arena.alloc(256, 256),
+                "nbytes": pad, "done": torch.zeros(4, dtype=torch.int32, device=plane.device),
+                "ok": torch.zeros(4, dtype=torch.int32, device=plane.device),
+                "stage": torch.zeros(pad, dtype=torch.uint8, device=plane.device)}
+        _gpu_slots[name] = slot
+    if slot["nbytes"] < nbytes:
+        raise ValueError(f"p2p slot {name!r} was created with {slot['nbytes']} bytes < {nbytes}")
+    return slot
+
+
+def save_variable(t: torch.Tensor, name: str, version: Optional[int] = None) -> None:
+    """Publish `t` under `name` so that peers can `request_variable` it. Collective on first use for CUDA tensors
+    (every rank must create the slot)."""
+    rt = get_runtime()
+    if t.is_cuda:
+        nb = t.numel() * t.element_size()
+        s = _gpu_slot(name, nb)
+        st = torch.cuda.current_stream()
+        s["stage"][:nb].copy_(t.detach().contiguous().view(-1).view(torch.uint8), non_blocking=True)
+        rt.gpu.ext.publish(s["arena"].mesh, 1, s["pub0"], s["pub1"], s["ver"], s["stage"].data_ptr(), s["nbytes"], s["done"].data_ptr(),
+                           16, 512, st.cuda_stream)
+        return
+    f = getattr(rt.control, "save", None)
+    if f is None:
+        _local_store[(name, version)] = t.detach().clone()
+        return
+    f(name, t.detach(), None if version is None else str(version))
+
+
+_local_store: Dict[Tuple[str, Optional[int]], torch.Tensor] = {}
+
+
+def request_variable(target: int, name: str, shape=None, dtype=None, version: Optional[int] = None,
+                     template: Optional[torch.Tensor] = None, device=None) -> Tuple[bool, torch.Tensor]:
+    """Pull the blob `name` last saved by rank `target`. Returns (ok, tensor); ok is False (tensor untouched/zero)
+    when the target has nothing under that name/version."""
+    rt = get_runtime()
+    if template is not None:
+        shape, dtype, device = template.shape, template.dtype, template.device
+    out = torch.zeros(tuple(shape), dtype=dtype, device=device or "cpu")
+    if out.is_cuda:
+        nb = out.numel() * out.element_size()
+        s = _gpu_slot(name, nb)
+        st = torch.cuda.current_stream()
+        tmp = torch.empty(s["nbytes"], dtype=torch.uint8, device=out.device)
+        rt.gpu.ext.pull(s["arena"].mesh, 1, int(target), s["pub0"], s["pub1"], s["ver"], tmp.data_ptr(), s["nbytes"], s["ok"].data_ptr(),
+                        16, 512, st.cuda_stream)
+        ok = int(s["ok"][0].item()) != 0
+        if ok:
+            out.view(-1).view(torch.uint8).copy_(tmp[:nb])
+        return ok, out
+    f = getattr(rt.control, "request", None)
+    if f is None:
+        t = _local_store.get((name, version))
+        if t is None or target != rt.rank:
+            return False, out
+        out.copy_(t)
+        return True, out
+    ok = f(int(target), name, out, None if version is None else str(version))
+    return bool(ok), out
+
+
+def request_variable_with_template(target: int, template: torch.Tensor, name: str, version: Optional[int] = None):
+    return request_variable(target, name, version=version, template=template)
+
+
+def save_variables(tensors, names, version: Optional[int] = None) -> None:
+    for t, n in zip(tensors, names):
+        save_variable(t, n, version)

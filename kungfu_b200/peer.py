@@ -26,13 +26,19 @@ def native_available() -> bool:
 
 
 _OPS = {"sum": dtypes.SUM, "min": dtypes.MIN, "max": dtypes.MAX, "prod": dtypes.PROD}
-_seq = itertools.count()
+_seq = {"version": None, "count": itertools.count()}
 
 
-def _auto_name(prefix: str, name: str) -> str:
+def _auto_name(prefix: str, name: str, version: int = 0) -> str:
     """Unique op names: the rendezvous key is (peer, name), so two in-flight ops must never share one
-    (reference: Appendix B — concurrency safety comes from unique tensor names)."""
-    return name if name else f"{prefix}::{next(_seq)}"
+    (reference: Appendix B — concurrency safety comes from unique tensor names). Numbering restarts with every
+    cluster version so that survivors and late joiners of an elastic job generate the same names."""
+    if name:
+        return name
+    if _seq["version"] != version:
+        _seq["version"] = version
+        _seq["count"] = itertools.count()
+    return f"{prefix}::v{version}::{next(_seq['count'])}"
 
 
 class NativeControl(Control):
@@ -40,6 +46,7 @@ class NativeControl(Control):
 
     def __init__(self, peer) -> None:
         self.peer = peer
+        self._version = 0
         self.peer.start()
         self._refresh()
         try:
@@ -63,6 +70,7 @@ class NativeControl(Control):
         self.size = self.peer.size()
         self.local_rank = self.peer.local_rank()
         self.local_size = self.peer.local_size()
+        self._version = self.peer.cluster_version()
 
     # ---- identity -------------------------------------------------------------------------------------
     def uid(self) -> int:
@@ -95,49 +103,49 @@ class NativeControl(Control):
 
     def all_reduce_cpu_(self, t: torch.Tensor, op: str = "sum", name: str = "") -> torch.Tensor:
         assert not t.is_cuda and t.is_contiguous()
-        self.peer.all_reduce(t.data_ptr(), t.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _OPS[op], _auto_name("allreduce", name))
+        self.peer.all_reduce(t.data_ptr(), t.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _OPS[op], _auto_name("allreduce", name, self._version))
         return t
 
     def all_reduce_cpu_async_(self, t: torch.Tensor, op: str = "sum", name: str = "") -> int:
         assert not t.is_cuda and t.is_contiguous()
         return self.peer.all_reduce_async(t.data_ptr(), t.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _OPS[op],
-                                          _auto_name("allreduce", name))
+                                          _auto_name("allreduce", name, self._version))
 
     def monitored_all_reduce_cpu_(self, t: torch.Tensor, tree: Optional[List[int]] = None, op: str = "sum", name: str = "") -> torch.Tensor:
         self.peer.monitored_all_reduce(t.data_ptr(), t.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _OPS[op],
-                                       _auto_name("mallreduce", name), list(tree or []))
+                                       _auto_name("mallreduce", name, self._version), list(tree or []))
         return t
 
     def cross_all_reduce_cpu_(self, t: torch.Tensor, op: str = "sum", name: str = "") -> torch.Tensor:
-        self.peer.cross_all_reduce(t.data_ptr(), t.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _OPS[op], _auto_name("xallreduce", name))
+        self.peer.cross_all_reduce(t.data_ptr(), t.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _OPS[op], _auto_name("xallreduce", name, self._version))
         return t
 
     def reduce_cpu(self, t: torch.Tensor, op: str = "sum", name: str = "") -> torch.Tensor:
         out = torch.empty_like(t)
-        self.peer.reduce(t.data_ptr(), out.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _OPS[op], _auto_name("reduce", name))
+        self.peer.reduce(t.data_ptr(), out.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _OPS[op], _auto_name("reduce", name, self._version))
         return out
 
     def broadcast_cpu_(self, t: torch.Tensor, name: str = "") -> torch.Tensor:
-        self.peer.broadcast(t.data_ptr(), t.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _auto_name("bcast", name))
+        self.peer.broadcast(t.data_ptr(), t.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _auto_name("bcast", name, self._version))
         return t
 
     def local_reduce_cpu(self, t: torch.Tensor, op: str = "sum", name: str = "") -> torch.Tensor:
         out = t.clone()
-        self.peer.local_reduce(t.data_ptr(), out.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _OPS[op], _auto_name("lreduce", name))
+        self.peer.local_reduce(t.data_ptr(), out.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _OPS[op], _auto_name("lreduce", name, self._version))
         return out
 
     def local_broadcast_cpu_(self, t: torch.Tensor, name: str = "") -> torch.Tensor:
-        self.peer.local_broadcast(t.data_ptr(), t.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _auto_name("lbcast", name))
+        self.peer.local_broadcast(t.data_ptr(), t.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _auto_name("lbcast", name, self._version))
         return t
 
     def gather_cpu(self, t: torch.Tensor, name: str = "") -> Optional[torch.Tensor]:
         out = t.new_empty((self.size,) + tuple(t.shape)) if self.rank == 0 else t.new_empty((0,))
-        self.peer.gather(t.data_ptr(), out.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _auto_name("gather", name))
+        self.peer.gather(t.data_ptr(), out.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _auto_name("gather", name, self._version))
         return out if self.rank == 0 else None
 
     def all_gather_cpu(self, t: torch.Tensor, name: str = "") -> torch.Tensor:
         out = t.new_empty((self.size,) + tuple(t.shape))
-        self.peer.all_gather(t.data_ptr(), out.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _auto_name("allgather", name))
+        self.peer.all_gather(t.data_ptr(), out.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _auto_name("allgather", name, self._version))
         return out
 
     def all_reduce_int_max(self, x: int) -> int:

@@ -1,22 +1,29 @@
 """`kungfu.python` parity: process identity and online control.
 
-Reference: srcs/python/kungfu/python/__init__.py:17-155 (ctypes into libkungfu); here a thin layer over the
-`Runtime` singleton.
+Reference: srcs/python/kungfu/python/__init__.py:17-155 (ctypes into libkungfu / libkungfu_python): `uid, detached,
+current_rank, current_local_rank, current_cluster_size, current_local_size, run_barrier, propose_new_size,
+resize(n=None) -> (changed, detached), all_reduce_int_max, check_interference, calc_stats, log_stats,
+print_strategy_stats, show_cuda_version, show_nccl_version, _get_cuda_index, _get_other_ranks`.
+Here: a thin layer over the `Runtime` singleton (native C++ peer underneath).
 """
 from __future__ import annotations
+
+from typing import Optional, Tuple
 
 from ..runtime import get_runtime, reset_runtime
 
 
+def _ctl():
+    return get_runtime().control
+
+
 def uid() -> int:
-    rt = get_runtime()
-    f = getattr(rt.control, "uid", None)
+    f = getattr(_ctl(), "uid", None)
     return int(f()) if f else 0
 
 
 def detached() -> bool:
-    rt = get_runtime()
-    f = getattr(rt.control, "detached", None)
+    f = getattr(_ctl(), "detached", None)
     return bool(f()) if f else False
 
 
@@ -36,10 +43,73 @@ def current_local_size() -> int:
     return get_runtime().local_size
 
 
+def current_cluster_version() -> int:
+    f = getattr(_ctl(), "cluster_version", None)
+    return int(f()) if f else 0
+
+
 def run_barrier() -> None:
     from ..ops.collective import barrier
 
     barrier()
+
+
+def propose_new_size(new_size: int) -> None:
+    """Rank 0 asks the config server for a cluster of `new_size` workers (takes effect at the next `resize()`)."""
+    f = getattr(_ctl(), "propose_new_size", None)
+    if f is None:
+        raise RuntimeError("kungfu_b200: elastic control needs the native runtime (kungfu-run -w)")
+    f(int(new_size))
+
+
+def resize(n: Optional[int] = None) -> Tuple[bool, bool]:
+    """Resize the cluster to `n` workers (or to whatever the config server says when n is None).
+
+    Returns (changed, detached). After `changed` the caller re-syncs its step (all-reduce max) and state (broadcast from
+    rank 0); a `detached` worker must stop. Reference: kungfu.python.resize (python/__init__.py:96-116) ->
+    Peer::ResizeCluster (srcs/go/kungfu/peer/peer.go:227-263). GPU side: every symmetric arena re-discovers its peers
+    and rebuilds the mappings (PeerMesh::connect), the counterpart of ResetNcclHelper.
+    """
+    rt = get_runtime()
+    f = getattr(rt.control, "resize", None)
+    if f is None:
+        return False, False
+    if rt._gpu is not None:
+        import torch
+
+        torch.cuda.synchronize()
+    changed, det = f(n)
+    if changed and not det and rt._gpu is not None:
+        rt._gpu.reconnect_all()
+    return changed, det
+
+
+def all_reduce_int_max(x: int) -> int:
+    f = getattr(_ctl(), "all_reduce_int_max", None)
+    return int(f(int(x))) if f else int(x)
+
+
+def check_interference() -> bool:
+    f = getattr(_ctl(), "check_interference", None)
+    return bool(f()) if f else False
+
+
+def calc_stats() -> None:
+    f = getattr(_ctl(), "calc_stats", None)
+    if f:
+        f()
+
+
+def log_stats() -> None:
+    f = getattr(_ctl(), "log_stats", None)
+    if f:
+        f()
+
+
+def print_strategy_stats() -> None:
+    f = getattr(_ctl(), "print_strategy_stats", None)
+    if f:
+        f()
 
 
 def _get_cuda_index() -> int:

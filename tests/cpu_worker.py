@@ -1,0 +1,366 @@
+"""CPU integration worker, run under `kungfu-run -np N` (the reference's model: every integration test is an ordinary
+program run by the launcher on loopback, scripts/tests/common.sh:14-25).
+
+Sub-commands mirror the reference's integration tests:
+  collectives  ≙ tests/python/integration/test_operators.py + tests/cpp/integration/fake_agent.cpp
+  p2p          ≙ tests/cpp/integration/test_p2p_apis.cpp + kungfu-test-public-apis (negative request test)
+  set_tree     ≙ tests/python/integration/test_set_tree.py
+  optimizers   ≙ tests/python/integration/test_optimizers.py (but with the values CHECKED against closed forms)
+  slp          ≙ tests/python/integration/test_mnist_slp.py (np-invariant result of S-SGD)
+  elastic      ≙ tests/python/integration/test_step_based_schedule.py / kungfu-fake-adaptive-trainer
+  recovery     ≙ examples/Failure_recovery_examples (automated here; the reference has no test)
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import kungfu_b200.python as kfp  # noqa: E402
+import kungfu_b200.torch as kf  # noqa: E402
+from kungfu_b200 import ops  # noqa: E402
+from kungfu_b200.ops import collective as coll  # noqa: E402
+from kungfu_b200.runtime import get_runtime  # noqa: E402
+
+DTYPES = [torch.float32, torch.float64, torch.float16, torch.bfloat16, torch.int32, torch.int64, torch.uint8, torch.int8, torch.int16]
+
+
+def check(cond, msg):
+    if not cond:
+        print("CHECK FAILED:", msg, flush=True)
+        sys.exit(3)
+
+
+def cmd_collectives(args):
+    rt = get_runtime()
+    n, r = rt.size, rt.rank
+    check(kfp.current_rank() == r and kfp.current_cluster_size() == n, "identity")
+    check(0 <= kfp.current_local_rank() < kfp.current_local_size() <= n, "local identity")
+    check(kfp.uid() != 0 or n == 1, "uid")
+    check(not kfp.detached(), "detached")
+    coll.barrier()
+    # all-reduce: y[i] = i * sum(ranks) style exact checks on every dtype / op
+    for dt in DTYPES:
+        base = (torch.arange(1000) % 5 + 1).to(dt)
+        x = (base * (r + 1)).to(dt) if dt != torch.uint8 else base.clone()
+        exp = base.to(torch.float64) * (sum(range(1, n + 1)) if dt != torch.uint8 else n)
+        y = ops.all_reduce(x, "sum")
+        check(torch.allclose(y.to(torch.float64), exp, rtol=2e-2 if dt in (torch.float16, torch.bfloat16) else 1e-9), f"sum {dt}")
+        check(torch.equal(ops.all_reduce(x, "max").to(torch.float64), (base * (n if dt != torch.uint8 else 1)).to(dt).to(torch.float64)), f"max {dt}")
+        check(torch.equal(ops.all_reduce(x, "min").to(torch.float64), base.to(torch.float64)), f"min {dt}")
+    p = ops.all_reduce(torch.full((7,), 2.0), "prod")
+    check(torch.equal(p, torch.full((7,), 2.0 ** n)), "prod")
+    # multi-chunk (> 1 MiB) message, 1-byte message, averaging, in-place async with names
+    big = torch.arange(700001, dtype=torch.int64) * (r + 1)
+    coll.all_reduce_(big, "sum")
+    check(torch.equal(big, torch.arange(700001, dtype=torch.int64) * sum(range(1, n + 1))), "big int64")
+    one = torch.tensor([r], dtype=torch.uint8)
+    check(int(ops.all_reduce(one, "max")) == n - 1, "1 byte")
+    avg = ops.all_reduce(torch.full((33,), float(r)), "avg")
+    check(torch.allclose(avg, torch.full((33,), (n - 1) / 2.0)), "avg")
+    ts = [torch.full((17 + i,), float(r + i)) for i in range(8)]
+    hs = [kf.ops.inplace_all_reduce_async_op(t, f"t{i}") for i, t in enumerate(ts)]
+    kf.ops.wait_all_handles(hs)
+    for i, t in enumerate(ts):
+        check(torch.allclose(t, torch.full((17 + i,), float(sum(range(n)) + n * i))), f"async {i}")
+    # group all-reduce incl. None
+    g = ops.group_all_reduce([torch.ones(3), None, torch.ones(2) * r])
+    check(g[1] is None and torch.equal(g[0], torch.ones(3) * n), "group")
+    # broadcast / all_gather / consensus
+    b = torch.full((1000,), float(r + 5))
+    coll.broadcast_(b, 0)
+    check(torch.equal(b, torch.full((1000,), 5.0)), "broadcast root 0")
+    b2 = torch.full((10,), float(r))
+    coll.broadcast_(b2, n - 1)
+    check(torch.equal(b2, torch.full((10,), float(n - 1))), "broadcast root n-1")
+    ag = kf.ops.all_gather(torch.full((2, 3), float(r)))
+    check(ag.shape == (n, 2, 3) and all(torch.equal(ag[i], torch.full((2, 3), float(i))) for i in range(n)), "all_gather")
+    check(ops.consensus(torch.ones(4)) is True, "consensus same")
+    check(ops.consensus(torch.full((4,), float(r))) == (n == 1), "consensus differs")
+    check(rt.control.consensus(b"x" * (r + 1)) == (n == 1), "consensus length differs")
+    check(kfp.all_reduce_int_max(r * 10) == (n - 1) * 10, "int max")
+    # reduce / gather / local / cross via the native control plane
+    c = rt.control
+    if hasattr(c, "reduce_cpu"):
+        red = c.reduce_cpu(torch.full((5,), float(r + 1)))
+        if r == 0:
+            check(torch.equal(red, torch.full((5,), float(sum(range(1, n + 1))))), "reduce")
+        gat = c.gather_cpu(torch.full((3,), float(r)))
+        if r == 0:
+            check(all(torch.equal(gat[i], torch.full((3,), float(i))) for i in range(n)), "gather")
+        lr = c.local_reduce_cpu(torch.full((4,), 1.0))
+        if c.local_rank == 0:
+            check(torch.equal(lr, torch.full((4,), float(c.local_size))), "local reduce")
+        lb = torch.full((4,), float(r))
+        c.local_broadcast_cpu_(lb)
+        x = torch.full((6,), float(r + 1))
+        c.cross_all_reduce_cpu_(x)
+        check(torch.equal(x, torch.full((6,), float(r + 1))) or c.host_count() > 1, "cross all-reduce on one host is identity")
+        lat = ops.get_peer_latencies()
+        check(lat.shape == (n,) and float(lat[r]) == 0.0 and all(float(v) >= 0 for v in lat), "latencies")
+        _ = ops.egress_rates()
+        m = ops.monitored_all_reduce(torch.ones(1 << 18, dtype=torch.int64))
+        check(torch.equal(m, torch.full((1 << 18,), n, dtype=torch.int64)), "monitored")
+        kfp.calc_stats(); kfp.log_stats(); kfp.print_strategy_stats()
+        check(kfp.check_interference() is False, "first interference check takes the reference window")
+    coll.barrier()
+    print(json.dumps({"ok": True, "rank": r, "size": n}), flush=True)
+
+
+def cmd_p2p(args):
+    rt = get_runtime()
+    n, r = rt.size, rt.rank
+    me = torch.full((1024,), float(r + 1))
+    ops.save_variable(me, "model")
+    for v in range(3):
+        ops.save_variable(me * (v + 1), "vmodel", version=v)
+    coll.barrier()
+    tgt = (r + 1) % n
+    ok, got = ops.request_variable(tgt, "model", (1024,), torch.float32)
+    check(ok and torch.equal(got, torch.full((1024,), float(tgt + 1))), "request")
+    ok, got = ops.request_variable(tgt, "vmodel", (1024,), torch.float32, version=2)
+    check(ok and torch.equal(got, torch.full((1024,), float(tgt + 1) * 3)), "versioned request")
+    ok, _ = ops.request_variable(tgt, "no-such-name", (4,), torch.float32)
+    check(ok is False, "unknown name must fail softly")
+    ok, _ = ops.request_variable(tgt, "vmodel", (1024,), torch.float32, version=99)
+    check(ok is False, "unknown version must fail softly")
+    # window of 3 versions: version 0 is gone after saving version 3
+    ops.save_variable(me, "vmodel", version=3)
+    coll.barrier()
+    ok, _ = ops.request_variable(tgt, "vmodel", (1024,), torch.float32, version=0)
+    check(ok is False, "versioned store keeps a sliding window of 3")
+    coll.barrier()
+    print(json.dumps({"ok": True}), flush=True)
+
+
+def cmd_set_tree(args):
+    import random
+
+    rt = get_runtime()
+    n, r = rt.size, rt.rank
+    rng = random.Random(1234)  # same trees on every rank
+    times = []
+    for it in range(16):
+        father = [0] * n
+        order = list(range(n))
+        rng.shuffle(order)
+        father[order[0]] = order[0]
+        for i in range(1, n):
+            father[order[i]] = order[rng.randrange(i)]
+        t0 = time.time()
+        ops.set_tree(father)
+        times.append(time.time() - t0)
+        x = ops.all_reduce(torch.full((4096,), float(r + 1)))
+        check(torch.equal(x, torch.full((4096,), float(sum(range(1, n + 1))))), f"all-reduce after set_tree {father}")
+    # latency-driven MST -> set_tree
+    lat = ops.get_peer_latencies()
+    father = ops.minimum_spanning_tree_father(lat)
+    check(len(father) == n and father[0] == 0, "mst father")
+    ops.set_tree(father)
+    edges = ops.global_minimum_spanning_tree(lat)
+    check(edges.shape == (max(0, n - 1), 2), "mst edges")
+    mask = ops.get_neighbour_mask(edges)
+    check(mask.shape == (n,), "neighbour mask")
+    x = ops.all_reduce(torch.ones(10))
+    check(torch.equal(x, torch.full((10,), float(n))), "all-reduce on the MST")
+    if r == 0:
+        print(f"set_tree latency: mean {1e3 * sum(times) / len(times):.2f}ms min {1e3 * min(times):.2f}ms max {1e3 * max(times):.2f}ms", flush=True)
+    print(json.dumps({"ok": True}), flush=True)
+
+
+def _slp():
+    torch.manual_seed(0)
+    m = torch.nn.Linear(20, 5)
+    with torch.no_grad():
+        m.weight.zero_()
+        m.bias.zero_()
+    return m
+
+
+def _data(total=240):
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(total, 20, generator=g)
+    w = torch.randn(20, 5, generator=g)
+    y = (x @ w).argmax(1)
+    return x, y
+
+
+def cmd_optimizers(args):
+    """Closed-form checks of S-SGD / SMA / PairAveraging on CPU tensors (the reference only smoke-runs them)."""
+    rt = get_runtime()
+    n, r = rt.size, rt.rank
+    lr = 0.1
+    # --- analytic S-SGD: f(x) = x^2 on every rank => x_k = (1 - 2 lr)^k x_0 (≙ v1/examples/__main__.py:26-46)
+    x = torch.nn.Parameter(torch.tensor([1.0]))
+    opt = kf.optimizers.SynchronousSGDOptimizer(torch.optim.SGD([x], lr=lr), named_parameters=[("x", x)])
+    for k in range(5):
+        opt.zero_grad()
+        (x * x).sum().backward()
+        opt.step()
+    check(abs(float(x) - (1 - 2 * lr) ** 5) < 1e-6, f"analytic ssgd {float(x)}")
+    # op='sum' (the reference torch binding): gradient is n times larger
+    x = torch.nn.Parameter(torch.tensor([1.0]))
+    opt = kf.optimizers.SynchronousSGDOptimizer(torch.optim.SGD([x], lr=lr / n), named_parameters=[("x", x)], op="sum")
+    opt.zero_grad(); (x * x).sum().backward(); opt.step()
+    check(abs(float(x) - (1 - 2 * lr)) < 1e-6, "sum semantics")
+    # --- S-SGD with rank-dependent gradients == averaged gradient
+    w = torch.nn.Parameter(torch.zeros(4))
+    opt = kf.optimizers.SynchronousSGDOptimizer(torch.optim.SGD([w], lr=1.0), named_parameters=[("w", w)])
+    opt.zero_grad(); (w * float(r + 1)).sum().backward(); opt.step()
+    check(torch.allclose(w.data, torch.full((4,), -(n + 1) / 2.0)), "ssgd averaged gradient")
+    # --- SMA: v <- (1-a) v + a mean(v), then local gradient step
+    a = 0.1
+    v = torch.nn.Parameter(torch.full((3,), float(r)))
+    sma = kf.optimizers.SynchronousAveragingOptimizer(torch.optim.SGD([v], lr=0.5), named_parameters=[("v", v)], alpha=a)
+    sma.zero_grad(); (v * 2.0).sum().backward(); sma.step()
+    mean = (n - 1) / 2.0
+    check(torch.allclose(v.data, torch.full((3,), (1 - a) * r + a * mean - 0.5 * 2.0)), f"sma closed form {v.data}")
+    # --- PairAveraging, deterministic round-robin, one rank at a time
+    p = torch.nn.Parameter(torch.full((2,), float(10 * (r + 1))))
+    pa = kf.optimizers.PairAveragingOptimizer(torch.optim.SGD([p], lr=1.0), named_parameters=[("p", p)], peer_selection="roundrobin")
+    sim = [float(10 * (i + 1)) for i in range(n)]
+    pub = list(sim)
+    for k in range(n):
+        if k == r:
+            pa.zero_grad(); p.sum().backward(); pa.step()
+        elif n > 1 and not pa._kf_published:
+            rt.control.save(pa._kf_model_name, pa._kf_flat_cpu()); rt.control.barrier(); pa._kf_published = True
+        if n > 1:
+            tgt = (k + 1) % n
+            sim[k] = 0.5 * (sim[k] + pub[tgt]) - 1.0
+        else:
+            sim[k] = sim[k] - 1.0
+        pub[k] = sim[k]
+        coll.barrier()
+    check(abs(float(p[0]) - sim[r]) < 1e-5, f"pair averaging {float(p[0])} vs {sim[r]}")
+    # --- monitors
+    q = torch.nn.Parameter(torch.zeros(8))
+    gns = kf.optimizers.MonitorGradientNoiseScaleOptimizer(torch.optim.SGD([q], lr=0.01), named_parameters=[("q", q)], device_batch_size=4)
+    for k in range(3):
+        gns.zero_grad(); ((q - float(r + k)) ** 2).sum().backward(); gns.step()
+    _ = gns.noise_scale()
+    var = kf.optimizers.MonitorGradientVarianceOptimizer(torch.optim.SGD([q], lr=0.0), named_parameters=[("q", q)])
+    var.zero_grad(); (q * float(r)).sum().backward(); var.step()
+    # grads: g_r = r per element; variance over ranks per element = mean(r^2) - mean(r)^2, summed over 8 elements
+    ev = 8 * (sum(i * i for i in range(n)) / n - ((n - 1) / 2.0) ** 2)
+    check(abs(var.variance() - ev) < 1e-4, f"variance {var.variance()} vs {ev}")
+    ada = kf.optimizers.AdaptiveSGDOptimizer(torch.optim.SGD([q], lr=0.01), named_parameters=[("q", q)], change_step=2)
+    for k in range(4):
+        ada.zero_grad(); (q * q).sum().backward(); ada.step()
+    check(ops.consensus(q.data), "after the switch to S-SGD every replica holds the same model")
+    print(json.dumps({"ok": True}), flush=True)
+
+
+def cmd_slp(args):
+    """S-SGD over np workers with global batch B ≡ one worker with batch B: the final weights must not depend on np."""
+    rt = get_runtime()
+    n, r = rt.size, rt.rank
+    m = _slp()
+    x, y = _data()
+    B = args.batch
+    check(B % n == 0, "global batch must divide evenly")
+    opt = kf.optimizers.SynchronousSGDOptimizer(torch.optim.SGD(m.parameters(), lr=0.1), named_parameters=m.named_parameters())
+    kf.broadcast_parameters(m.state_dict())
+    lb = B // n
+    for epoch in range(2):
+        for s in range(0, len(x) - B + 1, B):
+            xb, yb = x[s + r * lb:s + (r + 1) * lb], y[s + r * lb:s + (r + 1) * lb]
+            opt.zero_grad()
+            torch.nn.functional.cross_entropy(m(xb), yb).backward()
+            opt.step()
+    acc = float((m(x).argmax(1) == y).float().mean())
+    digest = float(m.weight.double().abs().sum() + m.bias.double().abs().sum())
+    if r == 0:
+        print(json.dumps({"slp": True, "np": n, "batch": B, "acc": round(acc, 6), "digest": round(digest, 6)}), flush=True)
+
+
+def cmd_elastic(args):
+    """Step-schedule driven resize under `kungfu-run -w`: sizes follow the schedule, state survives resizes."""
+    from kungfu_b200.elastic import KungFuElasticTrainHook
+
+    rt = get_runtime()
+    m = torch.nn.Linear(4, 2)
+    opt = kf.optimizers.SynchronousSGDOptimizer(torch.optim.SGD(m.parameters(), lr=0.01), named_parameters=m.named_parameters())
+    hook = KungFuElasticTrainHook(args.schedule, args.max_step, m, opt)
+    hook.begin()
+    seen = []
+    while True:
+        # every member applies the same number of steps: value == step count on all replicas
+        opt.zero_grad()
+        (m(torch.ones(3, 4)).sum() * 0).backward()
+        opt.step()
+        with torch.no_grad():
+            m.bias.add_(1.0)  # "training progress" that newcomers must inherit
+        seen.append((hook.state.step, kfp.current_cluster_size()))
+        check(ops.consensus(m.bias.data), f"replicas diverged at step {hook.state.step}")
+        want = hook.schedule(hook.state.step)
+        check(kfp.current_cluster_size() == want, f"step {hook.state.step}: size {kfp.current_cluster_size()} != schedule {want}")
+        if not hook.after_step():
+            break
+    if kfp.detached():
+        print(json.dumps({"detached": True, "step": hook.state.step}), flush=True)
+        return
+    if kfp.current_rank() == 0:
+        print(json.dumps({"elastic": True, "final_step": hook.state.step, "bias": float(m.bias[0]), "sizes": sorted(set(s for _, s in seen)),
+                          "resizes": len(hook.profiler.records)}), flush=True)
+        print(hook.profiler.report(), flush=True)
+
+
+def cmd_recovery(args):
+    """One rank stalls inside a batch once; the launcher's failure detector must restart the job, which resumes from the
+    checkpoint with the remaining epochs."""
+    from kungfu_b200 import checkpoint
+    from kungfu_b200.cmd import monitor_batch_begin, monitor_batch_end, monitor_epoch_end, monitor_train_end
+
+    rt = get_runtime()
+    r = rt.rank
+    m = torch.nn.Linear(2, 1)
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    ck = os.path.join(args.dir, "ckpt.pt")
+    meta = checkpoint.load(ck, m, opt) if args.restart else {"epoch": 0, "found": False}
+    start_epoch = meta["epoch"]
+    marker = os.path.join(args.dir, "crashed")
+    for e in range(args.n_epochs):
+        for b in range(3):
+            monitor_batch_begin()
+            if r == 1 and not args.restart and e == 1 and b == 1 and not os.path.exists(marker):
+                open(marker, "w").write("x")
+                time.sleep(3600)  # a hung worker: never reports `end`
+            x = ops.all_reduce(torch.ones(1))
+            monitor_batch_end()
+        monitor_epoch_end()
+        checkpoint.save(ck, m, opt, epoch=start_epoch + e + 1)
+    monitor_train_end()
+    if r == 0:
+        print(json.dumps({"recovered": bool(args.restart), "epochs_run_now": args.n_epochs, "start_epoch": start_epoch}), flush=True)
+    time.sleep(0.5)
+
+
+def cmd_bad(args):
+    rt = get_runtime()
+    if rt.rank == 0:
+        time.sleep(0.5)
+        sys.exit(7)
+    time.sleep(60)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what")
+    ap.add_argument("--batch", type=int, default=60)
+    ap.add_argument("--schedule", default="1:3,2:3,4:3,2:3,1:3")
+    ap.add_argument("--max-step", type=int, default=15)
+    ap.add_argument("--dir", default="/tmp")
+    ap.add_argument("--n-epochs", type=int, default=3)
+    ap.add_argument("--restart", type=int, default=0)
+    args = ap.parse_args()
+    globals()["cmd_" + args.what](args)
+
+
+if __name__ == "__main__":
+    main()
