@@ -38,6 +38,15 @@ ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH_FLAGS + ["-ccbin", CXX, "-lineinfo", "-O3", "-std=c++17", "--use_fast_math", "-Xcompiler", "-fPIC", "-Xcompiler",
                            "-fvisibility=hidden", "--expt-relaxed-constexpr", "-diag-suppress", "177,550,2361"]
 CXX_FLAGS = ["-O2", "-g", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", "-pthread", "-fvisibility=hidden"]
+LINK_FLAGS: list[str] = []
+# Sanitizer presets for the C++ runtime (the reference configures none): KUNGFU_SANITIZE=thread | address
+_san = os.environ.get("KUNGFU_SANITIZE", "")
+if _san in ("thread", "address"):
+    _f = ["-fsanitize=" + ("thread" if _san == "thread" else "address,undefined"), "-fno-omit-frame-pointer"]
+    CXX_FLAGS += _f
+    LINK_FLAGS += _f
+    OBJ = PKG / ("build-" + _san)
+    BIN = PKG / ("bin-" + _san)
 
 
 def _pybind_includes() -> list[str]:
@@ -122,7 +131,8 @@ def build_runtime(verbose: bool = False, force: bool = False) -> Path | None:
     srcs = sorted(rdir.glob("*.cpp"))
     if not srcs:
         return None
-    out = PKG / ("_kfrt" + _ext_suffix())
+    out = (PKG if not _san else OBJ) / ("_kfrt" + _ext_suffix())
+    OBJ.mkdir(parents=True, exist_ok=True)
     hdrs = _headers(rdir, ldir)
     inc = ["-I" + str(rdir)] + _pybind_includes()
     jobs, objs = [], []
@@ -139,7 +149,7 @@ def build_runtime(verbose: bool = False, force: bool = False) -> Path | None:
         for f in futs:
             changed |= bool(f.result())
     if changed or not out.exists():
-        _run([CXX, "-shared", "-o", str(out)] + [str(o) for o in objs] + ["-pthread", "-ldl"])
+        _run([CXX, "-shared", "-o", str(out)] + [str(o) for o in objs] + LINK_FLAGS + ["-pthread", "-ldl"])
         if verbose:
             print(f"[kungfu_b200] linked {out.name}")
     # launcher + tools: every launcher/*.cpp with a main() links against the runtime objects (minus bindings)
@@ -150,7 +160,7 @@ def build_runtime(verbose: bool = False, force: bool = False) -> Path | None:
         obj = OBJ / "launcher" / (cpp.stem + ".o")
         c = _compile(cpp, obj, [CXX] + CXX_FLAGS + ["-I" + str(rdir), "-I" + str(ldir), "-c", str(cpp), "-o", str(obj)], hdrs)
         if c or changed or not exe.exists():
-            _run([CXX, "-o", str(exe), str(obj)] + lib_objs + ["-pthread", "-ldl"])
+            _run([CXX, "-o", str(exe), str(obj)] + lib_objs + LINK_FLAGS + ["-pthread", "-ldl"])
             if verbose:
                 print(f"[kungfu_b200] linked bin/{exe.name}")
     return out

@@ -1,0 +1,127 @@
+// kungfu-fake-agent — C++ integration program over the C ABI, run under `kungfu-run -np N -strategy S`.
+//
+// Reference: tests/cpp/integration/fake_agent.cpp:15-205 (AllReduce correctness y[i] = i*np, Reduce / AllReduce
+// micro-bench loops, Gather, AllGatherTransform + distributed MST) and test_p2p_apis.cpp:7-38 (versioned Save -> Barrier
+// -> Request). Also the model-shaped all-reduce micro-benchmark of `kungfu-bench-allreduce`
+// (tests/go/cmd/kungfu-bench-allreduce/kungfu-bench-allreduce.go:73-110): prints
+// `RESULT: <rate> GiB/s` with the reference's "equivalent data rate" 4(np-1)*S/t.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "capi.h"
+#include "graph.hpp"
+
+#define CHECK(cond)                                                                   \
+    do {                                                                              \
+        if (!(cond)) {                                                                \
+            fprintf(stderr, "CHECK FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);   \
+            exit(3);                                                                  \
+        }                                                                             \
+    } while (0)
+
+static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// gradient tensor sizes of the reference's fake models (srcs/python/kungfu/tensorflow/v1/benchmarks/model_sizes.py)
+static std::vector<size_t> model_sizes(const std::string& name) {
+    if (name == "vgg16")
+        return {1728, 64, 36864, 64, 73728, 128, 147456, 128, 294912, 256, 589824, 256, 589824, 256, 1179648, 512, 2359296, 512, 2359296, 512,
+                2359296, 512, 2359296, 512, 2359296, 512, 102760448, 4096, 16777216, 4096, 4096000, 1000};
+    if (name == "slp") return {7840, 10};
+    // resnet50-like: 161 tensors, 25.5M elements (conv / bn / fc of the torchvision model)
+    std::vector<size_t> v = {9408, 64, 64};
+    auto block = [&](size_t in, size_t mid, size_t out, bool down) {
+        v.insert(v.end(), {in * mid, mid, mid, mid * mid * 9, mid, mid, mid * out, out, out});
+        if (down) v.insert(v.end(), {in * out, out, out});
+    };
+    size_t in = 64;
+    const size_t mids[4] = {64, 128, 256, 512};
+    const int reps[4] = {3, 4, 6, 3};
+    for (int s = 0; s < 4; ++s)
+        for (int b = 0; b < reps[s]; ++b) {
+            block(in, mids[s], mids[s] * 4, b == 0);
+            in = mids[s] * 4;
+        }
+    v.insert(v.end(), {2048 * 1000, 1000});
+    return v;
+}
+
+int main(int argc, char** argv) {
+    std::string mode = argc > 1 ? argv[1] : "test";
+    std::string model = argc > 2 ? argv[2] : "resnet50";
+    CHECK(kungfu_init() == 0);
+    const int np = kungfu_size(), rank = kungfu_rank();
+    if (mode == "test") {
+        // all-reduce correctness: y[i] = i * np
+        for (size_t n : {1ul, 7ul, 1024ul, (size_t)3 << 18}) {
+            std::vector<int32_t> x(n), y(n, -1);
+            for (size_t i = 0; i < n; ++i) x[i] = (int32_t)(i % 1000);
+            CHECK(kungfu_all_reduce(x.data(), y.data(), n, KungFu_I32, KungFu_SUM, ("ar" + std::to_string(n)).c_str(), nullptr, nullptr) == 0);
+            for (size_t i = 0; i < n; ++i) CHECK(y[i] == (int32_t)(i % 1000) * np);
+        }
+        // gather + all_gather
+        std::vector<float> mine(3, (float)rank), all(3 * np, -1.f);
+        CHECK(kungfu_all_gather(mine.data(), all.data(), 3, KungFu_F32, "ag") == 0);
+        for (int r = 0; r < np; ++r) CHECK(all[3 * r] == (float)r);
+        std::vector<float> g(rank == 0 ? 3 * np : 0);
+        CHECK(kungfu_gather(mine.data(), g.data(), 3, KungFu_F32, "g") == 0);
+        if (rank == 0)
+            for (int r = 0; r < np; ++r) CHECK(g[3 * r + 2] == (float)r);
+        // AllGatherTransform: distributed MST over latencies (gather -> Prim -> same result everywhere)
+        std::vector<float> lat(np);
+        CHECK(kungfu_get_peer_latencies(lat.data(), np) == 0);
+        std::vector<float> allw((size_t)np * np);
+        CHECK(kungfu_all_gather(lat.data(), allw.data(), np, KungFu_F32, "mstw") == 0);
+        auto edges = kfrt::minimum_spanning_tree(std::vector<double>(allw.begin(), allw.end()), np);
+        CHECK((int)edges.size() == np - 1);
+        // p2p: versioned save -> barrier -> request; unknown blob must fail softly
+        std::vector<int32_t> blob(256, rank + 1), got(256, 0);
+        CHECK(kungfu_save_version("v1", "blob", blob.data(), blob.size() * 4) == 0);
+        CHECK(kungfu_barrier() == 0);
+        int ok = 0;
+        const int tgt = (rank + 1) % np;
+        CHECK(kungfu_request(tgt, "v1", "blob", got.data(), got.size() * 4, &ok) == 0 && ok == 1 && got[0] == tgt + 1);
+        CHECK(kungfu_request(tgt, "v9", "blob", got.data(), got.size() * 4, &ok) == 0 && ok == 0);
+        int agreed = 0;
+        CHECK(kungfu_consensus("abc", 3, "c", &agreed) == 0 && agreed == 1);
+        CHECK(kungfu_barrier() == 0);
+        if (rank == 0) printf("fake-agent ok np=%d\n", np);
+    } else {
+        // model-shaped all-reduce micro-benchmark (fused or per tensor)
+        const bool fuse = mode == "bench-fused";
+        auto sizes = model_sizes(model);
+        size_t total = 0;
+        for (auto s : sizes) total += s;
+        std::vector<float> buf(total, 1.0f), out(total);
+        const int warm = 2, iters = 8;
+        std::vector<double> rates;
+        for (int it = 0; it < warm + iters; ++it) {
+            kungfu_barrier();
+            const double t0 = now();
+            if (fuse) {
+                CHECK(kungfu_all_reduce(buf.data(), out.data(), total, KungFu_F32, KungFu_SUM, ("fused" + std::to_string(it)).c_str(), nullptr, nullptr) == 0);
+            } else {
+                size_t off = 0;
+                for (size_t i = 0; i < sizes.size(); ++i) {
+                    CHECK(kungfu_all_reduce(buf.data() + off, out.data() + off, sizes[i], KungFu_F32, KungFu_SUM,
+                                            ("t" + std::to_string(i) + "_" + std::to_string(it)).c_str(), nullptr, nullptr) == 0);
+                    off += sizes[i];
+                }
+            }
+            const double dt = now() - t0;
+            if (it >= warm) rates.push_back(4.0 * (np - 1) * total * 4 / dt / (1 << 30));
+        }
+        double mean = 0, var = 0;
+        for (double r : rates) mean += r / rates.size();
+        for (double r : rates) var += (r - mean) * (r - mean) / rates.size();
+        if (rank == 0)
+            printf("RESULT: %.3f +-%.3f {\"model\": \"%s\", \"np\": %d, \"fuse\": %s, \"unit\": \"GiB/s equivalent data rate\", \"tensors\": %zu, \"bytes\": %zu}\n",
+                   mean, 1.96 * std::sqrt(var), model.c_str(), np, fuse ? "true" : "false", sizes.size(), total * 4);
+    }
+    kungfu_finalize();
+    return 0;
+}

@@ -176,6 +176,41 @@ StallGuard::~StallGuard() {
     }
 }
 
+// ---- scope tracer ---------------------------------------------------------------------------------
+namespace {
+struct Tracer {
+    bool on = getenv_bool("KUNGFU_ENABLE_TRACE", false);
+    std::mutex mu;
+    std::map<std::string, std::pair<uint64_t, double>> scopes;
+    ~Tracer() {
+        if (on && !scopes.empty()) fprintf(stderr, "%s", report().c_str());
+    }
+    std::string report() {
+        std::lock_guard<std::mutex> g(mu);
+        std::string s = "[kungfu trace] scope                                   calls      total(ms)     mean(us)\n";
+        for (auto& kv : scopes)
+            s += strprintf("[kungfu trace] %-40s %8llu %14.3f %12.3f\n", kv.first.c_str(), (unsigned long long)kv.second.first,
+                           kv.second.second * 1e3, kv.second.first ? kv.second.second * 1e6 / kv.second.first : 0.0);
+        return s;
+    }
+};
+Tracer& tracer() {
+    static Tracer t;
+    return t;
+}
+} // namespace
+TraceScope::TraceScope(const char* name) : name_(name), t0_(tracer().on ? now_s() : 0) {}
+TraceScope::~TraceScope() {
+    Tracer& t = tracer();
+    if (!t.on) return;
+    const double d = now_s() - t0_;
+    std::lock_guard<std::mutex> g(t.mu);
+    auto& e = t.scopes[name_];
+    e.first += 1;
+    e.second += d;
+}
+std::string trace_report() { return tracer().report(); }
+
 std::string merge_errors(const std::vector<std::string>& errs, const std::string& hint) {
     std::string msg;
     int n = 0;

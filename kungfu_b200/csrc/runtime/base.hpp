@@ -103,6 +103,22 @@ private:
     uint64_t id_ = 0;
 };
 
+// ---------------------------------------------------------------------------------------------------
+// scope tracer (reference: TRACE_SCOPE / stdtracer, srcs/cpp/include/kungfu/utils/trace.hpp:2-16): per-scope call count
+// and accumulated time, active when KUNGFU_ENABLE_TRACE is truthy, summary via trace_report() / at exit.
+// ---------------------------------------------------------------------------------------------------
+class TraceScope {
+public:
+    explicit TraceScope(const char* name);
+    ~TraceScope();
+
+private:
+    const char* name_;
+    double t0_;
+};
+std::string trace_report();
+#define KF_TRACE_SCOPE(name) ::kfrt::TraceScope _kf_trace_scope_##__LINE__(name)
+
 double now_s();            // monotonic seconds
 uint64_t unix_time_ns();   // wall clock
 void sleep_ms(int ms);

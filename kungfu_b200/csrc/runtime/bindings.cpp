@@ -404,6 +404,21 @@ PYBIND11_MODULE(_kfrt, m) {
         })
         .def("ping", [](Peer& p, const std::string& target) { return p.client().ping(PeerID::parse(target)); }, py::call_guard<py::gil_scoped_release>());
 
+    // fire-and-forget control message from a process that is not a peer (≙ kungfu-test-util -kill / -propose,
+    // tests/go/cmd/kungfu-test-util/kungfu-test-util.go:28-35, and kungfu-notify-start)
+    m.def("send_control", [](const std::string& target, const std::string& name, const std::string& payload) {
+        py::gil_scoped_release rel;
+        Client c(PeerID{parse_ipv4("127.0.0.1"), 0});
+        c.send(PeerID::parse(target), name, payload.data(), payload.size(), kConnControl, kNoFlag);
+        c.close_all();
+    }, py::arg("target"), py::arg("name"), py::arg("payload") = "");
+    m.def("ping", [](const std::string& target) {
+        py::gil_scoped_release rel;
+        Client c(PeerID{parse_ipv4("127.0.0.1"), 0});
+        return c.ping(PeerID::parse(target));
+    });
+    m.def("trace_report", [] { return trace_report(); });
+
     m.def("wait", [](int64_t h) { handles().wait(h); }, py::call_guard<py::gil_scoped_release>());
     m.def("wait_all", [](const std::vector<int64_t>& hs) {
         for (auto h : hs) handles().wait(h);

@@ -121,6 +121,7 @@ void Session::run_strategies(const Workspace& w, const StratList& sl, bool monit
 }
 
 void Session::all_reduce(const Workspace& w) {
+    KF_TRACE_SCOPE("Session::all_reduce");
     StallGuard sg("AllReduce(" + w.name + ")");
     StratList sl;
     {
@@ -161,6 +162,7 @@ void Session::reduce(const Workspace& w) {
     run_graphs(w, gs, 1);
 }
 void Session::broadcast(const Workspace& w) {
+    KF_TRACE_SCOPE("Session::broadcast");
     StallGuard sg("Broadcast(" + w.name + ")");
     const Graph* gs[1] = {&global_[0].g.bcast};
     run_graphs(w, gs, 1);
@@ -175,6 +177,7 @@ void Session::local_broadcast(const Workspace& w) {
 }
 
 void Session::barrier() {
+    KF_TRACE_SCOPE("Session::barrier");
     StallGuard sg("Barrier");
     const int n = size();
     std::vector<uint8_t> a(n, 0), b(n, 0);
@@ -227,6 +230,7 @@ void Session::gather(const Workspace& w) {
 }
 
 void Session::all_gather(const Workspace& w) {
+    KF_TRACE_SCOPE("Session::all_gather");
     StallGuard sg("AllGather(" + w.name + ")");
     const size_t bytes = w.bytes();
     char* out = static_cast<char*>(w.recv);
