@@ -1,0 +1,83 @@
+"""kungfu-rrun / kungfu-distribute: SSH fan-out of `kungfu-run` (or any command) to every host of a job.
+
+Reference: srcs/go/cmd/kungfu-rrun, srcs/go/cmd/kungfu-distribute, srcs/go/utils/runner/remote/remote.go:22-131
+(`RunStaticKungFuJob` / `RunElasticKungFuJob`) and srcs/go/utils/ssh. One `ssh user@host kungfu-run -self <ip> -np N -H
+... prog args` per host, output prefixed per host, first failure cancels the rest.
+
+    python -m kungfu_b200.cmd.rrun -np 16 -H 10.0.0.1:8,10.0.0.2:8 [-u user] [-w] [--dry-run] prog args...
+"""
+from __future__ import annotations
+
+import argparse
+import shlex
+import subprocess
+import sys
+import threading
+from typing import List
+
+
+def build_commands(np: int, hosts: str, prog: List[str], user: str = "", watch: bool = False, strategy: str = "", extra: List[str] = (),
+                   kungfu_run: str = "kungfu-run") -> List[List[str]]:
+    """One ssh command line per host."""
+    cmds = []
+    for h in hosts.split(","):
+        ip = h.split(":")[0]
+        inner = [kungfu_run, "-self", ip, "-np", str(np), "-H", hosts]
+        if watch:
+            inner.append("-w")
+        if strategy:
+            inner += ["-strategy", strategy]
+        inner += list(extra) + list(prog)
+        target = f"{user}@{ip}" if user else ip
+        cmds.append(["ssh", "-o", "StrictHostKeyChecking=no", target, " ".join(shlex.quote(x) for x in inner)])
+    return cmds
+
+
+def distribute_commands(hosts: str, prog: List[str], user: str = "") -> List[List[str]]:
+    """kungfu-distribute: run the same command on every host."""
+    return [["ssh", "-o", "StrictHostKeyChecking=no", (f"{user}@" if user else "") + h.split(":")[0], " ".join(shlex.quote(x) for x in prog)]
+            for h in hosts.split(",")]
+
+
+def run_all(cmds: List[List[str]]) -> int:
+    procs = [subprocess.Popen(c, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for c in cmds]
+    rc = [0] * len(procs)
+
+    def pump(i: int) -> None:
+        for line in procs[i].stdout:  # type: ignore[union-attr]
+            sys.stdout.write(f"[{cmds[i][3]}] {line}")
+        rc[i] = procs[i].wait()
+        if rc[i] != 0:
+            for p in procs:
+                if p.poll() is None:
+                    p.terminate()  # the exact children we started
+
+    ts = [threading.Thread(target=pump, args=(i,)) for i in range(len(procs))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    return next((c for c in rc if c), 0)
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(prog="kungfu-rrun")
+    ap.add_argument("-np", type=int, default=1)
+    ap.add_argument("-H", dest="hosts", required=True)
+    ap.add_argument("-u", dest="user", default="")
+    ap.add_argument("-w", dest="watch", action="store_true")
+    ap.add_argument("-strategy", default="")
+    ap.add_argument("--distribute", action="store_true", help="kungfu-distribute: run the command itself on every host")
+    ap.add_argument("--dry-run", action="store_true")
+    ap.add_argument("prog", nargs=argparse.REMAINDER)
+    a = ap.parse_args(argv)
+    cmds = distribute_commands(a.hosts, a.prog, a.user) if a.distribute else build_commands(a.np, a.hosts, a.prog, a.user, a.watch, a.strategy)
+    if a.dry_run:
+        for c in cmds:
+            print(" ".join(shlex.quote(x) for x in c))
+        return 0
+    return run_all(cmds)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,98 @@
+"""BERT encoder (base / large) for the PairAveraging configuration of BASELINE.json ("BERT-large PairAveragingOptimizer
+async gossip"). The reference ships no BERT model — only a gradient-size list of BERT-base + Adam slots
+(srcs/python/kungfu/tensorflow/v1/benchmarks/model_sizes.py:27-81, tests/cpp/integration/bert.hpp) and a link to an external
+example (README.md:136-137); BERT-large shapes therefore come from this module: 24 layers, hidden 1024, 16 heads,
+≈335 M parameters. Attention uses `F.scaled_dot_product_attention` (library flash kernels); the gossip step over the
+1.3 GB parameter set is our `pair_avg_kernel`.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+@dataclass
+class BertConfig:
+    vocab_size: int = 30522
+    hidden: int = 1024
+    layers: int = 24
+    heads: int = 16
+    intermediate: int = 4096
+    max_position: int = 512
+    type_vocab: int = 2
+    num_labels: int = 2
+    dropout: float = 0.0
+
+    @staticmethod
+    def large() -> "BertConfig":
+        return BertConfig()
+
+    @staticmethod
+    def base() -> "BertConfig":
+        return BertConfig(hidden=768, layers=12, heads=12, intermediate=3072)
+
+    @staticmethod
+    def tiny() -> "BertConfig":
+        return BertConfig(vocab_size=1000, hidden=64, layers=2, heads=4, intermediate=128, max_position=64)
+
+
+class BertLayer(nn.Module):
+    def __init__(self, c: BertConfig) -> None:
+        super().__init__()
+        self.heads = c.heads
+        self.qkv = nn.Linear(c.hidden, 3 * c.hidden)
+        self.out = nn.Linear(c.hidden, c.hidden)
+        self.ln1 = nn.LayerNorm(c.hidden, eps=1e-12)
+        self.ff1 = nn.Linear(c.hidden, c.intermediate)
+        self.ff2 = nn.Linear(c.intermediate, c.hidden)
+        self.ln2 = nn.LayerNorm(c.hidden, eps=1e-12)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        B, S, H = x.shape
+        q, k, v = self.qkv(x).view(B, S, 3, self.heads, H // self.heads).permute(2, 0, 3, 1, 4)
+        a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H)
+        x = self.ln1(x + self.out(a))
+        return self.ln2(x + self.ff2(F.gelu(self.ff1(x))))
+
+
+class Bert(nn.Module):
+    def __init__(self, c: BertConfig) -> None:
+        super().__init__()
+        self.cfg = c
+        self.word = nn.Embedding(c.vocab_size, c.hidden)
+        self.pos = nn.Embedding(c.max_position, c.hidden)
+        self.typ = nn.Embedding(c.type_vocab, c.hidden)
+        self.ln = nn.LayerNorm(c.hidden, eps=1e-12)
+        self.layers = nn.ModuleList([BertLayer(c) for _ in range(c.layers)])
+        self.pooler = nn.Linear(c.hidden, c.hidden)
+        self.classifier = nn.Linear(c.hidden, c.num_labels)
+
+    def forward(self, ids: torch.Tensor) -> torch.Tensor:
+        B, S = ids.shape
+        pos = torch.arange(S, device=ids.device)
+        x = self.ln(self.word(ids) + self.pos(pos)[None] + self.typ.weight[0][None, None])
+        for l in self.layers:
+            x = l(x)
+        return self.classifier(torch.tanh(self.pooler(x[:, 0])))
+
+
+def bert_large() -> Bert:
+    return Bert(BertConfig.large())
+
+
+def bert_base() -> Bert:
+    return Bert(BertConfig.base())
+
+
+def parameter_sizes(c: BertConfig) -> List[int]:
+    """Parameter tensor sizes without instantiating the weights."""
+    H, I = c.hidden, c.intermediate
+    s = [c.vocab_size * H, c.max_position * H, c.type_vocab * H, H, H]
+    for _ in range(c.layers):
+        s += [3 * H * H, 3 * H, H * H, H, H, H, H * I, I, I * H, H, H, H]
+    s += [H * H, H, H * c.num_labels, c.num_labels]
+    return s

@@ -1,0 +1,131 @@
+"""Small tools and adapters: rrun command generation, ModelArts env parsing, test-util kill, examples smoke, C ABI tool."""
+import os
+import subprocess
+import sys
+import time
+
+import torch
+
+from test_runtime_multiproc import ROOT, kungfu_run, launch, ports
+
+
+def test_rrun_command_generation():
+    from kungfu_b200.cmd import rrun
+
+    cmds = rrun.build_commands(16, "10.0.0.1:8,10.0.0.2:8", ["python3", "train.py", "--x", "a b"], user="ubuntu", watch=True, strategy="RING")
+    assert len(cmds) == 2 and cmds[0][:3] == ["ssh", "-o", "StrictHostKeyChecking=no"] and cmds[1][3] == "ubuntu@10.0.0.2"
+    assert "-self 10.0.0.2 -np 16 -H 10.0.0.1:8,10.0.0.2:8 -w -strategy RING python3 train.py --x 'a b'" in cmds[1][4]
+    d = rrun.distribute_commands("10.0.0.1:8,10.0.0.2:8", ["hostname"])
+    assert [c[3] for c in d] == ["10.0.0.1", "10.0.0.2"] and d[0][4] == "hostname"
+    assert rrun.main(["-np", "2", "-H", "127.0.0.1:2", "--dry-run", "echo", "hi"]) == 0
+
+
+def test_modelarts_env():
+    from kungfu_b200.platforms import modelarts
+
+    env = {"DLS_TASK_NUMBER": "2", "DLS_TASK_INDEX": "1", "BATCH_CUSTOM0_HOSTS": "10.1.0.1:6666", "BATCH_CUSTOM1_HOSTS": "10.1.0.2:6666"}
+    idx, runners, workers = modelarts.parse_env(env, slots=2)
+    assert idx == 1 and runners == ["10.1.0.1:38080", "10.1.0.2:38080"]
+    assert workers == ["10.1.0.1:10000", "10.1.0.1:10001", "10.1.0.2:10000", "10.1.0.2:10001"]
+    assert modelarts.kungfu_run_args(env, slots=2) == ["-np", "4", "-H", "10.1.0.1:2,10.1.0.2:2", "-self", "10.1.0.2"]
+
+
+def test_kill_worker_via_control_message():
+    """≙ `kungfu-test-util -kill ip:port`: the `exit` control message stops a worker (exit 0); its siblings then fail and the
+    launcher reports a non-zero status (fail-fast)."""
+    rport, prange = ports()
+    base = int(prange.split("-")[0])
+    cmd = [kungfu_run(), "-q", "-np", "2", "-H", "127.0.0.1:2", "-port", str(rport), "-port-range", prange, sys.executable,
+           os.path.join(ROOT, "tests", "cpu_worker.py"), "bad"]
+    # use sleeping workers: rank 0 of `bad` exits 7 after 0.5 s, so instead run a sleeper via python -c
+    code = "import sys,time; sys.path.insert(0,%r); import kungfu_b200.torch as kf; kf.run_barrier(); print('up', flush=True); time.sleep(60)" % ROOT
+    cmd = cmd[:-2] + ["-c", code]
+    p = subprocess.Popen(cmd, cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    from kungfu_b200 import _kfrt as rt
+
+    target = f"127.0.0.1:{base + 1}"
+    for _ in range(300):
+        if rt.ping(target) >= 0:
+            break
+        time.sleep(0.1)
+    time.sleep(1.0)
+    assert subprocess.call([sys.executable, "-m", "kungfu_b200.cmd.test_util", "--kill", target], cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT)) == 0
+    t0 = time.time()
+    while rt.ping(target) >= 0 and time.time() - t0 < 10:
+        time.sleep(0.1)
+    assert rt.ping(target) < 0, "worker should be gone"
+    p.terminate()
+    p.wait(timeout=20)
+
+
+def test_fake_agent_c_abi():
+    """C++ program over the C ABI under the launcher, ring strategy (≙ run-integration-tests.sh)."""
+    from kungfu_b200.cmd import _bin
+
+    r = launch(3, "unused", expect_rc=None, flags=())  # warm: ensures binaries are built
+    rport, prange = ports()
+    out = subprocess.run([kungfu_run(), "-q", "-np", "3", "-H", "127.0.0.1:3", "-port", str(rport), "-port-range", prange, "-strategy", "RING",
+                          _bin("kungfu-fake-agent"), "test"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
+    assert out.returncode == 0 and "fake-agent ok np=3" in out.stdout, out.stdout[-2000:]
+    out = subprocess.run([kungfu_run(), "-q", "-np", "2", "-H", "127.0.0.1:2", "-port", str(rport), "-port-range", prange,
+                          _bin("kungfu-fake-agent"), "bench", "slp"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
+    assert out.returncode == 0 and "RESULT:" in out.stdout, out.stdout[-2000:]
+
+
+def test_examples_and_microbench_run():
+    rport, prange = ports()
+    env = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN")
+    base = [kungfu_run(), "-q", "-np", "2", "-H", "127.0.0.1:2", "-port", str(rport), "-port-range", prange, sys.executable]
+    r = subprocess.run(base + [os.path.join(ROOT, "examples", "torch_mnist_example.py"), "--epochs", "1"], env=env, cwd=ROOT,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=180)
+    assert r.returncode == 0 and "acc" in r.stdout, r.stdout[-2000:]
+    r = subprocess.run(base + ["-m", "kungfu_b200.benchmarks", "--model", "slp", "--steps", "3"], env=env, cwd=ROOT,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=180)
+    assert r.returncode == 0 and "RESULT:" in r.stdout, r.stdout[-2000:]
+    r = subprocess.run(base + [os.path.join(ROOT, "examples", "adapt_strategy.py")], env=env, cwd=ROOT,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=180)
+    assert r.returncode == 0, r.stdout[-2000:]
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    from kungfu_b200 import checkpoint
+
+    m = torch.nn.Linear(3, 2)
+    opt = torch.optim.SGD(m.parameters(), lr=0.1, momentum=0.9)
+    m(torch.ones(1, 3)).sum().backward()
+    opt.step()
+    path = str(tmp_path / "c.pt")
+    assert checkpoint.save(path, m, opt, step=7, epoch=2, trained_samples=99, extra={"k": 1}) == path
+    m2 = torch.nn.Linear(3, 2)
+    opt2 = torch.optim.SGD(m2.parameters(), lr=0.1, momentum=0.9)
+    meta = checkpoint.load(path, m2, opt2)
+    assert meta["found"] and meta["step"] == 7 and meta["epoch"] == 2 and meta["trained_samples"] == 99 and meta["extra"] == {"k": 1}
+    assert all(torch.equal(a, b) for a, b in zip(m.parameters(), m2.parameters()))
+    assert checkpoint.load(str(tmp_path / "missing.pt"), m2)["found"] is False
+
+
+def test_policy_hook_scheduled_batch_size():
+    """≙ tests/python/unit/test_tensorflow_policy.py with scheduled_batch_size_policy.py."""
+    from kungfu_b200.elastic import PolicyHook, ScheduledBatchSizePolicy
+
+    hook = PolicyHook([ScheduledBatchSizePolicy({0: 10, 1: 20, 2: 50})], epoch_size=100, epoch_num=3, init_batch_size=10)
+    hook.begin()
+    sizes = []
+    while hook.before_step():
+        sizes.append(hook.batch_size)
+        hook.after_step()
+    hook.end()
+    assert sizes == [10] * 10 + [20] * 5 + [50] * 2
+    assert hook.vars["kungfu_trained_samples"] == 300 and hook.vars["epoch"] == 3
+
+
+def test_elastic_data_adaptor():
+    from kungfu_b200.elastic import ElasticDataAdaptor
+
+    data, labels = torch.arange(100).float().view(100, 1), torch.arange(100)
+    ad = ElasticDataAdaptor(data, labels, batch_size=8)
+    x, y = ad.next_batch()
+    assert y.tolist() == list(range(8)) and ad.offset == 8
+    ad.set_offset(96)
+    _, y = ad.next_batch()
+    assert y.tolist() == [96, 97, 98, 99, 0, 1, 2, 3]
