@@ -158,5 +158,24 @@ PYBIND11_MODULE(_kfcuda, m) {
     m.def("u8_normalize", [](uintptr_t src, uintptr_t dst, int ddt, size_t npix, uintptr_t mean3, uintptr_t invstd3, uintptr_t st) {
         launch_u8_normalize(P<const uint8_t>(src), P<void>(dst), ddt, npix, P<const float>(mean3), P<const float>(invstd3), S(st));
     });
+    m.def("bn_num_blocks", &bn_num_blocks);
+    m.def("bn_fwd", [](uintptr_t x, uintptr_t res, uintptr_t y, uintptr_t mask, int dtype, size_t rows, int C, uintptr_t gamma, uintptr_t beta,
+                       uintptr_t rmean, uintptr_t rvar, int pdtype, float eps, float momentum, int relu, uintptr_t partial, uintptr_t mean,
+                       uintptr_t invstd, uintptr_t scale, uintptr_t shift, uintptr_t st) {
+        launch_bn_fwd(P<const void>(x), P<const void>(res), P<void>(y), P<uint8_t>(mask), dtype, rows, C, P<const void>(gamma), P<const void>(beta),
+                      P<void>(rmean), P<void>(rvar), pdtype, eps, momentum, relu, P<float>(partial), P<float>(mean), P<float>(invstd), P<float>(scale),
+                      P<float>(shift), S(st));
+    });
+    m.def("bn_apply", [](uintptr_t x, uintptr_t res, uintptr_t y, uintptr_t mask, int dtype, size_t rows, int C, uintptr_t scale, uintptr_t shift,
+                         int relu, uintptr_t st) {
+        launch_bn_apply(P<const void>(x), P<const void>(res), P<void>(y), P<uint8_t>(mask), dtype, rows, C, P<const float>(scale), P<const float>(shift),
+                        relu, S(st));
+    });
+    m.def("bn_bwd", [](uintptr_t dy, uintptr_t x, uintptr_t mask, uintptr_t dx, uintptr_t dres, int dtype, size_t rows, int C, uintptr_t gamma,
+                       uintptr_t dgamma, uintptr_t dbeta, int pdtype, uintptr_t mean, uintptr_t invstd, int relu, uintptr_t partial, uintptr_t coef,
+                       uintptr_t st) {
+        launch_bn_bwd(P<const void>(dy), P<const void>(x), P<const uint8_t>(mask), P<void>(dx), P<void>(dres), dtype, rows, C, P<const void>(gamma),
+                      P<void>(dgamma), P<void>(dbeta), pdtype, P<const float>(mean), P<const float>(invstd), relu, P<float>(partial), P<float>(coef), S(st));
+    });
     m.def("fill_u32", [](uintptr_t p, uint32_t v, size_t n, uintptr_t st) { launch_fill_u32(P<uint32_t>(p), v, n, S(st)); });
 }

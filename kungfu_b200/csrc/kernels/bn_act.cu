@@ -1,0 +1,346 @@
+// kungfu_b200 — fused BatchNorm (+ residual add) + ReLU for channels_last activations, forward and backward.
+//
+// ResNet-50 training at batch 256 on a B200 spends ~40 % of the step in memory-bound BatchNorm / ReLU / add kernels
+// (profiles/resnet50_step_kernels.md). PyTorch runs them as separate passes: stats, normalise, relu, add in forward;
+// relu-backward, reduce, elementwise in backward = 13–16 activation-sized passes per BN layer. These kernels do the same
+// math in 8–10 passes: the normalise + add + ReLU of forward is one pass that also emits a 1-bit/element ReLU mask, and
+// backward needs only (dy, x, mask) — the saved output is never re-read.
+//
+// Layout: x is [rows = N*H*W, C] with C contiguous (channels_last), C % 8 == 0. One thread owns one 8-channel vector
+// (16 bytes of bf16) and strides over rows, so its per-channel coefficients live in registers. Cross-block reductions
+// are two-stage (per-block partials in a scratch buffer, reduced by the tiny finalize kernels): deterministic and free
+// of global atomics.
+//
+// The reference ships no model code; its benchmark uses the stock framework model (benchmarks/system/
+// benchmark_kungfu_torch.py:58). This is part of the "model family" layer of the new framework (models/resnet.py BNAct).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace kf {
+
+namespace {
+
+constexpr int kBnThreads = 256;
+
+template <typename T> struct Vec8 {
+    float f[8];
+    __device__ __forceinline__ void load(const T* p) {
+        const Vec16 v = ld_stream(p);
+        const AccVec<T> a = unpack<T>(v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = a.a[i];
+    }
+    __device__ __forceinline__ void store(T* p) const {
+        AccVec<T> a;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a.a[i] = f[i];
+        st_stream(p, pack<T>(a));
+    }
+};
+
+// ---- forward: per-block partial sums ------------------------------------------------------------------------
+// partial[block][0][c] = sum x, partial[block][1][c] = sum x^2 over the rows handled by the block
+template <typename T>
+__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restrict__ x, size_t rows, int C, float* __restrict__ partial) {
+    extern __shared__ float sm[]; // [2][C]
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int cvn = C / 8;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    const int cv = (int)(tid % cvn);
+    const size_t row0 = tid / cvn, rstride = nthreads / cvn;
+    float s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+    for (size_t r = row0; r < rows; r += rstride) {
+        Vec8<T> v;
+        v.load(x + r * C + (size_t)cv * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s[i] += v.f[i];
+            q[i] = fmaf(v.f[i], v.f[i], q[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        atomicAdd(&sm[cv * 8 + i], s[i]);
+        atomicAdd(&sm[C + cv * 8 + i], q[i]);
+    }
+    __syncthreads();
+    float* out = partial + (size_t)blockIdx.x * 2 * C;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) out[i] = sm[i];
+}
+
+// reduce partials, produce mean / invstd / scale / shift, update the running statistics
+template <typename P>
+__global__ void bn_fwd_finalize_kernel(const float* __restrict__ partial, int nblocks, size_t rows, int C, const P* __restrict__ gamma,
+                                       const P* __restrict__ beta, float eps, float momentum, float* __restrict__ mean_out,
+                                       float* __restrict__ invstd_out, float* __restrict__ scale_out, float* __restrict__ shift_out,
+                                       P* running_mean, P* running_var) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f, q = 0.f;
+    for (int b = 0; b < nblocks; ++b) {
+        s += partial[(size_t)b * 2 * C + c];
+        q += partial[(size_t)b * 2 * C + C + c];
+    }
+    const float m = (float)rows;
+    const float mean = s / m;
+    float var = q / m - mean * mean;
+    var = var < 0.f ? 0.f : var;
+    const float invstd = rsqrtf(var + eps);
+    const float g = gamma ? (float)Elem<P>::up(gamma[c]) : 1.f;
+    const float b = beta ? (float)Elem<P>::up(beta[c]) : 0.f;
+    mean_out[c] = mean;
+    invstd_out[c] = invstd;
+    scale_out[c] = g * invstd;
+    shift_out[c] = b - mean * g * invstd;
+    if (running_mean) {
+        const float unbiased = m > 1.f ? var * m / (m - 1.f) : var;
+        running_mean[c] = Elem<P>::down((1.f - momentum) * (float)Elem<P>::up(running_mean[c]) + momentum * mean);
+        running_var[c] = Elem<P>::down((1.f - momentum) * (float)Elem<P>::up(running_var[c]) + momentum * unbiased);
+    }
+}
+
+// y = relu(x * scale + shift (+ res)); mask byte per 8-channel vector (bit i = y_i > 0)
+template <typename T, bool RES, bool RELU>
+__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
+                                                              uint8_t* __restrict__ mask, size_t nvec, int C, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift) {
+    const int cvn = C / 8;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x; // multiple of cvn: the channel vector of a thread is fixed
+    const int cv = (int)(tid % cvn);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        sc[i] = __ldg(scale + cv * 8 + i);
+        sh[i] = __ldg(shift + cv * 8 + i);
+    }
+    for (size_t v = tid; v < nvec; v += stride) {
+        Vec8<T> a, r;
+        a.load(x + v * 8);
+        if constexpr (RES) r.load(res + v * 8);
+        uint32_t m = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float z = fmaf(a.f[i], sc[i], sh[i]);
+            if constexpr (RES) z += r.f[i];
+            if constexpr (RELU) {
+                m |= (z > 0.f ? 1u : 0u) << i;
+                z = z > 0.f ? z : 0.f;
+            }
+            a.f[i] = z;
+        }
+        a.store(y + v * 8);
+        if constexpr (RELU) mask[v] = (uint8_t)m;
+    }
+}
+
+// ---- backward ---------------------------------------------------------------------------------------------------
+// partial[block][0][c] = sum dz, partial[block][1][c] = sum dz * xhat, dz = dy masked by the ReLU bit
+template <typename T, bool RELU>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                   const uint8_t* __restrict__ mask, size_t rows, int C,
+                                                                   const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                   float* __restrict__ partial) {
+    extern __shared__ float sm[];
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    const int cvn = C / 8;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    const int cv = (int)(tid % cvn);
+    const size_t row0 = tid / cvn, rstride = nthreads / cvn;
+    float mu[8], is[8], s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        mu[i] = __ldg(mean + cv * 8 + i);
+        is[i] = __ldg(invstd + cv * 8 + i);
+        s[i] = q[i] = 0.f;
+    }
+    for (size_t r = row0; r < rows; r += rstride) {
+        const size_t v = r * cvn + cv;
+        Vec8<T> g, a;
+        g.load(dy + v * 8);
+        a.load(x + v * 8);
+        uint32_t m = 0xffu;
+        if constexpr (RELU) m = mask[v];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float dz = (m >> i) & 1u ? g.f[i] : 0.f;
+            s[i] += dz;
+            q[i] = fmaf(dz, (a.f[i] - mu[i]) * is[i], q[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        atomicAdd(&sm[cv * 8 + i], s[i]);
+        atomicAdd(&sm[C + cv * 8 + i], q[i]);
+    }
+    __syncthreads();
+    float* out = partial + (size_t)blockIdx.x * 2 * C;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) out[i] = sm[i];
+}
+
+// dgamma / dbeta (parameter dtype) and the per-channel coefficients of the elementwise pass:
+//   dx = a * (dz - b - xhat * c),  a = gamma * invstd, b = sum(dz) / M, c = sum(dz * xhat) / M
+template <typename P>
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, size_t rows, int C, const P* __restrict__ gamma,
+                                       const float* __restrict__ invstd, P* __restrict__ dgamma, P* __restrict__ dbeta,
+                                       float* __restrict__ coef /*[3][C]*/) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f, q = 0.f;
+    for (int b = 0; b < nblocks; ++b) {
+        s += partial[(size_t)b * 2 * C + c];
+        q += partial[(size_t)b * 2 * C + C + c];
+    }
+    if (dgamma) dgamma[c] = Elem<P>::down(q);
+    if (dbeta) dbeta[c] = Elem<P>::down(s);
+    const float g = gamma ? (float)Elem<P>::up(gamma[c]) : 1.f;
+    const float m = (float)rows;
+    coef[c] = g * invstd[c];
+    coef[C + c] = s / m;
+    coef[2 * C + c] = q / m;
+}
+
+template <typename T, bool RES, bool RELU>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                  const uint8_t* __restrict__ mask, T* __restrict__ dx, T* __restrict__ dres,
+                                                                  size_t nvec, int C, const float* __restrict__ mean,
+                                                                  const float* __restrict__ invstd, const float* __restrict__ coef) {
+    const int cvn = C / 8;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const int cv = (int)(tid % cvn);
+    float mu[8], is[8], ca[8], cb[8], cc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int c = cv * 8 + i;
+        mu[i] = __ldg(mean + c);
+        is[i] = __ldg(invstd + c);
+        ca[i] = __ldg(coef + c);
+        cb[i] = __ldg(coef + C + c);
+        cc[i] = __ldg(coef + 2 * C + c);
+    }
+    for (size_t v = tid; v < nvec; v += stride) {
+        Vec8<T> g, a;
+        g.load(dy + v * 8);
+        a.load(x + v * 8);
+        uint32_t m = 0xffu;
+        if constexpr (RELU) m = mask[v];
+        Vec8<T> dz;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float z = (m >> i) & 1u ? g.f[i] : 0.f;
+            dz.f[i] = z;
+            a.f[i] = ca[i] * (z - cb[i] - (a.f[i] - mu[i]) * is[i] * cc[i]);
+        }
+        a.store(dx + v * 8);
+        if constexpr (RES) dz.store(dres + v * 8);
+    }
+}
+
+int bn_grid(size_t nvec, int C) {
+    // every thread must keep a fixed channel vector: total threads is a multiple of C/8 (C/8 divides 256 or equals it)
+    size_t blocks = (nvec + (size_t)kBnThreads * 4 - 1) / ((size_t)kBnThreads * 4);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (C / 8 > kBnThreads) {
+        const size_t k = (C / 8) / kBnThreads; // blocks must come in groups of k
+        blocks = (blocks + k - 1) / k * k;
+    }
+    return (int)blocks;
+}
+
+void bn_check(size_t rows, int C) {
+    if (C <= 0 || C % 8 != 0) throw std::runtime_error("kungfu_b200 bn_act: C must be a positive multiple of 8");
+    const int cvn = C / 8;
+    if (!((cvn <= kBnThreads && kBnThreads % cvn == 0) || (cvn > kBnThreads && cvn % kBnThreads == 0)))
+        throw std::runtime_error("kungfu_b200 bn_act: C/8 must divide or be a multiple of 256");
+    if (2 * (size_t)C * sizeof(float) > 96 * 1024) throw std::runtime_error("kungfu_b200 bn_act: C too large");
+    (void)rows;
+}
+
+} // namespace
+
+int bn_num_blocks(size_t rows, int C) {
+    bn_check(rows, C);
+    return bn_grid(rows * (size_t)(C / 8), C);
+}
+
+#define KF_BN_T(dtype, CALL)                                                                   \
+    do {                                                                                       \
+        if (dtype == kBF16) { using T = __nv_bfloat16; CALL; }                                 \
+        else if (dtype == kF16) { using T = __half; CALL; }                                    \
+        else throw std::runtime_error("kungfu_b200 bn_act: activations must be bf16 or fp16"); \
+    } while (0)
+
+#define KF_BN_P(pdtype, CALL)                                                                           \
+    do {                                                                                                \
+        if (pdtype == kBF16) { using P = __nv_bfloat16; CALL; }                                         \
+        else if (pdtype == kF16) { using P = __half; CALL; }                                            \
+        else if (pdtype == kF32) { using P = float; CALL; }                                             \
+        else throw std::runtime_error("kungfu_b200 bn_act: parameters must be bf16, fp16 or fp32");     \
+    } while (0)
+
+void launch_bn_fwd(const void* x, const void* res, void* y, uint8_t* mask, int dtype, size_t rows, int C, const void* gamma, const void* beta,
+                   void* running_mean, void* running_var, int pdtype, float eps, float momentum, int relu, float* partial, float* mean,
+                   float* invstd, float* scale, float* shift, cudaStream_t st) {
+    bn_check(rows, C);
+    const size_t nvec = rows * (size_t)(C / 8);
+    const int blocks = bn_grid(nvec, C);
+    const size_t smem = 2 * (size_t)C * sizeof(float);
+    KF_BN_T(dtype, (bn_stats_kernel<T><<<blocks, kBnThreads, smem, st>>>((const T*)x, rows, C, partial)));
+    KF_BN_P(pdtype, (bn_fwd_finalize_kernel<P><<<(C + 127) / 128, 128, 0, st>>>(partial, blocks, rows, C, (const P*)gamma, (const P*)beta, eps,
+                                                                                momentum, mean, invstd, scale, shift, (P*)running_mean,
+                                                                                (P*)running_var)));
+    launch_bn_apply(x, res, y, mask, dtype, rows, C, scale, shift, relu, st);
+    count_launch(2);
+    KF_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_bn_apply(const void* x, const void* res, void* y, uint8_t* mask, int dtype, size_t rows, int C, const float* scale, const float* shift,
+                     int relu, cudaStream_t st) {
+    bn_check(rows, C);
+    const size_t nvec = rows * (size_t)(C / 8);
+    const int blocks = bn_grid(nvec, C);
+    if (relu && !mask) throw std::runtime_error("kungfu_b200 bn_act: relu needs a mask buffer");
+#define KF_BN_APPLY(RES, RELU) \
+    KF_BN_T(dtype, (bn_apply_kernel<T, RES, RELU><<<blocks, kBnThreads, 0, st>>>((const T*)x, (const T*)res, (T*)y, mask, nvec, C, scale, shift)))
+    if (res && relu) KF_BN_APPLY(true, true);
+    else if (res) KF_BN_APPLY(true, false);
+    else if (relu) KF_BN_APPLY(false, true);
+    else KF_BN_APPLY(false, false);
+#undef KF_BN_APPLY
+    count_launch();
+    KF_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_bn_bwd(const void* dy, const void* x, const uint8_t* mask, void* dx, void* dres, int dtype, size_t rows, int C, const void* gamma,
+                   void* dgamma, void* dbeta, int pdtype, const float* mean, const float* invstd, int relu, float* partial, float* coef,
+                   cudaStream_t st) {
+    bn_check(rows, C);
+    const size_t nvec = rows * (size_t)(C / 8);
+    const int blocks = bn_grid(nvec, C);
+    const size_t smem = 2 * (size_t)C * sizeof(float);
+    if (relu && !mask) throw std::runtime_error("kungfu_b200 bn_act: relu backward needs the mask");
+    if (relu) KF_BN_T(dtype, (bn_bwd_reduce_kernel<T, true><<<blocks, kBnThreads, smem, st>>>((const T*)dy, (const T*)x, mask, rows, C, mean, invstd, partial)));
+    else KF_BN_T(dtype, (bn_bwd_reduce_kernel<T, false><<<blocks, kBnThreads, smem, st>>>((const T*)dy, (const T*)x, mask, rows, C, mean, invstd, partial)));
+    KF_BN_P(pdtype, (bn_bwd_finalize_kernel<P><<<(C + 127) / 128, 128, 0, st>>>(partial, blocks, rows, C, (const P*)gamma, invstd, (P*)dgamma,
+                                                                                (P*)dbeta, coef)));
+#define KF_BN_BWD(RES, RELU)                                                                                                              \
+    KF_BN_T(dtype, (bn_bwd_apply_kernel<T, RES, RELU><<<blocks, kBnThreads, 0, st>>>((const T*)dy, (const T*)x, mask, (T*)dx, (T*)dres, nvec, C, \
+                                                                                       mean, invstd, coef)))
+    if (dres && relu) KF_BN_BWD(true, true);
+    else if (dres) KF_BN_BWD(true, false);
+    else if (relu) KF_BN_BWD(false, true);
+    else KF_BN_BWD(false, false);
+#undef KF_BN_BWD
+    count_launch(3);
+    KF_CUDA_CHECK(cudaGetLastError());
+}
+
+} // namespace kf

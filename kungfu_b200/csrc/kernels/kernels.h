@@ -76,6 +76,20 @@ void launch_u8_normalize(const uint8_t* src, void* dst, int dst_dtype, size_t np
                          const float* invstd3, cudaStream_t st);
 void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t st);
 
+// ---- bn_act.cu: fused BatchNorm (+residual) + ReLU on channels_last activations
+int bn_num_blocks(size_t rows, int C);
+// forward (training): partial is [bn_num_blocks][2][C] scratch; mean/invstd/scale/shift are [C] outputs; mask rows*C/8 bytes
+void launch_bn_fwd(const void* x, const void* res, void* y, uint8_t* mask, int dtype, size_t rows, int C, const void* gamma, const void* beta,
+                   void* running_mean, void* running_var, int pdtype, float eps, float momentum, int relu, float* partial, float* mean,
+                   float* invstd, float* scale, float* shift, cudaStream_t st);
+// forward with given scale/shift (eval mode, or the second half of training forward)
+void launch_bn_apply(const void* x, const void* res, void* y, uint8_t* mask, int dtype, size_t rows, int C, const float* scale, const float* shift,
+                     int relu, cudaStream_t st);
+// backward: coef is [3][C] scratch; dres may be null
+void launch_bn_bwd(const void* dy, const void* x, const uint8_t* mask, void* dx, void* dres, int dtype, size_t rows, int C, const void* gamma,
+                   void* dgamma, void* dbeta, int pdtype, const float* mean, const float* invstd, int relu, float* partial, float* coef,
+                   cudaStream_t st);
+
 void count_launch(int n = 1);
 uint64_t launch_count();
 

@@ -23,7 +23,16 @@ class BNAct(nn.BatchNorm2d):
         if zero_init:
             nn.init.zeros_(self.weight)
 
+    fused = True  # use the fused sm_100a kernel (ops/bn_act.py) when the layout/dtype allows it
+
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:  # type: ignore[override]
+        if BNAct.fused and x.is_cuda:
+            from ..ops.bn_act import bn_act
+
+            if self.training and self.track_running_stats and self.num_batches_tracked is not None:
+                self.num_batches_tracked.add_(1)
+            return bn_act(x, self.weight, self.bias, self.running_mean, self.running_var, residual, self.relu,
+                          self.training or not self.track_running_stats, self.momentum if self.momentum is not None else 0.1, self.eps)
         y = super().forward(x)
         if residual is not None:
             y = y + residual

@@ -280,3 +280,73 @@ def test_image_trainer_cuda_graph(plane):
     opt.engine.check()
     assert all(math.isfinite(l) for l in losses)
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("C,HW,residual,relu", [(64, 56, False, True), (256, 14, True, True), (2048, 7, True, True), (512, 28, False, False), (128, 9, True, False)])
+def test_fused_bn_act_matches_torch(plane, C, HW, residual, relu):
+    """Fused BN(+add)+ReLU forward/backward == PyTorch batch_norm + add + relu in fp32 (bf16 activations)."""
+    from kungfu_b200.ops.bn_act import bn_act, supported
+
+    torch.manual_seed(C + HW)
+    N = 8
+    x = (torch.randn(N, C, HW, HW, device="cuda") * 2 + 0.5).bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_()
+    res = torch.randn(N, C, HW, HW, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_() if residual else None
+    w = (torch.rand(C, device="cuda") + 0.5).bfloat16().requires_grad_()
+    b = torch.randn(C, device="cuda").bfloat16().requires_grad_()
+    rm, rv = torch.zeros(C, device="cuda").bfloat16(), torch.ones(C, device="cuda").bfloat16()
+    assert supported(x, w)
+    y = bn_act(x, w, b, rm, rv, res, relu, True, 0.1, 1e-5)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    # fp32 reference
+    xf, wf, bf = x.detach().float().requires_grad_(), w.detach().float().requires_grad_(), b.detach().float().requires_grad_()
+    rf = res.detach().float().requires_grad_() if residual else None
+    rmf, rvf = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    z = torch.nn.functional.batch_norm(xf, rmf, rvf, wf, bf, True, 0.1, 1e-5)
+    if residual:
+        z = z + rf
+    yf = torch.relu(z) if relu else z
+    yf.backward(dy.float())
+    assert torch.allclose(y.float(), yf, atol=3e-2, rtol=3e-2), (y.float() - yf).abs().max()
+    assert torch.allclose(x.grad.float(), xf.grad, atol=3e-2, rtol=5e-2), (x.grad.float() - xf.grad).abs().max()
+    if residual:
+        assert torch.allclose(res.grad.float(), rf.grad, atol=1e-2, rtol=1e-2)
+    scale = max(1.0, float(wf.grad.abs().max()))
+    assert torch.allclose(w.grad.float(), wf.grad, atol=2e-2 * scale, rtol=3e-2), (w.grad.float() - wf.grad).abs().max()
+    assert torch.allclose(b.grad.float(), bf.grad, atol=2e-2 * max(1.0, float(bf.grad.abs().max())), rtol=3e-2)
+    assert torch.allclose(rm.float(), rmf, atol=1e-2) and torch.allclose(rv.float(), rvf, atol=2e-2, rtol=2e-2)
+    # eval mode uses the running statistics
+    ye = bn_act(x.detach(), w.detach(), b.detach(), rm, rv, res.detach() if residual else None, relu, False, 0.1, 1e-5)
+    ze = torch.nn.functional.batch_norm(x.detach().float(), rm.float(), rv.float(), w.detach().float(), b.detach().float(), False, 0.1, 1e-5)
+    if residual:
+        ze = ze + res.detach().float()
+    assert torch.allclose(ye.float(), torch.relu(ze) if relu else ze, atol=5e-2, rtol=3e-2)
+
+
+def test_resnet_fused_bn_trains(plane):
+    """ResNet-18 with the fused BN kernels trains as well as with the PyTorch ops (same seed, loss curves agree)."""
+    from kungfu_b200.models import resnet
+
+    def run(fused):
+        resnet.BNAct.fused = fused
+        torch.manual_seed(0)
+        m = resnet.to_b200(resnet.resnet18(num_classes=10), torch.bfloat16, "cuda")
+        opt = torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9)
+        g = torch.Generator(device="cuda").manual_seed(1)
+        x = torch.randn(16, 3, 64, 64, device="cuda", generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+        y = torch.randint(0, 10, (16,), device="cuda", generator=g)
+        losses = []
+        for _ in range(8):
+            opt.zero_grad()
+            loss = torch.nn.functional.cross_entropy(m(x).float(), y)
+            loss.backward()
+            opt.step()
+            losses.append(loss.item())
+        return losses
+
+    try:
+        a, b = run(True), run(False)
+    finally:
+        resnet.BNAct.fused = True
+    assert a[-1] < a[0] and b[-1] < b[0]
+    assert abs(a[0] - b[0]) < 0.05 and abs(a[-1] - b[-1]) < 0.35, (a, b)
