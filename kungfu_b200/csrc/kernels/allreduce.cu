@@ -58,13 +58,15 @@ template <typename T> __device__ __forceinline__ void apply_scale(AccVec<T>& x, 
 
 // Load vector `v` of the message from every peer (all loads issued before any use so that
 // nranks NVLink requests are in flight per thread) and reduce. `pre` accumulates sum_r |x_r|^2.
-template <typename T, int OP, bool SUMSQ>
+// CANON: peers are visited in rank order 0..N-1 on every rank, so that ranks which all reduce the same data (one-shot)
+// produce bit-identical results; the sliced algorithms have a single reducer per element and rotate for load balance.
+template <typename T, int OP, bool SUMSQ, bool CANON = false>
 __device__ __forceinline__ AccVec<T> gather_reduce(const MeshArgs& m, size_t byte_off, float& pre) {
     Vec16 buf[kMaxRanks];
 #pragma unroll
     for (int i = 0; i < kMaxRanks; ++i) {
         if (i < m.nranks) {
-            int r = m.rank + i;
+            int r = CANON ? i : m.rank + i;
             if (r >= m.nranks) r -= m.nranks;
             buf[i] = ld_stream(reinterpret_cast<const char*>(m.data[r]) + byte_off);
         }
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(512) allreduce_oneshot_kernel(const __grid_con
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     float pre = 0.f, post = 0.f;
     for (size_t v = tid; v < a.nvec; v += stride) {
-        AccVec<T> acc = gather_reduce<T, OP, SUMSQ>(m, a.off + v * 16, pre);
+        AccVec<T> acc = gather_reduce<T, OP, SUMSQ, true>(m, a.off + v * 16, pre);
         if (a.flags & kArScale) apply_scale<T>(acc, a.scale);
         if constexpr (SUMSQ) post += vec_sumsq<T>(acc);
         st_plain(reinterpret_cast<char*>(a.out) + v * 16, pack<T>(acc));
