@@ -42,7 +42,7 @@ def main():
     dt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     code = dtypes.dtype_code(dt)
     max_bytes = args.max_mb << 20
-    arena = plane.new_arena(max_bytes + (4 << 20), "bw")
+    arena = plane.new_arena(max_bytes + (4 << 20), "bw").ensure()
     off = arena.alloc(max_bytes, align=4096)
     buf = arena.view(off, max_bytes // dt.itemsize, dt)
     buf.fill_(0.001)

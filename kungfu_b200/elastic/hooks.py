@@ -49,10 +49,18 @@ class ResizeProfiler:
 
 def sync_after_resize(state: ElasticState, model: torch.nn.Module, optimizer: Optional[torch.optim.Optimizer] = None) -> ElasticState:
     """What every member does right after `changed`: agree on progress (max), adopt rank 0's model/optimizer state."""
+    from ..runtime import get_runtime
+
+    rt = get_runtime()
+    if rt.has_gpu() and (rt._gpu is not None or (optimizer is not None and getattr(optimizer, "engine", None) is not None)):
+        rt.gpu.reconnect_all()  # re-discover peers, rebuild VMM mappings + NVLS multicast for the new membership
     state.step = all_reduce_int_max(state.step)
     state.trained_samples = all_reduce_int_max(state.trained_samples)
     state.epoch = all_reduce_int_max(state.epoch)
-    BroadcastGlobalVariablesOp(model, optimizer, 0)
+    eng = getattr(optimizer, "engine", None) if optimizer is not None else None
+    BroadcastGlobalVariablesOp(model, optimizer if eng is None else None, 0)
+    if eng is not None:
+        eng.sync_state_from_root(0)  # re-shard fp32 master weights / optimizer state for the new world size
     return state
 
 

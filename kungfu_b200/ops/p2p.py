@@ -29,6 +29,7 @@ def _gpu_slot(name: str, nbytes: int) -> dict:
                 "ok": torch.zeros(4, dtype=torch.int32, device=plane.device),
                 "stage": torch.zeros(pad, dtype=torch.uint8, device=plane.device)}
         _gpu_slots[name] = slot
+    slot["arena"].ensure()
     if slot["nbytes"] < nbytes:
         raise ValueError(f"p2p slot {name!r} was created with {slot['nbytes']} bytes < {nbytes}")
     return slot

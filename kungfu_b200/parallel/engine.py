@@ -97,7 +97,7 @@ class FlatEngine:
             self.sets.append(_Set(s["group"], FlatLayout(s["items"], s["dtype"], bb)))
         if not self.sets:
             raise ValueError("kungfu_b200: optimizer has no trainable parameters")
-        self._check_consensus()
+        self._consensus_key = None  # checked lazily, once per membership (constructors never communicate)
         self._build_arena(name)
         self._adopt_tensors()
         self.sumsq = torch.zeros(4, dtype=torch.float32, device=self.plane.device)
@@ -107,11 +107,17 @@ class FlatEngine:
         self._pending_event: Optional[torch.cuda.Event] = None
         self.steps = 0
         self.kernel_launches = 0
+        self._full_state: Optional[Dict[str, torch.Tensor]] = None
+        self.plane.engines.append(self)
         if self.overlap:
             self._install_hooks()
 
     # ---------------------------------------------------------------------------------------------
     def _check_consensus(self) -> None:
+        key = self.plane.membership_key()
+        if self._consensus_key == key:
+            return
+        self._consensus_key = key
         if self.nranks == 1:
             return
         import hashlib
@@ -265,6 +271,8 @@ class FlatEngine:
         if self._step_open:
             return
         self._step_open = True
+        self._check_consensus()
+        self.arena.ensure()
         self._sync_hyper()
         self._ensure_state()
         cs = self.plane.comm_stream
@@ -359,6 +367,8 @@ class FlatEngine:
             self.kernel_launches += 1
 
     def publish(self) -> None:
+        self._check_consensus()
+        self.arena.ensure()
         cs = self.plane.comm_stream
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
@@ -404,6 +414,97 @@ class FlatEngine:
 
     def check(self) -> None:
         self.arena.check()
+
+    # ---- elastic membership ------------------------------------------------------------------------
+    def prepare_resize(self) -> None:
+        """Called on every CURRENT member right before the membership changes: un-shard the fp32 master weights and
+        optimizer state (they are partitioned by the old world size) while the old peer mappings still exist."""
+        torch.cuda.synchronize(self.plane.device_index)
+        self._full_state = None
+        if all(s.state_ready for s in self.sets) and self.mode in ("ssgd", "sma", "pair") and self.opt_kind is not None:
+            self._full_state = self.gather_state()
+
+    def finish_resize(self) -> None:
+        """Called after the arenas have been reconnected to the new membership."""
+        self.rank, self.nranks = self.rt.rank, self.rt.size
+        for s in self.sets:
+            s.hyper_cache = None
+            hp_step = s.hyper.clone()
+            s.state_ready = False
+            s._saved_hyper = hp_step  # type: ignore[attr-defined]
+        self._step_open = False
+        self._launched = [0 for _ in self.sets]
+
+    def sync_state_from_root(self, root: int = 0) -> None:
+        """Collective over the NEW membership (survivors and newcomers): rank `root` broadcasts the full fp32 state,
+        every rank keeps the shard it now owns. Newcomers call it with no local state."""
+        if self.mode == "grads" or self.opt_kind is None:
+            for s in self.sets:
+                s.state_ready = self.mode == "grads"
+            return
+        dev = self.plane.device
+        for si, s in enumerate(self.sets):
+            lay = s.layout
+            need1, need2 = self._needs_state(s)
+            keys = [("master", lay.dtype != torch.float32 and self.mode == "ssgd"), ("s1", need1), ("s2", need2)]
+            # the device-side step counter / bias corrections travel too
+            coll.broadcast_(s.hyper, root)
+            s.hyper_cache = None
+            for key, needed in keys:
+                if not needed:
+                    continue
+                full = None
+                if self._full_state is not None:
+                    full = self._full_state.get(f"set{si}.{key}")
+                have = torch.tensor([1 if full is not None else 0], dtype=torch.int32, device=dev)
+                coll.broadcast_(have, root)
+                if int(have.item()) == 0:
+                    continue  # the root never stepped: lazily initialised state is right for everybody
+                if full is None or full.numel() != sum(b.numel for b in lay.buckets):
+                    full = torch.zeros(sum(b.numel for b in lay.buckets), dtype=torch.float32, device=dev)
+                full = full.contiguous()
+                coll.broadcast_(full, root)
+                off = 0
+                shards = getattr(s, key)
+                for b in lay.buckets:
+                    if self.mode == "ssgd" and self.nranks > 1:
+                        n = lay.shard_elems(b, self.nranks)
+                        lo, hi = lay.shard_range(b, self.nranks, self.rank)
+                    else:
+                        n = b.numel
+                        lo, hi = b.start, b.start + b.numel
+                    t = torch.zeros(n, dtype=torch.float32, device=dev)
+                    t[:hi - lo].copy_(full[off + (lo - b.start):off + (hi - b.start)])
+                    shards[b.index] = t
+                    off += b.numel
+                setattr(s, "_have_" + key, True)
+            # anything not received is created lazily (zeros / from the broadcast parameters)
+            s.state_ready = False
+        self._ensure_state_keep_existing()
+        self._full_state = None
+
+    def _ensure_state_keep_existing(self) -> None:
+        for s in self.sets:
+            lay = s.layout
+            need1, need2 = self._needs_state(s)
+            dev = self.plane.device
+            for b in lay.buckets:
+                if self.mode == "ssgd" and self.nranks > 1:
+                    n = lay.shard_elems(b, self.nranks)
+                    lo, hi = lay.shard_range(b, self.nranks, self.rank)
+                else:
+                    n = b.numel
+                    lo, hi = b.start, b.start + b.numel
+                ok = lambda t: t is not None and t.numel() == n
+                if lay.dtype != torch.float32 and self.mode == "ssgd" and not ok(s.master[b.index]):
+                    m = torch.zeros(n, dtype=torch.float32, device=dev)
+                    m[:hi - lo].copy_(s.params[lo:hi])
+                    s.master[b.index] = m
+                if need1 and not ok(s.s1[b.index]):
+                    s.s1[b.index] = torch.zeros(n, dtype=torch.float32, device=dev)
+                if need2 and not ok(s.s2[b.index]):
+                    s.s2[b.index] = torch.zeros(n, dtype=torch.float32, device=dev)
+            s.state_ready = True
 
     # ---- monitoring --------------------------------------------------------------------------------
     def read_sumsq(self, reset: bool = True) -> torch.Tensor:

@@ -51,14 +51,15 @@ class SymmetricArena:
         self.name = name
         self.ext = ext
         rt = plane.runtime
-        mode = os.environ.get("KUNGFU_MESH_MODE", "auto" if rt.size > 1 else "local")
-        if rt.size == 1 and mode == "auto":
-            mode = "local"
+        # an elastic job may grow beyond one rank later: its arenas must be exportable (VMM) from the start
+        elastic = bool(os.environ.get("KUNGFU_CONFIG_SERVER")) or "KUNGFU_SELF_SPEC" in os.environ
+        mode = os.environ.get("KUNGFU_MESH_MODE", "auto" if (rt.size > 1 or elastic) else "local")
         self.mesh = ext.PeerMesh(plane.device_index, int(nbytes), mode)
         self.mesh.set_timeout_ms(float(os.environ.get("KUNGFU_DEVICE_TIMEOUT_MS", "20000")))
         self._cursor = 0
         self._regions: Dict[str, Tuple[int, int]] = {}
-        self._connect(want_multicast)
+        self._want_multicast = want_multicast
+        self._epoch = None  # membership this arena is connected for; connection is lazy (see `ensure`)
         base = _CudaView(self.mesh.local_ptr, self.mesh.arena_bytes, self)
         with torch.cuda.device(plane.device_index):
             self._bytes = torch.as_tensor(base, device=torch.device("cuda", plane.device_index))
@@ -68,10 +69,17 @@ class SymmetricArena:
         want_mc = want_multicast and os.environ.get("KUNGFU_DISABLE_NVLS", "0") != "1"
         self.mesh.connect(rt.rank, rt.size, rt.control.all_gather_bytes, want_mc)
 
-    def reconnect(self, want_multicast: bool = True) -> None:
-        """Rebuild peer mappings after a membership change (local memory and views survive)."""
-        torch.cuda.synchronize(self.plane.device_index)
-        self._connect(want_multicast)
+    def ensure(self) -> "SymmetricArena":
+        """Connect (or re-connect after a membership change) to the current peers. COLLECTIVE when it has work to do:
+        every rank reaches the first use of an arena in the same program order, and after a resize all members call
+        `GpuPlane.reconnect_all()` from `sync_after_resize`. Constructors never communicate, so late joiners can build
+        their objects without the survivors taking part. Local memory and every tensor viewing it survive."""
+        key = self.plane.membership_key()
+        if self._epoch != key:
+            torch.cuda.synchronize(self.plane.device_index)
+            self._connect(self._want_multicast)
+            self._epoch = key
+        return self
 
     # ---- allocation -------------------------------------------------------------------------------
     @property
@@ -139,12 +147,23 @@ class GpuPlane:
         self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
         self.side_stream = torch.cuda.Stream(device=self.device, priority=-1)
         self._arenas: List[SymmetricArena] = []
+        self.engines: list = []  # FlatEngines living on this plane (told about membership changes)
         self._staging: Optional[SymmetricArena] = None
         self._staging_off = 0
         self._staging_bytes = 0
         self.sm_count = torch.cuda.get_device_properties(self.device_index).multi_processor_count
 
+    def membership_key(self):
+        rt = self.runtime
+        ver = getattr(rt.control, "cluster_version", None)
+        return (rt.size, rt.rank, ver() if ver else 0)
+
     def new_arena(self, nbytes: int, name: str, want_multicast: bool = True) -> SymmetricArena:
+        names = {a.name for a in self._arenas}
+        base, k = name, 1
+        while name in names:  # unique, deterministic names: the reconnect order after a resize is by name
+            k += 1
+            name = f"{base}#{k}"
         a = SymmetricArena(self, nbytes, name, want_multicast)
         self._arenas.append(a)
         return a
@@ -156,11 +175,23 @@ class GpuPlane:
             self._staging = self.new_arena((mb + 2) << 20, "staging")
             self._staging_bytes = mb << 20
             self._staging_off = self._staging.alloc(self._staging_bytes, name="stage")
+        self._staging.ensure()
         return self._staging, self._staging_off, self._staging_bytes
 
     def reconnect_all(self) -> None:
-        for a in self._arenas:
-            a.reconnect()
+        """After a membership change: all members (survivors and newcomers) re-discover their peers and rebuild the
+        mappings of every arena they have in common, in name order (K4 / `PeerMesh::connect`)."""
+        rt = self.runtime
+        self.staging()
+        mine = sorted(a.name for a in self._arenas)
+        if rt.size > 1:
+            lists = [set(b.decode().split("\n")) for b in rt.control.all_gather_bytes("\n".join(mine).encode())]
+            common = set.intersection(*lists)
+        else:
+            common = set(mine)
+        for a in sorted(self._arenas, key=lambda a: a.name):
+            if a.name in common:
+                a.ensure()
 
     def topology(self) -> dict:
         st, _, _ = self.staging()

@@ -78,9 +78,13 @@ def resize(n: Optional[int] = None) -> Tuple[bool, bool]:
         import torch
 
         torch.cuda.synchronize()
+        for e in rt._gpu.engines:
+            e.prepare_resize()
     changed, det = f(n)
     if changed and not det and rt._gpu is not None:
-        rt._gpu.reconnect_all()
+        # peer mappings are rebuilt collectively by ALL members of the new cluster in `sync_after_resize`
+        for e in rt._gpu.engines:
+            e.finish_resize()
     return changed, det
 
 

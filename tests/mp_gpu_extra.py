@@ -127,7 +127,7 @@ def check_pull_publish(rt, log):
     N, me = rt.size, rt.rank
     plane = rt.gpu
     ext = plane.ext
-    arena = plane.new_arena(8 << 20, "pubtest")
+    arena = plane.new_arena(8 << 20, "pubtest").ensure()
     n = 1 << 18
     pub0, pub1, ver = arena.alloc(n * 4), arena.alloc(n * 4), arena.alloc(256)
     done = torch.zeros(4, dtype=torch.int32, device="cuda")

@@ -41,3 +41,19 @@ def test_fused_optimizers_all_gpus():
 def test_sma_pair_all_gpus():
     n = torch.cuda.device_count()
     _run(n if n in (2, 4, 8) else 2, ["extra"])
+
+
+def test_gpu_elastic_resize_under_kungfu_run():
+    """1 -> 2 -> 1 GPUs under `kungfu-run -w` with the builtin config server: survivors keep training, newcomers inherit
+    state, arenas rebuild their peer mappings; the trajectory equals a plain torch.optim reference."""
+    from kungfu_b200.cmd import kungfu_run_path
+
+    port = 9300 + os.getpid() % 300
+    cmd = [kungfu_run_path(), "-q", "-w", "-np", "1", "-H", "127.0.0.1:2", "-port", str(31000 + os.getpid() % 3000), "-port-range",
+           f"{21000 + os.getpid() % 3000}-{21000 + os.getpid() % 3000 + 40}", "-builtin-config-port", str(port), sys.executable,
+           os.path.join(ROOT, "tests", "gpu_elastic_worker.py"), "1:4,2:4,1:4"]
+    env = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_DEVICE_TIMEOUT_MS="15000", KUNGFU_CONFIG_LOG_LEVEL="WARN")
+    r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    print(r.stdout[-4000:])
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert '"gpu_elastic": true' in r.stdout and '"ok": true' in r.stdout and '"sizes_seen": [1, 2]' in r.stdout
