@@ -195,12 +195,9 @@ class FlatEngine:
                 v[HP["momentum"]] = float(g.get("momentum", 0.0))
                 v[HP["dampening"]] = float(g.get("dampening", 0.0))
                 v[HP["nesterov"]] = 1.0 if g.get("nesterov", False) else 0.0
-            if s.hyper_cache is None:
-                s.hyper.copy_(torch.tensor(v, dtype=torch.float32))
-                s.hyper_cache = v
-            elif any(v[i] != s.hyper_cache[i] for i in (0, 1, 2, 3, 4, 5, 7, 8, 9, 13, 14)):
-                # keep the device-side step counter / bias corrections
-                idx = [0, 1, 2, 3, 4, 5, 7, 8, 9, 13, 14]
+            idx = [0, 1, 2, 3, 4, 5, 7, 8, 9, 13, 14]  # configuration slots only: the device-side step counter, first-step
+            # flag and Adam bias corrections (6, 10, 11, 12) belong to the kernels and survive resizes / lr changes
+            if s.hyper_cache is None or any(v[i] != s.hyper_cache[i] for i in idx):
                 s.hyper[idx] = torch.tensor([v[i] for i in idx], dtype=torch.float32, device=s.hyper.device)
                 s.hyper_cache = v
 
