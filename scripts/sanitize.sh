@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# Race / memory checking (the reference configures no sanitizers).
+#   scripts/sanitize.sh thread      -> TSan build of the C++ runtime + launcher, then the C ABI integration program
+#   scripts/sanitize.sh address     -> ASan/UBSan
+#   scripts/sanitize.sh cuda        -> compute-sanitizer (memcheck, racecheck, synccheck) over the single-GPU kernel tests
+set -euo pipefail
+cd "$(dirname "$0")/.."
+mode="${1:-thread}"
+if [ "$mode" = "cuda" ]; then
+    for tool in memcheck racecheck synccheck; do
+        compute-sanitizer --tool "$tool" --error-exitcode 1 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "allreduce or flat_opt or cast or bn"
+    done
+    exit 0
+fi
+KUNGFU_SANITIZE="$mode" python -c "from kungfu_b200 import _build; _build.build_runtime(verbose=True)"
+bin="kungfu_b200/bin-$mode"
+R=$((32000 + RANDOM % 4000))
+"$bin/kungfu-run" -q -np 4 -H 127.0.0.1:4 -port "$R" -port-range "$((R + 1))-$((R + 50))" -strategy RING "$bin/kungfu-fake-agent" test
+"$bin/kungfu-run" -q -np 3 -H 127.0.0.1:3 -port "$R" -port-range "$((R + 1))-$((R + 50))" -strategy BINARY_TREE "$bin/kungfu-fake-agent" bench slp
+echo "sanitizer run ($mode) passed"
