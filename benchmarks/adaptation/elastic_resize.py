@@ -39,11 +39,14 @@ def main():
     dtype = torch.bfloat16 if use_gpu else torch.float32
     torch.manual_seed(0)
     model = getattr(resnet, a.model)().to(dev, dtype)
-    # the generic (non-fused) path keeps `param.data` outside the arenas, so a plain broadcast re-syncs newcomers
-    opt = kf.optimizers.MonitorGradientNoiseScaleOptimizer(torch.optim.SGD(model.parameters(), lr=0.01), model.named_parameters(),
-                                                           device_batch_size=a.batch_size, fused=False)
-    state = sync_after_resize(ElasticState(), model, None)
+    if use_gpu:
+        model = model.to(memory_format=torch.channels_last)
+    opt = kf.optimizers.MonitorGradientNoiseScaleOptimizer(torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9), model.named_parameters(),
+                                                           device_batch_size=a.batch_size)
+    state = sync_after_resize(ElasticState(), model, opt)
     x = torch.randn(a.batch_size, 3, 64 if not use_gpu else 224, 64 if not use_gpu else 224, device=dev, dtype=dtype)
+    if use_gpu:
+        x = x.contiguous(memory_format=torch.channels_last)
     y = torch.randint(0, 1000, (a.batch_size,), device=dev)
     t_phase, n_phase = time.time(), 0
     while state.step < sch.total_steps:
@@ -65,7 +68,7 @@ def main():
             if detached:
                 return
             if changed:
-                state = sync_after_resize(state, model, None)
+                state = sync_after_resize(state, model, opt)
                 if kf.current_rank() == 0:
                     print(json.dumps({"resize_to": kf.current_cluster_size(), "latency_s": round(time.time() - t0, 3)}), flush=True)
             t_phase, n_phase = time.time(), 0

@@ -49,6 +49,23 @@ if _san in ("thread", "address"):
     BIN = PKG / ("bin-" + _san)
 
 
+def _cutlass_root():
+    """CUTLASS / CuTe header tree vendored in the image (used by gemm_sm100.cu only). None -> that kernel is stubbed."""
+    cands = [os.environ.get("CUTLASS_HOME", "")]
+    try:
+        import flashinfer  # noqa: F401
+
+        cands.append(str(Path(flashinfer.__file__).resolve().parent / "data" / "cutlass"))
+    except Exception:
+        pass
+    sp = sysconfig.get_paths()["purelib"]
+    cands += [sp + "/flashinfer/data/cutlass", sp + "/tilelang/3rdparty/cutlass"]
+    for c in cands:
+        if c and (Path(c) / "include" / "cutlass" / "gemm" / "collective" / "collective_builder.hpp").exists():
+            return c
+    return None
+
+
 def _pybind_includes() -> list[str]:
     import pybind11
 
@@ -101,7 +118,12 @@ def build_cuda(verbose: bool = False, force: bool = False) -> Path:
     objs = []
     for cu in sorted(kdir.glob("*.cu")):
         obj = OBJ / "cuda" / (cu.stem + ".o")
-        cmd = [NVCC] + NVCC_FLAGS + ["-I" + str(kdir), "-c", str(cu), "-o", str(obj)]
+        extra = []
+        if cu.stem == "gemm_sm100":
+            root = _cutlass_root()
+            if root:
+                extra = ["-DKF_WITH_CUTLASS", "-I" + root + "/include", "-I" + root + "/tools/util/include"]
+        cmd = [NVCC] + NVCC_FLAGS + extra + ["-I" + str(kdir), "-c", str(cu), "-o", str(obj)]
         jobs.append((cu, obj, cmd))
         objs.append(obj)
     host_inc = ["-I" + str(kdir), "-I" + str(mdir), "-I" + CUDA_HOME + "/include"] + _pybind_includes()

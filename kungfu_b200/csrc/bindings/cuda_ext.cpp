@@ -158,6 +158,12 @@ PYBIND11_MODULE(_kfcuda, m) {
     m.def("u8_normalize", [](uintptr_t src, uintptr_t dst, int ddt, size_t npix, uintptr_t mean3, uintptr_t invstd3, uintptr_t st) {
         launch_u8_normalize(P<const uint8_t>(src), P<void>(dst), ddt, npix, P<const float>(mean3), P<const float>(invstd3), S(st));
     });
+    m.def("gemm_sm100_available", &gemm_sm100_available);
+    m.def("gemm_bias_act_workspace", &gemm_bias_act_workspace);
+    m.def("gemm_bias_act", [](uintptr_t x, uintptr_t w, uintptr_t bias, uintptr_t y, int tokens, int in_f, int out_f, int act, uintptr_t ws,
+                              size_t ws_bytes, uintptr_t st) {
+        launch_gemm_bias_act(P<const void>(x), P<const void>(w), P<const void>(bias), P<void>(y), tokens, in_f, out_f, act, P<void>(ws), ws_bytes, S(st));
+    });
     m.def("bn_num_blocks", &bn_num_blocks);
     m.def("bn_fwd", [](uintptr_t x, uintptr_t res, uintptr_t y, uintptr_t mask, int dtype, size_t rows, int C, uintptr_t gamma, uintptr_t beta,
                        uintptr_t rmean, uintptr_t rvar, int pdtype, float eps, float momentum, int relu, uintptr_t partial, uintptr_t mean,

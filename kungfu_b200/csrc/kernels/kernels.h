@@ -90,6 +90,12 @@ void launch_bn_bwd(const void* dy, const void* x, const uint8_t* mask, void* dx,
                    void* dgamma, void* dbeta, int pdtype, const float* mean, const float* invstd, int relu, float* partial, float* coef,
                    cudaStream_t st);
 
+// ---- gemm_sm100.cu: tcgen05 GEMM + bias (+GELU) epilogue (CUTLASS/CuTe sm100 collectives); act: 0 = identity, 1 = GELU
+bool gemm_sm100_available();
+size_t gemm_bias_act_workspace(int tokens, int in_f, int out_f, int act);
+void launch_gemm_bias_act(const void* x, const void* w, const void* bias, void* y, int tokens, int in_f, int out_f, int act, void* workspace,
+                          size_t workspace_bytes, cudaStream_t st);
+
 void count_launch(int n = 1);
 uint64_t launch_count();
 

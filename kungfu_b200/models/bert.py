@@ -26,6 +26,7 @@ class BertConfig:
     type_vocab: int = 2
     num_labels: int = 2
     dropout: float = 0.0
+    fused_mlp: bool = False  # FFN up-projection + GELU on the tcgen05 GEMM with a fused epilogue (ops/linear_act.py)
 
     @staticmethod
     def large() -> "BertConfig":
@@ -47,7 +48,13 @@ class BertLayer(nn.Module):
         self.qkv = nn.Linear(c.hidden, 3 * c.hidden)
         self.out = nn.Linear(c.hidden, c.hidden)
         self.ln1 = nn.LayerNorm(c.hidden, eps=1e-12)
-        self.ff1 = nn.Linear(c.hidden, c.intermediate)
+        self.fused_mlp = c.fused_mlp
+        if c.fused_mlp:
+            from ..ops.linear_act import FusedLinear
+
+            self.ff1 = FusedLinear(c.hidden, c.intermediate, act="gelu")
+        else:
+            self.ff1 = nn.Linear(c.hidden, c.intermediate)
         self.ff2 = nn.Linear(c.intermediate, c.hidden)
         self.ln2 = nn.LayerNorm(c.hidden, eps=1e-12)
 
@@ -56,7 +63,8 @@ class BertLayer(nn.Module):
         q, k, v = self.qkv(x).view(B, S, 3, self.heads, H // self.heads).permute(2, 0, 3, 1, 4)
         a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H)
         x = self.ln1(x + self.out(a))
-        return self.ln2(x + self.ff2(F.gelu(self.ff1(x))))
+        h = self.ff1(x) if self.fused_mlp else F.gelu(self.ff1(x))
+        return self.ln2(x + self.ff2(h))
 
 
 class Bert(nn.Module):

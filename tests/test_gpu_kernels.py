@@ -350,3 +350,29 @@ def test_resnet_fused_bn_trains(plane):
         resnet.BNAct.fused = True
     assert a[-1] < a[0] and b[-1] < b[0]
     assert abs(a[0] - b[0]) < 0.05 and abs(a[-1] - b[-1]) < 0.35, (a, b)
+
+
+@pytest.mark.parametrize("tokens,in_f,out_f", [(256, 1024, 4096), (4096, 1024, 4096), (136, 64, 128)])
+@pytest.mark.parametrize("act", [None, "gelu"])
+def test_tcgen05_linear_act_matches_torch(plane, tokens, in_f, out_f, act):
+    """tcgen05 GEMM + fused bias/GELU epilogue == fp32 reference of the same op (forward and backward)."""
+    from kungfu_b200.ops.linear_act import linear_act, supported
+
+    torch.manual_seed(tokens + out_f)
+    x = (torch.randn(tokens, in_f, device="cuda") * 0.5).bfloat16().requires_grad_()
+    w = (torch.randn(out_f, in_f, device="cuda") * in_f ** -0.5).bfloat16().requires_grad_()
+    b = torch.randn(out_f, device="cuda").bfloat16().requires_grad_()
+    assert supported(x, w, b), "the tcgen05 GEMM must be built and usable on this GPU"
+    c0 = plane.ext.launch_count()
+    y = linear_act(x, w, b, act)
+    assert plane.ext.launch_count() == c0 + 1
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xf, wf, bf = x.detach().float().requires_grad_(), w.detach().float().requires_grad_(), b.detach().float().requires_grad_()
+    z = torch.nn.functional.linear(xf, wf, bf)
+    yf = torch.nn.functional.gelu(z) if act == "gelu" else z
+    yf.backward(dy.float())
+    assert torch.allclose(y.float(), yf, atol=3e-2, rtol=3e-2), (y.float() - yf).abs().max()
+    assert torch.allclose(x.grad.float(), xf.grad, atol=5e-2, rtol=5e-2)
+    assert torch.allclose(w.grad.float(), wf.grad, atol=2e-1 * (tokens / 256) ** 0.5, rtol=5e-2)
+    assert torch.allclose(b.grad.float(), bf.grad, atol=2e-1 * (tokens / 256) ** 0.5, rtol=5e-2)
