@@ -158,6 +158,12 @@ PYBIND11_MODULE(_kfcuda, m) {
     m.def("u8_normalize", [](uintptr_t src, uintptr_t dst, int ddt, size_t npix, uintptr_t mean3, uintptr_t invstd3, uintptr_t st) {
         launch_u8_normalize(P<const uint8_t>(src), P<void>(dst), ddt, npix, P<const float>(mean3), P<const float>(invstd3), S(st));
     });
+    m.def("maxpool3x3s2_fwd", [](uintptr_t x, uintptr_t y, uintptr_t idx, int dtype, int N, int H, int W, int C, uintptr_t st) {
+        launch_maxpool3x3s2_fwd(P<const void>(x), P<void>(y), P<uint8_t>(idx), dtype, N, H, W, C, S(st));
+    });
+    m.def("maxpool3x3s2_bwd", [](uintptr_t dy, uintptr_t idx, uintptr_t dx, int dtype, int N, int H, int W, int C, uintptr_t st) {
+        launch_maxpool3x3s2_bwd(P<const void>(dy), P<const uint8_t>(idx), P<void>(dx), dtype, N, H, W, C, S(st));
+    });
     m.def("gemm_sm100_available", &gemm_sm100_available);
     m.def("gemm_bias_act_workspace", &gemm_bias_act_workspace);
     m.def("gemm_bias_act", [](uintptr_t x, uintptr_t w, uintptr_t bias, uintptr_t y, int tokens, int in_f, int out_f, int act, uintptr_t ws,

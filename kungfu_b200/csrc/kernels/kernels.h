@@ -90,6 +90,10 @@ void launch_bn_bwd(const void* dy, const void* x, const uint8_t* mask, void* dx,
                    void* dgamma, void* dbeta, int pdtype, const float* mean, const float* invstd, int relu, float* partial, float* coef,
                    cudaStream_t st);
 
+// ---- pool.cu: 3x3 stride-2 pad-1 max pooling, channels_last, 1-byte arg-max indices, gather backward
+void launch_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* idx, int dtype, int N, int H, int W, int C, cudaStream_t st);
+void launch_maxpool3x3s2_bwd(const void* dy, const uint8_t* idx, void* dx, int dtype, int N, int H, int W, int C, cudaStream_t st);
+
 // ---- gemm_sm100.cu: tcgen05 GEMM + bias (+GELU) epilogue (CUTLASS/CuTe sm100 collectives); act: 0 = identity, 1 = GELU
 bool gemm_sm100_available();
 size_t gemm_bias_act_workspace(int tokens, int in_f, int out_f, int act);

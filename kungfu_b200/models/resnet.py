@@ -95,7 +95,9 @@ class ResNet(nn.Module):
         self.inplanes = 64
         self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
         self.bn1 = BNAct(64)
-        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        from ..ops.pool import MaxPool3x3s2
+
+        self.maxpool = MaxPool3x3s2()  # fused sm_100a kernel on channels_last bf16, F.max_pool2d otherwise
         self.layer1 = self._make_layer(block, 64, layers[0], 1)
         self.layer2 = self._make_layer(block, 128, layers[1], 2)
         self.layer3 = self._make_layer(block, 256, layers[2], 2)

@@ -108,6 +108,12 @@ class FlatEngine:
         self.steps = 0
         self.kernel_launches = 0
         self._full_state: Optional[Dict[str, torch.Tensor]] = None
+        # Overlap mode "steals" gradients: `.grad` is None during backward, autograd hands us its freshly produced tensor
+        # (no accumulate kernel), and each bucket moves its gradients into the arena with ONE multi-tensor copy right
+        # before its fused kernel (instead of one `grad += new` launch per parameter).
+        self._steal = self.overlap and os.environ.get("KUNGFU_STEAL_GRADS", "1") != "0"
+        self._pending = [[[] for _ in s.layout.buckets] for s in self.sets]
+        self._got = [[False] * len(s.layout.entries) for s in self.sets]
         self.plane.engines.append(self)
         if self.overlap:
             self._install_hooks()
@@ -236,15 +242,16 @@ class FlatEngine:
     # ---------------------------------------------------------------------------------------------
     def _install_hooks(self) -> None:
         for si, s in enumerate(self.sets):
-            for e in s.layout.entries:
+            for ei, e in enumerate(s.layout.entries):
                 gv = _view_like(s.grads, e.offset, e.param)
 
-                def hook(p, si=si, bi=e.bucket, gv=gv):
+                def hook(p, si=si, bi=e.bucket, gv=gv, ei=ei):
                     g = p.grad
                     if g is not None and g.data_ptr() != gv.data_ptr():
-                        # somebody replaced .grad (e.g. zero_grad(set_to_none=True)): move it back into the arena
-                        gv.copy_(g)
+                        # autograd produced a fresh tensor (.grad was None): queue it for the bucket's multi-tensor copy
+                        self._pending[si][bi].append((gv, g))
                         p.grad = gv
+                    self._got[si][ei] = True
                     self._on_grad_ready(si, bi)
                 self._hooks.append(e.param.register_post_accumulate_grad_hook(hook))
 
@@ -290,6 +297,11 @@ class FlatEngine:
         lay = s.layout
         self._open_step()
         cs = self.plane.comm_stream
+        pend = self._pending[si][b.index]
+        if pend:
+            torch._foreach_copy_([a for a, _ in pend], [g for _, g in pend])
+            pend.clear()
+            after_current = True
         if after_current:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())
@@ -381,6 +393,12 @@ class FlatEngine:
     # ---------------------------------------------------------------------------------------------
     def flush(self) -> None:
         """Launch every bucket that the hooks have not launched yet (unused params, overlap disabled)."""
+        if self._steal:
+            for si, s in enumerate(self.sets):
+                for ei, e in enumerate(s.layout.entries):
+                    if not self._got[si][ei] and self._launched[si] <= e.bucket:
+                        # a parameter that received no gradient this step contributes zeros
+                        _view_like(s.grads, e.offset, e.param).zero_()
         for si, s in enumerate(self.sets):
             first = True
             while self._launched[si] < len(s.layout.buckets):
@@ -399,6 +417,8 @@ class FlatEngine:
             self._launched[si] = 0
             for i in range(len(s.ready)):
                 s.ready[i] = 0
+            for i in range(len(self._got[si])):
+                self._got[si][i] = False
         self.steps += 1
 
     def step_buckets(self) -> None:
@@ -406,6 +426,11 @@ class FlatEngine:
         self.finish()
 
     def zero_grad(self) -> None:
+        if self._steal:
+            for s in self.sets:
+                for e in s.layout.entries:
+                    e.param.grad = None  # nothing to clear: the next backward hands over fresh gradient tensors
+            return
         for s in self.sets:
             s.grads.zero_()
 

@@ -376,3 +376,19 @@ def test_tcgen05_linear_act_matches_torch(plane, tokens, in_f, out_f, act):
     assert torch.allclose(x.grad.float(), xf.grad, atol=5e-2, rtol=5e-2)
     assert torch.allclose(w.grad.float(), wf.grad, atol=2e-1 * (tokens / 256) ** 0.5, rtol=5e-2)
     assert torch.allclose(b.grad.float(), bf.grad, atol=2e-1 * (tokens / 256) ** 0.5, rtol=5e-2)
+
+
+@pytest.mark.parametrize("N,C,H,W", [(4, 64, 112, 112), (2, 8, 7, 9), (3, 16, 10, 10)])
+def test_maxpool3x3s2_matches_torch(plane, N, C, H, W):
+    from kungfu_b200.ops.pool import max_pool3x3s2
+
+    torch.manual_seed(H * W)
+    x = torch.randn(N, C, H, W, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_()
+    y = max_pool3x3s2(x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr = x.detach().clone().requires_grad_()
+    yr = torch.nn.functional.max_pool2d(xr, 3, 2, 1)
+    yr.backward(dy)
+    assert y.shape == yr.shape and torch.equal(y, yr)
+    assert torch.allclose(x.grad.float(), xr.grad.float(), atol=1e-2, rtol=1e-2), (x.grad.float() - xr.grad.float()).abs().max()
