@@ -31,14 +31,16 @@ def main():
     torch.cuda.set_device(rt.cuda_index())
     torch.manual_seed(rt.rank)  # replicas start different: gossip has work to do
     cfg = getattr(bert.BertConfig, a.model)()
-    model = bert.Bert(cfg).cuda().to(torch.bfloat16)
+    model = bert.Bert(cfg).cuda()  # fp32 parameters (the gossip blob is the fp32 model, 1.34 GB for BERT-large); bf16 autocast compute
     opt = kf.optimizers.PairAveragingOptimizer(torch.optim.AdamW(model.parameters(), lr=1e-4), named_parameters=model.named_parameters())
     ids = torch.randint(0, cfg.vocab_size, (a.batch, a.seq), device="cuda")
     y = torch.randint(0, cfg.num_labels, (a.batch,), device="cuda")
 
     def step():
         opt.zero_grad()
-        F.cross_entropy(model(ids).float(), y).backward()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = F.cross_entropy(model(ids).float(), y)
+        loss.backward()
         opt.step()
 
     for _ in range(a.warmup):

@@ -28,6 +28,7 @@ import torch
 from ..ops import collective as coll
 from ..runtime import get_runtime
 from ..utils import dtypes
+from ..utils.trace import trace_scope
 from .flat import Bucket, FlatLayout, group_params
 
 HP = dict(lr=0, momentum=1, dampening=2, weight_decay=3, nesterov=4, grad_scale=5, first_step=6, beta1=7, beta2=8, eps=9,
@@ -422,8 +423,9 @@ class FlatEngine:
         self.steps += 1
 
     def step_buckets(self) -> None:
-        self.flush()
-        self.finish()
+        with trace_scope(f"engine.step[{self.mode}]"):
+            self.flush()
+            self.finish()
 
     def zero_grad(self) -> None:
         if self._steal:

@@ -80,7 +80,10 @@ def resize(n: Optional[int] = None) -> Tuple[bool, bool]:
         torch.cuda.synchronize()
         for e in rt._gpu.engines:
             e.prepare_resize()
-    changed, det = f(n)
+    from ..utils.trace import trace_scope
+
+    with trace_scope("resize"):
+        changed, det = f(n)
     if changed and not det and rt._gpu is not None:
         # peer mappings are rebuilt collectively by ALL members of the new cluster in `sync_after_resize`
         for e in rt._gpu.engines:
