@@ -53,6 +53,11 @@ def main():
              f"total kernel time per step: {total / a.steps / 1e3:.2f} ms\n", "| ms/step | share | calls/step | kernel |", "|---:|---:|---:|---|"]
     for e in evs[:32]:
         lines.append(f"| {e.self_device_time_total / a.steps / 1e3:.3f} | {100 * e.self_device_time_total / total:.1f}% | {e.count / a.steps:.0f} | `{e.key[:110]}` |")
+    if a.shapes:
+        lines.append("\n## aten::copy_ / contiguous calls by input shape (layout conversions)\n")
+        for e in sorted(prof.key_averages(group_by_input_shape=True), key=lambda e: -e.device_time_total):
+            if e.key in ("aten::copy_", "aten::contiguous", "aten::clone", "aten::add_", "aten::add") and e.device_time_total > 50 * a.steps:
+                lines.append(f"- {e.key} {e.input_shapes} x{e.count / a.steps:.0f}/step: {e.device_time_total / a.steps / 1e3:.3f} ms/step")
     ours = sum(e.self_device_time_total for e in evs if "kf::" in e.key)
     lines.append(f"\nkungfu_b200 kernels (`kf::`): {100 * ours / total:.1f}% of kernel time")
     text = "\n".join(lines)

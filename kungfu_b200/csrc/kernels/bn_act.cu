@@ -73,16 +73,16 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restric
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) out[i] = sm[i];
 }
 
-// Sum the per-block partials of 32 channels with 8 thread groups striding over the blocks (coalesced 128-byte rows of the
-// partial matrix, 8-way parallel), then a shared-memory fold. A serial per-channel loop over ~600 partials costs ~80 us
+// Sum the per-block partials of 32 channels with 16 thread groups striding over the blocks (coalesced 128-byte rows of the
+// partial matrix, 16-way parallel), then a shared-memory fold. A serial per-channel loop over ~600 partials costs ~80 us
 // of pure load latency per BN layer; this shape brings it to a few microseconds.
 __device__ __forceinline__ bool bn_fold_partials(const float* __restrict__ partial, int nblocks, int C, int c, float& s, float& q) {
-    __shared__ float ss[8][33], sq[8][33];
-    const int cl = threadIdx.x & 31, bg = threadIdx.x >> 5;
+    __shared__ float ss[16][33], sq[16][33];
+    const int cl = threadIdx.x & 31, bg = threadIdx.x >> 5; // 32 channels x 16 partial groups
     float a0 = 0.f, a1 = 0.f;
     if (c < C) {
 #pragma unroll 4
-        for (int b = bg; b < nblocks; b += 8) {
+        for (int b = bg; b < nblocks; b += 16) {
             a0 += partial[(size_t)b * 2 * C + c];
             a1 += partial[(size_t)b * 2 * C + C + c];
         }
@@ -93,7 +93,7 @@ __device__ __forceinline__ bool bn_fold_partials(const float* __restrict__ parti
     if (bg != 0 || c >= C) return false;
     s = q = 0.f;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
+    for (int g = 0; g < 16; ++g) {
         s += ss[g][cl];
         q += sq[g][cl];
     }
@@ -102,7 +102,7 @@ __device__ __forceinline__ bool bn_fold_partials(const float* __restrict__ parti
 
 // reduce partials, produce mean / invstd / scale / shift, update the running statistics. grid = ceil(C / 32), block = 256
 template <typename P>
-__global__ void __launch_bounds__(256) bn_fwd_finalize_kernel(const float* __restrict__ partial, int nblocks, size_t rows, int C,
+__global__ void __launch_bounds__(512) bn_fwd_finalize_kernel(const float* __restrict__ partial, int nblocks, size_t rows, int C,
                                                               const P* __restrict__ gamma, const P* __restrict__ beta, float eps, float momentum,
                                                               float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                                               float* __restrict__ scale_out, float* __restrict__ shift_out, P* running_mean,
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __re
 // dgamma / dbeta (parameter dtype) and the per-channel coefficients of the elementwise pass:
 //   dx = a * (dz - b - xhat * c),  a = gamma * invstd, b = sum(dz) / M, c = sum(dz * xhat) / M
 template <typename P>
-__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, size_t rows, int C,
+__global__ void __launch_bounds__(512) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblocks, size_t rows, int C,
                                                               const P* __restrict__ gamma, const float* __restrict__ invstd,
                                                               P* __restrict__ dgamma, P* __restrict__ dbeta, float* __restrict__ coef /*[3][C]*/) {
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -271,7 +271,7 @@ int bn_grid(size_t nvec, int C) {
     // every thread must keep a fixed channel vector: total threads is a multiple of C/8 (C/8 divides 256 or equals it)
     size_t blocks = (nvec + (size_t)kBnThreads * 4 - 1) / ((size_t)kBnThreads * 4);
     if (blocks < 1) blocks = 1;
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks > 148 * 8) blocks = 148 * 8; // 8 x 256 threads per SM: full occupancy keeps enough loads in flight for HBM
     if (C / 8 > kBnThreads) {
         const size_t k = (C / 8) / kBnThreads; // blocks must come in groups of k
         blocks = (blocks + k - 1) / k * k;
@@ -318,7 +318,7 @@ void launch_bn_fwd(const void* x, const void* res, void* y, uint8_t* mask, int d
     const int blocks = bn_grid(nvec, C);
     const size_t smem = 2 * (size_t)C * sizeof(float);
     KF_BN_T(dtype, (bn_stats_kernel<T><<<blocks, kBnThreads, smem, st>>>((const T*)x, rows, C, partial)));
-    KF_BN_P(pdtype, (bn_fwd_finalize_kernel<P><<<(C + 31) / 32, 256, 0, st>>>(partial, blocks, rows, C, (const P*)gamma, (const P*)beta, eps,
+    KF_BN_P(pdtype, (bn_fwd_finalize_kernel<P><<<(C + 31) / 32, 512, 0, st>>>(partial, blocks, rows, C, (const P*)gamma, (const P*)beta, eps,
                                                                                 momentum, mean, invstd, scale, shift, (P*)running_mean,
                                                                                 (P*)running_var)));
     launch_bn_apply(x, res, y, mask, dtype, rows, C, scale, shift, relu, st);
@@ -353,7 +353,7 @@ void launch_bn_bwd(const void* dy, const void* x, const uint8_t* mask, void* dx,
     if (relu && !mask) throw std::runtime_error("kungfu_b200 bn_act: relu backward needs the mask");
     if (relu) KF_BN_T(dtype, (bn_bwd_reduce_kernel<T, true><<<blocks, kBnThreads, smem, st>>>((const T*)dy, (const T*)x, mask, rows, C, mean, invstd, partial)));
     else KF_BN_T(dtype, (bn_bwd_reduce_kernel<T, false><<<blocks, kBnThreads, smem, st>>>((const T*)dy, (const T*)x, mask, rows, C, mean, invstd, partial)));
-    KF_BN_P(pdtype, (bn_bwd_finalize_kernel<P><<<(C + 31) / 32, 256, 0, st>>>(partial, blocks, rows, C, (const P*)gamma, invstd, (P*)dgamma,
+    KF_BN_P(pdtype, (bn_bwd_finalize_kernel<P><<<(C + 31) / 32, 512, 0, st>>>(partial, blocks, rows, C, (const P*)gamma, invstd, (P*)dgamma,
                                                                                 (P*)dbeta, coef)));
 #define KF_BN_BWD(RES, RELU)                                                                                                              \
     KF_BN_T(dtype, (bn_bwd_apply_kernel<T, RES, RELU><<<blocks, kBnThreads, 0, st>>>((const T*)dy, (const T*)x, mask, (T*)dx, (T*)dres, nvec, C, \
