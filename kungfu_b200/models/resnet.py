@@ -89,7 +89,29 @@ class _Down(nn.Sequential):
         super().__init__(conv1x1(i, o, stride), BNAct(o, relu=False))
 
 
+def stem_conv_s2d(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """The 7x7 / stride-2 / pad-3 stem convolution evaluated as a 4x4 / stride-1 convolution on a space-to-depth(2) input.
+
+    Identical math (the 7x7 kernel is zero-padded to 8x8 at the front and folded 2x2 into channels), but the GEMM sees
+    C_in = 12 (padded to 16) instead of 3, so cuDNN runs its Blackwell tensor-core kernels instead of the legacy
+    `sm80_xmma` / padded `align8` paths that make the C_in = 3 stem cost 2.2 ms per step at batch 256
+    (profiles/resnet50_step_cupti.md). The parameter keeps its [64, 3, 7, 7] shape; gradients flow back through the fold.
+    """
+    N, C, H, W = x.shape
+    O = weight.shape[0]
+    w8 = F.pad(weight, (1, 0, 1, 0))  # [O, C, 8, 8], zero tap in front: kh' = kh + 1 = 2a + b
+    w4 = w8.reshape(O, C, 4, 2, 4, 2).permute(0, 3, 5, 1, 2, 4).reshape(O, 4 * C, 4, 4)  # channels ordered (b, b2, c)
+    cpad = (-4 * C) % 8
+    w4 = F.pad(w4, (0, 0, 0, 0, 0, cpad)).contiguous(memory_format=torch.channels_last)
+    t = x.permute(0, 2, 3, 1)  # NHWC view
+    t = t.reshape(N, H // 2, 2, W // 2, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(N, H // 2, W // 2, 4 * C)
+    t = F.pad(t, (0, cpad, 2, 1, 2, 1))  # channels -> multiple of 8; ih = 2 (oh - 2 + a) + b => pad 2 before, 1 after
+    return F.conv2d(t.permute(0, 3, 1, 2), w4)
+
+
 class ResNet(nn.Module):
+    s2d_stem = True  # use `stem_conv_s2d` for CUDA inputs with even spatial size
+
     def __init__(self, block: Type[nn.Module], layers: List[int], num_classes: int = 1000) -> None:
         super().__init__()
         self.inplanes = 64
@@ -118,7 +140,11 @@ class ResNet(nn.Module):
         return nn.Sequential(*layers)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        x = self.maxpool(self.bn1(self.conv1(x)))
+        if ResNet.s2d_stem and x.is_cuda and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
+            x = stem_conv_s2d(x, self.conv1.weight)
+        else:
+            x = self.conv1(x)
+        x = self.maxpool(self.bn1(x))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(torch.flatten(self.avgpool(x), 1))
 

@@ -242,3 +242,20 @@ def test_flat_layout_buckets():
         lo7, hi7 = lay.shard_range(b, 8, 7)
         assert lo0 == b.start and hi7 <= b.start + b.numel and hi0 - lo0 <= lay.shard_elems(b, 8)
     assert lay.digest() == FlatLayout(ps, torch.bfloat16, 100 * 1024).digest()
+
+
+def test_s2d_stem_equals_plain_conv():
+    """The space-to-depth stem is the same function (and has the same weight gradient) as the 7x7/2 convolution."""
+    import torch.nn.functional as F
+
+    from kungfu_b200.models.resnet import stem_conv_s2d
+
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 32, 40).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(64, 3, 7, 7, requires_grad=True)
+    y0, y1 = F.conv2d(x, w, None, 2, 3), stem_conv_s2d(x, w)
+    assert y0.shape == y1.shape and torch.allclose(y0, y1, atol=1e-4)
+    g = torch.randn_like(y0)
+    (g0,) = torch.autograd.grad(y0, w, g, retain_graph=True)
+    (g1,) = torch.autograd.grad(y1, w, g)
+    assert torch.allclose(g0, g1, atol=1e-3)
