@@ -267,11 +267,15 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
     }
 }
 
-int bn_grid(size_t nvec, int C) {
+// Element-wise passes want full occupancy (8 x 256 threads per SM keep enough loads in flight for HBM); the reducing
+// passes pay a per-block epilogue (shared-memory fold + 2C partials), so they use fewer, longer-running blocks.
+int bn_grid(size_t nvec, int C, bool reducing = false) {
     // every thread must keep a fixed channel vector: total threads is a multiple of C/8 (C/8 divides 256 or equals it)
-    size_t blocks = (nvec + (size_t)kBnThreads * 4 - 1) / ((size_t)kBnThreads * 4);
+    const size_t per_block = (size_t)kBnThreads * (reducing ? 16 : 4);
+    size_t blocks = (nvec + per_block - 1) / per_block;
     if (blocks < 1) blocks = 1;
-    if (blocks > 148 * 8) blocks = 148 * 8; // 8 x 256 threads per SM: full occupancy keeps enough loads in flight for HBM
+    const size_t cap = reducing ? 148 * 4 : 148 * 8;
+    if (blocks > cap) blocks = cap;
     if (C / 8 > kBnThreads) {
         const size_t k = (C / 8) / kBnThreads; // blocks must come in groups of k
         blocks = (blocks + k - 1) / k * k;
@@ -292,7 +296,7 @@ void bn_check(size_t rows, int C) {
 
 int bn_num_blocks(size_t rows, int C) {
     bn_check(rows, C);
-    return bn_grid(rows * (size_t)(C / 8), C);
+    return bn_grid(rows * (size_t)(C / 8), C, true);
 }
 
 #define KF_BN_T(dtype, CALL)                                                                   \
@@ -315,7 +319,7 @@ void launch_bn_fwd(const void* x, const void* res, void* y, uint8_t* mask, int d
                    float* invstd, float* scale, float* shift, cudaStream_t st) {
     bn_check(rows, C);
     const size_t nvec = rows * (size_t)(C / 8);
-    const int blocks = bn_grid(nvec, C);
+    const int blocks = bn_grid(nvec, C, true);
     const size_t smem = 2 * (size_t)C * sizeof(float);
     KF_BN_T(dtype, (bn_stats_kernel<T><<<blocks, kBnThreads, smem, st>>>((const T*)x, rows, C, partial)));
     KF_BN_P(pdtype, (bn_fwd_finalize_kernel<P><<<(C + 31) / 32, 512, 0, st>>>(partial, blocks, rows, C, (const P*)gamma, (const P*)beta, eps,
@@ -348,12 +352,13 @@ void launch_bn_bwd(const void* dy, const void* x, const uint8_t* mask, void* dx,
                    cudaStream_t st) {
     bn_check(rows, C);
     const size_t nvec = rows * (size_t)(C / 8);
+    const int rblocks = bn_grid(nvec, C, true);
     const int blocks = bn_grid(nvec, C);
     const size_t smem = 2 * (size_t)C * sizeof(float);
     if (relu && !mask) throw std::runtime_error("kungfu_b200 bn_act: relu backward needs the mask");
-    if (relu) KF_BN_T(dtype, (bn_bwd_reduce_kernel<T, true><<<blocks, kBnThreads, smem, st>>>((const T*)dy, (const T*)x, mask, rows, C, mean, invstd, partial)));
-    else KF_BN_T(dtype, (bn_bwd_reduce_kernel<T, false><<<blocks, kBnThreads, smem, st>>>((const T*)dy, (const T*)x, mask, rows, C, mean, invstd, partial)));
-    KF_BN_P(pdtype, (bn_bwd_finalize_kernel<P><<<(C + 31) / 32, 512, 0, st>>>(partial, blocks, rows, C, (const P*)gamma, invstd, (P*)dgamma,
+    if (relu) KF_BN_T(dtype, (bn_bwd_reduce_kernel<T, true><<<rblocks, kBnThreads, smem, st>>>((const T*)dy, (const T*)x, mask, rows, C, mean, invstd, partial)));
+    else KF_BN_T(dtype, (bn_bwd_reduce_kernel<T, false><<<rblocks, kBnThreads, smem, st>>>((const T*)dy, (const T*)x, mask, rows, C, mean, invstd, partial)));
+    KF_BN_P(pdtype, (bn_bwd_finalize_kernel<P><<<(C + 31) / 32, 512, 0, st>>>(partial, rblocks, rows, C, (const P*)gamma, invstd, (P*)dgamma,
                                                                                 (P*)dbeta, coef)));
 #define KF_BN_BWD(RES, RELU)                                                                                                              \
     KF_BN_T(dtype, (bn_bwd_apply_kernel<T, RES, RELU><<<blocks, kBnThreads, 0, st>>>((const T*)dy, (const T*)x, mask, (T*)dx, (T*)dres, nvec, C, \

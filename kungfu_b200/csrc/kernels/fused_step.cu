@@ -433,36 +433,48 @@ __global__ void __launch_bounds__(512) pair_avg_kernel(const __grid_constant__ M
     const Hyper h = load_hyper(a.hyper);
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t v = tid; v < a.nvec; v += stride) {
-        Vec16 ov;
-        if (vr != 0) ov = ld_stream(src + v * 16); // NVLink read issued first
-        AccVec<T> p = unpack<T>(ld_plain(P + v * 16));
-        const size_t idx = v * L;
-        float g[L];
-        if (a.do_step) load_lanes_rt<L>(a.grads, a.grad_dtype, idx, g);
-        F32Lanes<L> m1, m2;
-        if (a.do_step && a.s1) m1.load(a.s1 + idx);
-        else m1.zero();
-        if (a.do_step && KIND == kOptAdam && a.s2) m2.load(a.s2 + idx);
-        else m2.zero();
-        if (vr != 0) {
-            const AccVec<T> o = unpack<T>(ov);
+    // four NVLink reads are issued per thread before any of them is consumed: a peer load has ~2-3 us of latency, so the
+    // pull needs megabytes in flight to approach link bandwidth
+    constexpr int U = 4;
+    for (size_t v0 = tid; v0 < a.nvec; v0 += stride * U) {
+        Vec16 ovs[U];
 #pragma unroll
-            for (int j = 0; j < L; ++j) p.a[j] = (typename Elem<T>::Acc)(0.5f * ((float)p.a[j] + (float)o.a[j]));
+        for (int u = 0; u < U; ++u) {
+            const size_t v = v0 + (size_t)u * stride;
+            if (vr != 0 && v < a.nvec) ovs[u] = ld_stream(src + v * 16);
         }
-        if (a.do_step) {
 #pragma unroll
-            for (int j = 0; j < L; ++j) {
-                float w = (float)p.a[j];
-                opt_update<KIND>(w, g[j] * h.v[kHpGradScale], m1.f[j], m2.f[j], h);
-                p.a[j] = (typename Elem<T>::Acc)w;
+        for (int u = 0; u < U; ++u) {
+            const size_t v = v0 + (size_t)u * stride;
+            if (v >= a.nvec) break;
+            AccVec<T> p = unpack<T>(ld_plain(P + v * 16));
+            const size_t idx = v * L;
+            float g[L];
+            if (a.do_step) load_lanes_rt<L>(a.grads, a.grad_dtype, idx, g);
+            F32Lanes<L> m1, m2;
+            if (a.do_step && a.s1) m1.load(a.s1 + idx);
+            else m1.zero();
+            if (a.do_step && KIND == kOptAdam && a.s2) m2.load(a.s2 + idx);
+            else m2.zero();
+            if (vr != 0) {
+                const AccVec<T> o = unpack<T>(ovs[u]);
+#pragma unroll
+                for (int j = 0; j < L; ++j) p.a[j] = (typename Elem<T>::Acc)(0.5f * ((float)p.a[j] + (float)o.a[j]));
             }
-            if (a.s1) m1.store(a.s1 + idx);
-            if (KIND == kOptAdam && a.s2) m2.store(a.s2 + idx);
+            if (a.do_step) {
+#pragma unroll
+                for (int j = 0; j < L; ++j) {
+                    float w = (float)p.a[j];
+                    opt_update<KIND>(w, g[j] * h.v[kHpGradScale], m1.f[j], m2.f[j], h);
+                    p.a[j] = (typename Elem<T>::Acc)w;
+                }
+                if (a.s1) m1.store(a.s1 + idx);
+                if (KIND == kOptAdam && a.s2) m2.store(a.s2 + idx);
+            }
+            const Vec16 res = pack<T>(p);
+            st_plain(P + v * 16, res);
+            st_stream(pub + v * 16, res);
         }
-        const Vec16 res = pack<T>(p);
-        st_plain(P + v * 16, res);
-        st_stream(pub + v * 16, res);
     }
     __syncthreads();
     if (threadIdx.x == 0 && vr != 0 && pair_torn(m, a.target, a.ver_off, vr) && m.status) *((volatile uint32_t*)&m.status[5]) = m.status[5] + 1u;
@@ -493,7 +505,15 @@ __global__ void __launch_bounds__(512) pull_kernel(const __grid_constant__ MeshA
     char* D = reinterpret_cast<char*>(a.dst);
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t v = tid; v < a.nvec; v += stride) st_plain(D + v * 16, ld_stream(src + v * 16));
+    for (size_t v0 = tid; v0 < a.nvec; v0 += stride * 4) {
+        Vec16 t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (v0 + (size_t)u * stride < a.nvec) t[u] = ld_stream(src + (v0 + (size_t)u * stride) * 16);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (v0 + (size_t)u * stride < a.nvec) st_plain(D + (v0 + (size_t)u * stride) * 16, t[u]);
+    }
     __syncthreads();
     if (threadIdx.x == 0 && pair_torn(m, a.target, a.ver_off, vr)) atomicAdd(&a.ok[1], 1u);
 }

@@ -19,7 +19,7 @@ class _MaxPool3x3s2(torch.autograd.Function):
     def forward(ctx, x):
         N, C, H, W = x.shape
         OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
-        y = torch.empty((N, C, OH, OW), dtype=x.dtype, device=x.device).contiguous(memory_format=torch.channels_last)
+        y = torch.empty((N, C, OH, OW), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
         idx = torch.empty(N * OH * OW * C, dtype=torch.uint8, device=x.device)
         _ext().maxpool3x3s2_fwd(x.data_ptr(), y.data_ptr(), idx.data_ptr(), dtypes.dtype_code(x.dtype), N, H, W, C,
                                 torch.cuda.current_stream().cuda_stream)
@@ -32,7 +32,7 @@ class _MaxPool3x3s2(torch.autograd.Function):
         (idx,) = ctx.saved_tensors
         N, C, H, W = ctx.shape
         dy = dy.contiguous(memory_format=torch.channels_last)
-        dx = torch.empty((N, C, H, W), dtype=dy.dtype, device=dy.device).contiguous(memory_format=torch.channels_last)
+        dx = torch.empty((N, C, H, W), dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
         _ext().maxpool3x3s2_bwd(dy.data_ptr(), idx.data_ptr(), dx.data_ptr(), dtypes.dtype_code(dy.dtype), N, H, W, C,
                                 torch.cuda.current_stream().cuda_stream)
         return dx

@@ -370,7 +370,7 @@ class FlatEngine:
         for s in self.sets:
             lay = s.layout
             dt = dtypes.dtype_code(lay.dtype)
-            blocks = coll.pick_blocks(lay.nbytes, 1, False, max(self.max_blocks, 64))
+            blocks = coll.pick_blocks(lay.nbytes, 1, False, 148)  # side stream at the end of a step: use every SM
             self.ext.pair_avg(self.arena.mesh, 1, target, s.x_off, s.x_off2, s.ver_off, s.params.data_ptr(), dt, lay.nbytes,
                               s.grads.data_ptr(), dt, ptr(s.s1[0]), ptr(s.s2[0]), s.hyper.data_ptr(), kind, 1 if do_step else 0,
                               s.done_counter.data_ptr(), blocks, self.threads, cs.cuda_stream)
