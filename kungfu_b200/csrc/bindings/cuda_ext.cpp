@@ -121,6 +121,11 @@ PYBIND11_MODULE(_kfcuda, m) {
               launch_pull(mesh.args(channel), target, pub0, pub1, ver_off, P<void>(dst), nbytes, P<uint32_t>(ok), blocks,
                           threads, S(st));
           });
+    m.def("pull_tma",
+          [](const PeerMesh& mesh, int channel, int target, size_t pub0, size_t pub1, size_t ver_off, uintptr_t dst, size_t nbytes,
+             uintptr_t ok, int blocks, uintptr_t st) {
+              launch_pull_tma(mesh.args(channel), target, pub0, pub1, ver_off, P<void>(dst), nbytes, P<uint32_t>(ok), blocks, S(st));
+          });
     m.def("broadcast",
           [](const PeerMesh& mesh, int channel, int algo, size_t off, size_t nbytes, int root, int blocks, int threads,
              uintptr_t st) { launch_broadcast(algo, mesh.args(channel), off, nbytes, root, blocks, threads, S(st)); });

@@ -51,6 +51,10 @@ void launch_publish(const MeshArgs& m, size_t pub_off0, size_t pub_off1, size_t 
 void launch_pull(const MeshArgs& m, int target, size_t pub_off0, size_t pub_off1, size_t ver_off, void* dst,
                  size_t nbytes, uint32_t* ok, int blocks, int threads, cudaStream_t st);
 
+// ---- tma_copy.cu: the same pull driven by the TMA engine (cp.async.bulk, 4-stage smem pipeline, one thread per CTA)
+void launch_pull_tma(const MeshArgs& m, int target, size_t pub_off0, size_t pub_off1, size_t ver_off, void* dst, size_t nbytes, uint32_t* ok,
+                     int blocks, cudaStream_t st);
+
 // ---- misc.cu
 void launch_broadcast(int algo, const MeshArgs& m, size_t off, size_t nbytes, int root, int blocks, int threads,
                       cudaStream_t st);

@@ -10,6 +10,8 @@ from __future__ import annotations
 
 from typing import Dict, Optional, Tuple
 
+import os
+
 import torch
 
 from ..runtime import get_runtime
@@ -57,6 +59,9 @@ def save_variable(t: torch.Tensor, name: str, version: Optional[int] = None) -> 
 _local_store: Dict[Tuple[str, Optional[int]], torch.Tensor] = {}
 
 
+_TMA_MIN_BYTES = int(os.environ.get("KUNGFU_PULL_TMA_MIN_BYTES", str(256 << 10)))
+
+
 def request_variable(target: int, name: str, shape=None, dtype=None, version: Optional[int] = None,
                      template: Optional[torch.Tensor] = None, device=None) -> Tuple[bool, torch.Tensor]:
     """Pull the blob `name` last saved by rank `target`. Returns (ok, tensor); ok is False (tensor untouched/zero)
@@ -70,8 +75,14 @@ def request_variable(target: int, name: str, shape=None, dtype=None, version: Op
         s = _gpu_slot(name, nb)
         st = torch.cuda.current_stream()
         tmp = torch.empty(s["nbytes"], dtype=torch.uint8, device=out.device)
-        rt.gpu.ext.pull(s["arena"].mesh, 1, int(target), s["pub0"], s["pub1"], s["ver"], tmp.data_ptr(), s["nbytes"], s["ok"].data_ptr(),
-                        16, 512, st.cuda_stream)
+        if s["nbytes"] >= _TMA_MIN_BYTES:
+            # large blobs: TMA bulk copies (cp.async.bulk through shared memory), one CTA per 32 KiB chunk up to one per SM
+            blocks = min(148, (s["nbytes"] + 32767) // 32768)
+            rt.gpu.ext.pull_tma(s["arena"].mesh, 1, int(target), s["pub0"], s["pub1"], s["ver"], tmp.data_ptr(), s["nbytes"],
+                                s["ok"].data_ptr(), blocks, st.cuda_stream)
+        else:
+            rt.gpu.ext.pull(s["arena"].mesh, 1, int(target), s["pub0"], s["pub1"], s["ver"], tmp.data_ptr(), s["nbytes"],
+                            s["ok"].data_ptr(), 16, 512, st.cuda_stream)
         ok = int(s["ok"][0].item()) != 0
         if ok:
             out.view(-1).view(torch.uint8).copy_(tmp[:nb])

@@ -151,6 +151,16 @@ def check_pull_publish(rt, log):
         if ok[0].item() != v or not torch.all(dst == float(100 * target + v)):
             fails += 1
             log(f"FAIL pull v={v} got version {ok[0].item()} value {dst[0].item()}")
+        # the TMA-driven pull (cp.async.bulk pipeline) must return the same bytes, including a ragged last chunk
+        for nb in (n * 4, n * 4 - 48, 4096):
+            dst.zero_()
+            ok.zero_()
+            ext.pull_tma(arena.mesh, 1, target, pub0, pub1, ver, dst.data_ptr(), nb, ok.data_ptr(), 148, st)
+            torch.cuda.synchronize()
+            k = nb // 4
+            if ok[0].item() != v or not torch.all(dst[:k] == float(100 * target + v)) or not torch.all(dst[k:] == 0):
+                fails += 1
+                log(f"FAIL pull_tma v={v} nbytes={nb} got version {ok[0].item()} value {dst[0].item()}")
         coll.barrier()
     return fails
 
