@@ -52,10 +52,12 @@ if _san in ("thread", "address"):
 def _cutlass_root():
     """CUTLASS / CuTe header tree vendored in the image (used by gemm_sm100.cu only). None -> that kernel is stubbed."""
     cands = [os.environ.get("CUTLASS_HOME", "")]
-    try:
-        import flashinfer  # noqa: F401
+    try:  # locate the package directory without importing it (importing flashinfer drags in half the image)
+        import importlib.util
 
-        cands.append(str(Path(flashinfer.__file__).resolve().parent / "data" / "cutlass"))
+        spec = importlib.util.find_spec("flashinfer")
+        if spec is not None and spec.origin:
+            cands.append(str(Path(spec.origin).resolve().parent / "data" / "cutlass"))
     except Exception:
         pass
     sp = sysconfig.get_paths()["purelib"]

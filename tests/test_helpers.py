@@ -1,0 +1,168 @@
+"""Dataset helpers, experimental tools and shell launch helpers (reference: srcs/python/kungfu/tensorflow/v1/helpers/*,
+experimental/{atari_pingpong,gradient_noise}, scripts/launcher.sh)."""
+import os
+import pickle
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from test_runtime_multiproc import ROOT, kungfu_run, ports
+
+from kungfu_b200 import helpers
+from kungfu_b200.helpers import cifar, idx, imagenet, mnist
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.int8, np.int16, np.int32, np.float32, np.float64])
+@pytest.mark.parametrize("gz", [False, True])
+def test_idx_roundtrip(tmp_path, dtype, gz):
+    a = (np.random.RandomState(0).randn(3, 4, 5) * 50).astype(dtype)
+    path = str(tmp_path / ("a.idx.gz" if gz else "a.idx"))
+    idx.write_idx_file(path, a)
+    b = idx.read_idx_file(path)
+    assert b.dtype == a.dtype and b.shape == a.shape and (a == b).all()
+    if not gz:  # header layout: 0 0 <code> <rank> then big-endian dims
+        raw = open(path, "rb").read()
+        assert raw[:2] == b"\0\0" and raw[3] == 3 and raw[4:16] == bytes([0, 0, 0, 3, 0, 0, 0, 4, 0, 0, 0, 5])
+
+
+def test_idx_rejects_bad_input(tmp_path):
+    p = tmp_path / "bad.idx"
+    p.write_bytes(b"\x01\x00\x08\x01\x00\x00\x00\x01\x00")
+    with pytest.raises(ValueError):
+        idx.read_idx_file(str(p))
+    p.write_bytes(b"\x00\x00\x08\x01\x00\x00\x00\x09\x00")  # promises 9 bytes, has 1
+    with pytest.raises(ValueError):
+        idx.read_idx_file(str(p))
+    with pytest.raises(ValueError):
+        idx.write_idx_file(str(tmp_path / "c.idx"), np.zeros(3, np.complex64))
+
+
+def test_npz_to_idx_tar(tmp_path):
+    src = str(tmp_path / "w.npz")
+    np.savez(src, a=np.arange(6, dtype=np.float32).reshape(2, 3), b=np.arange(4, dtype=np.int32))
+    tar = idx.npz2idxtar(src)
+    assert tar.endswith("w.idx.tar")
+    back = idx.idxtar2dict(tar)
+    assert set(back) == {"a", "b"} and (back["a"] == np.arange(6).reshape(2, 3)).all() and back["b"].dtype == np.int32
+
+
+def test_mnist_loader(tmp_path):
+    sets = mnist.synthetic(100, 20, seed=3)
+    mnist.write_datasets(str(tmp_path), sets)
+    raw = mnist.load_datasets(str(tmp_path))
+    assert raw.train.images.shape == (100, 28, 28) and raw.train.images.dtype == np.uint8 and raw.test.labels.shape == (20,)
+    assert (raw.train.images == sets.train.images).all() and (raw.test.labels == sets.test.labels).all()
+    full = mnist.load_datasets(str(tmp_path), normalize=True, one_hot=True, padded=True)
+    assert full.train.images.shape == (100, 32, 32, 1) and full.train.images.dtype == np.float32 and full.train.images.max() <= 1.0
+    assert full.train.labels.shape == (100, 10) and (full.train.labels.sum(1) == 1).all()
+    assert (full.train.labels.argmax(1) == raw.train.labels).all()
+    with pytest.raises(ValueError):
+        mnist.load_mnist_data(str(tmp_path), "valid", False, False)
+
+
+def test_cifar_loaders(tmp_path):
+    rng = np.random.RandomState(0)
+    d10 = tmp_path / "cifar-10-batches-py"
+    d10.mkdir()
+    for name in [f"data_batch_{i}" for i in range(1, 6)] + ["test_batch"]:
+        with open(d10 / name, "wb") as f:
+            pickle.dump({b"data": rng.randint(0, 256, (20, 3072), dtype=np.uint8), b"labels": [int(v) for v in rng.randint(0, 10, 20)]}, f)
+    sets = cifar.Cifar10Loader(str(tmp_path), normalize=True, one_hot=True).load_datasets()
+    assert sets.train.images.shape == (100, 32, 32, 3) and sets.train.images.dtype == np.float32 and sets.train.labels.shape == (100, 10)
+    assert sets.test.images.shape == (20, 32, 32, 3)
+    d100 = tmp_path / "cifar-100-python"
+    d100.mkdir()
+    for name, n in (("train", 30), ("test", 10)):
+        with open(d100 / name, "wb") as f:
+            pickle.dump({b"data": rng.randint(0, 256, (n, 3072), dtype=np.uint8), b"fine_labels": [int(v) for v in rng.randint(0, 100, n)]}, f)
+    s100 = cifar.Cifar100Loader(str(tmp_path)).load_datasets()
+    assert s100.train.images.shape == (30, 32, 32, 3) and s100.train.images.dtype == np.uint8 and s100.test.labels.max() < 100
+    # the raw layout is planar RGB: pixel (0,0) of image 0 is bytes 0, 1024, 2048
+    first = pickle.load(open(d100 / "train", "rb"), encoding="bytes")[b"data"][0]
+    assert tuple(s100.train.images[0, 0, 0]) == (first[0], first[1024], first[2048])
+
+
+def test_imagenet_pipeline(tmp_path):
+    rng = np.random.RandomState(0)
+    for i in range(2):
+        imagenet.write_shard(str(tmp_path / f"train-{i:05d}-of-00002.npz"), rng.randint(0, 256, (10, 40, 48, 3), dtype=np.uint8),
+                             np.arange(10 * i, 10 * i + 10))
+    batches = list(imagenet.create_dataset(str(tmp_path), batch_size=8, n=2))
+    assert len(batches) == 2 and batches[0][0].shape == (8, 40, 48, 3) and batches[1][1].tolist() == list(range(8, 16))
+    assert len(list(imagenet.create_dataset(str(tmp_path), batch_size=8, n=1))) == 1  # n limits the shard count
+    r0 = [y for _, y in imagenet.create_dataset(str(tmp_path), batch_size=5, n=2, shard=(0, 2))]
+    r1 = [y for _, y in imagenet.create_dataset(str(tmp_path), batch_size=5, n=2, shard=(1, 2))]
+    assert sorted(torch.cat(r0 + r1).tolist()) == list(range(20))  # the two workers cover every sample once
+    g = torch.Generator().manual_seed(0)
+    x = imagenet.train_augment(batches[0][0], out_hw=(32, 32), dtype=torch.float32, generator=g)
+    assert x.shape == (8, 3, 32, 32) and x.is_contiguous(memory_format=torch.channels_last) and torch.isfinite(x).all()
+    g2 = torch.Generator().manual_seed(0)
+    assert torch.equal(x, imagenet.train_augment(batches[0][0], out_hw=(32, 32), dtype=torch.float32, generator=g2))
+    # with the full-image crop, no flip randomness left out and no colour jitter, a constant image stays constant
+    const = torch.full((2, 40, 48, 3), 128, dtype=torch.uint8)
+    y = imagenet.train_augment(const, out_hw=(16, 16), color=False, dtype=torch.float32)
+    want = torch.tensor([(128 / 255 - m) / s for m, s in zip(imagenet.MEAN, imagenet.STD)]).view(1, 3, 1, 1)
+    assert torch.allclose(y, want.expand_as(y), atol=1e-5)
+    e = imagenet.eval_preprocess(const, out_hw=(16, 16), dtype=torch.float32)
+    assert torch.allclose(e, want.expand_as(e), atol=1e-5)
+    img, label = imagenet.record_to_labeled_image({"image": const[0].numpy(), "label": 7}, training=False)
+    assert img.shape == (3, 224, 224) and label == 7
+
+
+def test_random_input_and_units():
+    x, y = helpers.random_input((4, 3), 10)
+    assert x.shape == (4, 3) and 0 <= int(y) < 9
+    assert helpers.show_size(1536) == "1.50Ki" and helpers.show_size(12) == "12" and helpers.show_rate(1 << 30, 0.5) == "2.00GiB/s"
+
+
+def test_plot_noise_parses_launcher_logs(tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "experimental", "gradient_noise"))
+    import plot_noise
+
+    log = tmp_path / "run.log"
+    log.write_text("\n".join([
+        '\x1b[1;32m[127.0.0.1.10000::stdout]\x1b[m {"phase_np": 4, "img_per_s": 100.0, "noise_scale": 60.0}',
+        '[127.0.0.1.10001::stdout] {"noise_scale": 1.0}',
+        'RESULT: 5.0 {"noise_scale": 14.0, "loss": 2.5}',
+        "not json {",
+    ]))
+    s = plot_noise.parse_log(str(log))
+    assert [v for _, v in s["noise_scale"]] == [60.0, 1.0, 14.0] and [v for _, v in s["loss"]] == [2.5]
+    only = plot_noise.parse_log(str(log), worker="10000")
+    assert [v for _, v in only["noise_scale"]] == [60.0, 14.0]  # unprefixed lines are kept, other workers dropped
+    assert plot_noise.ema([1.0, 3.0], 0.5) == [1.0, 2.0] and len(plot_noise.sparkline(list(range(500)))) <= 64
+    assert plot_noise.main([str(log), "--out", str(tmp_path / "n"), "--ema", "0.5"]) == 0
+    assert (tmp_path / "n.csv").read_text().splitlines()[0] == "index,noise_scale,loss,img_per_s"
+
+
+def test_pingpong_data_parallel_policy_gradient(tmp_path):
+    script = os.path.join(ROOT, "experimental", "pingpong", "pingpong.py")
+    ckpt = str(tmp_path / "pp.npz")
+    env = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN")
+    r = subprocess.run([sys.executable, script, "--init", "--checkpoint", ckpt], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=120)
+    assert r.returncode == 0 and os.path.exists(ckpt), r.stdout[-2000:]
+    rport, prange = ports()
+    r = subprocess.run([kungfu_run(), "-q", "-np", "2", "-H", "127.0.0.1:2", "-port", str(rport), "-port-range", prange, sys.executable, script,
+                        "--checkpoint", ckpt, "--batch-size", "1", "--episodes", "3"], env=env, cwd=ROOT, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=240)
+    assert r.returncode == 0 and "replicas identical = True" in r.stdout, r.stdout[-3000:]
+
+
+def test_launcher_sh_helpers(tmp_path):
+    rport, prange = ports()
+    script = tmp_path / "t.sh"
+    script.write_text(f"""
+KF_LAUNCHER_SH={ROOT}/scripts/launcher.sh
+. {ROOT}/scripts/launcher.sh
+export KF_LOGDIR={tmp_path}/logs
+srun echo single-ok
+prun 2 -H 127.0.0.1:2 -port {rport} -port-range {prange} {sys.executable} {ROOT}/examples/torch_simple_example.py
+""")
+    env = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_RUN=kungfu_run(), KUNGFU_CONFIG_LOG_LEVEL="WARN")
+    r = subprocess.run(["sh", str(script)], env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=180)
+    assert r.returncode == 0 and "single-ok" in r.stdout and "rank 1/2" in r.stdout and "BEGIN" in r.stdout and "END" in r.stdout, r.stdout[-3000:]
+    assert os.path.isdir(tmp_path / "logs")
