@@ -38,39 +38,95 @@ template <typename T> struct Vec8 {
     }
 };
 
+// ---- block-level fold of per-thread channel sums -------------------------------------------------------------------
+// Every thread holds sums for one 8-channel vector `cv`; threads of a block that share a vector are folded without atomics
+// (shared-memory float atomics are CAS loops: with C = 64 there are 32 contenders per address and the tail of the kernel
+// costs more than the streaming part). C/8 is a power of two here (bn_check): lanes sharing a vector are first folded with
+// xor-shuffles, the remaining sharers (one per warp or per C/8-thread group) meet in a [groups][2][C] shared array.
+constexpr int kBnUnroll = 4; // independent 16-byte loads in flight per thread and per input tensor
+
+__host__ __device__ inline int bn_fold_groups(int cvn) { return cvn < 32 ? kBnThreads / 32 : (cvn <= kBnThreads ? kBnThreads / cvn : 1); }
+
+__device__ __forceinline__ void bn_block_fold(float (&s)[8], float (&q)[8], int cv, int cvn, int C, float* __restrict__ out, float* sm) {
+    if (cvn > kBnThreads) { // C > 2048: a block covers a slice of the channels, no two threads share one
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            sm[cv * 8 + i] = s[i];
+            sm[C + cv * 8 + i] = q[i];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) out[i] = sm[i];
+        return;
+    }
+    for (int off = cvn; off < 32; off <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s[i] += __shfl_xor_sync(0xffffffffu, s[i], off);
+            q[i] += __shfl_xor_sync(0xffffffffu, q[i], off);
+        }
+    }
+    const int lane = threadIdx.x & 31;
+    const int g = cvn < 32 ? (int)(threadIdx.x >> 5) : (int)threadIdx.x / cvn;
+    if (cvn >= 32 || lane < cvn) {
+        float4* ps = reinterpret_cast<float4*>(sm + (size_t)g * 2 * C + cv * 8);
+        float4* pq = reinterpret_cast<float4*>(sm + (size_t)g * 2 * C + C + cv * 8);
+        ps[0] = make_float4(s[0], s[1], s[2], s[3]);
+        ps[1] = make_float4(s[4], s[5], s[6], s[7]);
+        pq[0] = make_float4(q[0], q[1], q[2], q[3]);
+        pq[1] = make_float4(q[4], q[5], q[6], q[7]);
+    }
+    __syncthreads();
+    const int groups = bn_fold_groups(cvn);
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        float a = 0.f;
+        for (int k = 0; k < groups; ++k) a += sm[(size_t)k * 2 * C + i];
+        out[i] = a;
+    }
+}
+
 // ---- forward: per-block partial sums ------------------------------------------------------------------------
 // partial[block][0][c] = sum x, partial[block][1][c] = sum x^2 over the rows handled by the block
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restrict__ x, size_t rows, int C, float* __restrict__ partial) {
-    extern __shared__ float sm[]; // [2][C]
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
+    extern __shared__ __align__(16) float sm[]; // [groups][2][C]
     const int cvn = C / 8;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const int cv = (int)(tid % cvn);
-    const size_t row0 = tid / cvn, rstride = nthreads / cvn;
+    const size_t rstride = nthreads / cvn;
+    const uint32_t zero = (uint32_t)(rows >> 62); // always 0, opaque to the compiler (see hold4)
+    size_t r = tid / cvn;
     float s[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-#pragma unroll 4
-    for (size_t r = row0; r < rows; r += rstride) {
-        Vec8<T> v;
-        v.load(x + r * C + (size_t)cv * 8);
+    const T* px = x + (size_t)cv * 8;
+    for (; r + (kBnUnroll - 1) * rstride < rows; r += kBnUnroll * rstride) { // kBnUnroll loads issued before the first use
+        Vec16 raw[kBnUnroll];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            s[i] += v.f[i];
-            q[i] = fmaf(v.f[i], v.f[i], q[i]);
+        for (int u = 0; u < kBnUnroll; ++u) raw[u] = ld_ro_stream(px + (r + u * rstride) * C);
+        static_assert(kBnUnroll == 4, "hold4 takes four vectors");
+        hold4(raw[0], raw[1], raw[2], raw[3], zero);
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+            const AccVec<T> v = unpack<T>(raw[u]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                s[i] += v.a[i];
+                q[i] = fmaf(v.a[i], v.a[i], q[i]);
+            }
         }
     }
+    for (; r < rows; r += rstride) {
+        const AccVec<T> v = unpack<T>(ld_ro_stream(px + r * C));
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        atomicAdd(&sm[cv * 8 + i], s[i]);
-        atomicAdd(&sm[C + cv * 8 + i], q[i]);
+        for (int i = 0; i < 8; ++i) {
+            s[i] += v.a[i];
+            q[i] = fmaf(v.a[i], v.a[i], q[i]);
+        }
     }
-    __syncthreads();
-    float* out = partial + (size_t)blockIdx.x * 2 * C;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) out[i] = sm[i];
+    bn_block_fold(s, q, cv, cvn, C, partial + (size_t)blockIdx.x * 2 * C, sm);
 }
 
 // Sum the per-block partials of 32 channels with 16 thread groups striding over the blocks (coalesced 128-byte rows of the
@@ -143,24 +199,42 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
         sc[i] = __ldg(scale + cv * 8 + i);
         sh[i] = __ldg(shift + cv * 8 + i);
     }
-#pragma unroll 2
-    for (size_t v = tid; v < nvec; v += stride) {
-        Vec8<T> a, r;
-        a.load(x + v * 8);
-        if constexpr (RES) r.load(res + v * 8);
+    const uint32_t zero = (uint32_t)(nvec >> 62); // always 0, opaque to the compiler (see hold4)
+    auto body = [&](const Vec16& rx, const Vec16& rr, size_t v) {
+        AccVec<T> a = unpack<T>(rx);
+        AccVec<T> r;
+        if constexpr (RES) r = unpack<T>(rr);
         uint32_t m = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            float z = fmaf(a.f[i], sc[i], sh[i]);
-            if constexpr (RES) z += r.f[i];
+            float z = fmaf(a.a[i], sc[i], sh[i]);
+            if constexpr (RES) z += r.a[i];
             if constexpr (RELU) {
                 m |= (z > 0.f ? 1u : 0u) << i;
                 z = z > 0.f ? z : 0.f;
             }
-            a.f[i] = z;
+            a.a[i] = z;
         }
-        a.store(y + v * 8);
+        st_stream(y + v * 8, pack<T>(a));
         if constexpr (RELU) mask[v] = (uint8_t)m;
+    };
+    size_t v = tid;
+    for (; v + stride < nvec; v += 2 * stride) { // two vectors per trip: all loads issued before the first use
+        Vec16 x0 = ld_ro_stream(x + v * 8), x1 = ld_ro_stream(x + (v + stride) * 8), r0{}, r1{};
+        if constexpr (RES) {
+            r0 = ld_ro_stream(res + v * 8);
+            r1 = ld_ro_stream(res + (v + stride) * 8);
+            hold4(x0, r0, x1, r1, zero);
+        } else {
+            hold2(x0, x1, zero);
+        }
+        body(x0, r0, v);
+        body(x1, r1, v + stride);
+    }
+    for (; v < nvec; v += stride) {
+        Vec16 r0{};
+        if constexpr (RES) r0 = ld_ro_stream(res + v * 8);
+        body(ld_ro_stream(x + v * 8), r0, v);
     }
 }
 
@@ -171,14 +245,14 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __re
                                                                    const uint8_t* __restrict__ mask, size_t rows, int C,
                                                                    const float* __restrict__ mean, const float* __restrict__ invstd,
                                                                    float* __restrict__ partial) {
-    extern __shared__ float sm[];
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
+    extern __shared__ __align__(16) float sm[]; // [groups][2][C]
     const int cvn = C / 8;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const int cv = (int)(tid % cvn);
-    const size_t row0 = tid / cvn, rstride = nthreads / cvn;
+    const size_t rstride = nthreads / cvn;
+    const uint32_t zero = (uint32_t)(rows >> 62); // always 0, opaque to the compiler (see hold4)
+    size_t r = tid / cvn;
     float mu[8], is[8], s[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -186,29 +260,39 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(const T* __re
         is[i] = __ldg(invstd + cv * 8 + i);
         s[i] = q[i] = 0.f;
     }
-#pragma unroll 2
-    for (size_t r = row0; r < rows; r += rstride) {
-        const size_t v = r * cvn + cv;
-        Vec8<T> g, a;
-        g.load(dy + v * 8);
-        a.load(x + v * 8);
-        uint32_t m = 0xffu;
-        if constexpr (RELU) m = mask[v];
+    auto accumulate = [&](const Vec16& rg, const Vec16& ra, uint32_t m) {
+        const AccVec<T> g = unpack<T>(rg), a = unpack<T>(ra);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float dz = (m >> i) & 1u ? g.f[i] : 0.f;
+            const float dz = (m >> i) & 1u ? g.a[i] : 0.f;
             s[i] += dz;
-            q[i] = fmaf(dz, (a.f[i] - mu[i]) * is[i], q[i]);
+            q[i] = fmaf(dz, (a.a[i] - mu[i]) * is[i], q[i]);
         }
-    }
+    };
+    constexpr int U = kBnUnroll / 2; // two tensors per row: 2 * U = kBnUnroll loads in flight
+    for (; r + (U - 1) * rstride < rows; r += U * rstride) {
+        Vec16 rg[U], ra[U];
+        uint32_t m[U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        atomicAdd(&sm[cv * 8 + i], s[i]);
-        atomicAdd(&sm[C + cv * 8 + i], q[i]);
+        for (int u = 0; u < U; ++u) {
+            const size_t v = (r + u * rstride) * cvn + cv;
+            rg[u] = ld_ro_stream(dy + v * 8);
+            ra[u] = ld_ro_stream(x + v * 8);
+            m[u] = 0xffu;
+            if constexpr (RELU) m[u] = mask[v];
+        }
+        static_assert(U == 2, "hold4 takes four vectors");
+        hold4(rg[0], ra[0], rg[1], ra[1], zero);
+#pragma unroll
+        for (int u = 0; u < U; ++u) accumulate(rg[u], ra[u], m[u]);
     }
-    __syncthreads();
-    float* out = partial + (size_t)blockIdx.x * 2 * C;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) out[i] = sm[i];
+    for (; r < rows; r += rstride) {
+        const size_t v = r * cvn + cv;
+        uint32_t m = 0xffu;
+        if constexpr (RELU) m = mask[v];
+        accumulate(ld_ro_stream(dy + v * 8), ld_ro_stream(x + v * 8), m);
+    }
+    bn_block_fold(s, q, cv, cvn, C, partial + (size_t)blockIdx.x * 2 * C, sm);
 }
 
 // dgamma / dbeta (parameter dtype) and the per-channel coefficients of the elementwise pass:
@@ -238,32 +322,42 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const T* __res
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const int cv = (int)(tid % cvn);
-    float mu[8], is[8], ca[8], cb[8], cc[8];
+    // dx = ca * (dz - cb - (x - mu) * is * cc)  folded to  dx = ca * dz + k1 * x + k0  (24 coefficient registers instead of 40)
+    float ca[8], k1[8], k0[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int c = cv * 8 + i;
-        mu[i] = __ldg(mean + c);
-        is[i] = __ldg(invstd + c);
+        const float mu = __ldg(mean + c), is = __ldg(invstd + c), cb = __ldg(coef + C + c), cc = __ldg(coef + 2 * C + c);
         ca[i] = __ldg(coef + c);
-        cb[i] = __ldg(coef + C + c);
-        cc[i] = __ldg(coef + 2 * C + c);
+        k1[i] = -ca[i] * cc * is;
+        k0[i] = -ca[i] * cb - k1[i] * mu;
     }
-#pragma unroll 2
-    for (size_t v = tid; v < nvec; v += stride) {
-        Vec8<T> g, a;
-        g.load(dy + v * 8);
-        a.load(x + v * 8);
-        uint32_t m = 0xffu;
-        if constexpr (RELU) m = mask[v];
-        Vec8<T> dz;
+    const uint32_t zero = (uint32_t)(nvec >> 62); // always 0, opaque to the compiler (see hold4)
+    auto body = [&](const Vec16& rg, const Vec16& rx, uint32_t m, size_t v) {
+        AccVec<T> g = unpack<T>(rg), a = unpack<T>(rx);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float z = (m >> i) & 1u ? g.f[i] : 0.f;
-            dz.f[i] = z;
-            a.f[i] = ca[i] * (z - cb[i] - (a.f[i] - mu[i]) * is[i] * cc[i]);
+            const float z = (m >> i) & 1u ? g.a[i] : 0.f;
+            g.a[i] = z;
+            a.a[i] = fmaf(ca[i], z, fmaf(k1[i], a.a[i], k0[i]));
         }
-        a.store(dx + v * 8);
-        if constexpr (RES) dz.store(dres + v * 8);
+        st_stream(dx + v * 8, pack<T>(a));
+        if constexpr (RES) st_stream(dres + v * 8, pack<T>(g));
+    };
+    size_t v = tid;
+    for (; v + stride < nvec; v += 2 * stride) {
+        Vec16 g0 = ld_ro_stream(dy + v * 8), x0 = ld_ro_stream(x + v * 8);
+        Vec16 g1 = ld_ro_stream(dy + (v + stride) * 8), x1 = ld_ro_stream(x + (v + stride) * 8);
+        uint32_t m0 = 0xffu, m1 = 0xffu;
+        if constexpr (RELU) m0 = mask[v], m1 = mask[v + stride];
+        hold4(g0, x0, g1, x1, zero);
+        body(g0, x0, m0, v);
+        body(g1, x1, m1, v + stride);
+    }
+    for (; v < nvec; v += stride) {
+        uint32_t m = 0xffu;
+        if constexpr (RELU) m = mask[v];
+        body(ld_ro_stream(dy + v * 8), ld_ro_stream(x + v * 8), m, v);
     }
 }
 
@@ -320,7 +414,7 @@ void launch_bn_fwd(const void* x, const void* res, void* y, uint8_t* mask, int d
     bn_check(rows, C);
     const size_t nvec = rows * (size_t)(C / 8);
     const int blocks = bn_grid(nvec, C, true);
-    const size_t smem = 2 * (size_t)C * sizeof(float);
+    const size_t smem = (size_t)bn_fold_groups(C / 8) * 2 * (size_t)C * sizeof(float);
     KF_BN_T(dtype, (bn_stats_kernel<T><<<blocks, kBnThreads, smem, st>>>((const T*)x, rows, C, partial)));
     KF_BN_P(pdtype, (bn_fwd_finalize_kernel<P><<<(C + 31) / 32, 512, 0, st>>>(partial, blocks, rows, C, (const P*)gamma, (const P*)beta, eps,
                                                                                 momentum, mean, invstd, scale, shift, (P*)running_mean,
@@ -354,7 +448,7 @@ void launch_bn_bwd(const void* dy, const void* x, const uint8_t* mask, void* dx,
     const size_t nvec = rows * (size_t)(C / 8);
     const int rblocks = bn_grid(nvec, C, true);
     const int blocks = bn_grid(nvec, C);
-    const size_t smem = 2 * (size_t)C * sizeof(float);
+    const size_t smem = (size_t)bn_fold_groups(C / 8) * 2 * (size_t)C * sizeof(float);
     if (relu && !mask) throw std::runtime_error("kungfu_b200 bn_act: relu backward needs the mask");
     if (relu) KF_BN_T(dtype, (bn_bwd_reduce_kernel<T, true><<<rblocks, kBnThreads, smem, st>>>((const T*)dy, (const T*)x, mask, rows, C, mean, invstd, partial)));
     else KF_BN_T(dtype, (bn_bwd_reduce_kernel<T, false><<<rblocks, kBnThreads, smem, st>>>((const T*)dy, (const T*)x, mask, rows, C, mean, invstd, partial)));

@@ -32,6 +32,28 @@ __device__ __forceinline__ Vec16 ld_stream(const void* p) {
                  : "memory");
     return v;
 }
+// Read-only streaming load for data no kernel in flight writes (activations, gradients): a compiler-visible load, so that
+// several of them can be hoisted ahead of their uses (an `asm volatile` load pins the schedule: each load is consumed
+// before the next one issues, i.e. one 16-byte request in flight per thread).
+__device__ __forceinline__ Vec16 ld_ro_stream(const void* p) {
+    const uint4 u = __ldcs(reinterpret_cast<const uint4*>(p));
+    Vec16 v;
+    v.w[0] = u.x, v.w[1] = u.y, v.w[2] = u.z, v.w[3] = u.w;
+    return v;
+}
+// Scheduling fence. ptxas sinks the later loads of a batch below the arithmetic on the earlier ones (PTX order is not kept,
+// and an empty asm leaves nothing in the PTX to anchor on), which leaves two requests in flight instead of four. Making the
+// first consumed vector data-dependent on the other three pins all four loads ahead of the first use; `zero` is a value the
+// compiler cannot prove to be 0 (callers derive it from a runtime argument), so the LOP3s stay (every word of `a`, or the
+// untouched words are consumed early).
+__device__ __forceinline__ void hold4(Vec16& a, const Vec16& b, const Vec16& c, const Vec16& d, uint32_t zero) {
+    const uint32_t m = (b.w[0] ^ c.w[0] ^ d.w[0]) & zero;
+    a.w[0] ^= m, a.w[1] ^= m, a.w[2] ^= m, a.w[3] ^= m;
+}
+__device__ __forceinline__ void hold2(Vec16& a, const Vec16& b, uint32_t zero) {
+    const uint32_t m = b.w[0] & zero;
+    a.w[0] ^= m, a.w[1] ^= m, a.w[2] ^= m, a.w[3] ^= m;
+}
 __device__ __forceinline__ void st_stream(void* p, const Vec16& v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]),
                  "r"(v.w[3])
