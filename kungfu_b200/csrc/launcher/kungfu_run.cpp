@@ -16,6 +16,8 @@
 //
 // B200 default: every worker sees ALL GPUs (P2P / NVLS need that) and is told its device through
 // KUNGFU_CUDA_VISIBLE_DEVICES; `-allow-nvlink=false` restores the reference's one-visible-GPU isolation.
+#include <arpa/inet.h>
+#include <dirent.h>
 #include <fcntl.h>
 #include <ifaddrs.h>
 #include <net/if.h>
@@ -760,9 +762,42 @@ int monitored_run(const Flags& f, Job job, const Cluster& cluster, uint32_t self
     return 1;
 }
 
+// GPU model names from the driver's procfs (no CUDA context in the launcher); reference: utils.ListNvidiaGPUNames
+std::vector<std::string> list_nvidia_gpu_names() {
+    std::vector<std::string> names;
+    DIR* d = opendir("/proc/driver/nvidia/gpus");
+    if (!d) return names;
+    while (dirent* e = readdir(d)) {
+        if (e->d_name[0] == '.') continue;
+        std::ifstream in(std::string("/proc/driver/nvidia/gpus/") + e->d_name + "/information");
+        std::string line;
+        while (std::getline(in, line))
+            if (line.rfind("Model:", 0) == 0) {
+                auto pos = line.find_first_not_of(" \t", 6);
+                names.push_back(std::string(e->d_name) + " " + (pos == std::string::npos ? "" : line.substr(pos)));
+            }
+    }
+    closedir(d);
+    std::sort(names.begin(), names.end());
+    return names;
+}
+
+// What the job will see: framework / CUDA / NCCL environment, IPv4 interfaces, GPUs (reference: utils.LogKungfuEnv,
+// LogCudaEnv, LogNCCLEnv, LogNICInfo). Debug level only.
 void log_env() {
     for (char** e = environ; *e; ++e)
         if (!strncmp(*e, "KUNGFU_", 7) || !strncmp(*e, "CUDA_", 5) || !strncmp(*e, "NCCL_", 5)) KF_LOGD("env %s", *e);
+    ifaddrs* ifa = nullptr;
+    if (getifaddrs(&ifa) == 0) {
+        for (auto* p = ifa; p; p = p->ifa_next)
+            if (p->ifa_addr && p->ifa_addr->sa_family == AF_INET) {
+                char buf[INET_ADDRSTRLEN] = {0};
+                inet_ntop(AF_INET, &reinterpret_cast<sockaddr_in*>(p->ifa_addr)->sin_addr, buf, sizeof buf);
+                KF_LOGD("nic %s %s", p->ifa_name, buf);
+            }
+        freeifaddrs(ifa);
+    }
+    for (const auto& g : list_nvidia_gpu_names()) KF_LOGD("gpu %s", g.c_str());
 }
 
 } // namespace
