@@ -141,6 +141,7 @@ def check_pull_publish(rt, log):
     if ok[0].item() != 0:
         fails += 1
         log("FAIL pull before publish reported a version")
+    coll.barrier()  # nobody publishes before every rank has done its "nothing there yet" pull
     for v in range(1, 4):
         src = torch.full((n,), float(100 * me + v), device="cuda")
         ext.publish(arena.mesh, 1, pub0, pub1, ver, src.data_ptr(), n * 4, done.data_ptr(), 8, 512, st)
