@@ -219,17 +219,25 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
         if constexpr (RELU) mask[v] = (uint8_t)m;
     };
     size_t v = tid;
-    for (; v + stride < nvec; v += 2 * stride) { // two vectors per trip: all loads issued before the first use
-        Vec16 x0 = ld_ro_stream(x + v * 8), x1 = ld_ro_stream(x + (v + stride) * 8), r0{}, r1{};
-        if constexpr (RES) {
-            r0 = ld_ro_stream(res + v * 8);
-            r1 = ld_ro_stream(res + (v + stride) * 8);
+    if constexpr (RES) {
+        for (; v + stride < nvec; v += 2 * stride) { // two vectors (x + residual each) per trip: four loads before the first use
+            Vec16 x0 = ld_ro_stream(x + v * 8), x1 = ld_ro_stream(x + (v + stride) * 8);
+            Vec16 r0 = ld_ro_stream(res + v * 8), r1 = ld_ro_stream(res + (v + stride) * 8);
             hold4(x0, r0, x1, r1, zero);
-        } else {
-            hold2(x0, x1, zero);
+            body(x0, r0, v);
+            body(x1, r1, v + stride);
         }
-        body(x0, r0, v);
-        body(x1, r1, v + stride);
+    } else {
+        for (; v + 3 * stride < nvec; v += 4 * stride) { // four vectors per trip
+            Vec16 x0 = ld_ro_stream(x + v * 8), x1 = ld_ro_stream(x + (v + stride) * 8);
+            Vec16 x2 = ld_ro_stream(x + (v + 2 * stride) * 8), x3 = ld_ro_stream(x + (v + 3 * stride) * 8);
+            hold4(x0, x1, x2, x3, zero);
+            const Vec16 none{};
+            body(x0, none, v);
+            body(x1, none, v + stride);
+            body(x2, none, v + 2 * stride);
+            body(x3, none, v + 3 * stride);
+        }
     }
     for (; v < nvec; v += stride) {
         Vec16 r0{};

@@ -50,10 +50,6 @@ __device__ __forceinline__ void hold4(Vec16& a, const Vec16& b, const Vec16& c, 
     const uint32_t m = (b.w[0] ^ c.w[0] ^ d.w[0]) & zero;
     a.w[0] ^= m, a.w[1] ^= m, a.w[2] ^= m, a.w[3] ^= m;
 }
-__device__ __forceinline__ void hold2(Vec16& a, const Vec16& b, uint32_t zero) {
-    const uint32_t m = b.w[0] & zero;
-    a.w[0] ^= m, a.w[1] ^= m, a.w[2] ^= m, a.w[3] ^= m;
-}
 __device__ __forceinline__ void st_stream(void* p, const Vec16& v) {
     asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]),
                  "r"(v.w[3])
