@@ -313,6 +313,11 @@ PYBIND11_MODULE(_kfrt, m) {
             py::gil_scoped_release rel;
             p.session()->monitored_all_reduce(mk(send, recv, count, dtype, op, name), tree);
         })
+        .def("subset_all_reduce", [](Peer& p, uintptr_t send, uintptr_t recv, size_t count, int dtype, int op, const std::string& name,
+                                     const std::vector<int32_t>& forest) {
+            py::gil_scoped_release rel;
+            p.session()->subset_all_reduce(mk(send, recv, count, dtype, op, name), forest);
+        })
         .def("cross_all_reduce", [](Peer& p, uintptr_t send, uintptr_t recv, size_t count, int dtype, int op, const std::string& name) {
             py::gil_scoped_release rel;
             p.session()->cross_all_reduce(mk(send, recv, count, dtype, op, name));

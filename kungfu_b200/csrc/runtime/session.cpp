@@ -151,6 +151,19 @@ void Session::monitored_all_reduce(const Workspace& w, const std::vector<int32_t
     run_strategies(w, sl, true);
 }
 
+// All-reduce inside every tree of a forest (father[i] == i marks a root; a root without children keeps its own data).
+// Reference: `SubsetAllReduce` / `subset_all_reduce(t, topology)` (srcs/go/kungfu/session/allreduce.go, ops/collective.py).
+// Peers outside every multi-node tree need not call it at all: no message is addressed to them.
+void Session::subset_all_reduce(const Workspace& w, const std::vector<int32_t>& forest) {
+    StallGuard sg("SubsetAllReduce(" + w.name + ")");
+    if ((int)forest.size() != size()) fail("subset_all_reduce: forest must have one entry per peer");
+    std::vector<int> father(forest.begin(), forest.end());
+    Graph bg;
+    int roots = 0;
+    if (!Graph::from_forest_array(father, bg, roots) || roots < 1) fail("subset_all_reduce: not a forest");
+    run_strategies(w, wrap({GraphPair{default_reduce_graph(bg), bg}}), false);
+}
+
 void Session::cross_all_reduce(const Workspace& w) {
     StallGuard sg("CrossAllReduce(" + w.name + ")");
     run_strategies(w, cross_, false);

@@ -59,6 +59,7 @@ public:
     void all_reduce(const Workspace& w);
     void monitored_all_reduce(const Workspace& w, const std::vector<int32_t>& tree); // tree may be empty
     void cross_all_reduce(const Workspace& w);
+    void subset_all_reduce(const Workspace& w, const std::vector<int32_t>& forest); // independent all-reduce per tree
     void reduce(const Workspace& w);          // result on rank 0
     void broadcast(const Workspace& w);       // from rank 0
     void local_reduce(const Workspace& w);

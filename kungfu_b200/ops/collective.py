@@ -121,6 +121,9 @@ def _gpu_all_reduce_(x: torch.Tensor, op_code: int, average: bool, stream: Optio
         raise TypeError("kungfu_b200: averaging all-reduce needs a floating point tensor")
     chunk_elems = (cap // esize) // 8 * 8
     n = flat.numel()
+    if plane.spans_hosts:
+        _gpu_all_reduce_hier_(plane, flat, op_code, average, st, algo)
+        return
     with torch.cuda.stream(st):
         for lo in range(0, n, chunk_elems):
             hi = min(n, lo + chunk_elems)
@@ -143,6 +146,101 @@ def _gpu_all_reduce_(x: torch.Tensor, op_code: int, average: bool, stream: Optio
                 ext.allreduce(arena.mesh, 0, a, off, 0, nb_pad, dt, op_code, scale, 0, flags, blocks, CONFIG.threads,
                               st.cuda_stream)
                 flat[lo:hi].view(torch.uint8).copy_(stage[:nb], non_blocking=True)
+
+
+_OPNAME = {0: "sum", 1: "min", 2: "max", 3: "prod"}
+
+
+def _group_masters(plane) -> List[int]:
+    """World ranks of the first rank of every NVLink group (COLLECTIVE on first use per membership)."""
+    key = plane.membership_key()
+    if getattr(plane, "_masters_key", None) != key:
+        rt = plane.runtime
+        bases = [int(b) for b in rt.control.all_gather_bytes(str(plane.group_base).encode())]
+        plane._masters = sorted(set(bases))
+        plane._masters_key = key
+    return plane._masters
+
+
+def _pinned(plane, nbytes: int) -> torch.Tensor:
+    buf = getattr(plane, "_pinned_buf", None)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, pin_memory=True)
+        plane._pinned_buf = buf
+    return buf
+
+
+def _cross_hosts_(plane, host: torch.Tensor, op_code: int) -> None:
+    """All-reduce a host tensor among the group masters (one rank per host) over the control plane. Reference:
+    `CrossAllReduceGpu` stages through host memory the same way (srcs/cpp/src/nccl/controller.cpp, K5 in SURVEY.md)."""
+    rt = plane.runtime
+    masters = _group_masters(plane)
+    if len(masters) < 2:
+        return
+    ctl = rt.control
+    if hasattr(ctl, "subset_all_reduce_cpu_"):
+        forest = list(range(rt.size))
+        for m in masters:
+            forest[m] = masters[0]
+        ctl.subset_all_reduce_cpu_(host, forest, _OPNAME[op_code])
+    elif op_code == dtypes.SUM:
+        ctl.all_reduce_cpu_(host, "sum")  # control planes without subset support: everyone joins, non-masters add zeros
+    else:
+        raise NotImplementedError("kungfu_b200: this control plane has no subset all-reduce for min/max/prod across hosts")
+
+
+def _gpu_all_reduce_hier_(plane, flat: torch.Tensor, op_code: int, average: bool, st, algo: Optional[str]) -> None:
+    """All-reduce for jobs that span hosts: (1) our kernel inside the NVLink group, (2) the group's first rank takes the
+    partial result across hosts through pinned memory and the control plane, (3) broadcast kernel inside the group."""
+    rt = plane.runtime
+    arena, off, cap = plane.staging()
+    ext = plane.ext
+    dt = dtypes.dtype_code(flat.dtype)
+    esize = flat.element_size()
+    gsize, grank = plane.group_size, plane.group_rank
+    masters = _group_masters(plane)
+    subset = hasattr(rt.control, "subset_all_reduce_cpu_")
+    chunk_elems = (cap // esize) // 8 * 8
+    n = flat.numel()
+    with torch.cuda.stream(st):
+        for lo in range(0, n, chunk_elems):
+            hi = min(n, lo + chunk_elems)
+            nb = (hi - lo) * esize
+            nb_pad = (nb + 15) // 16 * 16
+            stage = arena.bytes_view(off, nb_pad)
+            stage[:nb].copy_(flat[lo:hi].view(torch.uint8), non_blocking=True)
+            if nb_pad != nb:
+                stage[nb:].zero_()
+            if gsize > 1:
+                a = pick_algo(arena, nb_pad, dt, op_code, inplace=True, force=algo)
+                if a == ext.ALGO_ONESHOT:
+                    a = ext.ALGO_TWOSHOT
+                ext.allreduce(arena.mesh, 0, a, off, 0, nb_pad, dt, op_code, 1.0, 0, 0, pick_blocks(nb_pad, gsize, sliced=True),
+                              CONFIG.threads, st.cuda_stream)
+            if len(masters) > 1:
+                joins = grank == 0 or not subset
+                if joins:
+                    host = _pinned(plane, nb_pad)[:nb]
+                    if grank == 0:
+                        host.copy_(stage[:nb], non_blocking=True)
+                        st.synchronize()
+                    else:
+                        host.zero_()
+                    _cross_hosts_(plane, host.view(flat.dtype), op_code)
+                    if grank == 0:
+                        stage[:nb].copy_(host, non_blocking=True)
+                if gsize > 1:
+                    # the group waits for its master on the host (not spinning on the device while the master is on the network)
+                    sync = getattr(rt.control, "local_broadcast_cpu_", None)
+                    if sync is not None:
+                        sync(torch.zeros(1, dtype=torch.int32))
+                    algo_b = ext.ALGO_NVLS if (arena.has_multicast and CONFIG.algo in ("auto", "nvls")) else ext.ALGO_TWOSHOT
+                    ext.broadcast(arena.mesh, 0, algo_b, off, nb_pad, 0, pick_blocks(nb_pad, 1, sliced=False), CONFIG.threads,
+                                  st.cuda_stream)
+            out = flat[lo:hi]
+            out.view(torch.uint8).copy_(stage[:nb], non_blocking=True)
+            if average:
+                out.mul_(1.0 / rt.size)
 
 
 def all_reduce_(x: torch.Tensor, op=None, name: str = "") -> torch.Tensor:
@@ -178,6 +276,36 @@ def all_reduce(x: torch.Tensor, op=None, name: str = "") -> torch.Tensor:
     return all_reduce_(x.clone(), op, name)
 
 
+def subset_all_reduce(x: torch.Tensor, topology, op=None, name: str = "") -> torch.Tensor:
+    """All-reduce inside every tree of the forest `topology` (father array: `topology[i] == i` marks a root; a root
+    without children keeps its own value). Reference: `subset_all_reduce(t, topology)` (srcs/python/kungfu/tensorflow/ops/
+    collective.py, kernel `KungfuSubsetAllReduce`). Members of multi-node trees must all call it; others may skip it."""
+    code, avg = dtypes.op_code(op)
+    rt = get_runtime()
+    forest = [int(v) for v in (topology.tolist() if isinstance(topology, torch.Tensor) else topology)]
+    if len(forest) != rt.size:
+        raise ValueError(f"subset_all_reduce: topology has {len(forest)} entries for {rt.size} peers")
+    if rt.size == 1:
+        return x.clone()
+    f = getattr(rt.control, "subset_all_reduce_cpu_", None)
+    if f is None:
+        raise NotImplementedError("kungfu_b200: subset_all_reduce needs the native control plane")
+    host = x.detach().to("cpu").contiguous().clone()
+    f(host, forest, _OPNAME[code], name)
+    if avg:
+        root = rt.rank
+        while forest[root] != root:
+            root = forest[root]
+        members = 0
+        for i in range(rt.size):
+            j = i
+            while forest[j] != j:
+                j = forest[j]
+            members += j == root
+        host = host / members if host.dtype.is_floating_point else host // members
+    return host.to(x.device)
+
+
 def all_reduce_async_(x: torch.Tensor, name: str = "", op=None) -> Handle:
     """Asynchronous in-place all-reduce on the comm stream; `Handle.wait()` makes the current stream
     wait for it (no host blocking)."""
@@ -205,6 +333,11 @@ def wait_all_handles(hs: List[Handle]) -> None:
 def broadcast_(x: torch.Tensor, root: int = 0, name: str = "") -> torch.Tensor:
     rt = get_runtime()
     if rt.size == 1:
+        return x
+    if x.is_cuda and rt.gpu.spans_hosts:
+        h = x.detach().to("cpu")
+        broadcast_(h, root, name)
+        x.copy_(h)
         return x
     if x.is_cuda:
         plane = rt.gpu
@@ -249,6 +382,9 @@ def all_gather(x: torch.Tensor, name: str = "") -> torch.Tensor:
     out = x.new_empty((n,) + tuple(x.shape))
     if n == 1:
         out[0].copy_(x)
+        return out
+    if x.is_cuda and rt.gpu.spans_hosts:
+        out.copy_(all_gather(x.detach().to("cpu"), name))
         return out
     if x.is_cuda:
         plane = rt.gpu

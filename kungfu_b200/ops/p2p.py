@@ -41,6 +41,8 @@ def save_variable(t: torch.Tensor, name: str, version: Optional[int] = None) -> 
     """Publish `t` under `name` so that peers can `request_variable` it. Collective on first use for CUDA tensors
     (every rank must create the slot)."""
     rt = get_runtime()
+    if t.is_cuda and rt.gpu.spans_hosts:
+        t = t.detach().to("cpu")  # peers on other hosts cannot map this GPU: the blob goes through the host store
     if t.is_cuda:
         nb = t.numel() * t.element_size()
         s = _gpu_slot(name, nb)
@@ -70,6 +72,11 @@ def request_variable(target: int, name: str, shape=None, dtype=None, version: Op
     if template is not None:
         shape, dtype, device = template.shape, template.dtype, template.device
     out = torch.zeros(tuple(shape), dtype=dtype, device=device or "cpu")
+    if out.is_cuda and rt.gpu.spans_hosts:
+        ok, host = request_variable(target, name, shape, dtype, version, device="cpu")
+        if ok:
+            out.copy_(host)
+        return ok, out
     if out.is_cuda:
         nb = out.numel() * out.element_size()
         s = _gpu_slot(name, nb)

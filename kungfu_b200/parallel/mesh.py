@@ -65,9 +65,11 @@ class SymmetricArena:
             self._bytes = torch.as_tensor(base, device=torch.device("cuda", plane.device_index))
 
     def _connect(self, want_multicast: bool) -> None:
-        rt = self.plane.runtime
+        plane = self.plane
         want_mc = want_multicast and os.environ.get("KUNGFU_DISABLE_NVLS", "0") != "1"
-        self.mesh.connect(rt.rank, rt.size, rt.control.all_gather_bytes, want_mc)
+        # peer memory exists only inside one NVLink domain: the mesh spans the ranks of THIS host (all of them in a
+        # single-host job); ranks on other hosts are reached through the hierarchical paths of ops/collective.py
+        self.mesh.connect(plane.group_rank, plane.group_size, plane.group_all_gather_bytes, want_mc)
 
     def ensure(self) -> "SymmetricArena":
         """Connect (or re-connect after a membership change) to the current peers. COLLECTIVE when it has work to do:
@@ -157,6 +159,49 @@ class GpuPlane:
         rt = self.runtime
         ver = getattr(rt.control, "cluster_version", None)
         return (rt.size, rt.rank, ver() if ver else 0)
+
+    # ---- the NVLink group of this rank ---------------------------------------------------------------------------------
+    # A job on one host: group == world. A job spanning hosts (reference: `kungfu-run -H a:8,b:8`, CrossAllReduceGpu in
+    # srcs/cpp/src/nccl/controller.cpp): the group is this host's ranks (contiguous in the peer list, which is host-major),
+    # kernels run inside the group and the host dimension goes through the control plane's cross-host collectives.
+    @property
+    def spans_hosts(self) -> bool:
+        rt = self.runtime
+        forced = os.environ.get("KUNGFU_FORCE_GROUP_SIZE")  # testing: split one box into several "hosts"
+        ls = int(forced) if forced else int(rt.local_size)
+        return 1 <= ls < rt.size
+
+    @property
+    def group_size(self) -> int:
+        rt = self.runtime
+        if not self.spans_hosts:
+            return rt.size
+        forced = os.environ.get("KUNGFU_FORCE_GROUP_SIZE")
+        return int(forced) if forced else int(rt.local_size)
+
+    @property
+    def group_rank(self) -> int:
+        rt = self.runtime
+        if not self.spans_hosts:
+            return rt.rank
+        forced = os.environ.get("KUNGFU_FORCE_GROUP_SIZE")
+        return rt.rank % int(forced) if forced else int(rt.local_rank)
+
+    @property
+    def group_base(self) -> int:
+        return self.runtime.rank - self.group_rank
+
+    def group_all_gather_bytes(self, b) -> List[bytes]:
+        """Out-of-band all-gather restricted to the NVLink group (built on the world all-gather: every rank of every
+        host reaches the same connect step in the same program order)."""
+        rt = self.runtime
+        everyone = rt.control.all_gather_bytes(b)
+        if not self.spans_hosts:
+            return everyone
+        base, n = self.group_base, self.group_size
+        if base < 0 or base + n > len(everyone):
+            raise RuntimeError(f"kungfu_b200: ranks of one host are not contiguous (rank {rt.rank}, local {self.group_rank}/{n})")
+        return everyone[base:base + n]
 
     def new_arena(self, nbytes: int, name: str, want_multicast: bool = True) -> SymmetricArena:
         names = {a.name for a in self._arenas}

@@ -116,6 +116,14 @@ class NativeControl(Control):
                                        _auto_name("mallreduce", name, self._version), list(tree or []))
         return t
 
+    def subset_all_reduce_cpu_(self, t: torch.Tensor, forest: List[int], op: str = "sum", name: str = "") -> torch.Tensor:
+        """All-reduce inside every tree of `forest` (father array, father[i] == i for roots). Only members of multi-node
+        trees need to call it."""
+        assert not t.is_cuda and t.is_contiguous()
+        self.peer.subset_all_reduce(t.data_ptr(), t.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _OPS[op],
+                                    _auto_name("sallreduce", name, self._version), [int(x) for x in forest])
+        return t
+
     def cross_all_reduce_cpu_(self, t: torch.Tensor, op: str = "sum", name: str = "") -> torch.Tensor:
         self.peer.cross_all_reduce(t.data_ptr(), t.data_ptr(), t.numel(), dtypes.dtype_code(t.dtype), _OPS[op], _auto_name("xallreduce", name, self._version))
         return t

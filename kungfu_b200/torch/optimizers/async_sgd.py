@@ -52,13 +52,13 @@ class _PairAveraging(KungFuMixin):
 
     # ---- CPU model store ----------------------------------------------------------------------------
     def _kf_flat_cpu(self) -> torch.Tensor:
-        return torch.cat([p.data.reshape(-1).float() for _, p in self._kf_named])
+        return torch.cat([p.data.reshape(-1).float() for _, p in self._kf_named]).cpu()
 
     def _kf_unflat_cpu(self, flat: torch.Tensor, blend: float) -> None:
         off = 0
         for _, p in self._kf_named:
             n = p.numel()
-            p.data.mul_(1.0 - blend).add_(flat[off:off + n].view_as(p).to(p.dtype), alpha=blend)
+            p.data.mul_(1.0 - blend).add_(flat[off:off + n].view_as(p).to(device=p.device, dtype=p.dtype), alpha=blend)
             off += n
 
     @torch.no_grad()

@@ -84,6 +84,10 @@ class KungFuMixin:
         self._kf_rt = get_runtime()
         self._kf_named = named_trainable(self, named_parameters)
         self._kf_gpu = use_gpu_engine and all_cuda(p for _, p in self._kf_named)
+        if self._kf_gpu and self._kf_rt.gpu.spans_hosts:
+            # the fused engines address every peer's HBM directly, which only exists inside one NVLink domain; a job that
+            # spans hosts takes the generic path (hierarchical all-reduce: kernels inside the host, control plane across)
+            self._kf_gpu = False
         self._kf_engine = None
         self._kf_step_count = 0
 
@@ -110,6 +114,18 @@ def cpu_all_reduce_grads(named, op: str, average: bool) -> None:
     rt = get_runtime()
     if rt.size == 1:
         return
+    cuda = [p for _, p in named if p.grad is not None and p.grad.is_cuda]
+    if cuda and rt.gpu.spans_hosts:
+        # one fused message per dtype instead of one host round trip per tensor
+        by_dtype = {}
+        for p in cuda:
+            by_dtype.setdefault(p.grad.dtype, []).append(p.grad)
+        for grads in by_dtype.values():
+            flat = torch._utils._flatten_dense_tensors(grads)
+            coll.all_reduce_(flat, "avg" if average else op, "fused-grads")
+            for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+                g.copy_(f)
+        named = [(n, p) for n, p in named if p.grad is not None and not p.grad.is_cuda]
     handles = []
     for name, p in named:
         if p.grad is None:

@@ -168,6 +168,24 @@ def cmd_set_tree(args):
     check(mask.shape == (n,), "neighbour mask")
     x = ops.all_reduce(torch.ones(10))
     check(torch.equal(x, torch.full((10,), float(n))), "all-reduce on the MST")
+    # subset all-reduce: independent all-reduce per tree of a forest; isolated peers keep their value and may skip the call
+    if n >= 2:
+        pairs = [2 * (i // 2) if 2 * (i // 2) + 1 < n else i for i in range(n)]  # {0,1} {2,3} ... (+ a singleton if n is odd)
+        mine = [i for i in range(n) if pairs[i] == pairs[r]]
+        for dt in (torch.float32, torch.int64, torch.bfloat16):
+            y = ops.subset_all_reduce(torch.full((1000,), r + 1).to(dt), pairs)
+            check(torch.equal(y, torch.full((1000,), sum(i + 1 for i in mine)).to(dt)), f"subset all-reduce {pairs} {dt}")
+        y = ops.subset_all_reduce(torch.full((8,), float(r + 1)), pairs, op="avg")
+        check(torch.allclose(y, torch.full((8,), sum(i + 1 for i in mine) / len(mine))), "subset all-reduce avg")
+        y = ops.subset_all_reduce(torch.full((8,), float(r)), pairs, op="max")
+        check(torch.equal(y, torch.full((8,), float(max(mine)))), "subset all-reduce max")
+        # one star over the even ranks (the shape of the cross-host stage); odd ranks are not part of it and do not call
+        evens = [i for i in range(n) if i % 2 == 0]
+        star = [0 if i % 2 == 0 else i for i in range(n)]
+        if r % 2 == 0:
+            y = ops.subset_all_reduce(torch.full((70000,), float(r + 1)), star)
+            check(torch.equal(y, torch.full((70000,), float(sum(i + 1 for i in evens)))), "subset all-reduce over a star of masters")
+        ops.barrier()
     if r == 0:
         print(f"set_tree latency: mean {1e3 * sum(times) / len(times):.2f}ms min {1e3 * min(times):.2f}ms max {1e3 * max(times):.2f}ms", flush=True)
     print(json.dumps({"ok": True}), flush=True)

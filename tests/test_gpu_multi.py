@@ -43,6 +43,24 @@ def test_sma_pair_all_gpus():
     _run(n if n in (2, 4, 8) else 2, ["extra"])
 
 
+def test_host_spanning_paths_with_forced_groups():
+    """Hierarchical (multi-host) code paths on one box: 4 GPUs as two groups of 2, or 2 GPUs as two groups of 1."""
+    n = torch.cuda.device_count()
+    world, group = (4, 2) if n >= 4 else (2, 1)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", "29650", os.path.join(ROOT, "tests", "mp_gpu_hier.py")]
+    env = dict(os.environ, KUNGFU_DEVICE_TIMEOUT_MS="15000", KUNGFU_FORCE_GROUP_SIZE=str(group))
+    r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    print(r.stdout[-6000:])
+    try:
+        with open(os.path.join(ROOT, "gpurun_out", f"mp_hier_{world}.log"), "w") as f:
+            f.write(r.stdout)
+    except OSError:
+        pass
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert '"fails": 0' in r.stdout
+
+
 def test_gpu_elastic_resize_under_kungfu_run():
     """1 -> 2 -> 1 GPUs under `kungfu-run -w` with the builtin config server: survivors keep training, newcomers inherit
     state, arenas rebuild their peer mappings; the trajectory equals a plain torch.optim reference."""
