@@ -359,6 +359,32 @@ def cmd_recovery(args):
     time.sleep(0.5)
 
 
+def cmd_metrics(args):
+    """Prometheus-style endpoint of every peer (reference: monitor/server.go, http://<peer>:<port+10000>/metrics)."""
+    from kungfu_b200 import _kfrt
+
+    rt = get_runtime()
+    n, r = rt.size, rt.rank
+    for _ in range(3):
+        ops.all_reduce(torch.ones(1 << 16))
+    ops.barrier()
+    port = int(os.environ["KUNGFU_SELF_SPEC"].rsplit(":", 1)[1]) + 10000
+    status, body = _kfrt.http_request("GET", f"http://127.0.0.1:{port}/metrics", "")
+    check(status == 200, f"metrics status {status}")
+    body = body.decode() if isinstance(body, (bytes, bytearray)) else body
+    lines = [ln for ln in body.splitlines() if ln]
+    eg = [ln for ln in lines if ln.startswith("egress_total_bytes{peer=")]
+    check(n == 1 or len(eg) >= 1, f"egress lines: {lines[:4]}")
+    check(n == 1 or any(int(ln.rsplit(" ", 1)[1]) >= (1 << 16) for ln in eg), "egress counters grew with the all-reduces")
+    check(n == 1 or any(ln.startswith("ingress_total_bytes{peer=") for ln in lines), "ingress lines")
+    status, _ = _kfrt.http_request("GET", f"http://127.0.0.1:{port}/nope", "")
+    check(status == 404, "unknown path is 404")
+    rates = ops.egress_rates()
+    check(len(rates) == n, "egress_rates has one entry per peer")
+    ops.barrier()
+    print(json.dumps({"ok": True, "metrics_lines": len(lines)}), flush=True)
+
+
 def cmd_bad(args):
     rt = get_runtime()
     if rt.rank == 0:

@@ -85,6 +85,11 @@ def test_p2p_store(np):
     assert len([j for j in json_lines(r.stdout) if j.get("ok")]) == np, r.stdout[-3000:]
 
 
+def test_metrics_endpoint():
+    r = launch(3, "metrics", env={"KUNGFU_CONFIG_ENABLE_MONITORING": "true"})
+    assert r.stdout.count('"ok": true') == 3, r.stdout[-3000:]
+
+
 @pytest.mark.parametrize("np", [2, 4])
 def test_set_tree(np):
     r = launch(np, "set_tree")
