@@ -5,6 +5,8 @@
 // -> Request). Also the model-shaped all-reduce micro-benchmark of `kungfu-bench-allreduce`
 // (tests/go/cmd/kungfu-bench-allreduce/kungfu-bench-allreduce.go:73-110): prints
 // `RESULT: <rate> GiB/s` with the reference's "equivalent data rate" 4(np-1)*S/t.
+#include <atomic>
+#include <unistd.h>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -88,6 +90,24 @@ int main(int argc, char** argv) {
         CHECK(kungfu_request(tgt, "v9", "blob", got.data(), got.size() * 4, &ok) == 0 && ok == 0);
         int agreed = 0;
         CHECK(kungfu_consensus("abc", 3, "c", &agreed) == 0 && agreed == 1);
+        CHECK(kungfu_barrier() == 0);
+        { // subset all-reduce: pairs {0,1} {2,3} ...; a trailing singleton keeps its value
+            std::vector<int32_t> forest(np);
+            for (int i = 0; i < np; ++i) forest[i] = (2 * (i / 2) + 1 < np) ? 2 * (i / 2) : i;
+            std::vector<float> a(1000, float(rank + 1)), b(1000, 0.f);
+            CHECK(kungfu_subset_all_reduce(a.data(), b.data(), a.size(), KungFu_F32, KungFu_SUM, forest.data(), np, "subset") == 0);
+            float want = 0;
+            for (int i = 0; i < np; ++i)
+                if (forest[i] == forest[rank]) want += float(i + 1);
+            CHECK(b[0] == want && b[999] == want);
+        }
+        { // noop with a completion callback: runs on the runtime's executor
+            static std::atomic<int> fired{0};
+            CHECK(kungfu_noop([](void*) { fired.fetch_add(1); }, nullptr) == 0);
+            for (int i = 0; i < 2000 && fired.load() == 0; ++i) usleep(1000);
+            CHECK(fired.load() == 1);
+            CHECK(kungfu_noop(nullptr, nullptr) == 0);
+        }
         CHECK(kungfu_barrier() == 0);
         if (rank == 0) printf("fake-agent ok np=%d\n", np);
     } else {

@@ -98,6 +98,12 @@ KF_API int kungfu_all_reduce(const void* s, void* r, size_t n, int dt, int op, c
 KF_API int kungfu_monitored_all_reduce(const void* s, void* r, size_t n, int dt, int op, const int32_t* tree, int tree_len, const char* name) {
     return guard([&] { peer().session()->monitored_all_reduce(mk(s, r, n, dt, op, name), std::vector<int32_t>(tree, tree + (tree ? tree_len : 0))); });
 }
+KF_API int kungfu_subset_all_reduce(const void* s, void* r, size_t n, int dt, int op, const int32_t* forest, int forest_len, const char* name) {
+    return guard([&] { peer().session()->subset_all_reduce(mk(s, r, n, dt, op, name), std::vector<int32_t>(forest, forest + (forest ? forest_len : 0))); });
+}
+KF_API int kungfu_noop(kungfu_callback_t done, void* arg) {
+    return run([] {}, done, arg); // completes on the runtime's executor: orders a callback after everything queued before it
+}
 KF_API int kungfu_cross_all_reduce(const void* s, void* r, size_t n, int dt, int op, const char* name) {
     return guard([&] { peer().session()->cross_all_reduce(mk(s, r, n, dt, op, name)); });
 }

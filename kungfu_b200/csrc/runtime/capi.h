@@ -37,6 +37,8 @@ int kungfu_barrier(void);
 int kungfu_consensus(const void* buf, size_t len, const char* name, int* agreed);
 int kungfu_all_reduce(const void* send, void* recv, size_t count, int dtype, int op, const char* name, kungfu_callback_t done, void* arg);
 int kungfu_monitored_all_reduce(const void* send, void* recv, size_t count, int dtype, int op, const int32_t* tree, int tree_len, const char* name);
+int kungfu_subset_all_reduce(const void* send, void* recv, size_t count, int dtype, int op, const int32_t* forest, int forest_len, const char* name);
+int kungfu_noop(kungfu_callback_t done, void* arg);
 int kungfu_cross_all_reduce(const void* send, void* recv, size_t count, int dtype, int op, const char* name);
 int kungfu_reduce(const void* send, void* recv, size_t count, int dtype, int op, const char* name);
 int kungfu_broadcast(const void* send, void* recv, size_t count, int dtype, const char* name, kungfu_callback_t done, void* arg);

@@ -7,7 +7,7 @@ from typing import List, Sequence
 import torch
 
 from .adapt import StepBasedSchedule, resize, resize_cluster, resize_cluster_from_url, set_tree, step_based_schedule
-from .collective import (Handle, all_gather, all_reduce, all_reduce_, all_reduce_async_, barrier, broadcast_, consensus, subset_all_reduce,
+from .collective import (Handle, all_gather, all_gather_transform, all_reduce, all_reduce_, all_reduce_async_, barrier, broadcast_, consensus, subset_all_reduce,
                          wait_all_handles, wait_handle)
 from .monitor import NoiseScale, egress_rates, global_noise_scale
 from .p2p import request_variable, request_variable_with_template, save_variable, save_variables

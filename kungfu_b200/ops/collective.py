@@ -416,6 +416,20 @@ def all_gather(x: torch.Tensor, name: str = "") -> torch.Tensor:
     return out
 
 
+def all_gather_transform(x: torch.Tensor, f, name: str = "") -> torch.Tensor:
+    """Gather every rank's `x`, apply `f(stacked [np, ...]) -> tensor shaped like x` ON RANK 0 and hand its result to everyone.
+    Reference: `Peer::AllGatherTransform` = Gather -> f on the root -> Broadcast (srcs/cpp/src/session.cpp:162-181)."""
+    rt = get_runtime()
+    stacked = all_gather(x, name)
+    out = torch.empty_like(x)
+    if rt.rank == 0:
+        y = f(stacked)
+        if tuple(y.shape) != tuple(x.shape) or y.dtype != x.dtype:
+            raise ValueError("all_gather_transform: f must return a tensor shaped and typed like its per-rank input")
+        out.copy_(y)
+    return broadcast_(out, 0, name)
+
+
 def barrier() -> None:
     """Host barrier over the control plane (+ device flag barrier when a GPU plane exists)."""
     rt = get_runtime()

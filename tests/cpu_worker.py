@@ -168,6 +168,9 @@ def cmd_set_tree(args):
     check(mask.shape == (n,), "neighbour mask")
     x = ops.all_reduce(torch.ones(10))
     check(torch.equal(x, torch.full((10,), float(n))), "all-reduce on the MST")
+    # gather -> transform on rank 0 -> broadcast
+    y = ops.all_gather_transform(torch.full((6,), float(r + 1)), lambda s: s.max(0).values * 10)
+    check(torch.equal(y, torch.full((6,), float(10 * n))), "all_gather_transform")
     # subset all-reduce: independent all-reduce per tree of a forest; isolated peers keep their value and may skip the call
     if n >= 2:
         pairs = [2 * (i // 2) if 2 * (i // 2) + 1 < n else i for i in range(n)]  # {0,1} {2,3} ... (+ a singleton if n is odd)
