@@ -18,6 +18,7 @@ import torch.nn.functional as F
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 import kungfu_b200.torch as kf  # noqa: E402
+from kungfu_b200 import models  # noqa: E402
 from kungfu_b200.models import resnet  # noqa: E402
 from kungfu_b200.runtime import get_runtime  # noqa: E402
 from kungfu_b200.utils.timing import max_over_ranks  # noqa: E402
@@ -41,7 +42,8 @@ def main():
     torch.manual_seed(1)
     n = rt.size
     dtype = torch.float32 if a.fp32 else torch.bfloat16
-    model = resnet.to_b200(getattr(resnet, a.model)(), dtype, "cuda")
+    model = resnet.to_b200(models.build(a.model), dtype, "cuda")  # resnet18/50/101, vgg11/16/19, inception_v3
+    side = models.input_size(a.model)
     base = torch.optim.SGD(model.parameters(), lr=0.01 * n, momentum=a.momentum)
     named = list(model.named_parameters())
     opt = {
@@ -52,7 +54,7 @@ def main():
         "variance": lambda: kf.optimizers.MonitorGradientVarianceOptimizer(base, named),
     }[a.kf_optimizer]()
     kf.broadcast_parameters(model.state_dict())
-    x = torch.randn(a.batch_size, 3, 224, 224, device="cuda", dtype=dtype).contiguous(memory_format=torch.channels_last)
+    x = torch.randn(a.batch_size, 3, side, side, device="cuda", dtype=dtype).contiguous(memory_format=torch.channels_last)
     y = torch.randint(0, 1000, (a.batch_size,), device="cuda")
 
     def step():

@@ -18,10 +18,10 @@ def sizes(model: str) -> List[int]:
         return list(VGG16)
     if model == "slp":
         return [7840, 10]
-    if model in ("resnet50", "resnet18", "resnet101"):
-        from ..models import resnet
+    if model in ("resnet50", "resnet18", "resnet101", "vgg11", "vgg19", "inception_v3"):
+        from .. import models
 
-        return [p.numel() for p in getattr(resnet, model)().parameters()]
+        return [p.numel() for p in models.build(model).parameters()]
     if model in ("bert", "bert-large", "bert_large"):
         from ..models import bert
 

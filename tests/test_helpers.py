@@ -166,3 +166,29 @@ prun 2 -H 127.0.0.1:2 -port {rport} -port-range {prange} {sys.executable} {ROOT}
     r = subprocess.run(["sh", str(script)], env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=180)
     assert r.returncode == 0 and "single-ok" in r.stdout and "rank 1/2" in r.stdout and "BEGIN" in r.stdout and "END" in r.stdout, r.stdout[-3000:]
     assert os.path.isdir(tmp_path / "logs")
+
+
+def test_vision_model_zoo_matches_reference_shapes():
+    """The three models of the reference's scalability charts (benchmarks/system/benchmark_kungfu.py:58-66)."""
+    from kungfu_b200 import models
+    from kungfu_b200.benchmarks import model_sizes
+
+    vgg16 = models.build("vgg16")
+    sizes = [p.numel() for p in vgg16.parameters()]
+    assert sum(sizes) == 138_357_544 and len(sizes) == 32 and sizes == model_sizes.VGG16  # reference model_sizes.py:1-5
+    inc = models.build("inception_v3")
+    assert sum(p.numel() for p in inc.parameters()) == 23_834_568 and models.input_size("inception_v3") == 299
+    assert sum(p.numel() for p in models.build("inception_v3", aux_logits=True).parameters()) == 27_161_264
+    assert sum(model_sizes.sizes("inception_v3")) == 23_834_568 and sum(model_sizes.sizes("resnet50")) == 25_557_032
+    small = models.vgg.vgg11(num_classes=10).eval()  # eval: no dropout noise
+    x = torch.randn(2, 3, 64, 64)
+    a = small(x)
+    b = small(x.contiguous(memory_format=torch.channels_last))
+    assert a.shape == (2, 10) and torch.allclose(a, b, atol=1e-5), "VGG output must not depend on the memory format"
+    inc.train()
+    out = inc(torch.randn(2, 3, 299, 299))
+    assert out.shape == (2, 1000)
+    out.sum().backward()
+    assert all(p.grad is not None for p in inc.parameters())
+    with pytest.raises(ValueError):
+        models.build("alexnet")
