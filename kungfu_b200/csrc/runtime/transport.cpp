@@ -26,7 +26,12 @@ Pool& Pool::get() {
 void Pool::submit(std::function<void()> fn) {
     std::unique_lock<std::mutex> lk(mu_);
     q_.push_back(std::move(fn));
-    if (idle_ == 0 && nthreads_ < 1024) {
+    // Tasks block on each other (a chunk's reduce step waits for the peer's task of the same chunk), so a queued task must
+    // never sit behind a running one: every queued task needs its own waiting worker. `idle_` still counts a worker that
+    // has been notified but has not yet woken up, hence the comparison with the queue length and not with zero — with
+    // `idle_ == 0` as the test, two quick submits both "used" the same idle worker and the second task starved
+    // (intermittent all-reduce deadlock with >= 7 chunks in flight).
+    if ((int)q_.size() > idle_ && nthreads_ < 1024) {
         ++nthreads_;
         std::thread([this] { worker(); }).detach();
     } else {

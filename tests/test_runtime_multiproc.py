@@ -85,6 +85,19 @@ def test_p2p_store(np):
     assert len([j for j in json_lines(r.stdout) if j.get("ok")]) == np, r.stdout[-3000:]
 
 
+def test_many_chunks_in_flight_do_not_starve_the_pool():
+    """ResNet-50 sized messages (up to nine 1 MiB chunks per tensor, 161 tensors) on the default tree strategy: every chunk
+    task blocks on its peer's task, so each needs its own worker thread. Regression test for a lost-wakeup style
+    under-provisioning in `Pool::submit` that deadlocked roughly one run in three."""
+    for _ in range(4):
+        rport, prange = ports()
+        cmd = [kungfu_run(), "-q", "-np", "4", "-H", "127.0.0.1:4", "-port", str(rport), "-port-range", prange, "-strategy", "BINARY_TREE_STAR",
+               sys.executable, "-m", "kungfu_b200.benchmarks", "--method", "CPU", "--warmup-steps", "1", "--steps", "2"]
+        r = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN"), stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True, timeout=90)
+        assert r.returncode == 0 and "RESULT:" in r.stdout, r.stdout[-3000:]
+
+
 def test_metrics_endpoint():
     r = launch(3, "metrics", env={"KUNGFU_CONFIG_ENABLE_MONITORING": "true"})
     assert r.stdout.count('"ok": true') == 3, r.stdout[-3000:]
