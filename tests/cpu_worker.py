@@ -388,6 +388,78 @@ def cmd_metrics(args):
     print(json.dumps({"ok": True, "metrics_lines": len(lines)}), flush=True)
 
 
+def cmd_stress(args):
+    """Randomised soak of the host plane: the same pseudo-random schedule of operations on every rank (sizes from 1 element to
+    several chunks, all dtypes / ops, multi-threaded async collectives, P2P traffic in between), every result checked."""
+    import random
+    import threading
+
+    rt = get_runtime()
+    n, r = rt.size, rt.rank
+    rng = random.Random(20240921)
+    iters = int(args.extra[0]) if args.extra else 120
+    sizes = [1, 3, 255, 4096, 65537, 262144, 300001, (1 << 20) + 17, 3 * (1 << 20) + 5]
+    dts = [torch.float32, torch.float64, torch.int32, torch.int64, torch.bfloat16, torch.float16, torch.uint8]
+    ops.save_variable(torch.full((1024,), float(r)), "soak")
+    ops.barrier()
+    for it in range(iters):
+        kind = rng.choice(["allreduce", "allreduce", "allreduce", "bcast", "gather", "threads", "p2p", "consensus", "barrier", "subset"])
+        if kind == "allreduce":
+            dt, op, m = rng.choice(dts), rng.choice(["sum", "min", "max"]), rng.choice(sizes)
+            base = (torch.arange(m) % 7 + 1)
+            x = (base * ((r % 3) + 1)).to(dt)
+            want = {"sum": base * sum((q % 3) + 1 for q in range(n)), "min": base * min((q % 3) + 1 for q in range(n)),
+                    "max": base * max((q % 3) + 1 for q in range(n))}[op].to(dt)
+            got = ops.all_reduce(x, op, name=f"soak{it}")
+            check(torch.equal(got, want), f"it {it}: all-reduce {dt} {op} n={m}")
+        elif kind == "bcast":
+            root, m = rng.randrange(n), rng.choice(sizes)
+            x = torch.full((m,), float(r + 1))
+            coll.broadcast_(x, root)
+            check(bool(torch.all(x == float(root + 1))), f"it {it}: broadcast from {root} n={m}")
+        elif kind == "gather":
+            m = rng.choice(sizes[:6])
+            g = ops.all_gather(torch.full((m,), r, dtype=torch.int32))
+            check(g.shape == (n, m) and all(int(g[q][0]) == q and int(g[q][-1]) == q for q in range(n)), f"it {it}: all_gather n={m}")
+        elif kind == "threads":
+            # several named collectives in flight at once from different threads (the reference's async ops do this)
+            k = rng.randrange(2, 6)
+            ms = [rng.choice(sizes[:8]) for _ in range(k)]
+            outs = [None] * k
+
+            def run(i):
+                outs[i] = ops.all_reduce(torch.full((ms[i],), float(i + 1)), "sum", name=f"thr{it}.{i}")
+
+            ths = [threading.Thread(target=run, args=(i,)) for i in range(k)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            for i in range(k):
+                check(outs[i] is not None and bool(torch.all(outs[i] == float((i + 1) * n))), f"it {it}: threaded all-reduce {i}")
+        elif kind == "p2p":
+            tgt = rng.randrange(n)
+            ok, v = ops.request_variable(tgt, "soak", shape=(1024,), dtype=torch.float32)
+            check(ok and bool(torch.all(v == float(tgt))), f"it {it}: request from {tgt}")
+        elif kind == "consensus":
+            same = rng.random() < 0.5
+            check(ops.consensus(torch.full((9,), 1.0 if same else float(r))) == (same or n == 1), f"it {it}: consensus")
+        elif kind == "subset" and n >= 2:
+            k = rng.randrange(2, n + 1)
+            members = sorted(rng.sample(range(n), k))
+            forest = list(range(n))
+            for q in members:
+                forest[q] = members[0]
+            m = rng.choice(sizes[:7])  # drawn by everyone: the schedule must stay identical on all ranks
+            if r in members:
+                got = ops.subset_all_reduce(torch.full((m,), float(r + 1)), forest, name=f"sub{it}")
+                check(bool(torch.all(got == float(sum(q + 1 for q in members)))), f"it {it}: subset {members}")
+        else:
+            ops.barrier()
+    ops.barrier()
+    print(json.dumps({"ok": True, "iters": iters}), flush=True)
+
+
 def cmd_bad(args):
     rt = get_runtime()
     if rt.rank == 0:
@@ -405,6 +477,7 @@ def main():
     ap.add_argument("--dir", default="/tmp")
     ap.add_argument("--n-epochs", type=int, default=3)
     ap.add_argument("--restart", type=int, default=0)
+    ap.add_argument("extra", nargs="*")
     args = ap.parse_args()
     globals()["cmd_" + args.what](args)
 

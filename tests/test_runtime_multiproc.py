@@ -98,6 +98,14 @@ def test_many_chunks_in_flight_do_not_starve_the_pool():
         assert r.returncode == 0 and "RESULT:" in r.stdout, r.stdout[-3000:]
 
 
+@pytest.mark.parametrize("np,strategy", [(4, "BINARY_TREE_STAR"), (3, "RING"), (4, "MULTI_BINARY_TREE_STAR")])
+def test_randomised_soak(np, strategy):
+    """150 pseudo-random operations (all-reduce over dtypes / ops / sizes up to several chunks, broadcast from random roots,
+    all-gather, threaded concurrent collectives, P2P requests, consensus, subset all-reduce), every result checked."""
+    r = launch(np, "stress", extra=["150"], flags=["-strategy", strategy], timeout=240)
+    assert r.stdout.count('"ok": true') == np, r.stdout[-3000:]
+
+
 def test_metrics_endpoint():
     r = launch(3, "metrics", env={"KUNGFU_CONFIG_ENABLE_MONITORING": "true"})
     assert r.stdout.count('"ok": true') == 3, r.stdout[-3000:]
