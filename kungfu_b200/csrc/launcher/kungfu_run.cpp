@@ -288,7 +288,7 @@ struct Cancel {
 };
 
 void pump(int fd, const std::string& tag, const char* color, bool verbose, FILE* console, const std::string& logpath) {
-    FILE* lf = logpath.empty() ? nullptr : fopen(logpath.c_str(), "w");
+    FILE* lf = logpath.empty() ? nullptr : fopen(logpath.c_str(), "we");
     FILE* in = fdopen(fd, "r");
     if (!in) {
         close(fd);
@@ -318,8 +318,12 @@ void pump(int fd, const std::string& tag, const char* color, bool verbose, FILE*
 
 // returns the exit code (128+signal when killed)
 int run_proc(const Proc& p, bool verbose, const std::string& logdir, Cancel* cancel, int color_idx) {
+    // O_CLOEXEC: workers are spawned from several threads at once; a plain pipe() leaks this worker's write ends into every
+    // sibling forked meanwhile, the pumps then never see EOF when this worker exits, its waiter thread never returns, and the
+    // watch loop (which joins the waiter of a removed worker before it handles the next stage) wedges. dup2 onto 1 / 2 in
+    // the child clears the flag on the copies that matter.
     int out_pipe[2], err_pipe[2];
-    if (pipe(out_pipe) != 0 || pipe(err_pipe) != 0) fail("pipe() failed");
+    if (pipe2(out_pipe, O_CLOEXEC) != 0 || pipe2(err_pipe, O_CLOEXEC) != 0) fail("pipe() failed");
     std::vector<std::string> envs;
     for (char** e = environ; *e; ++e) {
         std::string kv = *e;
@@ -566,7 +570,9 @@ int watch_run(const Flags& f, const Job& job, const Cluster& init, const PeerID&
     server.set_control_handler([&](const PeerID& src, const std::string& name, const Bytes& payload) {
         if (name == "update") {
             try {
-                w.push(Stage::from_json(std::string(payload.begin(), payload.end())));
+                Stage st = Stage::from_json(std::string(payload.begin(), payload.end()));
+                KF_LOGD("stage v%d (%d workers) proposed by %s", st.version, (int)st.cluster.workers.size(), src.str().c_str());
+                w.push(st);
             } catch (const std::exception& e) {
                 KF_LOGE("bad stage from %s: %s", src.str().c_str(), e.what());
             }

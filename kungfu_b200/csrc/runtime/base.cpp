@@ -40,7 +40,7 @@ void Logger::set_level(const std::string& name) {
 }
 void Logger::set_output(const std::string& path) {
     std::lock_guard<std::mutex> g(mu_);
-    FILE* f = fopen(path.c_str(), "a");
+    FILE* f = fopen(path.c_str(), "ae");
     if (f) {
         if (out_) fclose(out_);
         out_ = f;

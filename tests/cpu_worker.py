@@ -325,6 +325,10 @@ def cmd_elastic(args):
             break
     if kfp.detached():
         print(json.dumps({"detached": True, "step": hook.state.step}), flush=True)
+        if os.environ.get("KF_DEBUG_EXIT"):
+            import faulthandler
+
+            faulthandler.dump_traceback_later(8, exit=False)
         return
     if kfp.current_rank() == 0:
         print(json.dumps({"elastic": True, "final_step": hook.state.step, "bias": float(m.bias[0]), "sizes": sorted(set(s for _, s in seen)),

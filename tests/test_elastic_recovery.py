@@ -93,6 +93,18 @@ def test_elastic_step_schedule_grow_and_shrink():
     assert "resize 1 -> 2 took" in r.stdout and "resize 4 -> 2 took" in r.stdout
 
 
+def test_elastic_churn_with_sibling_survivors():
+    """Seven back-to-back resizes incl. 3 -> 2 -> 4, where a worker leaves while a sibling spawned at the same time stays and the
+    next stage arrives within milliseconds. Regression test: worker stdout/stderr pipes leaked into concurrently forked siblings,
+    the leaver's waiter thread never saw EOF and the watch loop never handled the next stage (about every second run hung)."""
+    for k in range(2):
+        cfg_port = 9500 + (os.getpid() + k) % 200
+        r = _watch(1, 4, "elastic", ["--schedule", "1:2,4:2,1:2,3:2,2:2,4:2,3:2,1:2", "--max-step", "16"], cfg_port, timeout=150)
+        assert r.returncode == 0, r.stdout[-5000:]
+        final = [j for j in json_lines(r.stdout) if j.get("elastic")]
+        assert len(final) == 1 and final[0]["final_step"] == 16 and final[0]["resizes"] == 7 and final[0]["sizes"] == [1, 2, 3, 4], r.stdout[-3000:]
+
+
 def test_failure_detection_and_auto_recovery(tmp_path):
     """A worker hangs inside a batch; the heartbeat detector restarts the job, which resumes from the checkpoint with
     the remaining epochs (`--n-epochs` patched, `--restart 1` appended)."""
