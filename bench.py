@@ -139,7 +139,7 @@ def main() -> int:
 
     # ---------------- kernel-only: resident device batch ----------------
     sampler = ClockSampler(dev_index).start() if rt.rank == 0 else None  # before the barrier: spawning costs host time
-    for _ in range(args.warmup):
+    for _ in range(max(3, args.warmup)):  # never fewer than 3 untimed steps, whatever W says
         trainer.device_step()
     barrier()
     align_devices()
