@@ -1,3 +1,5 @@
+// Implementation of peer_mesh.h (replaces the reference NCCLHelper / communicator bootstrap, srcs/cpp/src/nccl/helper.cpp, with
+// CUDA VMM export/import + NVLS multicast binding; design notes in the header).
 #include "peer_mesh.h"
 
 #include <cuda.h>

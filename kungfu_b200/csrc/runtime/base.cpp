@@ -1,3 +1,4 @@
+// Implementation of base.hpp (the header carries the design notes and the reference file:line mapping).
 #include "base.hpp"
 
 #include <condition_variable>

@@ -1,3 +1,4 @@
+// Implementation of capi.h (reference mapping there: libkungfu-comm cgo exports, srcs/go/libkungfu-comm/*.go).
 #include "capi.h"
 
 #include <memory>

@@ -1,3 +1,4 @@
+// Implementation of config_server.hpp (the header carries the design notes and the reference file:line mapping).
 #include "config_server.hpp"
 
 #include "base.hpp"

@@ -1,3 +1,4 @@
+// Implementation of graph.hpp (the header carries the design notes and the reference file:line mapping).
 #include "graph.hpp"
 
 #include <algorithm>

@@ -1,3 +1,4 @@
+// Implementation of http.hpp (the header carries the design notes and the reference file:line mapping).
 #include "http.hpp"
 
 #include <arpa/inet.h>

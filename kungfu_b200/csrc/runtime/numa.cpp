@@ -1,3 +1,4 @@
+// Implementation of numa.hpp (the header carries the design notes and the reference file:line mapping).
 #include "numa.hpp"
 
 #include <sched.h>

@@ -1,3 +1,4 @@
+// Implementation of plan.hpp (the header carries the design notes and the reference file:line mapping).
 #include "plan.hpp"
 
 #include <arpa/inet.h>

@@ -1,3 +1,4 @@
+// Implementation of store.hpp (the header carries the design notes and the reference file:line mapping).
 #include "store.hpp"
 
 #include <cstring>

@@ -1,3 +1,4 @@
+// Implementation of transport.hpp (the header carries the design notes and the reference file:line mapping).
 #include "transport.hpp"
 
 #include <arpa/inet.h>
