@@ -25,8 +25,25 @@ def broadcast_parameters(state_dict, root: int = 0) -> None:
             coll.broadcast_(v, root)
 
 
+def _numeric_hyper(group) -> list:
+    """(key, index-or-None) of every numeric hyper-parameter of a param group, in a rank-independent order."""
+    slots = []
+    for k in sorted(group.keys()):
+        v = group[k]
+        if k == "params" or isinstance(v, bool) or v is None:
+            continue
+        if isinstance(v, (int, float)):
+            slots.append((k, None))
+        elif isinstance(v, (tuple, list)) and v and all(isinstance(x, (int, float)) and not isinstance(x, bool) for x in v):
+            slots += [(k, i) for i in range(len(v))]
+    return slots
+
+
 def broadcast_optimizer_state(optimizer: torch.optim.Optimizer, root: int = 0) -> None:
-    """Broadcast every tensor in the optimizer state (momentum buffers, Adam moments, step counters)."""
+    """Broadcast every tensor in the optimizer state (momentum buffers, Adam moments, step counters) and the numeric
+    hyper-parameters of the param groups (lr, momentum, betas, weight decay, ...): in the reference these are graph variables
+    and `BroadcastGlobalVariablesOp` covers them; a learning rate that a scheduler already moved on the root must reach
+    workers that join or restart."""
     for group in optimizer.param_groups:
         for p in group["params"]:
             st = optimizer.state.get(p, {})
@@ -34,6 +51,18 @@ def broadcast_optimizer_state(optimizer: torch.optim.Optimizer, root: int = 0) -
                 v = st[k]
                 if isinstance(v, torch.Tensor):
                     coll.broadcast_(v, root)
+        slots = _numeric_hyper(group)
+        if not slots:
+            continue
+        vals = torch.tensor([float(group[k] if i is None else group[k][i]) for k, i in slots], dtype=torch.float64)
+        coll.broadcast_(vals, root)
+        for (k, i), v in zip(slots, vals.tolist()):
+            if i is None:
+                group[k] = type(group[k])(v)
+            else:
+                seq = list(group[k])
+                seq[i] = type(seq[i])(v)
+                group[k] = type(group[k])(seq)
 
 
 def BroadcastGlobalVariablesOp(model: torch.nn.Module, optimizer: Optional[torch.optim.Optimizer] = None, root: int = 0) -> None:

@@ -464,6 +464,47 @@ def cmd_stress(args):
     print(json.dumps({"ok": True, "iters": iters}), flush=True)
 
 
+def cmd_initializer(args):
+    """BroadcastGlobalVariablesOp / Callback / optimizer-state broadcast (reference: initializer.py + torch broadcast_parameters),
+    scope tracing and the max-over-ranks timing helper."""
+    from kungfu_b200 import initializer
+    from kungfu_b200.utils import timing, trace
+
+    rt = get_runtime()
+    n, r = rt.size, rt.rank
+    torch.manual_seed(100 + r)  # replicas start different
+    m = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.BatchNorm1d(5), torch.nn.Linear(5, 2))
+    opt = torch.optim.SGD(m.parameters(), lr=0.1 * (r + 1), momentum=0.9)
+    m(torch.randn(4, 6)).sum().backward()
+    opt.step()  # momentum buffers exist and differ
+    with trace.trace_scope("init.broadcast"):
+        initializer.BroadcastGlobalVariablesOp(m, opt)
+    flat = torch.cat([v.detach().reshape(-1).float() for v in m.state_dict().values()])
+    check(ops.consensus(flat), "parameters and buffers identical after BroadcastGlobalVariablesOp")
+    bufs = torch.cat([opt.state[p]["momentum_buffer"].reshape(-1) for p in m.parameters()])
+    check(ops.consensus(bufs), "optimizer state identical after the broadcast")
+    check(opt.param_groups[0]["lr"] == 0.1, f"hyper-parameters follow the root: lr={opt.param_groups[0]['lr']}")
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(float(r))
+    cb = initializer.BroadcastGlobalVariablesCallback(m)
+    cb.on_batch_end(0)
+    cb.on_batch_end(1)  # only the first batch broadcasts
+    flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+    check(ops.consensus(flat), "callback broadcast at the end of the first batch")
+    t = [torch.full((3,), float(r)), torch.full((2, 2), float(r + 1))]
+    initializer.broadcast_variables(t, root=n - 1)
+    check(bool(torch.all(t[0] == float(n - 1))) and bool(torch.all(t[1] == float(n))), "broadcast_variables from the last rank")
+    check(timing.max_over_ranks(float(r)) == float(n - 1), "max_over_ranks")
+    s = timing.ClockSampler(0).start()
+    time.sleep(0.05)
+    out = s.stop()  # no nvidia-smi on a CPU box: an empty summary, not an error
+    check(set(out) >= {"sm_mhz", "reasons", "samples"}, "clock sampler summary keys")
+    rep = trace.report()
+    check(("init.broadcast" in rep) == trace.ENABLED, "trace report lists the scope when tracing is on")
+    print(json.dumps({"ok": True, "traced": trace.ENABLED}), flush=True)
+
+
 def cmd_bad(args):
     rt = get_runtime()
     if rt.rank == 0:

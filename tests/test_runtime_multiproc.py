@@ -106,6 +106,17 @@ def test_randomised_soak(np, strategy):
     assert r.stdout.count('"ok": true') == np, r.stdout[-3000:]
 
 
+def test_initializer_tracing_and_timing_helpers(tmp_path):
+    trace_file = tmp_path / "trace.json"
+    r = launch(2, "initializer", env={"KUNGFU_ENABLE_TRACE": "1", "KUNGFU_TRACE_FILE": str(trace_file)})
+    assert r.stdout.count('"ok": true') == 2 and '"traced": true' in r.stdout, r.stdout[-3000:]
+    assert "[kungfu trace]" in r.stdout and "init.broadcast" in r.stdout  # per-scope summary printed at exit
+    ev = json.loads(trace_file.read_text())["traceEvents"]
+    assert any(e["name"] == "init.broadcast" and e["ph"] == "X" and e["dur"] > 0 for e in ev)
+    r = launch(3, "initializer")
+    assert r.stdout.count('"ok": true') == 3 and '"traced": false' in r.stdout, r.stdout[-3000:]
+
+
 def test_metrics_endpoint():
     r = launch(3, "metrics", env={"KUNGFU_CONFIG_ENABLE_MONITORING": "true"})
     assert r.stdout.count('"ok": true') == 3, r.stdout[-3000:]
