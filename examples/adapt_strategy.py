@@ -5,6 +5,11 @@ the reference window, switch to an alternative tree (here: the minimum spanning 
 
     kungfu-run -np 4 -strategy STAR python examples/adapt_strategy.py
 """
+import os
+import sys
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))  # run from a checkout without installing
+
 import torch
 
 import kungfu_b200.python as kfp

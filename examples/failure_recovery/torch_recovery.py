@@ -3,6 +3,11 @@ docs/monitor_proposal.md). Heartbeats around every batch; a checkpoint per epoch
 
     kungfu-run -np 4 -auto-recover 10s python examples/failure_recovery/torch_recovery.py --n-epochs 5
 """
+import os
+import sys
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "../..")))  # run from a checkout without installing
+
 import argparse
 import os
 

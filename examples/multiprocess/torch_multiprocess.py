@@ -1,5 +1,10 @@
 """In-process launch of a KungFu cluster without kungfu-run (reference: examples/multiprocess/torch_multiprocess.py)."""
+import os
+import sys
+
 import torch
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "../..")))  # run from a checkout without installing
 
 
 def worker(rank):

@@ -3,6 +3,11 @@
 
     kungfu-run -w -np 1 -H 127.0.0.1:4 -builtin-config-port 9100 python examples/torch_elastic/torch_mnist_elastic.py
 """
+import os
+import sys
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "../..")))  # run from a checkout without installing
+
 import torch
 import torch.nn.functional as F
 

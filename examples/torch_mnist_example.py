@@ -2,6 +2,11 @@
 
     kungfu-run -np 2 python examples/torch_mnist_example.py --epochs 2
 """
+import os
+import sys
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))  # run from a checkout without installing
+
 import argparse
 
 import torch

@@ -2,6 +2,11 @@
 
     kungfu-run -np 4 python examples/torch_simple_example.py
 """
+import os
+import sys
+
+sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))  # run from a checkout without installing
+
 import torch
 
 import kungfu_b200.torch as kf
