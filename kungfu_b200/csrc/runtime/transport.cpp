@@ -380,6 +380,57 @@ void Client::close_all() {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// BufferPool
+// ---------------------------------------------------------------------------------------------------
+BufferPool& BufferPool::get() {
+    static BufferPool* p = new BufferPool(); // leaked on purpose: buffers may be returned during static destruction
+    return *p;
+}
+int BufferPool::bucket_of(size_t n) {
+    if (n > ((size_t)1 << kMaxShift)) return -1;
+    int s = kMinShift;
+    while (((size_t)1 << s) < n) ++s;
+    return s - kMinShift;
+}
+void* BufferPool::take(size_t n) {
+    const int b = bucket_of(n);
+    if (b < 0) return ::operator new(n);
+    {
+        std::lock_guard<std::mutex> g(mu_);
+        if (!free_[b].empty()) {
+            void* p = free_[b].back();
+            free_[b].pop_back();
+            retained_ -= (size_t)1 << (b + kMinShift);
+            ++hits_;
+            return p;
+        }
+    }
+    return ::operator new((size_t)1 << (b + kMinShift));
+}
+void BufferPool::give(void* p, size_t n) {
+    if (!p) return;
+    const int b = bucket_of(n);
+    if (b >= 0) {
+        const size_t sz = (size_t)1 << (b + kMinShift);
+        std::lock_guard<std::mutex> g(mu_);
+        if (retained_ + sz <= kMaxRetained) {
+            free_[b].push_back(p);
+            retained_ += sz;
+            return;
+        }
+    }
+    ::operator delete(p);
+}
+size_t BufferPool::retained_bytes() {
+    std::lock_guard<std::mutex> g(mu_);
+    return retained_;
+}
+size_t BufferPool::hits() {
+    std::lock_guard<std::mutex> g(mu_);
+    return hits_;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // CollectiveEndpoint
 // ---------------------------------------------------------------------------------------------------
 std::string CollectiveEndpoint::key(const PeerID& src, const std::string& name) {

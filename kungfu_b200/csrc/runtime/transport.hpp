@@ -117,8 +117,42 @@ private:
     std::map<std::pair<uint64_t, int>, std::shared_ptr<Conn>> pool_;
 };
 
+// ---- message buffers ------------------------------------------------------------------------------------
+// Received chunks that no receiver is waiting for yet are parked in `Bytes`. Their storage comes from a size-bucketed free
+// list (reference: the sync.Pool buffer pool of srcs/go/rchannel/connection/buffer_pool.go) and is NOT zero-filled: a plain
+// std::vector<uint8_t>(1 MiB) costs a malloc, a memset and — once glibc has trimmed the heap — a page fault per 4 KiB,
+// for every chunk of every all-reduce.
+class BufferPool {
+public:
+    static BufferPool& get();
+    void* take(size_t n);            // >= n bytes, uninitialised
+    void give(void* p, size_t n);    // n as passed to take()
+    size_t retained_bytes();
+    size_t hits();
+
+private:
+    static int bucket_of(size_t n);  // -1: not pooled (tiny or huge)
+    static constexpr int kMinShift = 9, kMaxShift = 26; // 512 B .. 64 MiB, powers of two
+    static constexpr size_t kMaxRetained = 256u << 20;
+    std::mutex mu_;
+    std::vector<void*> free_[kMaxShift - kMinShift + 1];
+    size_t retained_ = 0, hits_ = 0;
+};
+
+template <typename T> struct PoolAllocator {
+    using value_type = T;
+    PoolAllocator() = default;
+    template <typename U> PoolAllocator(const PoolAllocator<U>&) {}
+    T* allocate(size_t n) { return static_cast<T*>(BufferPool::get().take(n * sizeof(T))); }
+    void deallocate(T* p, size_t n) { BufferPool::get().give(p, n * sizeof(T)); }
+    template <typename U> void construct(U* p) { ::new (static_cast<void*>(p)) U; } // default-init: bytes stay uninitialised
+    template <typename U, typename... A> void construct(U* p, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A>(a)...); }
+    template <typename U> bool operator==(const PoolAllocator<U>&) const { return true; }
+    template <typename U> bool operator!=(const PoolAllocator<U>&) const { return false; }
+};
+
 // ---- endpoints ------------------------------------------------------------------------------------------
-using Bytes = std::vector<uint8_t>;
+using Bytes = std::vector<uint8_t, PoolAllocator<uint8_t>>;
 
 class CollectiveEndpoint {
 public:

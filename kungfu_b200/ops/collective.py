@@ -314,11 +314,40 @@ def all_reduce_async_(x: torch.Tensor, name: str = "", op=None) -> Handle:
     if rt.size == 1:
         return Handle()
     if not x.is_cuda:
-        all_reduce_(x, op, name)
-        return Handle()
+        # Host tensors: the native collective releases the GIL, so a small FIFO executor keeps several named collectives in
+        # flight (the reference's TF ops run concurrently the same way; per-tensor latency, not bandwidth, dominates a model
+        # with 160 small tensors). The op name is fixed HERE, in program order, so that every rank pairs the same tensors.
+        if getattr(rt.control, "kind", "") != "native" or os.environ.get("KUNGFU_CPU_ASYNC", "1") == "0":
+            all_reduce_(x, op, name)
+            return Handle()
+        fut = _cpu_executor().submit(all_reduce_, x, op, name or _async_name(rt))
+        return Handle(post=fut.result)
     plane = rt.gpu
     done = _run_on_comm(plane, lambda s: _gpu_all_reduce_(x, code, avg, stream=s), (x,), wait=False)
     return Handle(event=done)
+
+
+_cpu_pool = None
+_async_seq = {"version": None, "n": 0}
+
+
+def _cpu_executor():
+    global _cpu_pool
+    if _cpu_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _cpu_pool = ThreadPoolExecutor(max_workers=int(os.environ.get("KUNGFU_CPU_ASYNC_THREADS", "8")), thread_name_prefix="kf-cpu-async")
+    return _cpu_pool
+
+
+def _async_name(rt) -> str:
+    """Deterministic name for an unnamed asynchronous op; numbering restarts with the cluster version (see peer._auto_name)."""
+    ver = getattr(rt.control, "cluster_version", None)
+    v = ver() if ver else 0
+    if _async_seq["version"] != v:
+        _async_seq["version"], _async_seq["n"] = v, 0
+    _async_seq["n"] += 1
+    return f"async-allreduce::v{v}::{_async_seq['n']}"
 
 
 def wait_handle(h: Handle) -> None:

@@ -130,8 +130,5 @@ def cpu_all_reduce_grads(named, op: str, average: bool) -> None:
     for name, p in named:
         if p.grad is None:
             continue
-        if p.grad.is_cuda:
-            handles.append(coll.all_reduce_async_(p.grad, name, "avg" if average else op))
-        else:
-            coll.all_reduce_(p.grad, "avg" if average else op, name)
+        handles.append(coll.all_reduce_async_(p.grad, name, "avg" if average else op))  # host tensors overlap too (FIFO executor)
     coll.wait_all_handles(handles)
