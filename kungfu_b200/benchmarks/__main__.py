@@ -98,6 +98,7 @@ def bench_p2p(rt, a, ts, nbytes) -> None:
     for _ in range(a.warmup_steps):
         epoch()
     d = np.array([epoch() for _ in range(a.steps)])
+    coll.barrier()  # nobody leaves while a neighbour is still pulling from it
     rate = 2 * n * nbytes / d / (1 << 30)
     if rt.rank == 0:
         attrs = {"np": n, "model": a.model, "method": a.method, "p2p": True, "fuse": a.fuse, "tensors": len(ts), "bytes": nbytes,
