@@ -63,7 +63,6 @@ def main() -> int:
         return reference_arm(args)
 
     import torch
-    import torch.nn.functional as F
 
     import kungfu_b200.torch as kf
     from kungfu_b200.models import resnet

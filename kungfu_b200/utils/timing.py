@@ -5,7 +5,6 @@ number we report is device-timed and, for multi-GPU runs, the max over ranks.
 """
 from __future__ import annotations
 
-import os
 import shutil
 import statistics
 import subprocess

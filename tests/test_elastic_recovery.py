@@ -11,7 +11,7 @@ import subprocess
 import sys
 import time
 
-import pytest
+
 
 from test_runtime_multiproc import ROOT, WORKER, json_lines, kungfu_run, ports
 
