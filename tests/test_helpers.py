@@ -192,3 +192,29 @@ def test_vision_model_zoo_matches_reference_shapes():
     assert all(p.grad is not None for p in inc.parameters())
     with pytest.raises(ValueError):
         models.build("alexnet")
+
+
+def test_reference_import_names_resolve():
+    """A script written against the reference keeps its imports: `import kungfu.torch as kf`, `kungfu.python`, `kungfu.cmd`."""
+    import kungfu
+    import kungfu.python as kfp
+    import kungfu.torch as kf
+    from kungfu._utils import measure, show_duration
+    from kungfu.cmd import launch_multiprocess  # noqa: F401
+    from kungfu.torch.ops import all_reduce_fn, broadcast_parameters, inplace_all_reduce_op  # noqa: F401
+    from kungfu.torch.optimizers import (PairAveragingOptimizer, SynchronousAveragingOptimizer,  # noqa: F401
+                                         SynchronousSGDOptimizer)
+
+    import kungfu_b200.torch
+
+    assert kf is kungfu_b200.torch and kungfu.__version__
+    assert kfp.current_rank() == 0 and kfp.current_cluster_size() == 1 and kfp.detached() is False
+    assert torch.equal(all_reduce_fn(torch.ones(3)), torch.ones(3))
+    dt, val = measure(lambda: 7)
+    assert val == 7 and dt >= 0 and isinstance(show_duration(1.5), str)
+    m = torch.nn.Linear(3, 2)
+    opt = SynchronousSGDOptimizer(torch.optim.SGD(m.parameters(), lr=0.1), named_parameters=m.named_parameters())
+    assert isinstance(opt, torch.optim.SGD)  # still an instance of the user's optimizer class
+    m(torch.ones(1, 3)).sum().backward()
+    opt.step()
+    assert isinstance(kungfu.info(), dict)
