@@ -16,4 +16,5 @@ for _sub in ("torch.ops", "torch.optimizers"):
     sys.modules[f"kungfu.{_sub}"] = importlib.import_module(f"kungfu_b200.{_sub}")
 sys.modules["kungfu._utils"] = sys.modules["kungfu.utils"]  # reference: kungfu/_utils.py (measure, show_duration, _log_event)
 _utils = sys.modules["kungfu.utils"]
-info = _impl.utils.info  # reference: `python -m kungfu.info`
+sys.modules["kungfu.info"] = importlib.import_module("kungfu_b200.info")
+info = sys.modules["kungfu.info"]  # reference: `python -m kungfu.info`

@@ -149,3 +149,8 @@ def init_from_env() -> None:
 
 def finalize() -> None:
     reset_runtime()
+
+
+def _resize_from_url():
+    """Reference name of `resize()` without an argument (python/__init__.py:135-140): follow the config server."""
+    return resize(None)
