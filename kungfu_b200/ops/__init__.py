@@ -38,6 +38,42 @@ def monitored_all_reduce(t: torch.Tensor, tree=None, op="sum") -> torch.Tensor:
     return out
 
 
+def group_nccl_all_reduce(ts: Sequence[torch.Tensor], op="sum") -> List[torch.Tensor]:
+    """All-reduce a list of device tensors concurrently. The reference schedules one NCCL all-reduce per tensor in a
+    negotiated order (ops/collective.py:96-106); here each tensor goes to the sm_100a kernels on the comm stream (their order is
+    the list order on every rank), host tensors to the native runtime. None entries pass through."""
+    outs = [None if t is None else t.detach().clone() for t in ts]
+    hs = [all_reduce_async_(t, f"group::{i}", op) for i, t in enumerate(outs) if t is not None]
+    wait_all_handles(hs)
+    return outs
+
+
+def group_hierarchical_nccl_all_reduce(ts: Sequence[torch.Tensor], op="sum") -> List[torch.Tensor]:
+    """Reference: local reduce -> cross-host all-reduce -> local broadcast per tensor (ops/collective.py:109-135). The
+    dispatcher of `all_reduce` already chooses flat (one NVLink domain) or hierarchical (job spans hosts)."""
+    return group_nccl_all_reduce(ts, op)
+
+
+def calc_stats():
+    """Communication-strategy throughput statistics (reference: ops/adapt.py:60-62)."""
+    from ..python import calc_stats as _calc
+
+    return _calc()
+
+
+def save_model(variables: Sequence[torch.Tensor], name: str = "kungfu::fused_model") -> None:
+    """Publish the fused model (all variables flattened into one blob) for peers to pull (reference: ops/local.py:27-33,
+    the store behind PairAveraging with fuse_requests=True)."""
+    save_variable(fuse([v.detach() for v in variables]), name)
+
+
+def request_model(target: int, variables: Sequence[torch.Tensor], name: str = "kungfu::fused_model"):
+    """Pull the fused model published by `target` with `save_model`; returns (ok, list of tensors shaped like `variables`)."""
+    template = fuse([v.detach() for v in variables])
+    ok, flat = request_variable_with_template(target, template, name)
+    return ok, (defuse(flat, [tuple(v.shape) for v in variables]) if ok else [])
+
+
 def fuse(ts: Sequence[torch.Tensor]) -> torch.Tensor:
     """Flatten + concatenate (reference: ops/__init__.py:29-33)."""
     return torch.cat([t.reshape(-1) for t in ts])

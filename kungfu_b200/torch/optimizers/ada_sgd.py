@@ -49,3 +49,33 @@ class _AdaptiveSGD(KungFuMixin):
 
 def AdaptiveSGDOptimizer(optimizer, named_parameters=None, change_step: int = 0, alpha: float = 0.1):
     return wrap_optimizer(optimizer, _AdaptiveSGD, lambda o: o._kf_init_ada(named_parameters, change_step, alpha))
+
+
+class AdaSGDHook:
+    """Training-loop hook of the reference (`AdaSGDHook(change_step)`, ada_sgd.py:68-83): at `change_step` every variable is
+    re-broadcast from rank 0. `AdaptiveSGDOptimizer` above does this by itself; the hook exists for loops that drive the
+    switch themselves (e.g. with a plain SMA optimizer before and an S-SGD optimizer after)."""
+
+    def __init__(self, change_step: int, model: torch.nn.Module = None, tensors=None) -> None:
+        self.change_step = int(change_step)
+        self._tensors = list(tensors) if tensors is not None else None
+        self._model = model
+        self.fired = False
+
+    def _targets(self):
+        if self._tensors is not None:
+            return self._tensors
+        if self._model is not None:
+            return [v for v in self._model.state_dict().values() if isinstance(v, torch.Tensor)]
+        return []
+
+    def after_run(self, global_step: int) -> bool:
+        """Call once per step with the step that just finished; returns True on the step where the broadcast happened."""
+        if self.fired or int(global_step) != self.change_step:
+            return False
+        for i, t in enumerate(self._targets()):
+            coll.broadcast_(t, 0, f"ada::hook::{i}")
+        self.fired = True
+        return True
+
+    after_step = after_run

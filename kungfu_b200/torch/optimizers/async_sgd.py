@@ -21,6 +21,15 @@ from ...ops import collective as coll
 from .core import KungFuMixin, fusable_kind, wrap_optimizer
 
 
+def get_random_peer(cluster_size: int, self_rank: int, rng: random.Random = None) -> int:
+    """A uniformly drawn rank; a draw that hits `self_rank` moves on to the next rank, exactly like the reference's graph
+    (async_sgd.py:71-75: `t = uniform(0, np); t == self ? (t + 1) % np : t`)."""
+    if cluster_size <= 1:
+        return int(self_rank)
+    t = (rng or random).randrange(cluster_size)
+    return (t + 1) % cluster_size if t == self_rank else t
+
+
 class _PairAveraging(KungFuMixin):
     def _kf_init_pair(self, named_parameters, fuse_requests, fused_model_name, fused, peer_selection, seed):
         self._kf_setup(named_parameters, True)

@@ -108,6 +108,24 @@ def cmd_collectives(args):
         check(torch.equal(m, torch.full((1 << 18,), n, dtype=torch.int64)), "monitored")
         kfp.calc_stats(); kfp.log_stats(); kfp.print_strategy_stats()
         check(kfp.check_interference() is False, "first interference check takes the reference window")
+    # reference names kept for scripts that use them: group_(hierarchical_)nccl_all_reduce, save_model / request_model, AdaSGDHook
+    g2 = ops.group_nccl_all_reduce([torch.full((5,), float(r)), None, torch.full((70000,), 1.0)])
+    check(g2[1] is None and torch.equal(g2[0], torch.full((5,), float(sum(range(n))))) and torch.equal(g2[2], torch.full((70000,), float(n))),
+          "group_nccl_all_reduce")
+    g3 = ops.group_hierarchical_nccl_all_reduce([torch.ones(4) * (r + 1)], op="max")
+    check(torch.equal(g3[0], torch.full((4,), float(n))), "group_hierarchical_nccl_all_reduce")
+    model = [torch.full((3, 2), float(r)), torch.full((7,), float(10 + r))]
+    ops.save_model(model)
+    coll.barrier()
+    ok, got = ops.request_model((r + 1) % n, model)
+    t = (r + 1) % n
+    check(ok and torch.equal(got[0], torch.full((3, 2), float(t))) and torch.equal(got[1], torch.full((7,), float(10 + t))), "save_model / request_model")
+    w = torch.full((6,), float(r))
+    hook = kf.optimizers.AdaSGDHook(change_step=2, tensors=[w])
+    fired = [hook.after_run(s) for s in range(4)]
+    check(fired == [False, False, True, False] and torch.equal(w, torch.zeros(6)), "AdaSGDHook broadcasts once at the change step")
+    peers = {kf.optimizers.get_random_peer(n, r) for _ in range(200)}
+    check(r not in peers or n == 1, "get_random_peer never returns self")
     coll.barrier()
     print(json.dumps({"ok": True, "rank": r, "size": n}), flush=True)
 
