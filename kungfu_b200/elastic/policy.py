@@ -10,7 +10,10 @@ from __future__ import annotations
 
 from typing import Dict, List, Sequence
 
+from .. import variables as kv
 from ..python import current_cluster_size, detached
+
+_PUBLISHED = (kv.GraphKeys.BATCH_SIZE, kv.GraphKeys.TRAINED_SAMPLES, kv.GraphKeys.TOTAL_SAMPLES)
 
 
 class BasePolicy:
@@ -62,10 +65,21 @@ class PolicyHook:
 
     def set_batch_size(self, bs: int) -> None:
         self.vars["kungfu_batch_size"] = int(bs)
+        self._publish()
+
+    def _publish(self) -> None:
+        """Mirror the counters into the global-variable registry (reference: PolicyHook owns `kungfu_batch_size`,
+        `kungfu_trained_samples`, `kungfu_total_samples`), so that `variables.eval_batch_size()` works anywhere in the program."""
+        import torch
+
+        for name in _PUBLISHED:
+            kv.get_or_create_global_variable(name, (), torch.int64).fill_(int(self.vars[name]))
 
     def begin(self) -> None:
+        self._publish()
         for p in self.policies:
             p.before_train(self.vars)
+        self._publish()
 
     def before_step(self) -> bool:
         if self._stopped or detached() or self.vars["kungfu_trained_samples"] >= self.vars["kungfu_total_samples"]:
@@ -76,6 +90,7 @@ class PolicyHook:
             self._in_epoch = True
         for p in self.policies:
             p.before_step(self.vars)
+        self._publish()
         return True
 
     def after_step(self) -> None:
@@ -88,6 +103,10 @@ class PolicyHook:
                 p.after_epoch(self.vars)
             self.vars["epoch"] += 1
             self._in_epoch = False
+        gns = kv.get_global_variable(kv.GraphKeys.GRADIENT_NOISE_SCALE)
+        if gns is not None and not gns.is_cuda:  # a device-resident estimate is read on demand, not every step
+            self.vars["kungfu_gradient_noise_scale"] = float(gns.item())
+        self._publish()
 
     def request_stop(self) -> None:
         self._stopped = True

@@ -28,10 +28,17 @@ class _MonitorGNS(_SynchronousSGD):
         self._kf_alpha = float(alpha)
         self._kf_cpu_ns = NoiseScale(alpha)
         self.noise_scale_value = 0.0
+        from ... import variables as kv
+
         if self._kf_engine is not None:
             dev = self._kf_engine.plane.device
             self._kf_gns_state = torch.zeros(4, dtype=torch.float32, device=dev)
             self._kf_gns_out = torch.zeros(4, dtype=torch.float32, device=dev)
+            # reference: the optimizer owns the global variable `kungfu_gradient_noise_scale`; here it is the device scalar the
+            # finalize kernel writes (reading it with eval_gradient_noise_scale() synchronises, nothing else does)
+            self._kf_gns_var = kv.bind_global_variable(kv.GraphKeys.GRADIENT_NOISE_SCALE, self._kf_gns_out[0])
+        else:
+            self._kf_gns_var = kv.bind_global_variable(kv.GraphKeys.GRADIENT_NOISE_SCALE, torch.zeros((), dtype=torch.float32))
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -50,6 +57,7 @@ class _MonitorGNS(_SynchronousSGD):
                 local_sq = float(t.item()) / n
             if (self._kf_step_count - 1) % self._kf_interval == 0 and n > 1:
                 self.noise_scale_value = self._kf_cpu_ns.update(self._kf_bs, self._kf_bs * n, local_sq, big_sq)
+                self._kf_gns_var.fill_(float(self.noise_scale_value))
             return loss
         loss = _SynchronousSGD.step(self, closure)
         sums = eng.read_sumsq(reset=True)  # [sum_r |g_r|^2, |g_avg|^2], device tensor

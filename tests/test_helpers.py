@@ -218,3 +218,61 @@ def test_reference_import_names_resolve():
     m(torch.ones(1, 3)).sum().backward()
     opt.step()
     assert isinstance(kungfu.info.collect(), dict) and kfp._resize_from_url is not None
+
+
+def test_global_variables_registry_and_dataset_adaptors():
+    """Reference: tensorflow/variables.py (named global variables, batch-size / noise-scale accessors, setters) and
+    v1/datasets/adaptor.py (BaseDatasetAdaptor / ExampleDatasetAdaptor)."""
+    from kungfu_b200 import variables as kv
+    from kungfu_b200.elastic import BaseDatasetAdaptor, ExampleDatasetAdaptor, PolicyHook, ScheduledBatchSizePolicy
+
+    for n in list(kv.global_variables()):
+        kv.remove_global_variable(n)
+    assert kv.get_global_variable("x") is None and kv.get_batch_size() is None
+    with pytest.raises(RuntimeError):
+        kv.eval_global_variable("x")
+    v = kv.create_global_variable("x", shape=(3,), dtype=torch.float32)
+    assert v.shape == (3,) and not v.requires_grad and kv.get_or_create_global_variable("x") is v
+    with pytest.raises(ValueError):
+        kv.create_global_variable("x")
+    set_x = kv.create_setter(v)
+    set_x([1.0, 2.0, 3.0])
+    assert kv.eval_global_variable("x").tolist() == [1.0, 2.0, 3.0]
+    op, place = kv.create_assign_op_for(v)
+    place.fill_(7.0)
+    op()
+    assert v.tolist() == [7.0, 7.0, 7.0] and kv.create_placeholder_for(v).shape == v.shape
+    bs = kv.get_or_create_batch_size(init=32)
+    assert bs.dtype == torch.int32 and kv.eval_batch_size() == 32 and kv.get_batch_size() is bs
+    kv.create_setter(bs)(48)
+    assert kv.eval_batch_size() == 48
+    kv.remove_global_variable(kv.GraphKeys.BATCH_SIZE)
+    # the policy hook publishes its counters; a policy that changes the batch size is visible through the registry
+    hook = PolicyHook([ScheduledBatchSizePolicy({0: 10, 1: 20})], epoch_size=100, epoch_num=2, init_batch_size=5)
+    hook.begin()
+    seen = []
+    while hook.before_step():
+        seen.append(kv.eval_batch_size())
+        hook.after_step()
+    hook.end()
+    assert seen == [10] * 10 + [20] * 5 and int(kv.eval_global_variable(kv.GraphKeys.TRAINED_SAMPLES)) == 200
+    assert int(kv.eval_global_variable(kv.GraphKeys.TOTAL_SAMPLES)) == 200
+    # the noise-scale monitor owns kungfu_gradient_noise_scale
+    m = torch.nn.Linear(2, 1)
+    import kungfu_b200.torch as kf
+
+    kf.optimizers.MonitorGradientNoiseScaleOptimizer(torch.optim.SGD(m.parameters(), lr=0.1), m.named_parameters(), device_batch_size=4)
+    assert kv.eval_gradient_noise_scale() == 0.0
+    kv.sync_global_variables()  # single process: a no-op that must not fail
+    # dataset adaptors
+    data = torch.arange(40)
+    a = BaseDatasetAdaptor(batch_size=4, shard_count=2, shard_id=1)
+    batches = [b.tolist() for b in a(data)]
+    assert batches[0] == [4, 5, 6, 7] and batches[1] == [12, 13, 14, 15] and len(batches) == 5
+    assert a.create_update_offset()() == 8 and [b.tolist() for b in a(data)][0] == [12, 13, 14, 15]
+    assert a.create_rewind()() == 0 and "offset=0, np=2, rank=1, batch size=4" == a.debug()
+    with pytest.raises(RuntimeError):
+        a.create_update_topology()
+    e = ExampleDatasetAdaptor(batch_size=4, shard_count=2, shard_id=1)
+    e.create_update_topology()()
+    assert (e._shard_count, e._shard_id, e._batch_size) == (3, 2, 6)
