@@ -8,7 +8,7 @@ import kungfu_b200 as _impl
 __version__ = _impl.__version__
 
 for _name in ("python", "torch", "cmd", "ops", "elastic", "initializer", "checkpoint", "utils", "models", "parallel", "helpers", "platforms",
-              "benchmarks", "variables"):
+              "benchmarks", "variables", "examples"):
     _mod = importlib.import_module(f"kungfu_b200.{_name}")
     sys.modules[f"kungfu.{_name}"] = _mod
     globals()[_name] = _mod

@@ -82,6 +82,9 @@ def test_examples_and_microbench_run():
     r = subprocess.run(base + ["-m", "kungfu_b200.benchmarks", "--model", "slp", "--steps", "3"], env=env, cwd=ROOT,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=180)
     assert r.returncode == 0 and "RESULT:" in r.stdout, r.stdout[-2000:]
+    r = subprocess.run(base + ["-m", "kungfu_b200.examples"], env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=180)  # self-checking: all-reduce of ones, closed-form S-SGD / SMA, PairAveraging envelope
+    assert r.returncode == 0 and "examples ok" in r.stdout, r.stdout[-2000:]
     r = subprocess.run(base + [os.path.join(ROOT, "examples", "adapt_strategy.py")], env=env, cwd=ROOT,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=180)
     assert r.returncode == 0, r.stdout[-2000:]
