@@ -80,17 +80,18 @@ def _watch(np, slots, what, extra, cfg_port, timeout=240, env=None):
 
 
 def test_elastic_step_schedule_grow_and_shrink():
-    """1 -> 2 -> 4 -> 2 -> 1 workers, three steps each; survivors keep state, newcomers inherit it, detached exit."""
+    """1 -> 2 -> 4 -> 8 -> 4 -> 2 -> 1 workers, three steps each (the reference's `test_step_based_schedule.py` under
+    `-w -np 1 -H 127.0.0.1:8`); survivors keep state, newcomers inherit it, detached workers exit."""
     cfg_port = 9700 + os.getpid() % 200
-    r = _watch(1, 4, "elastic", ["--schedule", "1:3,2:3,4:3,2:3,1:3", "--max-step", "15"], cfg_port)
+    r = _watch(1, 8, "elastic", ["--schedule", "1:3,2:3,4:3,8:3,4:3,2:3,1:3", "--max-step", "21"], cfg_port, timeout=300)
     assert r.returncode == 0, r.stdout[-5000:]
     js = json_lines(r.stdout)
     final = [j for j in js if j.get("elastic")]
     assert len(final) == 1, r.stdout[-5000:]
-    assert final[0]["final_step"] == 15 and final[0]["bias"] != 0 and final[0]["resizes"] == 4
-    assert final[0]["sizes"] == [1, 2, 4]
-    assert len([j for j in js if j.get("detached")]) == 3  # 2 leave at 4->2, 1 leaves at 2->1
-    assert "resize 1 -> 2 took" in r.stdout and "resize 4 -> 2 took" in r.stdout
+    assert final[0]["final_step"] == 21 and final[0]["bias"] != 0 and final[0]["resizes"] == 6
+    assert final[0]["sizes"] == [1, 2, 4, 8]
+    assert len([j for j in js if j.get("detached")]) == 7  # 4 leave at 8->4, 2 at 4->2, 1 at 2->1
+    assert "resize 1 -> 2 took" in r.stdout and "resize 8 -> 4 took" in r.stdout
 
 
 def test_elastic_churn_with_sibling_survivors():
