@@ -70,6 +70,11 @@ def test_fake_agent_c_abi():
     out = subprocess.run([kungfu_run(), "-q", "-np", "2", "-H", "127.0.0.1:2", "-port", str(rport), "-port-range", prange,
                           _bin("kungfu-fake-agent"), "bench", "slp"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
     assert out.returncode == 0 and "RESULT:" in out.stdout, out.stdout[-2000:]
+    # fake trainer, asynchronous flavour: all 161 ResNet-50 tensors in flight through the callback form of the C ABI
+    rport, prange = ports()
+    out = subprocess.run([kungfu_run(), "-q", "-np", "3", "-H", "127.0.0.1:3", "-port", str(rport), "-port-range", prange,
+                          _bin("kungfu-fake-agent"), "bench-async", "resnet50"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert out.returncode == 0 and "RESULT:" in out.stdout and "Img/sec" in out.stdout, out.stdout[-2000:]
 
 
 def test_examples_and_microbench_run():
