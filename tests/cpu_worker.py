@@ -354,6 +354,39 @@ def cmd_elastic(args):
         print(hook.profiler.report(), flush=True)
 
 
+def cmd_follow(args):
+    """Workers that only FOLLOW the config server (somebody else rewrites it, e.g. `kungfu_b200.cmd.config_client --random`):
+    every step ends with `resize()`; state must stay consistent through whatever sequence of sizes arrives."""
+    from kungfu_b200.elastic import ElasticState, sync_after_resize
+
+    m = torch.nn.Linear(4, 2)
+    opt = kf.optimizers.SynchronousSGDOptimizer(torch.optim.SGD(m.parameters(), lr=0.01), named_parameters=m.named_parameters())
+    state = sync_after_resize(ElasticState(), m, opt)
+    sizes, resizes = set(), 0
+    while state.step < args.max_step:
+        opt.zero_grad()
+        (m(torch.ones(3, 4)).sum() * 0).backward()
+        opt.step()
+        with torch.no_grad():
+            m.bias.add_(1.0)
+        state.step += 1
+        sizes.add(kfp.current_cluster_size())
+        check(ops.consensus(m.bias.data), f"replicas diverged at step {state.step}")
+        time.sleep(0.05)
+        changed, det = kfp.resize(None)
+        if det:
+            print(json.dumps({"detached": True, "step": state.step}), flush=True)
+            return
+        if changed:
+            resizes += 1
+            state = sync_after_resize(state, m, opt)
+    # every member did exactly max_step increments of the bias, wherever it joined
+    check(abs(float(m.bias[0]) - float(m.bias.detach()[0])) == 0 and state.step == args.max_step, "final step")
+    if kfp.current_rank() == 0:
+        print(json.dumps({"followed": True, "final_step": state.step, "sizes": sorted(sizes), "resizes": resizes,
+                          "final_size": kfp.current_cluster_size()}), flush=True)
+
+
 def cmd_recovery(args):
     """One rank stalls inside a batch once; the launcher's failure detector must restart the job, which resumes from the
     checkpoint with the remaining epochs."""

@@ -106,6 +106,43 @@ def test_elastic_churn_with_sibling_survivors():
         assert len(final) == 1 and final[0]["final_step"] == 16 and final[0]["resizes"] == 7 and final[0]["sizes"] == [1, 2, 3, 4], r.stdout[-3000:]
 
 
+def test_random_resizes_from_an_external_config_client():
+    """The chaos half of the reference's elastic test (kungfu-config-client-example): an external client rewrites the cluster
+    config with random sizes every 0.7 s while the workers just follow the config server."""
+    import threading
+
+    from kungfu_b200.cmd import config_client
+
+    cfg_port = 9300 + os.getpid() % 200
+    url = f"http://127.0.0.1:{cfg_port}/config"
+    log = []
+
+    def chaos():
+        t_end = time.time() + 60
+        while time.time() < t_end and config_client.current_size(url) < 0:
+            time.sleep(0.2)
+        time.sleep(1.0)
+        import random
+
+        rng = random.Random(7)
+        for _ in range(10):
+            n = rng.randint(1, 4)
+            if config_client.put_size(url, n):
+                log.append(n)
+            time.sleep(0.7)
+        config_client.put_size(url, 2)
+        log.append(2)
+
+    th = threading.Thread(target=chaos, daemon=True)
+    th.start()
+    r = _watch(2, 4, "follow", ["--max-step", "400"], cfg_port, timeout=280)
+    th.join(timeout=30)
+    assert r.returncode == 0, r.stdout[-5000:]
+    final = [j for j in json_lines(r.stdout) if j.get("followed")]
+    assert len(final) == 1 and final[0]["final_step"] == 400 and final[0]["final_size"] == 2, r.stdout[-3000:]
+    assert final[0]["resizes"] >= 2 and len(log) >= 5, (final, log)
+
+
 def test_failure_detection_and_auto_recovery(tmp_path):
     """A worker hangs inside a batch; the heartbeat detector restarts the job, which resumes from the checkpoint with
     the remaining epochs (`--n-epochs` patched, `--restart 1` appended)."""
