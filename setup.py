@@ -24,6 +24,7 @@ setup(
     package_data={"kungfu_b200": ["*.so", "bin/*", "csrc/**/*"]},
     cmdclass={"build_py": BuildNative},
     entry_points={"console_scripts": ["kungfu-run=kungfu_b200.cmd:run", "kungfu-rrun=kungfu_b200.cmd.rrun:main",
-                                      "kungfu-test-util=kungfu_b200.cmd.test_util:main"]},
+                                      "kungfu-test-util=kungfu_b200.cmd.test_util:main",
+                                      "kungfu-config-client=kungfu_b200.cmd.config_client:main"]},
     python_requires=">=3.10",
 )
