@@ -82,7 +82,8 @@ void Peer::start() {
         if (Config::get().enable_monitoring) {
             metrics_.reset(new HttpServer());
             try {
-                const int port = metrics_->start("0.0.0.0", cfg_.self.port + 10000, [](const HttpRequest& r) {
+                const std::string bind_to = (cfg_.self.ipv4 >> 24) == 127 ? format_ipv4(cfg_.self.ipv4) : std::string("0.0.0.0");
+                const int port = metrics_->start(bind_to, cfg_.self.port + 10000, [](const HttpRequest& r) {
                     HttpResponse resp;
                     if (r.path == "/metrics") resp.body = NetMonitor::get().metrics_text();
                     else resp.status = 404;

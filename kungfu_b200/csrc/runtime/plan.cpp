@@ -74,7 +74,11 @@ PeerID PeerID::parse(const std::string& s) {
     p.port = (uint16_t)port;
     return p;
 }
-std::string PeerID::sock_file() const { return "/tmp/kungfu-b200-" + std::to_string(port) + ".sock"; }
+std::string PeerID::sock_file() const {
+    // the address is part of the name so that loopback-alias "hosts" (127.0.0.2:10000 next to 127.0.0.1:10000) do not collide
+    if (ipv4 == 0x7f000001u) return "/tmp/kungfu-b200-" + std::to_string(port) + ".sock";
+    return "/tmp/kungfu-b200-" + format_ipv4(ipv4) + "-" + std::to_string(port) + ".sock";
+}
 
 // ---- PeerList -------------------------------------------------------------------------------------
 int PeerList::rank_of(const PeerID& p) const {

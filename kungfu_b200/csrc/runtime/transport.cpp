@@ -700,7 +700,12 @@ void Server::start() {
     sockaddr_in a{};
     a.sin_family = AF_INET;
     a.sin_port = htons(self_.port);
-    a.sin_addr.s_addr = htonl(INADDR_ANY);
+    // Listen on the peer's own address when it is a loopback alias (127.x.y.z): several "hosts" can then share one machine
+    // (127.0.0.1, 127.0.0.2, ... each with the same port numbering), which is how multi-host runs are tested without a cluster
+    // (the reference needs docker-compose for that). Real addresses keep INADDR_ANY: behind NAT the advertised address need
+    // not be a local interface.
+    const bool loopback_alias = (self_.ipv4 >> 24) == 127;
+    a.sin_addr.s_addr = htonl(loopback_alias ? self_.ipv4 : INADDR_ANY);
     if (::bind(tcp_fd_, reinterpret_cast<sockaddr*>(&a), sizeof(a)) != 0 || ::listen(tcp_fd_, 256) != 0) {
         std::string e = strerror(errno);
         ::close(tcp_fd_);

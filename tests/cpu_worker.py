@@ -354,6 +354,43 @@ def cmd_elastic(args):
         print(hook.profiler.report(), flush=True)
 
 
+def cmd_multihost(args):
+    """Semantics that only show with more than one host (run on loopback aliases 127.0.0.1, 127.0.0.2, ...): local rank / size by
+    address, host count, local reduce / broadcast inside a host, cross all-reduce over the hosts' first ranks only."""
+    rt = get_runtime()
+    n, r = rt.size, rt.rank
+    c = rt.control
+    spec = os.environ["KUNGFU_SELF_SPEC"]
+    hosts = [p.rsplit(":", 1)[0] for p in os.environ["KUNGFU_INIT_PEERS"].split(",")]
+    mine = spec.rsplit(":", 1)[0]
+    same = [i for i, h in enumerate(hosts) if h == mine]
+    check(c.local_size == len(same) and c.local_rank == same.index(r), f"local identity {c.local_rank}/{c.local_size} vs {same}")
+    check(c.host_count() == len(set(hosts)) and c.host_count() > 1, f"host count {c.host_count()}")
+    masters = sorted({hosts.index(h) for h in set(hosts)})
+    # local reduce: the host's first rank gets the sum over its host
+    lr = c.local_reduce_cpu(torch.full((5,), float(r + 1)))
+    if c.local_rank == 0:
+        check(torch.equal(lr, torch.full((5,), float(sum(i + 1 for i in same)))), "local reduce sums the host")
+    lb = torch.full((4,), float(r))
+    c.local_broadcast_cpu_(lb)
+    check(torch.equal(lb, torch.full((4,), float(same[0]))), "local broadcast from the host's first rank")
+    x = torch.full((70000,), float(r + 1))
+    c.cross_all_reduce_cpu_(x)
+    want = float(sum(m + 1 for m in masters)) if r in masters else float(r + 1)
+    check(torch.equal(x, torch.full((70000,), want)), f"cross all-reduce over the masters {masters}")
+    # the hierarchical composition equals the flat all-reduce
+    y = c.local_reduce_cpu(torch.full((9,), float(r + 1)))
+    if c.local_rank != 0:
+        y = torch.zeros(9)
+    c.cross_all_reduce_cpu_(y)
+    c.local_broadcast_cpu_(y)
+    check(torch.equal(y, ops.all_reduce(torch.full((9,), float(r + 1)))), "local reduce -> cross all-reduce -> local broadcast == all-reduce")
+    lat = ops.get_peer_latencies()
+    check(lat.shape == (n,), "latencies across hosts")
+    ops.barrier()
+    print(json.dumps({"ok": True, "rank": r, "hosts": c.host_count(), "local": [c.local_rank, c.local_size]}), flush=True)
+
+
 def cmd_follow(args):
     """Workers that only FOLLOW the config server (somebody else rewrites it, e.g. `kungfu_b200.cmd.config_client --random`):
     every step ends with `resize()`; state must stay consistent through whatever sequence of sizes arrives."""

@@ -1,0 +1,104 @@
+"""Multi-host jobs without a cluster: every "host" is a loopback alias (127.0.0.1, 127.0.0.2, ...) with its own `kungfu-run`,
+its own workers and the same per-host port numbering; peers listen on their own alias, so the hosts do not collide.
+
+The reference tests this tier with docker-compose on a private subnet (tests/go/cmd/kungfu-cluster-manager-example,
+scripts/tests gen-compose.py; SURVEY.md §4 "Multi-host without a cluster"). Here it is ordinary processes.
+"""
+import os
+import subprocess
+import sys
+import threading
+
+import pytest
+
+from test_runtime_multiproc import ROOT, WORKER, json_lines, kungfu_run, ports
+
+
+def launch_hosts(slots, what, extra=(), flags=(), timeout=240):
+    """slots = workers per host, e.g. [2, 2] -> 127.0.0.1:2,127.0.0.2:2. One launcher per host, started together."""
+    hosts = [f"127.0.0.{i + 1}" for i in range(len(slots))]
+    hostlist = ",".join(f"{h}:{s}" for h, s in zip(hosts, slots))
+    rport, prange = ports()
+    env = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN")
+    outs = [None] * len(hosts)
+
+    def run(i):
+        cmd = [kungfu_run(), "-q", "-np", str(sum(slots)), "-H", hostlist, "-self", hosts[i], "-port", str(rport), "-port-range", prange,
+               *flags, sys.executable, WORKER, what, *extra]
+        outs[i] = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+
+    ths = [threading.Thread(target=run, args=(i,)) for i in range(len(hosts))]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    text = "\n".join(o.stdout for o in outs)
+    assert all(o.returncode == 0 for o in outs), text[-6000:]
+    return text
+
+
+@pytest.mark.parametrize("slots,strategy", [([2, 2], "BINARY_TREE_STAR"), ([2, 1, 1], "TREE"), ([1, 3], "MULTI_BINARY_TREE_STAR"), ([2, 2], "RING")])
+def test_collectives_across_hosts(slots, strategy):
+    out = launch_hosts(slots, "collectives", flags=["-strategy", strategy])
+    assert len([j for j in json_lines(out) if j.get("ok")]) == sum(slots), out[-4000:]
+
+
+@pytest.mark.parametrize("slots", [[2, 2], [3, 1], [1, 1, 2]])
+def test_local_and_cross_collectives(slots):
+    out = launch_hosts(slots, "multihost")
+    js = [j for j in json_lines(out) if j.get("ok")]
+    assert len(js) == sum(slots) and all(j["hosts"] == len(slots) for j in js), out[-4000:]
+    assert sorted(j["local"][1] for j in js) == sorted(s for s in slots for _ in range(s))
+
+
+def test_p2p_and_set_tree_across_hosts():
+    out = launch_hosts([2, 2], "p2p")
+    assert len([j for j in json_lines(out) if j.get("ok")]) == 4, out[-4000:]
+    out = launch_hosts([2, 2], "set_tree")
+    assert out.count('"ok": true') == 4 and "set_tree latency" in out, out[-4000:]
+
+
+def test_randomised_soak_across_hosts():
+    out = launch_hosts([2, 2], "stress", extra=["100"], flags=["-strategy", "BINARY_TREE_STAR"])
+    assert out.count('"ok": true') == 4, out[-4000:]
+
+
+def test_training_result_does_not_depend_on_the_host_layout():
+    """S-SGD on the SLP: 4 workers on one host and 2 + 2 on two hosts reach the same parameters (np-invariance test across
+    layouts)."""
+    from test_runtime_multiproc import launch
+
+    one = [j for j in json_lines(launch(4, "slp").stdout) if j.get("slp")]
+    two = [j for j in json_lines(launch_hosts([2, 2], "slp")) if j.get("slp")]
+    assert len(one) == 1 and len(two) == 1
+    assert one[0]["acc"] == two[0]["acc"] and abs(one[0]["digest"] - two[0]["digest"]) < 1e-4, (one[0], two[0])
+
+
+def test_elastic_resize_across_hosts():
+    """2 workers on host A grow to 4 (two of them on host B, whose launcher was idling in `-w -k` mode), shrink to 3, then to 1.
+    Host A runs the builtin config server, host B points at it; newcomers on B inherit the state, the job result is intact."""
+    import time
+
+    from kungfu_b200 import _kfrt
+
+    rport, prange = ports()
+    cfg = 9100 + os.getpid() % 300
+    hostlist = "127.0.0.1:2,127.0.0.2:2"
+    env = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN")
+    work = [sys.executable, WORKER, "elastic", "--schedule", "2:3,4:3,3:3,1:3", "--max-step", "12"]
+    base = [kungfu_run(), "-q", "-w", "-np", "2", "-H", hostlist, "-port", str(rport), "-port-range", prange]
+    b = subprocess.Popen(base + ["-k", "-self", "127.0.0.2", "-config-server", f"http://127.0.0.1:{cfg}/config"] + work, cwd=ROOT, env=env,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        a = subprocess.run(base + ["-self", "127.0.0.1", "-builtin-config-port", str(cfg)] + work, cwd=ROOT, env=env, stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True, timeout=240)
+        assert a.returncode == 0, a.stdout[-5000:]
+        final = [j for j in json_lines(a.stdout) if j.get("elastic")]
+        assert len(final) == 1 and final[0]["final_step"] == 12 and final[0]["sizes"] == [1, 2, 3, 4] and final[0]["resizes"] == 3, a.stdout[-3000:]
+        time.sleep(0.5)
+        _kfrt.send_control(f"127.0.0.2:{rport}", "exit", "")  # host B's launcher idles by design (-k): tell it to leave
+        out_b, _ = b.communicate(timeout=30)
+        assert len([j for j in json_lines(out_b) if j.get("detached")]) == 2, out_b[-3000:]  # B's two workers came and went
+    finally:
+        if b.poll() is None:
+            b.kill()
