@@ -31,7 +31,8 @@ def main():
             fails.append(what)
             print(f"[rank {me}] FAIL {what}", flush=True)
 
-    check(plane.spans_hosts and plane.group_size == int(os.environ["KUNGFU_FORCE_GROUP_SIZE"]), "forced groups active")
+    want_group = int(os.environ.get("KUNGFU_FORCE_GROUP_SIZE") or os.environ.get("KUNGFU_EXPECT_GROUP") or 1)
+    check(plane.spans_hosts and plane.group_size == want_group, "the job spans NVLink groups")
     if me == 0:
         print(f"groups of {plane.group_size}: masters {coll._group_masters(plane)}", flush=True)
     else:

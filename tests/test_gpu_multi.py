@@ -66,6 +66,37 @@ def test_host_spanning_paths_with_forced_groups():
     assert '"fails": 0' in r.stdout
 
 
+def test_host_spanning_paths_on_loopback_aliases():
+    """Same worker as above, but the hosts are real to the runtime: two launchers on 127.0.0.1 / 127.0.0.2 with one GPU each, so
+    `local_size < size` comes from the peer list and not from KUNGFU_FORCE_GROUP_SIZE. Opt-in (KUNGFU_TEST_HIER_ALIASES=1) until it
+    has been run on hardware once."""
+    import threading
+
+    if os.environ.get("KUNGFU_TEST_HIER_ALIASES") != "1":
+        pytest.skip("set KUNGFU_TEST_HIER_ALIASES=1")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from kungfu_b200.cmd import kungfu_run_path
+
+    base = 31000 + os.getpid() % 3000
+    outs = [None, None]
+
+    def run(i):
+        cmd = [kungfu_run_path(), "-q", "-np", "2", "-H", "127.0.0.1:1,127.0.0.2:1", "-self", f"127.0.0.{i + 1}", "-port", str(base),
+               "-port-range", f"{base + 1}-{base + 20}", sys.executable, os.path.join(ROOT, "tests", "mp_gpu_hier.py")]
+        env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES=str(i), KUNGFU_DEVICE_TIMEOUT_MS="15000", KUNGFU_EXPECT_GROUP="1")
+        outs[i] = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+
+    ths = [threading.Thread(target=run, args=(i,)) for i in range(2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    text = "\n".join(o.stdout for o in outs)
+    print(text[-6000:])
+    assert all(o.returncode == 0 for o in outs) and text.count('"fails": 0') == 2, text[-3000:]
+
+
 def test_gpu_elastic_resize_under_kungfu_run():
     """1 -> 2 -> 1 GPUs under `kungfu-run -w` with the builtin config server: survivors keep training, newcomers inherit
     state, arenas rebuild their peer mappings; the trajectory equals a plain torch.optim reference."""
