@@ -651,7 +651,8 @@ public:
         }
         HttpServer http;
         try {
-            http.start("0.0.0.0", port, [this](const HttpRequest& r) { return handle(r); });
+            // a loopback-alias host (127.0.0.x) listens on its own address so that several "hosts" can share a machine in tests
+            http.start(self_ip.rfind("127.", 0) == 0 ? self_ip : std::string("0.0.0.0"), port, [this](const HttpRequest& r) { return handle(r); });
         } catch (const std::exception& e) {
             KF_LOGE("monitor server: %s", e.what());
         }

@@ -102,3 +102,29 @@ def test_elastic_resize_across_hosts():
     finally:
         if b.poll() is None:
             b.kill()
+
+
+def test_failure_recovery_across_hosts(tmp_path):
+    """One worker per host; the worker on the second host hangs inside a batch. The main monitor server (first host) notices
+    the stall, tells the other host's server (`otherdown:<epochs>`), both launchers kill and restart their workers with the
+    remaining epochs, and the job finishes (reference: runner/monitorserver, G17 — there it is never tested)."""
+    rport, prange = ports()
+    mon = 17000 + os.getpid() % 2000
+    env = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN", KUNGFU_MONITOR_PORT=str(mon))
+    outs = [None, None]
+
+    def run(i):
+        cmd = [kungfu_run(), "-q", "-np", "2", "-H", "127.0.0.1:1,127.0.0.2:1", "-self", f"127.0.0.{i + 1}", "-port", str(rport), "-port-range", prange,
+               "-auto-recover", "3s", sys.executable, WORKER, "recovery", "--dir", str(tmp_path), "--n-epochs", "3"]
+        outs[i] = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
+
+    ths = [threading.Thread(target=run, args=(i,)) for i in range(2)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    text = "\n".join(o.stdout for o in outs)
+    assert all(o.returncode == 0 for o in outs), text[-5000:]
+    assert all("worker failure detected" in o.stdout for o in outs), text[-5000:]  # both hosts restarted
+    js = [j for j in json_lines(text) if "recovered" in j]
+    assert js and js[-1] == {"recovered": True, "epochs_run_now": 2, "start_epoch": 1}, text[-5000:]
