@@ -5,6 +5,10 @@ Reference: srcs/go/cmd/kungfu-rrun, srcs/go/cmd/kungfu-distribute, srcs/go/utils
 ... prog args` per host, output prefixed per host, first failure cancels the rest.
 
     python -m kungfu_b200.cmd.rrun -np 16 -H 10.0.0.1:8,10.0.0.2:8 [-u user] [-w] [--dry-run] prog args...
+    python -m kungfu_b200.cmd.rrun -np 4 -H 127.0.0.1:2,127.0.0.2:2 --local prog args...   # loopback-alias "hosts", no ssh
+
+`--local` starts the per-host launchers as local processes instead of through ssh: with loopback aliases as hosts this runs a
+multi-host job on one machine (every peer listens on its own alias), which is how the multi-host tier is tested here.
 """
 from __future__ import annotations
 
@@ -17,8 +21,8 @@ from typing import List
 
 
 def build_commands(np: int, hosts: str, prog: List[str], user: str = "", watch: bool = False, strategy: str = "", extra: List[str] = (),
-                   kungfu_run: str = "kungfu-run") -> List[List[str]]:
-    """One ssh command line per host."""
+                   kungfu_run: str = "kungfu-run", local: bool = False) -> List[List[str]]:
+    """One command line per host: through ssh, or (local=True) the launcher itself for loopback-alias hosts on this machine."""
     cmds = []
     for h in hosts.split(","):
         ip = h.split(":")[0]
@@ -28,6 +32,9 @@ def build_commands(np: int, hosts: str, prog: List[str], user: str = "", watch: 
         if strategy:
             inner += ["-strategy", strategy]
         inner += list(extra) + list(prog)
+        if local:
+            cmds.append(inner)
+            continue
         target = f"{user}@{ip}" if user else ip
         cmds.append(["ssh", "-o", "StrictHostKeyChecking=no", target, " ".join(shlex.quote(x) for x in inner)])
     return cmds
@@ -39,13 +46,17 @@ def distribute_commands(hosts: str, prog: List[str], user: str = "") -> List[Lis
             for h in hosts.split(",")]
 
 
+def _tag(cmd: List[str]) -> str:
+    return cmd[3] if cmd[0] == "ssh" else cmd[cmd.index("-self") + 1]
+
+
 def run_all(cmds: List[List[str]]) -> int:
     procs = [subprocess.Popen(c, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for c in cmds]
     rc = [0] * len(procs)
 
     def pump(i: int) -> None:
         for line in procs[i].stdout:  # type: ignore[union-attr]
-            sys.stdout.write(f"[{cmds[i][3]}] {line}")
+            sys.stdout.write(f"[{_tag(cmds[i])}] {line}")
         rc[i] = procs[i].wait()
         if rc[i] != 0:
             for p in procs:
@@ -68,10 +79,17 @@ def main(argv=None) -> int:
     ap.add_argument("-w", dest="watch", action="store_true")
     ap.add_argument("-strategy", default="")
     ap.add_argument("--distribute", action="store_true", help="kungfu-distribute: run the command itself on every host")
+    ap.add_argument("--local", action="store_true", help="start the per-host launchers locally (loopback-alias hosts), no ssh")
     ap.add_argument("--dry-run", action="store_true")
     ap.add_argument("prog", nargs=argparse.REMAINDER)
     a = ap.parse_args(argv)
-    cmds = distribute_commands(a.hosts, a.prog, a.user) if a.distribute else build_commands(a.np, a.hosts, a.prog, a.user, a.watch, a.strategy)
+    kr = "kungfu-run"
+    if a.local:
+        from . import kungfu_run_path
+
+        kr = kungfu_run_path()
+    cmds = distribute_commands(a.hosts, a.prog, a.user) if a.distribute else build_commands(a.np, a.hosts, a.prog, a.user, a.watch, a.strategy,
+                                                                                           kungfu_run=kr, local=a.local)
     if a.dry_run:
         for c in cmds:
             print(" ".join(shlex.quote(x) for x in c))

@@ -128,3 +128,15 @@ def test_failure_recovery_across_hosts(tmp_path):
     assert all("worker failure detected" in o.stdout for o in outs), text[-5000:]  # both hosts restarted
     js = [j for j in json_lines(text) if "recovered" in j]
     assert js and js[-1] == {"recovered": True, "epochs_run_now": 2, "start_epoch": 1}, text[-5000:]
+
+
+def test_rrun_local_fans_out_one_launcher_per_alias():
+    """`kungfu-rrun --local`: the per-host launchers the ssh fan-out would start, run as local processes on loopback aliases."""
+    env = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN")
+    r = subprocess.run([sys.executable, "-m", "kungfu_b200.cmd.rrun", "-np", "4", "-H", "127.0.0.1:2,127.0.0.2:2", "--local", sys.executable,
+                        os.path.join(ROOT, "examples", "torch_simple_example.py")], cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=180)
+    assert r.returncode == 0, r.stdout[-3000:]
+    for k in range(4):
+        assert f"rank {k}/4: [4.0" in r.stdout, r.stdout[-3000:]
+    assert "[127.0.0.2] " in r.stdout and "[127.0.0.1] " in r.stdout
