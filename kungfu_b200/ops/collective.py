@@ -170,7 +170,7 @@ def _pinned(plane, nbytes: int) -> torch.Tensor:
     return buf
 
 
-def _cross_hosts_(plane, host: torch.Tensor, op_code: int) -> None:
+def _cross_hosts_(plane, host: torch.Tensor, op_code: int, tag: str = "") -> None:
     """All-reduce a host tensor among the group masters (one rank per host) over the control plane. Reference:
     `CrossAllReduceGpu` stages through host memory the same way (srcs/cpp/src/nccl/controller.cpp, K5 in SURVEY.md)."""
     rt = plane.runtime
@@ -178,13 +178,16 @@ def _cross_hosts_(plane, host: torch.Tensor, op_code: int) -> None:
     if len(masters) < 2:
         return
     ctl = rt.control
-    if hasattr(ctl, "subset_all_reduce_cpu_"):
+    if "KUNGFU_FORCE_GROUP_SIZE" not in os.environ and hasattr(ctl, "cross_all_reduce_cpu_"):
+        # real hosts: the session's cross-host strategies (ring / binary tree over the hosts' first ranks, chosen by -strategy)
+        ctl.cross_all_reduce_cpu_(host, _OPNAME[op_code], tag)
+    elif hasattr(ctl, "subset_all_reduce_cpu_"):
         forest = list(range(rt.size))
         for m in masters:
             forest[m] = masters[0]
-        ctl.subset_all_reduce_cpu_(host, forest, _OPNAME[op_code])
+        ctl.subset_all_reduce_cpu_(host, forest, _OPNAME[op_code], tag)
     elif op_code == dtypes.SUM:
-        ctl.all_reduce_cpu_(host, "sum")  # control planes without subset support: everyone joins, non-masters add zeros
+        ctl.all_reduce_cpu_(host, "sum", tag)  # control planes without subset support: everyone joins, non-masters add zeros
     else:
         raise NotImplementedError("kungfu_b200: this control plane has no subset all-reduce for min/max/prod across hosts")
 
@@ -200,6 +203,10 @@ def _gpu_all_reduce_hier_(plane, flat: torch.Tensor, op_code: int, average: bool
     gsize, grank = plane.group_size, plane.group_rank
     masters = _group_masters(plane)
     subset = hasattr(rt.control, "subset_all_reduce_cpu_")
+    ver = getattr(rt.control, "cluster_version", None)
+    key_version = ver() if ver else 0
+    if getattr(plane, "_hier_version", None) != key_version:  # numbering restarts with the membership, like every op name
+        plane._hier_version, plane._hier_seq = key_version, 0
     chunk_elems = (cap // esize) // 8 * 8
     n = flat.numel()
     with torch.cuda.stream(st):
@@ -207,6 +214,10 @@ def _gpu_all_reduce_hier_(plane, flat: torch.Tensor, op_code: int, average: bool
             hi = min(n, lo + chunk_elems)
             nb = (hi - lo) * esize
             nb_pad = (nb + 15) // 16 * 16
+            # every rank numbers the hierarchical chunks identically; the host-side ops below are named after that number, so that
+            # ops only the hosts' first ranks perform cannot shift anybody's automatic op names
+            plane._hier_seq = getattr(plane, "_hier_seq", 0) + 1
+            tag = f"kungfu::hier::v{key_version}::{plane._hier_seq}"
             stage = arena.bytes_view(off, nb_pad)
             stage[:nb].copy_(flat[lo:hi].view(torch.uint8), non_blocking=True)
             if nb_pad != nb:
@@ -226,14 +237,14 @@ def _gpu_all_reduce_hier_(plane, flat: torch.Tensor, op_code: int, average: bool
                         st.synchronize()
                     else:
                         host.zero_()
-                    _cross_hosts_(plane, host.view(flat.dtype), op_code)
+                    _cross_hosts_(plane, host.view(flat.dtype), op_code, tag + "::x")
                     if grank == 0:
                         stage[:nb].copy_(host, non_blocking=True)
                 if gsize > 1:
                     # the group waits for its master on the host (not spinning on the device while the master is on the network)
                     sync = getattr(rt.control, "local_broadcast_cpu_", None)
                     if sync is not None:
-                        sync(torch.zeros(1, dtype=torch.int32))
+                        sync(torch.zeros(1, dtype=torch.int32), tag + "::s")
                     algo_b = ext.ALGO_NVLS if (arena.has_multicast and CONFIG.algo in ("auto", "nvls")) else ext.ALGO_TWOSHOT
                     ext.broadcast(arena.mesh, 0, algo_b, off, nb_pad, 0, pick_blocks(nb_pad, 1, sliced=False), CONFIG.threads,
                                   st.cuda_stream)

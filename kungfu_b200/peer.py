@@ -26,19 +26,23 @@ def native_available() -> bool:
 
 
 _OPS = {"sum": dtypes.SUM, "min": dtypes.MIN, "max": dtypes.MAX, "prod": dtypes.PROD}
-_seq = {"version": None, "count": itertools.count()}
+_seq = {"version": None, "counts": {}}
 
 
 def _auto_name(prefix: str, name: str, version: int = 0) -> str:
     """Unique op names: the rendezvous key is (peer, name), so two in-flight ops must never share one
     (reference: Appendix B — concurrency safety comes from unique tensor names). Numbering restarts with every
-    cluster version so that survivors and late joiners of an elastic job generate the same names."""
+    cluster version so that survivors and late joiners of an elastic job generate the same names, and it is kept PER KIND
+    of operation: ops that only some ranks take part in (cross-host / subset all-reduce on the hosts' first ranks, local
+    reduce) must not shift the numbers of the ops everybody calls."""
     if name:
         return name
     if _seq["version"] != version:
         _seq["version"] = version
-        _seq["count"] = itertools.count()
-    return f"{prefix}::v{version}::{next(_seq['count'])}"
+        _seq["counts"] = {}
+    k = _seq["counts"].get(prefix, 0)
+    _seq["counts"][prefix] = k + 1
+    return f"{prefix}::v{version}::{k}"
 
 
 class NativeControl(Control):

@@ -385,6 +385,15 @@ def cmd_multihost(args):
     c.cross_all_reduce_cpu_(y)
     c.local_broadcast_cpu_(y)
     check(torch.equal(y, ops.all_reduce(torch.full((9,), float(r + 1)))), "local reduce -> cross all-reduce -> local broadcast == all-reduce")
+    # the shape of the GPU hierarchical all-reduce: only the hosts' first ranks take part in the cross-host step, then everybody
+    # joins an automatically named op — op numbering is per kind, so the extra op on the masters must not shift the others
+    for it in range(3):
+        z = torch.full((5,), float(r + 1))
+        if c.local_rank == 0:
+            c.cross_all_reduce_cpu_(z)
+        c.local_broadcast_cpu_(z)
+        check(torch.equal(z, torch.full((5,), float(sum(m + 1 for m in masters)))), f"masters-only cross step then local broadcast ({it})")
+        check(torch.equal(ops.all_reduce(torch.ones(3)), torch.full((3,), float(n))), f"auto-named all-reduce stays aligned ({it})")
     lat = ops.get_peer_latencies()
     check(lat.shape == (n,), "latencies across hosts")
     ops.barrier()
