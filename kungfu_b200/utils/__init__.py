@@ -32,6 +32,26 @@ def show_rate(bytes_per_s: float) -> str:
     return f"{bytes_per_s:.2f}B/s"
 
 
+def map_maybe(f: Callable, lst):
+    """Apply `f` to the non-None entries (reference: _utils.py:5-6)."""
+    return [f(x) if x is not None else None for x in lst]
+
+
+def one_based_range(n: int):
+    return range(1, n + 1)
+
+
+def _since_job_start() -> float:
+    """Seconds since `kungfu-run` started the job (KUNGFU_JOB_START_TIMESTAMP; reference: _utils.py:32-36)."""
+    t0 = float(os.environ.get("KUNGFU_JOB_START_TIMESTAMP", "0") or 0)
+    return time.time() - t0 if t0 else 0.0
+
+
+def _since_proc_start() -> float:
+    t0 = float(os.environ.get("KUNGFU_PROC_START_TIMESTAMP", "0") or 0)
+    return time.time() - t0 if t0 else 0.0
+
+
 def _log_event(name: str) -> None:
     """`TS=... <name> :: <d> since proc started` using KUNGFU_PROC_START_TIMESTAMP (elastic join latency profiling)."""
     t0 = float(os.environ.get("KUNGFU_PROC_START_TIMESTAMP", "0") or 0)

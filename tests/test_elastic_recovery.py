@@ -158,3 +158,17 @@ def test_failure_detection_and_auto_recovery(tmp_path):
     assert js and js[-1] == {"recovered": True, "epochs_run_now": 2, "start_epoch": 1}, r.stdout[-5000:]
     assert os.path.exists(tmp_path / "crashed") and os.path.exists(tmp_path / "ckpt.pt")
     assert time.time() - t0 < 120
+
+
+def test_scaling_benchmark_with_resize_schedule():
+    """benchmarks/scaling/benchmark_kungfu_scaling.py (+ debug_hooks.LogPerfHook): one RESULT line per phase of the schedule."""
+    rport, prange = ports()
+    cfg_port = 9400 + os.getpid() % 100
+    cmd = [kungfu_run(), "-q", "-w", "-np", "1", "-H", "127.0.0.1:4", "-port", str(rport), "-port-range", prange, "-builtin-config-port", str(cfg_port),
+           sys.executable, os.path.join(ROOT, "benchmarks", "scaling", "benchmark_kungfu_scaling.py"), "--elastic", "--resize-schedule", "1:4,2:4,3:4",
+           "--train-steps", "12", "--show-training-throughput"]
+    e = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN")
+    r = subprocess.run(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-4000:]
+    assert r.stdout.count("RESULT:") >= 3 and "cluster size 3" in r.stdout and "local step 1, took" in r.stdout, r.stdout[-4000:]
+    assert "_since_job_start:" in r.stdout and "BEGIN :: main" in r.stdout
