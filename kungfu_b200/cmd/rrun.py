@@ -78,6 +78,9 @@ def main(argv=None) -> int:
     ap.add_argument("-u", dest="user", default="")
     ap.add_argument("-w", dest="watch", action="store_true")
     ap.add_argument("-strategy", default="")
+    ap.add_argument("-port", default="", help="runner port, forwarded to kungfu-run")
+    ap.add_argument("-port-range", dest="port_range", default="", help="worker port range, forwarded to kungfu-run")
+    ap.add_argument("-q", dest="quiet", action="store_true", help="forwarded to kungfu-run")
     ap.add_argument("--distribute", action="store_true", help="kungfu-distribute: run the command itself on every host")
     ap.add_argument("--local", action="store_true", help="start the per-host launchers locally (loopback-alias hosts), no ssh")
     ap.add_argument("--dry-run", action="store_true")
@@ -88,8 +91,9 @@ def main(argv=None) -> int:
         from . import kungfu_run_path
 
         kr = kungfu_run_path()
+    extra = (["-port", a.port] if a.port else []) + (["-port-range", a.port_range] if a.port_range else []) + (["-q"] if a.quiet else [])
     cmds = distribute_commands(a.hosts, a.prog, a.user) if a.distribute else build_commands(a.np, a.hosts, a.prog, a.user, a.watch, a.strategy,
-                                                                                           kungfu_run=kr, local=a.local)
+                                                                                           extra=extra, kungfu_run=kr, local=a.local)
     if a.dry_run:
         for c in cmds:
             print(" ".join(shlex.quote(x) for x in c))

@@ -133,7 +133,9 @@ def test_failure_recovery_across_hosts(tmp_path):
 def test_rrun_local_fans_out_one_launcher_per_alias():
     """`kungfu-rrun --local`: the per-host launchers the ssh fan-out would start, run as local processes on loopback aliases."""
     env = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN")
-    r = subprocess.run([sys.executable, "-m", "kungfu_b200.cmd.rrun", "-np", "4", "-H", "127.0.0.1:2,127.0.0.2:2", "--local", sys.executable,
+    rport, prange = ports()
+    r = subprocess.run([sys.executable, "-m", "kungfu_b200.cmd.rrun", "-np", "4", "-H", "127.0.0.1:2,127.0.0.2:2", "--local", "-q", "-port", str(rport),
+                        "-port-range", prange, sys.executable,
                         os.path.join(ROOT, "examples", "torch_simple_example.py")], cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                        text=True, timeout=180)
     assert r.returncode == 0, r.stdout[-3000:]
