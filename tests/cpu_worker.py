@@ -481,6 +481,12 @@ def cmd_metrics(args):
     check(n == 1 or len(eg) >= 1, f"egress lines: {lines[:4]}")
     check(n == 1 or any(int(ln.rsplit(" ", 1)[1]) >= (1 << 16) for ln in eg), "egress counters grew with the all-reduces")
     check(n == 1 or any(ln.startswith("ingress_total_bytes{peer=") for ln in lines), "ingress lines")
+    from kungfu_b200 import monitor
+
+    parsed = monitor.fetch_metrics()
+    check(n == 1 or (len(parsed.get("egress_total_bytes", {})) >= 1 and max(parsed["egress_total_bytes"].values()) >= (1 << 16)),
+          f"monitor.fetch_metrics: {parsed}")
+    check(monitor.metrics_url("10.0.0.5:10003") == "http://10.0.0.5:20003/metrics", "metrics_url")
     status, _ = _kfrt.http_request("GET", f"http://127.0.0.1:{port}/nope", "")
     check(status == 404, "unknown path is 404")
     rates = ops.egress_rates()
