@@ -224,6 +224,9 @@ PYBIND11_MODULE(_kfrt, m) {
     m.def("apply_affinity_from_env", &apply_affinity_from_env);
 
     // ---- http / config server
+    m.def("metric_set", [](const std::string& name, double v) { NetMonitor::get().set_gauge(name, v); });
+    m.def("metric_add", [](const std::string& name, double d) { NetMonitor::get().add_counter(name, d); });
+    m.def("metrics_text", []() { return NetMonitor::get().metrics_text(); });
     m.def("http_request", [](const std::string& method, const std::string& url, const std::string& body) {
         std::string out;
         int st;

@@ -151,6 +151,9 @@ bool Peer::update_to(const PeerList& pl) {
     sess->barrier(); // meets the barrier of every other member of the new cluster version
     session_ = sess;
     updated_ = true;
+    NetMonitor::get().set_gauge("kungfu_cluster_version", cluster_version_);
+    NetMonitor::get().set_gauge("kungfu_cluster_size", (double)pl.size());
+    NetMonitor::get().set_gauge("kungfu_rank", sess->rank());
     return true;
 }
 

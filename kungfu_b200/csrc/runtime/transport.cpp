@@ -266,7 +266,18 @@ std::string NetMonitor::metrics_text() {
         PeerID p{(uint32_t)(kv.first >> 16), (uint16_t)(kv.first & 0xffff)};
         os << "ingress_total_bytes{peer=\"" << p.str() << "\"} " << kv.second << "\n";
     }
+    os.precision(12);
+    for (auto& kv : gauges_) os << kv.first << " " << kv.second << "\n";
+    for (auto& kv : counters_) os << kv.first << " " << kv.second << "\n";
     return os.str();
+}
+void NetMonitor::set_gauge(const std::string& name, double value) {
+    std::lock_guard<std::mutex> g(mu_);
+    gauges_[name] = value;
+}
+void NetMonitor::add_counter(const std::string& name, double delta) {
+    std::lock_guard<std::mutex> g(mu_);
+    counters_[name] += delta;
 }
 void NetMonitor::reset() {
     std::lock_guard<std::mutex> g(mu_);

@@ -84,11 +84,16 @@ public:
     std::map<uint64_t, uint64_t> egress_totals();
     std::string metrics_text(); // prometheus-style
     void reset();
+    // application metrics published next to the network counters: gauges are overwritten, counters accumulate. `name` may
+    // carry labels, e.g. gpu_collective_bytes_total{op="all_reduce"}
+    void set_gauge(const std::string& name, double value);
+    void add_counter(const std::string& name, double delta);
 
 private:
     std::mutex mu_;
     std::map<uint64_t, uint64_t> eg_, in_;
     std::map<uint64_t, std::pair<uint64_t, double>> last_; // (total, time) at the previous rate query
+    std::map<std::string, double> gauges_, counters_;
 };
 
 // ---- client ---------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@ from typing import Dict, Optional
 
 from ..ops.monitor import NoiseScale, egress_rates, global_noise_scale  # noqa: F401
 
+_PLAIN = re.compile(r'^(?P<metric>[A-Za-z_][A-Za-z0-9_]*(?:\{[^}]*\})?)\s+(?P<value>[0-9.eE+-]+|nan|inf|-inf)\s*$')
 _LINE = re.compile(r'^(?P<metric>[a-z_]+)\{peer="(?P<peer>[^"]+)"\}\s+(?P<value>[0-9.eE+-]+)\s*$')
 
 
@@ -29,7 +30,30 @@ def parse_metrics(text: str) -> Dict[str, Dict[str, float]]:
         m = _LINE.match(line.strip())
         if m:
             out.setdefault(m.group("metric"), {})[m.group("peer")] = float(m.group("value"))
+            continue
+        m = _PLAIN.match(line.strip())
+        if m:  # application gauges / counters: {'kungfu_cluster_size': {'': 4.0}, 'gpu_collective_bytes_total{op="all_reduce"}': {'': ...}}
+            out.setdefault(m.group("metric"), {})[""] = float(m.group("value"))
     return out
+
+
+def set_gauge(name: str, value: float) -> None:
+    """Publish a gauge on this worker's `/metrics` (no-op without the native runtime)."""
+    try:
+        from .. import _kfrt  # type: ignore[attr-defined]
+
+        _kfrt.metric_set(name, float(value))
+    except ImportError:
+        pass
+
+
+def add_counter(name: str, delta: float) -> None:
+    try:
+        from .. import _kfrt  # type: ignore[attr-defined]
+
+        _kfrt.metric_add(name, float(delta))
+    except ImportError:
+        pass
 
 
 def fetch_metrics(peer: Optional[str] = None) -> Dict[str, Dict[str, float]]:

@@ -121,6 +121,7 @@ def _gpu_all_reduce_(x: torch.Tensor, op_code: int, average: bool, stream: Optio
         raise TypeError("kungfu_b200: averaging all-reduce needs a floating point tensor")
     chunk_elems = (cap // esize) // 8 * 8
     n = flat.numel()
+    _count_gpu_bytes("all_reduce", n * esize)
     if plane.spans_hosts:
         _gpu_all_reduce_hier_(plane, flat, op_code, average, st, algo)
         return
@@ -149,6 +150,21 @@ def _gpu_all_reduce_(x: torch.Tensor, op_code: int, average: bool, stream: Optio
 
 
 _OPNAME = {0: "sum", 1: "min", 2: "max", 3: "prod"}
+_metric_add = None
+
+
+def _count_gpu_bytes(op: str, nbytes: int) -> None:
+    """`gpu_collective_bytes_total{op=...}` on this worker's /metrics: payload bytes handed to the staged device collectives
+    (the fused optimizer engines run inside CUDA graphs and account for themselves per step, not per launch)."""
+    global _metric_add
+    if _metric_add is None:
+        try:
+            from .. import _kfrt  # type: ignore[attr-defined]
+
+            _metric_add = _kfrt.metric_add
+        except ImportError:
+            _metric_add = lambda *_: None  # noqa: E731
+    _metric_add('gpu_collective_bytes_total{op="%s"}' % op, float(nbytes))
 
 
 def _group_masters(plane) -> List[int]:

@@ -20,6 +20,12 @@ from .core import wrap_optimizer
 from .sync_sgd import _SynchronousSGD
 
 
+def _publish_gauge(v: float) -> None:
+    from ...monitor import set_gauge
+
+    set_gauge("kungfu_gradient_noise_scale", v)
+
+
 class _MonitorGNS(_SynchronousSGD):
     def _kf_init_gns(self, named_parameters, device_batch_size, monitor_interval, alpha, fused, overlap, bucket_mb, algo):
         self._kf_init_ssgd(named_parameters, "avg", fused, overlap, bucket_mb, True, algo)
@@ -58,6 +64,7 @@ class _MonitorGNS(_SynchronousSGD):
             if (self._kf_step_count - 1) % self._kf_interval == 0 and n > 1:
                 self.noise_scale_value = self._kf_cpu_ns.update(self._kf_bs, self._kf_bs * n, local_sq, big_sq)
                 self._kf_gns_var.fill_(float(self.noise_scale_value))
+                _publish_gauge(self.noise_scale_value)
             return loss
         loss = _SynchronousSGD.step(self, closure)
         sums = eng.read_sumsq(reset=True)  # [sum_r |g_r|^2, |g_avg|^2], device tensor
@@ -70,7 +77,9 @@ class _MonitorGNS(_SynchronousSGD):
     def noise_scale(self) -> float:
         """Latest noise-scale estimate (host value; syncs the stream on the GPU path)."""
         if self._kf_engine is not None:
-            return float(self._kf_gns_out[0].item())
+            v = float(self._kf_gns_out[0].item())
+            _publish_gauge(v)  # the device value reaches /metrics whenever somebody reads it
+            return v
         return float(self.noise_scale_value)
 
     def noise_scale_tensor(self) -> Optional[torch.Tensor]:

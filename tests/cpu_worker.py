@@ -487,6 +487,13 @@ def cmd_metrics(args):
     check(n == 1 or (len(parsed.get("egress_total_bytes", {})) >= 1 and max(parsed["egress_total_bytes"].values()) >= (1 << 16)),
           f"monitor.fetch_metrics: {parsed}")
     check(monitor.metrics_url("10.0.0.5:10003") == "http://10.0.0.5:20003/metrics", "metrics_url")
+    # application metrics: cluster gauges from the runtime, gauges / counters published from Python
+    check(parsed.get("kungfu_cluster_size", {}).get("") == float(n) and parsed.get("kungfu_rank", {}).get("") == float(r), f"cluster gauges {parsed}")
+    monitor.set_gauge("kungfu_gradient_noise_scale", 12.5)
+    monitor.add_counter('gpu_collective_bytes_total{op="all_reduce"}', 1000)
+    monitor.add_counter('gpu_collective_bytes_total{op="all_reduce"}', 24)
+    again = monitor.fetch_metrics()
+    check(again["kungfu_gradient_noise_scale"][""] == 12.5 and again['gpu_collective_bytes_total{op="all_reduce"}'][""] == 1024.0, f"published metrics {again}")
     status, _ = _kfrt.http_request("GET", f"http://127.0.0.1:{port}/nope", "")
     check(status == 404, "unknown path is 404")
     rates = ops.egress_rates()
