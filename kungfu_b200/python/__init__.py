@@ -18,37 +18,45 @@ def _ctl():
 
 
 def uid() -> int:
+    """64-bit identity of this worker process: (ipv4, port, initial cluster version); 0 in single-process mode (python/__init__.py:50-53)."""
     f = getattr(_ctl(), "uid", None)
     return int(f()) if f else 0
 
 
 def detached() -> bool:
+    """True once a resize removed this worker from the cluster: it must stop training and exit (python/__init__.py:55-58)."""
     f = getattr(_ctl(), "detached", None)
     return bool(f()) if f else False
 
 
 def current_rank() -> int:
+    """Index of this worker in the current peer list (changes with resizes)."""
     return get_runtime().rank
 
 
 def current_local_rank() -> int:
+    """Index among the workers that share this worker's host."""
     return get_runtime().local_rank
 
 
 def current_cluster_size() -> int:
+    """Number of workers in the current cluster version."""
     return get_runtime().size
 
 
 def current_local_size() -> int:
+    """Number of workers on this worker's host."""
     return get_runtime().local_size
 
 
 def current_cluster_version() -> int:
+    """Membership epoch: starts at KUNGFU_INIT_CLUSTER_VERSION, +1 per accepted resize; also the token that fences stale connections."""
     f = getattr(_ctl(), "cluster_version", None)
     return int(f()) if f else 0
 
 
 def run_barrier() -> None:
+    """Block until every worker arrived (host barrier, plus a device flag barrier when a GPU plane exists)."""
     from ..ops.collective import barrier
 
     barrier()
@@ -92,49 +100,58 @@ def resize(n: Optional[int] = None) -> Tuple[bool, bool]:
 
 
 def all_reduce_int_max(x: int) -> int:
+    """Max of a Python int over all workers — how newcomers adopt the survivors' step counter (python/__init__.py:152-155)."""
     f = getattr(_ctl(), "all_reduce_int_max", None)
     return int(f(int(x))) if f else int(x)
 
 
 def check_interference() -> bool:
+    """Majority vote "collective throughput dropped below 80 % of the reference window" (session/adaptiveStrategies.go:61-127)."""
     f = getattr(_ctl(), "check_interference", None)
     return bool(f()) if f else False
 
 
 def calc_stats() -> None:
+    """Recompute the throughput statistics of the active communication strategies."""
     f = getattr(_ctl(), "calc_stats", None)
     if f:
         f()
 
 
 def log_stats() -> None:
+    """Snapshot the strategy statistics into the runtime log."""
     f = getattr(_ctl(), "log_stats", None)
     if f:
         f()
 
 
 def print_strategy_stats() -> None:
+    """Print per-strategy accumulated bytes / time / throughput."""
     f = getattr(_ctl(), "print_strategy_stats", None)
     if f:
         f()
 
 
 def _get_cuda_index() -> int:
+    """Logical CUDA device of this worker (KUNGFU_CUDA_VISIBLE_DEVICES mapped through CUDA_VISIBLE_DEVICES), -1 without a GPU."""
     return get_runtime().cuda_index()
 
 
 def _get_other_ranks():
+    """Every rank but this one (peer selection of PairAveraging)."""
     rt = get_runtime()
     return [r for r in range(rt.size) if r != rt.rank]
 
 
 def show_cuda_version() -> None:
+    """Print the CUDA version torch was built with (reference prints the runtime libcudart version)."""
     import torch
 
     print("CUDA (torch build):", torch.version.cuda)
 
 
 def show_nccl_version() -> None:
+    """Print the NCCL version bundled with torch (baseline arm only: our collectives do not use NCCL)."""
     import torch
 
     try:
