@@ -31,10 +31,12 @@ def run() -> None:
 
 
 def kungfu_run_path() -> str:
+    """Path of the native `kungfu-run` binary built in-tree."""
     return _bin("kungfu-run")
 
 
 def config_server_path() -> str:
+    """Path of the native `kungfu-config-server` binary."""
     return _bin("kungfu-config-server")
 
 
@@ -62,14 +64,17 @@ def monitor_batch_begin() -> bool:
 
 
 def monitor_batch_end() -> bool:
+    """Heartbeat: the batch finished (clears the stall timer of this rank)."""
     return _send_signal("end")
 
 
 def monitor_train_end() -> bool:
+    """This rank finished training; when every rank has said so the launcher ends the job successfully."""
     return _send_signal("trainend")
 
 
 def monitor_epoch_end() -> bool:
+    """One more epoch is done (and checkpointed): after a restart `--n-epochs` is reduced by the minimum over ranks."""
     return _send_signal("epoch")
 
 

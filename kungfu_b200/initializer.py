@@ -15,11 +15,13 @@ from .ops import collective as coll
 
 
 def broadcast_variables(tensors: Iterable[torch.Tensor], root: int = 0) -> None:
+    """Broadcast a list of tensors in place from `root` (reference: initializer `broadcast_variables`)."""
     for t in tensors:
         coll.broadcast_(t, root)
 
 
 def broadcast_parameters(state_dict, root: int = 0) -> None:
+    """Broadcast every tensor of a state dict (parameters and buffers) from `root`."""
     for _, v in state_dict.items():
         if isinstance(v, torch.Tensor):
             coll.broadcast_(v, root)

@@ -300,6 +300,7 @@ def all_reduce_(x: torch.Tensor, op=None, name: str = "") -> torch.Tensor:
 
 
 def all_reduce(x: torch.Tensor, op=None, name: str = "") -> torch.Tensor:
+    """Out-of-place all-reduce (`op`: sum | min | max | prod | avg). Reference: ops/collective.py `all_reduce`, torch `all_reduce_fn`."""
     return all_reduce_(x.clone(), op, name)
 
 
@@ -378,15 +379,18 @@ def _async_name(rt) -> str:
 
 
 def wait_handle(h: Handle) -> None:
+    """Make the current stream (CUDA) or thread (host tensors) wait for one asynchronous collective."""
     h.wait()
 
 
 def wait_all_handles(hs: List[Handle]) -> None:
+    """`wait_handle` for every handle of a list (reference: torch/ops/collective.py wait_all_handles)."""
     for h in hs:
         h.wait()
 
 
 def broadcast_(x: torch.Tensor, root: int = 0, name: str = "") -> torch.Tensor:
+    """In-place broadcast of `x` from rank `root` (NVLS multicast push or P2P pull on GPUs, graph broadcast on the host plane)."""
     rt = get_runtime()
     if rt.size == 1:
         return x
@@ -498,6 +502,7 @@ def barrier() -> None:
 
 
 def consensus(x) -> bool:
+    """True iff every worker passed identical bytes (tensor or bytes-like). Reference: `consensus` op / `BytesConsensus`."""
     rt = get_runtime()
     if isinstance(x, torch.Tensor):
         b = x.detach().cpu().contiguous().view(-1).view(torch.uint8).numpy().tobytes()

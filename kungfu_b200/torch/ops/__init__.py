@@ -13,14 +13,17 @@ def all_reduce_fn(x: torch.Tensor, op=None) -> torch.Tensor:
 
 
 def inplace_all_reduce_op(x: torch.Tensor, op=None) -> None:
+    """Synchronous in-place all-reduce (reference: torch/ops/collective.py:8-27)."""
     _c.all_reduce_(x, op or "sum")
 
 
 def inplace_all_reduce_async_op(x: torch.Tensor, name: str = "", op=None) -> Handle:
+    """Asynchronous in-place all-reduce; returns a handle for `wait_handle` / `wait_all_handles` (reference: :29-48)."""
     return _c.all_reduce_async_(x, name, op or "sum")
 
 
 def inplace_broadcast_op(x: torch.Tensor, root: int = 0) -> None:
+    """In-place broadcast from `root` (reference: torch/ops/collective.py broadcast)."""
     _c.broadcast_(x, root)
 
 

@@ -28,6 +28,7 @@ class GraphKeys:
 
 
 def get_global_variable(name: str) -> Optional[torch.Tensor]:
+    """The tensor registered under `name`, or None."""
     with _lock:
         return _registry.get(name)
 
@@ -48,12 +49,14 @@ def create_global_variable(name: str, shape=(), dtype: torch.dtype = torch.float
 
 
 def get_or_create_global_variable(name: str, shape=(), dtype: torch.dtype = torch.float32, init=None, device="cpu") -> torch.Tensor:
+    """Existing variable `name`, or a new one created with the given shape / dtype / initial value."""
     with _lock:
         v = _registry.get(name)
         return v if v is not None else create_global_variable(name, shape, dtype, init, device)
 
 
 def eval_global_variable(name: str):
+    """Current value: a Python scalar for one-element variables, a CPU copy otherwise; raises when the variable does not exist."""
     v = get_global_variable(name)
     if v is None:
         raise RuntimeError('"%s" not exist' % name)
@@ -68,11 +71,13 @@ def bind_global_variable(name: str, tensor: torch.Tensor) -> torch.Tensor:
 
 
 def remove_global_variable(name: str) -> None:
+    """Forget `name` (tests; a new job in the same process)."""
     with _lock:
         _registry.pop(name, None)
 
 
 def global_variables() -> Dict[str, torch.Tensor]:
+    """Snapshot of the registry {name: tensor}."""
     with _lock:
         return dict(_registry)
 
@@ -85,6 +90,7 @@ def create_placeholder_for(t: torch.Tensor) -> torch.Tensor:
 
 
 def create_assign_op_for(t: torch.Tensor) -> Tuple[Callable[[], None], torch.Tensor]:
+    """(op, placeholder): fill the placeholder, call op() to copy it into `t` (async H2D for device variables)."""
     p = create_placeholder_for(t)
 
     def op() -> None:
@@ -94,6 +100,7 @@ def create_assign_op_for(t: torch.Tensor) -> Tuple[Callable[[], None], torch.Ten
 
 
 def create_setter(v: torch.Tensor) -> Callable:
+    """`set_value(value)` that writes `value` into the variable in place."""
     op, place = create_assign_op_for(v)
 
     def set_value(value) -> None:
@@ -105,6 +112,7 @@ def create_setter(v: torch.Tensor) -> Callable:
 
 # ---- well-known variables -------------------------------------------------------------------------------------------------
 def get_or_create_batch_size(init=None) -> torch.Tensor:
+    """The int32 scalar `kungfu_batch_size` (created on first use)."""
     return get_or_create_global_variable(GraphKeys.BATCH_SIZE, shape=(), dtype=torch.int32, init=init)
 
 
@@ -114,10 +122,12 @@ def get_batch_size() -> Optional[torch.Tensor]:
 
 
 def eval_batch_size() -> int:
+    """Value of `kungfu_batch_size`."""
     return int(eval_global_variable(GraphKeys.BATCH_SIZE))
 
 
 def eval_gradient_noise_scale() -> float:
+    """Value of `kungfu_gradient_noise_scale` (synchronises when the estimate lives on the GPU)."""
     return float(eval_global_variable(GraphKeys.GRADIENT_NOISE_SCALE))
 
 
