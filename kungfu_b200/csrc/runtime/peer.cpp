@@ -31,7 +31,9 @@ PeerConfig PeerConfig::from_env() {
         const uint32_t ip = resolve_ipv4(getenv_str("MASTER_ADDR", "127.0.0.1"));
         const int master_port = atoi(getenv_str("MASTER_PORT", "29500").c_str());
         int base = atoi(getenv_str("KUNGFU_PORT_BASE", "0").c_str());
-        if (base <= 0) base = 10000 + (master_port * 7 + 131) % 40000;
+        // stay below the kernel's ephemeral port range (32768+): listening up there collides now and then with the source
+        // port of somebody's outgoing connection
+        if (base <= 0) base = 10000 + (master_port * 7 + 131) % 20000;
         for (int i = 0; i < n; ++i) c.init_peers.push_back(PeerID{ip, (uint16_t)(base + i)});
         c.self = c.init_peers[r];
         c.strategy = parse_strategy(getenv_str(envkeys::kAllReduceStrategy, "AUTO"));

@@ -78,7 +78,7 @@ def test_host_spanning_paths_on_loopback_aliases():
         pytest.skip("needs 2 GPUs")
     from kungfu_b200.cmd import kungfu_run_path
 
-    base = 31000 + os.getpid() % 3000
+    base = 25000 + os.getpid() % 3000  # below the ephemeral port range
     outs = [None, None]
 
     def run(i):
@@ -103,7 +103,7 @@ def test_gpu_elastic_resize_under_kungfu_run():
     from kungfu_b200.cmd import kungfu_run_path
 
     port = 9300 + os.getpid() % 300
-    cmd = [kungfu_run_path(), "-q", "-w", "-np", "1", "-H", "127.0.0.1:2", "-port", str(31000 + os.getpid() % 3000), "-port-range",
+    cmd = [kungfu_run_path(), "-q", "-w", "-np", "1", "-H", "127.0.0.1:2", "-port", str(25000 + os.getpid() % 3000), "-port-range",
            f"{21000 + os.getpid() % 3000}-{21000 + os.getpid() % 3000 + 40}", "-builtin-config-port", str(port), sys.executable,
            os.path.join(ROOT, "tests", "gpu_elastic_worker.py"), "1:4,2:4,1:4"]
     env = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_DEVICE_TIMEOUT_MS="15000", KUNGFU_CONFIG_LOG_LEVEL="WARN")

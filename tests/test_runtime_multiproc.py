@@ -27,7 +27,9 @@ def kungfu_run():
 def ports():
     """Disjoint (runner port, worker port range) per launch."""
     k = next(_counter)
-    base = 30000 + ((os.getpid() * 37 + k * 64) % 20000)
+    # below the kernel's ephemeral range (32768+): a listening port up there can collide with the source port of any outgoing
+    # connection on the machine ("Address already in use" once in a few hundred launches)
+    base = 11000 + ((os.getpid() * 37 + k * 64) % 18000)
     return base, f"{base + 1}-{base + 60}"
 
 
