@@ -125,7 +125,7 @@ def test_random_resizes_from_an_external_config_client():
         import random
 
         rng = random.Random(7)
-        for _ in range(10):
+        for _ in range(8):
             n = rng.randint(1, 4)
             if config_client.put_size(url, n):
                 log.append(n)
@@ -135,11 +135,11 @@ def test_random_resizes_from_an_external_config_client():
 
     th = threading.Thread(target=chaos, daemon=True)
     th.start()
-    r = _watch(2, 4, "follow", ["--max-step", "400"], cfg_port, timeout=280)
+    r = _watch(2, 4, "follow", ["--max-step", "320"], cfg_port, timeout=280)
     th.join(timeout=30)
     assert r.returncode == 0, r.stdout[-5000:]
     final = [j for j in json_lines(r.stdout) if j.get("followed")]
-    assert len(final) == 1 and final[0]["final_step"] == 400 and final[0]["final_size"] == 2, r.stdout[-3000:]
+    assert len(final) == 1 and final[0]["final_step"] == 320 and final[0]["final_size"] == 2, r.stdout[-3000:]
     assert final[0]["resizes"] >= 2 and len(log) >= 5, (final, log)
 
 
