@@ -121,7 +121,7 @@ def test_random_resizes_from_an_external_config_client():
         t_end = time.time() + 60
         while time.time() < t_end and config_client.current_size(url) < 0:
             time.sleep(0.2)
-        time.sleep(1.0)
+        time.sleep(5.0)  # the workers need a few seconds to import torch and start stepping; resize while they train
         import random
 
         rng = random.Random(7)
