@@ -125,7 +125,7 @@ def test_random_resizes_from_an_external_config_client():
         import random
 
         rng = random.Random(7)
-        for _ in range(8):
+        for _ in range(15):  # ~10.5 s of random sizes; the workers step for >= 16 s, the last proposal (2) lands well before they finish
             n = rng.randint(1, 4)
             if config_client.put_size(url, n):
                 log.append(n)
