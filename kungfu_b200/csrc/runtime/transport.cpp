@@ -156,6 +156,11 @@ Socket Socket::connect_tcp(uint32_t ipv4, uint16_t port, int timeout_ms) {
     a.sin_family = AF_INET;
     a.sin_port = htons(port);
     a.sin_addr.s_addr = htonl(ipv4);
+    // the automatically chosen source port of this connection may be a port some worker wants to LISTEN on later (default
+    // runner port 38080 and torchrun-style jobs sit in the ephemeral range): with SO_REUSEADDR on both sides the listener's bind
+    // still succeeds
+    int reuse = 1;
+    setsockopt(fd, SOL_SOCKET, SO_REUSEADDR, &reuse, sizeof(reuse));
     int fl = fcntl(fd, F_GETFL, 0);
     fcntl(fd, F_SETFL, fl | O_NONBLOCK);
     int r = ::connect(fd, reinterpret_cast<sockaddr*>(&a), sizeof(a));
