@@ -33,14 +33,15 @@ class _AdaptiveSGD(KungFuMixin):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        self._kf_membership_changed()  # joiners adopt the survivors' step count: everybody is in the same phase
         if self._kf_step_count < self._kf_change_step:
             self._kf_average_model()
         else:
-            if not self._kf_switched:
+            if not self._kf_switched and self._kf_step_count == self._kf_change_step:
                 # AdaSGDHook: one broadcast so that S-SGD starts from a single model
                 for name, p in self._kf_named:
                     coll.broadcast_(p.data, 0, "ada::switch::" + name)
-                self._kf_switched = True
+            self._kf_switched = True  # a worker that joins after the switch inherited the model through sync_after_resize
             cpu_all_reduce_grads(self._kf_named, "sum", True)
         self._kf_inner_step()
         self._kf_step_count += 1

@@ -99,7 +99,9 @@ class _PairAveraging(KungFuMixin):
         else:
             ctl = rt.control
             if rt.size > 1 and hasattr(ctl, "save"):
-                if not self._kf_published:
+                if self._kf_membership_changed() or not self._kf_published:
+                    # first step of this membership (start of the job, or right after a resize): everybody publishes, then a
+                    # barrier, so that no pull can find an empty store — joiners and survivors meet here together
                     ctl.save(self._kf_model_name, self._kf_flat_cpu())
                     ctl.barrier()
                     self._kf_published = True

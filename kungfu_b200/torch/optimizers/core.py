@@ -91,6 +91,22 @@ class KungFuMixin:
         self._kf_engine = None
         self._kf_step_count = 0
 
+    def _kf_membership_changed(self) -> bool:
+        """True once per cluster version: at the first `step()` after the membership changed (and at the very first step).
+        Survivors reach their next step and newcomers their first one after the same `sync_after_resize`, so every member of the
+        new cluster sees the change at the same point and collectives keyed to it stay matched. The per-process step counter is
+        re-agreed here (max over the workers): schedules that depend on it (AdaptiveSGD's switch) then hold for joiners too."""
+        ver = getattr(self._kf_rt.control, "cluster_version", None)
+        key = (ver() if ver else 0, self._kf_rt.size)
+        if getattr(self, "_kf_membership", None) == key:
+            return False
+        self._kf_membership = key
+        if self._kf_rt.size > 1:
+            from ...python import all_reduce_int_max
+
+            self._kf_step_count = all_reduce_int_max(self._kf_step_count)
+        return True
+
     def _kf_inner_step(self, closure=None):
         return self._kf_inner_cls.step(self, closure)
 

@@ -11,6 +11,8 @@ import subprocess
 import sys
 import time
 
+import pytest
+
 
 
 from test_runtime_multiproc import ROOT, WORKER, json_lines, kungfu_run, ports
@@ -172,3 +174,18 @@ def test_scaling_benchmark_with_resize_schedule():
     assert r.returncode == 0, r.stdout[-4000:]
     assert r.stdout.count("RESULT:") >= 3 and "cluster size 3" in r.stdout and "local step 1, took" in r.stdout, r.stdout[-4000:]
     assert "_since_job_start:" in r.stdout and "BEGIN :: main" in r.stdout
+
+
+@pytest.mark.parametrize("which", ["pair", "ada", "sma", "gns", "variance"])
+def test_every_optimizer_survives_resizes(which):
+    """1 -> 3 -> 2 workers with each distributed optimizer. PairAveraging publishes + barriers once per membership (joiners used to
+    barrier alone), AdaptiveSGD re-agrees its step counter so that joiners are in the same phase (both hung before)."""
+    rport, prange = ports()
+    cfg_port = 9500 + (os.getpid() + hash(which)) % 200
+    cmd = [kungfu_run(), "-q", "-w", "-np", "1", "-H", "127.0.0.1:4", "-port", str(rport), "-port-range", prange, "-builtin-config-port", str(cfg_port),
+           sys.executable, os.path.join(ROOT, "tests", "elastic_opt_worker.py"), which, "1:2,3:3,2:3", "8"]
+    e = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN")
+    r = subprocess.run(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=150)
+    assert r.returncode == 0, r.stdout[-4000:]
+    done = [j for j in json_lines(r.stdout) if j.get("done")]
+    assert done == [{"done": which, "step": 8, "sizes": [1, 2, 3], "finite": True}], r.stdout[-3000:]
