@@ -268,6 +268,9 @@ def cmd_optimizers(args):
         if k == r:
             pa.zero_grad(); p.sum().backward(); pa.step()
         elif n > 1 and not pa._kf_published:
+            # the first step of a membership is collective (publish, agree on the step counter, barrier): ranks that do not step
+            # yet take part in it the way step() does
+            pa._kf_membership_changed()
             rt.control.save(pa._kf_model_name, pa._kf_flat_cpu()); rt.control.barrier(); pa._kf_published = True
         if n > 1:
             tgt = (k + 1) % n

@@ -142,3 +142,11 @@ def test_rrun_local_fans_out_one_launcher_per_alias():
     for k in range(4):
         assert f"rank {k}/4: [4.0" in r.stdout, r.stdout[-3000:]
     assert "[127.0.0.2] " in r.stdout and "[127.0.0.1] " in r.stdout
+
+
+@pytest.mark.parametrize("slots,strategy", [([2, 2], "BINARY_TREE_STAR"), ([2, 1, 1], "TREE")])
+def test_optimizer_closed_forms_across_hosts(slots, strategy):
+    """S-SGD / SMA / PairAveraging closed forms, noise-scale / variance monitors, AdaptiveSGD switch — with the workers spread over
+    several hosts."""
+    out = launch_hosts(slots, "optimizers", flags=["-strategy", strategy])
+    assert out.count('"ok": true') == sum(slots), out[-4000:]
