@@ -189,3 +189,17 @@ def test_every_optimizer_survives_resizes(which):
     assert r.returncode == 0, r.stdout[-4000:]
     done = [j for j in json_lines(r.stdout) if j.get("done")]
     assert done == [{"done": which, "step": 8, "sizes": [1, 2, 3], "finite": True}], r.stdout[-3000:]
+
+
+def test_sample_count_driven_elastic_hook():
+    """`ElasticHook`: the loop ends after epochs x epoch_size samples whatever sizes the cluster went through (1 -> 2 -> 3 -> 1)."""
+    rport, prange = ports()
+    cfg_port = 9500 + os.getpid() % 200
+    cmd = [kungfu_run(), "-q", "-w", "-np", "1", "-H", "127.0.0.1:4", "-port", str(rport), "-port-range", prange, "-builtin-config-port", str(cfg_port),
+           sys.executable, os.path.join(ROOT, "tests", "elastic_opt_worker.py"), "elastichook", "3=2,6=3,9=1", "0"]
+    e = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN")
+    r = subprocess.run(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=150)
+    assert r.returncode == 0, r.stdout[-4000:]
+    done = [j for j in json_lines(r.stdout) if j.get("done")]
+    # steps 1-3 at np=1 (12 samples), 4-6 at np=2 (24), 7-9 at np=3 (36), then np=1 until 96 samples are reached
+    assert done == [{"done": "elastichook", "trained": 96, "steps": 15, "sizes": [1, 2, 3]}], r.stdout[-3000:]
