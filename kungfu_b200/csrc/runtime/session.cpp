@@ -71,7 +71,9 @@ void Session::run_graphs(const Workspace& w, const Graph* const* graphs, int ngr
         if (g.is_self_loop(rank_)) {
             std::string err = parallel_for((int)prevs.size(), [&](int i) {
                 Bytes m = coll_->recv(peers_[prevs[i]], w.name);
-                if (m.size() != bytes) fail("all-reduce chunk size mismatch for " + w.name);
+                if (m.size() != bytes)
+                    fail("all-reduce chunk size mismatch for " + w.name + ": " + peers_[prevs[i]].str() + " sent " + std::to_string(m.size()) +
+                         " bytes, this rank has " + std::to_string(bytes) + " (do all workers pass tensors of the same shape and dtype?)");
                 std::lock_guard<std::mutex> lk(mu);
                 transform2(w.recv, effective(), m.data(), w.count, w.dtype, w.op);
                 ++recv_count;
@@ -110,7 +112,9 @@ void Session::run_strategies(const Workspace& w, const StratList& sl, bool monit
         c.count = be.second - be.first;
         c.send = static_cast<const char*>(w.send) + be.first * esz;
         c.recv = static_cast<char*>(w.recv) + be.first * esz;
-        c.name = "part::" + w.name + "[" + std::to_string(be.first) + ":" + std::to_string(be.second) + "]";
+        // chunk i of the op, NOT its element range: two ranks that disagree on the tensor size must still rendezvous, so that the
+        // receiver can report "chunk size mismatch" instead of both sides waiting forever for a name the other never uses
+        c.name = "part::" + w.name + "#" + std::to_string(i);
         const Strat& s = sl[strategy_hash((size_t)i, w.name) % sl.size()];
         const Graph* gs[2] = {&s.g.reduce, &s.g.bcast};
         const double t0 = monitored ? now_s() : 0;

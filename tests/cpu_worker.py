@@ -618,6 +618,13 @@ def cmd_initializer(args):
     print(json.dumps({"ok": True, "traced": trace.ENABLED}), flush=True)
 
 
+def cmd_mismatch(args):
+    """Workers that disagree on a tensor's size must get an error quickly, not wait for each other forever."""
+    rt = get_runtime()
+    ops.all_reduce(torch.ones(10 + 2 * rt.rank), name="bad")
+    print("unexpected success", flush=True)
+
+
 def cmd_bad(args):
     rt = get_runtime()
     if rt.rank == 0:

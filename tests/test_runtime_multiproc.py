@@ -119,6 +119,13 @@ def test_initializer_tracing_and_timing_helpers(tmp_path):
     assert r.stdout.count('"ok": true') == 3 and '"traced": false' in r.stdout, r.stdout[-3000:]
 
 
+def test_size_mismatch_fails_fast_with_a_message():
+    t0 = time.time()
+    r = launch(2, "mismatch", timeout=60, expect_rc=None)
+    assert r.returncode != 0 and "chunk size mismatch" in r.stdout and "unexpected success" not in r.stdout, r.stdout[-3000:]
+    assert "same shape and dtype" in r.stdout and time.time() - t0 < 40
+
+
 def test_metrics_endpoint():
     r = launch(3, "metrics", env={"KUNGFU_CONFIG_ENABLE_MONITORING": "true"})
     assert r.stdout.count('"ok": true') == 3, r.stdout[-3000:]
