@@ -2,7 +2,7 @@
 
 Reference: `TRACE_SCOPE` / stdtracer in C++ (srcs/cpp/include/kungfu/utils/trace.hpp:2-16; the native runtime has the
 equivalent `KF_TRACE_SCOPE`), `_log_event`, `ResizeProfiler`, `LogPerfHook`. Enabled by
-KUNGFU_ENABLE_TRACE=1; `KUNGFU_TRACE_FILE=path.json` additionally writes chrome://tracing events at exit.
+KUNGFU_ENABLE_TRACE=1; `KUNGFU_TRACE_FILE=path.json` additionally writes chrome://tracing events at exit (`path.<ip_port>.json` per worker under a launcher).
 """
 from __future__ import annotations
 
@@ -73,5 +73,10 @@ def _dump() -> None:
     print(report(), flush=True)
     path = os.environ.get("KUNGFU_TRACE_FILE")
     if path:
+        # one file per worker: under a launcher every process inherits the same KUNGFU_TRACE_FILE
+        spec = os.environ.get("KUNGFU_SELF_SPEC") or os.environ.get("RANK")
+        if spec:
+            root, ext = os.path.splitext(path)
+            path = f"{root}.{spec.replace(':', '_')}{ext}"
         with open(path, "w") as f:
             json.dump({"traceEvents": _events}, f)

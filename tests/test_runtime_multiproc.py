@@ -113,7 +113,9 @@ def test_initializer_tracing_and_timing_helpers(tmp_path):
     r = launch(2, "initializer", env={"KUNGFU_ENABLE_TRACE": "1", "KUNGFU_TRACE_FILE": str(trace_file)})
     assert r.stdout.count('"ok": true') == 2 and '"traced": true' in r.stdout, r.stdout[-3000:]
     assert "[kungfu trace]" in r.stdout and "init.broadcast" in r.stdout  # per-scope summary printed at exit
-    ev = json.loads(trace_file.read_text())["traceEvents"]
+    files = sorted(tmp_path.glob("trace.*.json"))  # one per worker
+    assert len(files) == 2, list(tmp_path.iterdir())
+    ev = json.loads(files[0].read_text())["traceEvents"]
     assert any(e["name"] == "init.broadcast" and e["ph"] == "X" and e["dur"] > 0 for e in ev)
     r = launch(3, "initializer")
     assert r.stdout.count('"ok": true') == 3 and '"traced": false' in r.stdout, r.stdout[-3000:]
