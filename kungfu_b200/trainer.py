@@ -22,11 +22,13 @@ IMAGENET_STD = (0.229 * 255, 0.224 * 255, 0.225 * 255)
 
 
 class LossFuture:
-    def __init__(self, host: torch.Tensor, event: torch.cuda.Event) -> None:
+    def __init__(self, host: torch.Tensor, event: Optional[torch.cuda.Event]) -> None:
         self._host = host
         self._event = event
 
     def result(self) -> float:
+        if self._event is None:  # host execution: the value is already there
+            return float(self._host.item())
         self._event.synchronize()
         return float(self._host.item())
 
@@ -130,7 +132,7 @@ class ImageTrainer:
     def step_async(self, images_u8: torch.Tensor, labels: torch.Tensor) -> LossFuture:
         """Full end-to-end step from pinned host memory; returns a future for the loss."""
         if self.device.type != "cuda":
-            raise RuntimeError("ImageTrainer.step_async needs a GPU")
+            return self._step_host(images_u8, labels)
         self.load_batch(images_u8, labels)
         self.device_step()
         i = self._i & 1
@@ -140,11 +142,23 @@ class ImageTrainer:
         self._i += 1
         return LossFuture(self.loss_host[i], ev)
 
+    def _step_host(self, images_u8: torch.Tensor, labels: torch.Tensor) -> LossFuture:
+        """The same step without a GPU (CI, debugging): normalise with torch ops, run the model and the optimizer eagerly."""
+        mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float32)
+        std = torch.tensor(IMAGENET_STD, dtype=torch.float32)
+        x = (images_u8.to(torch.float32) - mean) / std  # NHWC
+        self.x.copy_(x.permute(0, 3, 1, 2).to(self.dtype))
+        self.y.copy_(labels)
+        self._train_body()
+        return LossFuture(self.loss.detach().clone(), None)
+
     def step(self, images_u8: torch.Tensor, labels: torch.Tensor) -> float:
         return self.step_async(images_u8, labels).result()
 
     @property
     def h2d_bytes_per_step(self) -> int:
+        if self.device.type != "cuda":
+            return 0
         return self.u8[0].numel() + self.yb[0].numel() * 8
 
     @property

@@ -276,3 +276,33 @@ def test_global_variables_registry_and_dataset_adaptors():
     e = ExampleDatasetAdaptor(batch_size=4, shard_count=2, shard_id=1)
     e.create_update_topology()()
     assert (e._shard_count, e._shard_id, e._batch_size) == (3, 2, 6)
+
+
+def test_image_trainer_host_path_matches_a_manual_step():
+    """`ImageTrainer.step()` without a GPU: uint8 NHWC batch -> normalise -> forward/backward -> optimizer, same numbers as the
+    hand-written loop (the GPU path replays the same body from a CUDA graph)."""
+    import kungfu_b200.torch as kf
+    from kungfu_b200.trainer import IMAGENET_MEAN, IMAGENET_STD, ImageTrainer
+
+    torch.manual_seed(0)
+    mk = lambda: torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.ReLU(), torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten(),  # noqa: E731
+                                     torch.nn.Linear(4, 5))
+    a, b = mk(), mk()
+    b.load_state_dict(a.state_dict())
+    opt = kf.optimizers.SynchronousSGDOptimizer(torch.optim.SGD(a.parameters(), lr=0.05, momentum=0.9), named_parameters=a.named_parameters())
+    tr = ImageTrainer(a, opt, 6, 16, torch.float32, use_graph=True, device=torch.device("cpu"))  # use_graph is ignored on the host
+    ref = torch.optim.SGD(b.parameters(), lr=0.05, momentum=0.9)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(3):
+        x = torch.randint(0, 256, (6, 16, 16, 3), dtype=torch.uint8, generator=g)
+        y = torch.randint(0, 5, (6,), generator=g)
+        loss = tr.step(x, y)
+        xn = ((x.float() - torch.tensor(IMAGENET_MEAN)) / torch.tensor(IMAGENET_STD)).permute(0, 3, 1, 2)
+        ref.zero_grad()
+        want = torch.nn.functional.cross_entropy(b(xn), y)
+        want.backward()
+        ref.step()
+        assert abs(loss - float(want)) < 1e-5
+    for p, q in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(p, q, atol=1e-6)
+    assert tr.h2d_bytes_per_step == 0 and tr.d2h_bytes_per_step == 4
