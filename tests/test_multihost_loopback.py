@@ -150,3 +150,20 @@ def test_optimizer_closed_forms_across_hosts(slots, strategy):
     several hosts."""
     out = launch_hosts(slots, "optimizers", flags=["-strategy", strategy])
     assert out.count('"ok": true') == sum(slots), out[-4000:]
+
+
+def test_hostfile_and_nic_discovery(tmp_path):
+    """OpenMPI-style hostfile instead of -H; the first launcher finds its own address through `-nic lo`, the second through -self."""
+    hf = tmp_path / "hosts.txt"
+    hf.write_text("# two hosts\n127.0.0.1 slots=2\n127.0.0.2 slots=2\n")
+    rport, prange = ports()
+    env = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN")
+    base = [kungfu_run(), "-q", "-np", "4", "-hostfile", str(hf), "-port", str(rport), "-port-range", prange]
+    prog = [sys.executable, os.path.join(ROOT, "examples", "torch_simple_example.py")]
+    b = subprocess.Popen(base + ["-self", "127.0.0.2"] + prog, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    a = subprocess.run(base + ["-nic", "lo"] + prog, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=180)
+    out_b, _ = b.communicate(timeout=60)
+    assert a.returncode == 0 and b.returncode == 0, a.stdout[-2000:] + out_b[-2000:]
+    text = a.stdout + out_b
+    for k in range(4):
+        assert f"rank {k}/4: [4.0" in text, text[-3000:]
