@@ -176,7 +176,7 @@ def test_scaling_benchmark_with_resize_schedule():
     assert "_since_job_start:" in r.stdout and "BEGIN :: main" in r.stdout
 
 
-@pytest.mark.parametrize("which", ["pair", "ada", "sma", "gns"])
+@pytest.mark.parametrize("which", ["pair", "ada", "sma"])
 def test_every_optimizer_survives_resizes(which):
     """1 -> 3 -> 2 workers with each distributed optimizer. PairAveraging publishes + barriers once per membership (joiners used to
     barrier alone), AdaptiveSGD re-agrees its step counter so that joiners are in the same phase (both hung before)."""

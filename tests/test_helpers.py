@@ -302,7 +302,7 @@ def test_image_trainer_host_path_matches_a_manual_step():
         want = torch.nn.functional.cross_entropy(b(xn), y)
         want.backward()
         ref.step()
-        assert abs(loss - float(want)) < 1e-5
+        assert abs(loss - float(want.detach())) < 1e-5
     for p, q in zip(a.parameters(), b.parameters()):
         assert torch.allclose(p, q, atol=1e-6)
     assert tr.h2d_bytes_per_step == 0 and tr.d2h_bytes_per_step == 4
