@@ -520,7 +520,7 @@ def cmd_stress(args):
     ops.save_variable(torch.full((1024,), float(r)), "soak")
     ops.barrier()
     for it in range(iters):
-        kind = rng.choice(["allreduce", "allreduce", "allreduce", "bcast", "gather", "threads", "p2p", "consensus", "barrier", "subset"])
+        kind = rng.choice(["allreduce", "allreduce", "allreduce", "bcast", "gather", "threads", "p2p", "consensus", "barrier", "subset", "mixed"])
         if kind == "allreduce":
             dt, op, m = rng.choice(dts), rng.choice(["sum", "min", "max"]), rng.choice(sizes)
             base = (torch.arange(m) % 7 + 1)
@@ -554,6 +554,34 @@ def cmd_stress(args):
                 t.join()
             for i in range(k):
                 check(outs[i] is not None and bool(torch.all(outs[i] == float((i + 1) * n))), f"it {it}: threaded all-reduce {i}")
+        elif kind == "mixed":
+            # different kinds of collectives at the same time from different threads (all-reduce, broadcast, all-gather, P2P pulls)
+            root, m1, m2 = rng.randrange(n), rng.choice(sizes[:7]), rng.choice(sizes[:6])
+            bad = []
+
+            def t_ar():
+                y = ops.all_reduce(torch.full((m1,), 2.0), name=f"mix{it}.ar")
+                bad.append("ar") if not bool(torch.all(y == 2.0 * n)) else None
+
+            def t_bc():
+                x = torch.full((m2,), float(r))
+                coll.broadcast_(x, root, name=f"mix{it}.bc")
+                bad.append("bc") if not bool(torch.all(x == float(root))) else None
+
+            def t_ag():
+                g = ops.all_gather(torch.full((257,), float(r)), name=f"mix{it}.ag")
+                bad.append("ag") if not all(bool(torch.all(g[q] == float(q))) for q in range(n)) else None
+
+            def t_pp():
+                ok, v = ops.request_variable((r + 1) % n, "soak", shape=(1024,), dtype=torch.float32)
+                bad.append("p2p") if not (ok and bool(torch.all(v == float((r + 1) % n)))) else None
+
+            ths = [threading.Thread(target=f) for f in (t_ar, t_bc, t_ag, t_pp)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+            check(not bad, f"it {it}: mixed concurrent collectives {bad}")
         elif kind == "p2p":
             tgt = rng.randrange(n)
             ok, v = ops.request_variable(tgt, "soak", shape=(1024,), dtype=torch.float32)
