@@ -92,6 +92,7 @@ static std::mutex g_cfg_mu;
 static void load_config(Config& c) {
     c.enable_monitoring = getenv_bool("KUNGFU_CONFIG_ENABLE_MONITORING", false);
     c.enable_stall_detection = getenv_bool("KUNGFU_CONFIG_ENABLE_STALL_DETECTION", false);
+    c.stall_detection_off = getenv("KUNGFU_CONFIG_ENABLE_STALL_DETECTION") != nullptr && !c.enable_stall_detection;
     c.monitoring_period_s = parse_duration_s(getenv_str("KUNGFU_CONFIG_MONITORING_PERIOD"), 1.0);
     c.strategy_hash = getenv_str("KUNGFU_CONFIG_STRATEGY_HASH_METHOD", "SIMPLE");
     c.wait_runner_timeout_s = parse_duration_s(getenv_str("KUNGFU_CONFIG_WAIT_RUNNER_TIMEOUT"), 300);
@@ -134,19 +135,27 @@ struct Watchdog {
         if (started) return;
         started = true;
         std::thread([this] {
+            const bool full = Config::get().enable_stall_detection;
+            const double threshold = full ? 3.0 : 30.0; // first report after this long, then once per `threshold` seconds
+            std::map<uint64_t, double> last_report;
             std::unique_lock<std::mutex> lk(mu);
-            std::map<uint64_t, int> reported;
             while (true) {
                 cv.wait_for(lk, std::chrono::seconds(3));
                 const double t = now_s();
+                std::vector<std::string> msgs; // formatted under the lock, logged after it is released (ops may change meanwhile)
                 for (auto& kv : ops) {
                     const double d = t - kv.second.second;
-                    if (d >= 3.0) {
-                        lk.unlock();
-                        KF_LOGW("%s stalled for %.0fs", kv.second.first.c_str(), d);
-                        lk.lock();
-                    }
+                    if (d < threshold) continue;
+                    auto it = last_report.find(kv.first);
+                    if (it != last_report.end() && t - it->second < threshold - 0.5) continue;
+                    last_report[kv.first] = t;
+                    msgs.push_back(strprintf("%s stalled for %.0fs", kv.second.first.c_str(), d));
                 }
+                for (auto it = last_report.begin(); it != last_report.end();) // forget finished operations
+                    it = ops.count(it->first) ? std::next(it) : last_report.erase(it);
+                lk.unlock();
+                for (auto& m : msgs) KF_LOGW("%s", m.c_str());
+                lk.lock();
             }
         }).detach();
     }
@@ -157,8 +166,9 @@ Watchdog& wd() {
 }
 } // namespace
 
-StallGuard::StallGuard(const std::string& what) {
-    if (!Config::get().enable_stall_detection) return;
+StallGuard::StallGuard(const std::string& what, bool fine) {
+    const Config& cfg = Config::get();
+    if (cfg.stall_detection_off || (fine && !cfg.enable_stall_detection)) return;
     Watchdog& w = wd();
     std::lock_guard<std::mutex> g(w.mu);
     w.ensure();
@@ -172,7 +182,7 @@ StallGuard::~StallGuard() {
     auto it = w.ops.find(id_);
     if (it != w.ops.end()) {
         const double d = now_s() - it->second.second;
-        if (d >= 3.0) KF_LOGW("%s recovered after %.1fs", it->second.first.c_str(), d);
+        if (d >= (Config::get().enable_stall_detection ? 3.0 : 30.0)) KF_LOGW("%s recovered after %.1fs", it->second.first.c_str(), d);
         w.ops.erase(it);
     }
 }

@@ -60,7 +60,8 @@ private:
 // ---------------------------------------------------------------------------------------------------
 struct Config {
     bool enable_monitoring = false;      // KUNGFU_CONFIG_ENABLE_MONITORING
-    bool enable_stall_detection = false; // KUNGFU_CONFIG_ENABLE_STALL_DETECTION
+    bool enable_stall_detection = false; // KUNGFU_CONFIG_ENABLE_STALL_DETECTION=true: every wait is watched, warnings every 3 s
+    bool stall_detection_off = false;    // ...=false: nothing is watched. Unset: whole operations only, warnings every 30 s
     double monitoring_period_s = 1.0;    // KUNGFU_CONFIG_MONITORING_PERIOD
     std::string strategy_hash = "SIMPLE"; // KUNGFU_CONFIG_STRATEGY_HASH_METHOD (SIMPLE | NAME)
     double wait_runner_timeout_s = 300;  // KUNGFU_CONFIG_WAIT_RUNNER_TIMEOUT
@@ -96,7 +97,10 @@ constexpr const char* kCudaVisibleDevices = "KUNGFU_CUDA_VISIBLE_DEVICES";
 // ---------------------------------------------------------------------------------------------------
 class StallGuard {
 public:
-    explicit StallGuard(const std::string& what);
+    // `fine` marks the inner waits (one per chunk and peer); they are watched only when stall detection is switched on explicitly.
+    // Whole operations (AllReduce(name), Barrier, Consensus, updateTo, request) are watched by default and reported after 30 s:
+    // a job that hangs because two workers called different operations says so instead of staying silent.
+    explicit StallGuard(const std::string& what, bool fine = false);
     ~StallGuard();
 
 private:

@@ -457,7 +457,7 @@ std::string CollectiveEndpoint::key(const PeerID& src, const std::string& name) 
 }
 
 void CollectiveEndpoint::wait_done(std::unique_lock<std::mutex>& lk, Waiter& w, const std::string& what) {
-    StallGuard sg(what);
+    StallGuard sg(what, /*fine=*/true);
     w.cv.wait(lk, [&] { return w.done; });
     if (w.failed) fail(w.err);
 }
