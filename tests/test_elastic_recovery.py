@@ -108,6 +108,7 @@ def test_elastic_churn_with_sibling_survivors():
         assert len(final) == 1 and final[0]["final_step"] == 16 and final[0]["resizes"] == 7 and final[0]["sizes"] == [1, 2, 3, 4], r.stdout[-3000:]
 
 
+@pytest.mark.extended
 def test_random_resizes_from_an_external_config_client():
     """The chaos half of the reference's elastic test (kungfu-config-client-example): an external client rewrites the cluster
     config with random sizes every 0.7 s while the workers just follow the config server."""
@@ -162,6 +163,7 @@ def test_failure_detection_and_auto_recovery(tmp_path):
     assert time.time() - t0 < 120
 
 
+@pytest.mark.extended
 def test_scaling_benchmark_with_resize_schedule():
     """benchmarks/scaling/benchmark_kungfu_scaling.py (+ debug_hooks.LogPerfHook): one RESULT line per phase of the schedule."""
     rport, prange = ports()
@@ -176,7 +178,7 @@ def test_scaling_benchmark_with_resize_schedule():
     assert "_since_job_start:" in r.stdout and "BEGIN :: main" in r.stdout
 
 
-@pytest.mark.parametrize("which", ["pair", "ada", "sma"])
+@pytest.mark.parametrize("which", ["pair", "ada", pytest.param("sma", marks=pytest.mark.extended), pytest.param("gns", marks=pytest.mark.extended)])
 def test_every_optimizer_survives_resizes(which):
     """1 -> 3 -> 2 workers with each distributed optimizer. PairAveraging publishes + barriers once per membership (joiners used to
     barrier alone), AdaptiveSGD re-agrees its step counter so that joiners are in the same phase (both hung before)."""

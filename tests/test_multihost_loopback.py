@@ -37,7 +37,9 @@ def launch_hosts(slots, what, extra=(), flags=(), timeout=240):
     return text
 
 
-@pytest.mark.parametrize("slots,strategy", [([2, 2], "BINARY_TREE_STAR"), ([2, 1, 1], "TREE"), ([1, 3], "MULTI_BINARY_TREE_STAR"), ([2, 2], "RING")])
+@pytest.mark.parametrize("slots,strategy", [([2, 2], "BINARY_TREE_STAR"), ([2, 1, 1], "TREE"),
+                                            pytest.param([1, 3], "MULTI_BINARY_TREE_STAR", marks=pytest.mark.extended),
+                                            pytest.param([2, 2], "RING", marks=pytest.mark.extended)])
 def test_collectives_across_hosts(slots, strategy):
     out = launch_hosts(slots, "collectives", flags=["-strategy", strategy])
     assert len([j for j in json_lines(out) if j.get("ok")]) == sum(slots), out[-4000:]
@@ -63,6 +65,7 @@ def test_randomised_soak_across_hosts():
     assert out.count('"ok": true') == 4, out[-4000:]
 
 
+@pytest.mark.extended
 def test_training_result_does_not_depend_on_the_host_layout():
     """S-SGD on the SLP: 4 workers on one host and 2 + 2 on two hosts reach the same parameters (np-invariance test across
     layouts)."""

@@ -100,7 +100,7 @@ def test_many_chunks_in_flight_do_not_starve_the_pool():
         assert r.returncode == 0 and "RESULT:" in r.stdout, r.stdout[-3000:]
 
 
-@pytest.mark.parametrize("np,strategy", [(4, "BINARY_TREE_STAR"), (3, "RING"), (4, "MULTI_BINARY_TREE_STAR")])
+@pytest.mark.parametrize("np,strategy", [(4, "BINARY_TREE_STAR"), (3, "RING"), pytest.param(4, "MULTI_BINARY_TREE_STAR", marks=pytest.mark.extended)])
 def test_randomised_soak(np, strategy):
     """150 pseudo-random operations (all-reduce over dtypes / ops / sizes up to several chunks, broadcast from random roots,
     all-gather, threaded concurrent collectives, P2P requests, consensus, subset all-reduce), every result checked."""
