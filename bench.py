@@ -11,8 +11,11 @@ figure), but device-timed with CUDA events, max over ranks.
       bench.py --gpus N --steps K --warmup W
 
 --impl ours       our framework (fused sm_100a reduce-scatter + optimizer + all-gather kernels)     [default]
---impl nccl       plain-NCCL baseline written against torch DDP + torch.optim (the "baseline, not the product")
+--impl nccl       the same-box baseline: SAME model, fused BN kernels, bf16 + fp32-master optimizer kernel, bucket plan, comm
+                  stream and CUDA graph — only the collective is `ncclAllReduce` (torch.distributed) instead of our kernels
+                  ("a path that only calls NCCL is the baseline, not the product")
 --impl reference  the unmodified reference from baseline/_ref (cannot be installed offline: needs Go + TensorFlow)
+--optimizer ssgd | sma    BASELINE.json configs #2 (SynchronousSGDOptimizer, default) and #3 (SynchronousAveragingOptimizer)
 """
 from __future__ import annotations
 
@@ -36,6 +39,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--momentum", type=float, default=0.0)
+    ap.add_argument("--optimizer", default="ssgd", choices=["ssgd", "sma"])
+    ap.add_argument("--trace", default="", help="after the timed runs: CUPTI kernel timeline of 3 steps per rank -> <prefix>.rank<r>.json")
     return ap.parse_args()
 
 
@@ -55,6 +60,35 @@ def reference_arm(args) -> int:
     if int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps({"impl": "reference", "unavailable": why}))
     return 0
+
+
+def _trace(args, trainer, rt) -> None:
+    """Real (not replayed) kernel timeline of 3 steps on every rank: start / duration / stream of each kernel, so that the
+    collective kernels can be placed against backward and the exposed tail of a step can be read off."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+
+    torch.cuda.synchronize()
+    rt.control.barrier()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(3):
+            trainer.device_step()
+        torch.cuda.synchronize()
+    evs = []
+    for e in prof.events():
+        if getattr(e, "device_type", None) is not None and e.device_type.name == "CUDA" and e.device_time_total > 0:
+            tr = e.time_range
+            evs.append({"name": e.name[:160], "ts": tr.start, "dur": tr.end - tr.start})
+    evs.sort(key=lambda x: x["ts"])
+    path = f"{args.trace}.rank{rt.rank}.json"
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    with open(path, "w") as f:
+        json.dump({"n_gpus": rt.size, "impl": args.impl, "optimizer": args.optimizer, "events": evs}, f)
+    try:
+        prof.export_chrome_trace(f"{args.trace}.rank{rt.rank}.chrome.json")
+    except Exception:
+        pass
+    rt.control.barrier()
 
 
 def main() -> int:
@@ -99,23 +133,29 @@ def main() -> int:
     lr = 0.01 * N
     base_opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=args.momentum)
 
-    if args.impl == "ours":
-        opt = kf.optimizers.SynchronousSGDOptimizer(base_opt, named_parameters=model.named_parameters())
-        kf.broadcast_parameters(model.state_dict())
-        train_model = model
-    else:  # plain NCCL baseline: DDP bucketed ncclAllReduce + torch.optim step
-        import torch.distributed as dist
-
+    backend = None
+    if args.impl == "nccl":
+        backend = "nccl"
         if N > 1:
+            import torch.distributed as dist
+
+            # CUDA-graph capture of NCCL collectives: the watchdog's event queries must not run against a capturing stream
+            os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
+            os.environ.setdefault("NCCL_ASYNC_ERROR_HANDLING", "0")
             if not dist.is_initialized():
                 dist.init_process_group("nccl", device_id=device)
-            train_model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[dev_index], gradient_as_bucket_view=True)
-        else:
-            train_model = model
-        opt = base_opt
+            warm = torch.ones(1 << 20, device=device)
+            dist.all_reduce(warm)  # communicator + channels exist before anything is captured
+            torch.cuda.synchronize()
+    if args.optimizer == "ssgd":
+        opt = kf.optimizers.SynchronousSGDOptimizer(base_opt, named_parameters=model.named_parameters(), backend=backend)
+    else:
+        opt = kf.optimizers.SynchronousAveragingOptimizer(base_opt, named_parameters=model.named_parameters(), backend=backend)
+    kf.broadcast_parameters(model.state_dict())
+    train_model = model
 
-    trainer = ImageTrainer(train_model, opt, B, 224, torch.bfloat16, use_graph=not args.no_graph and args.impl == "ours",
-                           warmup_iters=3, device=device)
+    trainer = ImageTrainer(train_model, opt, B, 224, torch.bfloat16, use_graph=not args.no_graph, warmup_iters=3 if backend is None else 12,
+                           device=device, capture_error_mode="thread_local" if backend == "nccl" else "global")
     # synthetic ImageNet-shaped data
     g = torch.Generator().manual_seed(rt.rank)
     host_images = [torch.randint(0, 256, (B, 224, 224, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(2)]
@@ -153,7 +193,7 @@ def main() -> int:
     rt.control.barrier()
     wall = time.time() - wall0
     ms = max_over_ranks(ms)
-    if args.impl == "ours" and opt.engine is not None:
+    if opt.engine is not None:
         opt.engine.check()
     loss_val = float(trainer.loss.item())
     img_s = N * B * args.steps / (ms / 1e3)
@@ -184,11 +224,14 @@ def main() -> int:
                "h2d_bytes_per_step": trainer.h2d_bytes_per_step, "d2h_bytes_per_step": trainer.d2h_bytes_per_step,
                "last_loss": round(last_loss, 4)}
     clocks = sampler.stop() if sampler is not None else None
+    if args.trace:
+        _trace(args, trainer, rt)
 
     if rt.rank == 0:
-        launches = trainer.launches_per_step * args.steps if args.impl == "ours" else 0
+        launches = trainer.launches_per_step * args.steps
+        opt_name = "SynchronousSGD" if args.optimizer == "ssgd" else "SynchronousAveraging"
         out = {
-            "metric": "ResNet-50 SynchronousSGD training throughput",
+            "metric": f"ResNet-50 {opt_name} training throughput",
             "value": round(img_s, 1),
             "unit": "images/sec",
             "n_gpus": N,
@@ -202,7 +245,9 @@ def main() -> int:
             "data": "synthetic",
             "impl": args.impl,
             "config": {"model": args.model, "global_batch": N * B, "per_gpu_batch": B, "image": "3x224x224",
-                       "parallelism": f"dp{N}", "optimizer": f"SynchronousSGD(SGD lr={lr}, momentum={args.momentum})",
+                       "parallelism": f"dp{N}", "optimizer": f"{opt_name}(SGD lr={lr}, momentum={args.momentum})",
+                       "collective": "ncclAllReduce via torch.distributed (baseline arm)" if backend == "nccl" else
+                       ("split-phase sm_100a kernels over peer-mapped HBM" if opt.engine.gated else "single-kernel sm_100a collectives"),
                        "memory_format": "channels_last", "cuda_graph": trainer.graph is not None,
                        "l2_policy": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
                        "baseline": "5507 img/s = reference S-SGD on 16xV100 (whole cluster), BASELINE.md"},
@@ -215,7 +260,7 @@ def main() -> int:
         }
         if trainer.graph_error:
             out["config"]["cuda_graph_error"] = trainer.graph_error[:200]
-        if args.impl == "ours" and opt.engine is not None:
+        if opt.engine is not None:
             out["config"]["mesh"] = {"mode": opt.engine.arena.mesh.mode, "multicast": bool(opt.engine.arena.has_multicast),
                                      "note": opt.engine.arena.mesh.multicast_note, "buckets": sum(len(s.layout.buckets) for s in opt.engine.sets)}
         print(json.dumps(out))

@@ -40,7 +40,7 @@ def main():
     done = torch.zeros(4, dtype=torch.int32, device="cuda")
     ok = torch.zeros(4, dtype=torch.int32, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
-    ext.publish(arena.mesh, 1, pub0, pub1, ver, src.data_ptr(), max_bytes, done.data_ptr(), 64, 512, st)
+    ext.publish(arena.mesh, 1, [pub0, pub1], ver, src.data_ptr(), max_bytes, done.data_ptr(), 64, 512, st)
     torch.cuda.synchronize()
     coll.barrier()
     target = (rt.rank + 1) % N
@@ -63,9 +63,9 @@ def main():
     while nb <= max_bytes:
         variants = {}
         for blocks in (32, 74, 148):
-            variants[f"ldg_b{blocks}"] = lambda b=blocks: ext.pull(arena.mesh, 1, target, pub0, pub1, ver, dst.data_ptr(), nb, ok.data_ptr(), b, 512, st)
+            variants[f"ldg_b{blocks}"] = lambda b=blocks: ext.pull(arena.mesh, 1, target, [pub0, pub1], ver, dst.data_ptr(), nb, ok.data_ptr(), 0, b, 512, st)
         for blocks in (37, 74, 148):
-            variants[f"tma_b{blocks}"] = lambda b=blocks: ext.pull_tma(arena.mesh, 1, target, pub0, pub1, ver, dst.data_ptr(), nb, ok.data_ptr(),
+            variants[f"tma_b{blocks}"] = lambda b=blocks: ext.pull_tma(arena.mesh, 1, target, [pub0, pub1], ver, dst.data_ptr(), nb, ok.data_ptr(), 0,
                                                                         min(b, (nb + 32767) // 32768), st)
         res = {k: timed(f) for k, f in variants.items()}
         best_ldg = min(v for k, v in res.items() if k.startswith("ldg"))

@@ -16,6 +16,14 @@ using namespace kf;
 
 static inline cudaStream_t S(uintptr_t s) { return reinterpret_cast<cudaStream_t>(s); }
 template <typename T> static inline T* P(uintptr_t p) { return reinterpret_cast<T*>(p); }
+static PubStore make_pub(const std::vector<size_t>& pubs, size_t ver_off) {
+    if (pubs.size() < 2 || pubs.size() > 3) throw std::runtime_error("kungfu_b200: a published-model store has 2 or 3 buffers");
+    PubStore ps{};
+    for (size_t i = 0; i < pubs.size(); ++i) ps.pub_off[i] = pubs[i];
+    ps.ver_off = ver_off;
+    ps.nbuf = (int)pubs.size();
+    return ps;
+}
 
 PYBIND11_MODULE(_kfcuda, m) {
     m.doc() = "kungfu_b200 sm_100a kernels and peer mesh";
@@ -28,6 +36,7 @@ PYBIND11_MODULE(_kfcuda, m) {
     m.attr("ALGO_NVLS") = (int)kAlgoNvls;
     m.attr("FLAG_SCALE") = (int)kArScale;
     m.attr("FLAG_SUMSQ") = (int)kArSumSq;
+    m.attr("FLAG_GATED") = (int)kArGated;
     m.attr("OPT_SGD") = (int)kOptSgd;
     m.attr("OPT_ADAM") = (int)kOptAdam;
     m.attr("HYPER_COUNT") = (int)kHpCount;
@@ -86,6 +95,22 @@ PYBIND11_MODULE(_kfcuda, m) {
               launch_allreduce(algo, mesh.args(channel), off, P<void>(out), nbytes, dtype, op, scale, P<float>(sumsq), flags,
                                blocks, threads, S(st));
           });
+    // out-of-place between two regions of the symmetric arena (sliced algorithms only)
+    m.def("allreduce_to",
+          [](const PeerMesh& mesh, int channel, int algo, size_t off, size_t out_off, size_t nbytes, int dtype, int op,
+             float scale, uintptr_t sumsq, int flags, int blocks, int threads, uintptr_t st) {
+              launch_allreduce(algo, mesh.args(channel), off, nullptr, nbytes, dtype, op, scale, P<float>(sumsq), flags, blocks,
+                               threads, S(st), out_off);
+          });
+    m.def("wait_done", [](const PeerMesh& mesh, int channel, int word, uint32_t add, uintptr_t st) {
+        launch_wait_done(mesh.args(channel), word, add, S(st));
+    });
+    m.def("sma_blend",
+          [](uintptr_t params, uintptr_t avg, int dtype, size_t nbytes, uintptr_t grads, int grad_dtype, uintptr_t s1, uintptr_t s2,
+             uintptr_t hyper, int opt_kind, int blocks, int threads, uintptr_t st) {
+              launch_sma_blend(P<void>(params), P<const void>(avg), dtype, nbytes, P<const void>(grads), grad_dtype, P<float>(s1),
+                               P<float>(s2), P<const float>(hyper), opt_kind, blocks, threads, S(st));
+          });
     m.def("ssgd_fused",
           [](const PeerMesh& mesh, int channel, int algo, size_t grad_off, size_t param_off, int dtype, size_t nbytes,
              uintptr_t master, uintptr_t s1, uintptr_t s2, uintptr_t hyper, int opt_kind, uintptr_t sumsq, int flags,
@@ -102,30 +127,41 @@ PYBIND11_MODULE(_kfcuda, m) {
                                blocks, threads, S(st));
           });
     m.def("pair_avg",
-          [](const PeerMesh& mesh, int channel, int target, size_t pub0, size_t pub1, size_t ver_off, uintptr_t params,
+          [](const PeerMesh& mesh, int channel, int target, const std::vector<size_t>& pubs, size_t ver_off, uintptr_t params,
              int dtype, size_t nbytes, uintptr_t grads, int grad_dtype, uintptr_t s1, uintptr_t s2, uintptr_t hyper,
-             int opt_kind, int do_step, uintptr_t done_counter, int blocks, int threads, uintptr_t st) {
-              launch_pair_avg(mesh.args(channel), target, pub0, pub1, ver_off, P<void>(params), dtype, nbytes,
+             int opt_kind, int do_step, uintptr_t done_counter, uintptr_t pulled, uintptr_t pulled_ok, int blocks, int threads,
+             uintptr_t st, uintptr_t target_dev, uintptr_t master) {
+              launch_pair_avg(mesh.args(channel), target, make_pub(pubs, ver_off), P<void>(params), dtype, nbytes,
                               P<const void>(grads), grad_dtype, P<float>(s1), P<float>(s2), P<const float>(hyper), opt_kind,
-                              do_step, P<uint32_t>(done_counter), blocks, threads, S(st));
-          });
+                              do_step, P<uint32_t>(done_counter), P<const void>(pulled), P<const uint32_t>(pulled_ok), blocks,
+                              threads, S(st), P<const int>(target_dev), P<float>(master));
+          },
+          py::arg("mesh"), py::arg("channel"), py::arg("target"), py::arg("pubs"), py::arg("ver_off"), py::arg("params"), py::arg("dtype"),
+          py::arg("nbytes"), py::arg("grads"), py::arg("grad_dtype"), py::arg("s1"), py::arg("s2"), py::arg("hyper"), py::arg("opt_kind"),
+          py::arg("do_step"), py::arg("done_counter"), py::arg("pulled"), py::arg("pulled_ok"), py::arg("blocks"), py::arg("threads"),
+          py::arg("stream"), py::arg("target_dev") = (uintptr_t)0, py::arg("master") = (uintptr_t)0);
     m.def("publish",
-          [](const PeerMesh& mesh, int channel, size_t pub0, size_t pub1, size_t ver_off, uintptr_t src, size_t nbytes,
+          [](const PeerMesh& mesh, int channel, const std::vector<size_t>& pubs, size_t ver_off, uintptr_t src, size_t nbytes,
              uintptr_t done_counter, int blocks, int threads, uintptr_t st) {
-              launch_publish(mesh.args(channel), pub0, pub1, ver_off, P<const void>(src), nbytes, P<uint32_t>(done_counter),
+              launch_publish(mesh.args(channel), make_pub(pubs, ver_off), P<const void>(src), nbytes, P<uint32_t>(done_counter),
                              blocks, threads, S(st));
           });
     m.def("pull",
-          [](const PeerMesh& mesh, int channel, int target, size_t pub0, size_t pub1, size_t ver_off, uintptr_t dst,
-             size_t nbytes, uintptr_t ok, int blocks, int threads, uintptr_t st) {
-              launch_pull(mesh.args(channel), target, pub0, pub1, ver_off, P<void>(dst), nbytes, P<uint32_t>(ok), blocks,
-                          threads, S(st));
-          });
+          [](const PeerMesh& mesh, int channel, int target, const std::vector<size_t>& pubs, size_t ver_off, uintptr_t dst,
+             size_t nbytes, uintptr_t ok, int retry, int blocks, int threads, uintptr_t st, uintptr_t target_dev) {
+              launch_pull(mesh.args(channel), target, make_pub(pubs, ver_off), P<void>(dst), nbytes, P<uint32_t>(ok), retry, blocks,
+                          threads, S(st), P<const int>(target_dev));
+          },
+          py::arg("mesh"), py::arg("channel"), py::arg("target"), py::arg("pubs"), py::arg("ver_off"), py::arg("dst"), py::arg("nbytes"),
+          py::arg("ok"), py::arg("retry"), py::arg("blocks"), py::arg("threads"), py::arg("stream"), py::arg("target_dev") = (uintptr_t)0);
     m.def("pull_tma",
-          [](const PeerMesh& mesh, int channel, int target, size_t pub0, size_t pub1, size_t ver_off, uintptr_t dst, size_t nbytes,
-             uintptr_t ok, int blocks, uintptr_t st) {
-              launch_pull_tma(mesh.args(channel), target, pub0, pub1, ver_off, P<void>(dst), nbytes, P<uint32_t>(ok), blocks, S(st));
-          });
+          [](const PeerMesh& mesh, int channel, int target, const std::vector<size_t>& pubs, size_t ver_off, uintptr_t dst,
+             size_t nbytes, uintptr_t ok, int retry, int blocks, uintptr_t st, uintptr_t target_dev) {
+              launch_pull_tma(mesh.args(channel), target, make_pub(pubs, ver_off), P<void>(dst), nbytes, P<uint32_t>(ok), retry,
+                              blocks, S(st), P<const int>(target_dev));
+          },
+          py::arg("mesh"), py::arg("channel"), py::arg("target"), py::arg("pubs"), py::arg("ver_off"), py::arg("dst"), py::arg("nbytes"),
+          py::arg("ok"), py::arg("retry"), py::arg("blocks"), py::arg("stream"), py::arg("target_dev") = (uintptr_t)0);
     m.def("broadcast",
           [](const PeerMesh& mesh, int channel, int algo, size_t off, size_t nbytes, int root, int blocks, int threads,
              uintptr_t st) { launch_broadcast(algo, mesh.args(channel), off, nbytes, root, blocks, threads, S(st)); });
@@ -174,6 +210,26 @@ PYBIND11_MODULE(_kfcuda, m) {
     m.def("gemm_bias_act", [](uintptr_t x, uintptr_t w, uintptr_t bias, uintptr_t y, int tokens, int in_f, int out_f, int act, uintptr_t ws,
                               size_t ws_bytes, uintptr_t st) {
         launch_gemm_bias_act(P<const void>(x), P<const void>(w), P<const void>(bias), P<void>(y), tokens, in_f, out_f, act, P<void>(ws), ws_bytes, S(st));
+    });
+    m.def("add_ln_num_blocks", &add_ln_num_blocks);
+    m.def("bias_gelu_num_blocks", &bias_gelu_num_blocks);
+    m.def("add_ln_fwd", [](uintptr_t x, uintptr_t res, uintptr_t gamma, uintptr_t beta, uintptr_t z, uintptr_t y, uintptr_t mean, uintptr_t rstd,
+                           int dtype, int rows, int H, float eps, uintptr_t st) {
+        launch_add_ln_fwd(P<const void>(x), P<const void>(res), P<const void>(gamma), P<const void>(beta), P<void>(z), P<void>(y), P<float>(mean),
+                          P<float>(rstd), dtype, rows, H, eps, S(st));
+    });
+    m.def("add_ln_bwd", [](uintptr_t dy, uintptr_t z, uintptr_t mean, uintptr_t rstd, uintptr_t gamma, uintptr_t dz, uintptr_t dgamma, uintptr_t dbeta,
+                           uintptr_t partial, int dtype, int rows, int H, uintptr_t st) {
+        launch_add_ln_bwd(P<const void>(dy), P<const void>(z), P<const float>(mean), P<const float>(rstd), P<const void>(gamma), P<void>(dz),
+                          P<void>(dgamma), P<void>(dbeta), P<float>(partial), dtype, rows, H, S(st));
+    });
+    m.def("bias_gelu_fwd", [](uintptr_t x, uintptr_t bias, uintptr_t y, int dtype, size_t rows, int I, uintptr_t st) {
+        launch_bias_gelu_fwd(P<const void>(x), P<const void>(bias), P<void>(y), dtype, rows, I, S(st));
+    });
+    m.def("bias_gelu_bwd", [](uintptr_t dy, uintptr_t x, uintptr_t bias, uintptr_t dx, uintptr_t dbias, uintptr_t partial, int dtype, int rows, int I,
+                              uintptr_t st) {
+        launch_bias_gelu_bwd(P<const void>(dy), P<const void>(x), P<const void>(bias), P<void>(dx), P<void>(dbias), P<float>(partial), dtype, rows,
+                             I, S(st));
     });
     m.def("bn_num_blocks", &bn_num_blocks);
     m.def("bn_fwd", [](uintptr_t x, uintptr_t res, uintptr_t y, uintptr_t mask, int dtype, size_t rows, int C, uintptr_t gamma, uintptr_t beta,

@@ -30,6 +30,7 @@ uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 struct ArArgs {
     size_t off;      // byte offset of the message inside every rank's arena
+    size_t out_off;  // sliced algorithms: byte offset the result is delivered to on every rank (== off: in place)
     size_t nvec;     // number of 16-byte vectors
     void* out;       // one-shot: local output (may be any device memory); others: unused
     float scale;     // applied to float-accumulated types when flags & kArScale
@@ -138,8 +139,12 @@ __global__ void __launch_bounds__(512) allreduce_oneshot_kernel(const __grid_con
 template <typename T, int OP, bool SUMSQ>
 __global__ void __launch_bounds__(512) allreduce_twoshot_kernel(const __grid_constant__ MeshArgs m,
                                                                 const __grid_constant__ ArArgs a) {
-    uint32_t seq = load_seq(m);
-    block_barrier<false>(m, seq);
+    const bool gated = (a.flags & kArGated) != 0;
+    uint32_t seq = 0;
+    if (!gated) {
+        seq = load_seq(m);
+        block_barrier<false>(m, seq);
+    }
     size_t s0, s1;
     slice_bounds(a.nvec, m.nranks, m.rank, s0, s1);
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -147,6 +152,7 @@ __global__ void __launch_bounds__(512) allreduce_twoshot_kernel(const __grid_con
     float pre = 0.f, post = 0.f;
     for (size_t v = s0 + tid; v < s1; v += stride) {
         const size_t bo = a.off + v * 16;
+        const size_t oo = a.out_off + v * 16;
         AccVec<T> acc = gather_reduce<T, OP, SUMSQ>(m, bo, pre);
         if (a.flags & kArScale) apply_scale<T>(acc, a.scale);
         if constexpr (SUMSQ) post += vec_sumsq<T>(acc);
@@ -156,11 +162,15 @@ __global__ void __launch_bounds__(512) allreduce_twoshot_kernel(const __grid_con
             if (i < m.nranks) {
                 int r = m.rank + i;
                 if (r >= m.nranks) r -= m.nranks;
-                st_stream(reinterpret_cast<char*>(m.data[r]) + bo, res);
+                st_stream(reinterpret_cast<char*>(m.data[r]) + oo, res);
             }
         }
     }
     flush_sumsq<SUMSQ>(a, pre, post);
+    if (gated) {
+        signal_done(m, 0);
+        return;
+    }
     block_barrier<true>(m, seq); // all slices have landed in my buffer / my stores are visible
     store_seq(m, seq);
 }
@@ -171,7 +181,8 @@ __global__ void __launch_bounds__(512) allreduce_twoshot_kernel(const __grid_con
 template <typename T, int OP, bool SUMSQ>
 __global__ void __launch_bounds__(512) allreduce_nvls_kernel(const __grid_constant__ MeshArgs m,
                                                              const __grid_constant__ ArArgs a) {
-    uint32_t seq = load_seq(m);
+    const bool gated = (a.flags & kArGated) != 0;
+    uint32_t seq = gated ? 0u : load_seq(m);
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     float pre = 0.f, post = 0.f;
@@ -188,10 +199,11 @@ __global__ void __launch_bounds__(512) allreduce_nvls_kernel(const __grid_consta
             }
         }
     }
-    block_barrier<false>(m, seq);
+    if (!gated) block_barrier<false>(m, seq);
     size_t s0, s1;
     slice_bounds(a.nvec, m.nranks, m.rank, s0, s1);
     char* mc = reinterpret_cast<char*>(m.mc) + a.off;
+    char* mco = reinterpret_cast<char*>(m.mc) + a.out_off;
     for (size_t v = s0 + tid; v < s1; v += stride) {
         Vec16 x = Multimem<T, OP>::ld_reduce(mc + v * 16);
         if ((a.flags & kArScale) || SUMSQ) {
@@ -200,9 +212,13 @@ __global__ void __launch_bounds__(512) allreduce_nvls_kernel(const __grid_consta
             if constexpr (SUMSQ) post += vec_sumsq<T>(acc);
             x = pack<T>(acc);
         }
-        multimem_st(mc + v * 16, x);
+        multimem_st(mco + v * 16, x);
     }
     flush_sumsq<SUMSQ>(a, pre, post);
+    if (gated) {
+        signal_done(m, 0);
+        return;
+    }
     block_barrier<true>(m, seq);
     store_seq(m, seq);
 }
@@ -249,7 +265,10 @@ bool nvls_supported(int dtype, int op) {
 }
 
 void launch_allreduce(int algo, const MeshArgs& m, size_t off, void* out, size_t nbytes, int dtype, int op, float scale,
-                      float* sumsq, int flags, int blocks, int threads, cudaStream_t st) {
+                      float* sumsq, int flags, int blocks, int threads, cudaStream_t st, size_t out_off) {
+    if (out_off == (size_t)-1) out_off = off;
+    if (out_off % 16 != 0) throw std::runtime_error("kungfu_b200: all-reduce output offset must be 16-byte aligned");
+    if ((flags & kArGated) && algo == kAlgoOneShot) throw std::runtime_error("kungfu_b200: the one-shot all-reduce has no split-phase form");
     if (nbytes % 16 != 0) throw std::runtime_error("kungfu_b200: all-reduce message must be padded to 16 bytes");
     if (off % 16 != 0) throw std::runtime_error("kungfu_b200: all-reduce offset must be 16-byte aligned");
     if (blocks < 1 || blocks > kMaxBlocks) throw std::runtime_error("kungfu_b200: bad block count");
@@ -258,6 +277,7 @@ void launch_allreduce(int algo, const MeshArgs& m, size_t off, void* out, size_t
     if (algo == kAlgoOneShot && out == nullptr) throw std::runtime_error("kungfu_b200: one-shot needs an output buffer");
     ArArgs a;
     a.off = off;
+    a.out_off = out_off;
     a.nvec = nbytes / 16;
     a.out = out;
     a.scale = scale;

@@ -147,7 +147,8 @@ template <typename T, int KIND, bool NVLS>
 __global__ void __launch_bounds__(512) ssgd_fused_kernel(const __grid_constant__ MeshArgs m,
                                                          const __grid_constant__ SsgdArgs a) {
     constexpr int L = Elem<T>::kLanes;
-    uint32_t seq = load_seq(m);
+    const bool gated = (a.flags & kArGated) != 0;
+    uint32_t seq = gated ? 0u : load_seq(m);
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const bool sumsq = (a.flags & kArSumSq) != 0;
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(512) ssgd_fused_kernel(const __grid_constant__
             }
         }
     }
-    block_barrier<false>(m, seq);
+    if (!gated) block_barrier<false>(m, seq);
     const Hyper h = load_hyper(a.hyper);
     const float gs = h.v[kHpGradScale];
     size_t s0, s1;
@@ -208,6 +209,10 @@ __global__ void __launch_bounds__(512) ssgd_fused_kernel(const __grid_constant__
             atomicAdd(&a.sumsq[0], p0);
             atomicAdd(&a.sumsq[1], p1);
         }
+    }
+    if (gated) {
+        signal_done(m, 0);
+        return;
     }
     block_barrier<true>(m, seq);
     store_seq(m, seq);
@@ -268,6 +273,46 @@ struct SmaArgs {
     const float* hyper;
 };
 
+// blend + local step on vector v: p <- p + alpha (avg - p), then the optimizer update with the LOCAL gradient
+template <typename T, int KIND>
+__device__ __forceinline__ void sma_blend_vec(char* P, const char* A, size_t v, const SmaArgs& a, const Hyper& h) {
+    constexpr int L = Elem<T>::kLanes;
+    const float alpha = h.v[kHpAlpha];
+    const AccVec<T> p = unpack<T>(ld_plain(P + v * 16));
+    const AccVec<T> av = unpack<T>(ld_plain(A + v * 16));
+    const size_t idx = v * L;
+    float g[L];
+    if (a.grads) load_lanes_rt<L>(a.grads, a.grad_dtype, idx, g);
+    F32Lanes<L> m1, m2;
+    if (a.s1) m1.load(a.s1 + idx);
+    else m1.zero();
+    if (KIND == kOptAdam && a.s2) m2.load(a.s2 + idx);
+    else m2.zero();
+    AccVec<T> out;
+    float wf[L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) {
+        float w = fmaf(alpha, (float)av.a[j] - (float)p.a[j], (float)p.a[j]);
+        if (a.grads) opt_update<KIND>(w, g[j] * h.v[kHpGradScale], m1.f[j], m2.f[j], h);
+        wf[j] = w;
+        out.a[j] = (typename Elem<T>::Acc)w;
+    }
+    st_plain(P + v * 16, pack<T>(out));
+    if (a.grads && a.s1) m1.store(a.s1 + idx);
+    if (a.grads && KIND == kOptAdam && a.s2) m2.store(a.s2 + idx);
+    if (a.model_out) store_lanes_rt<L>(a.model_out, a.model_dtype, idx, wf);
+}
+
+// LOCAL blend + step over a whole region (the overlapped SMA: the average was produced earlier by an out-of-place
+// all-reduce that ran under forward/backward)
+template <typename T, int KIND>
+__global__ void __launch_bounds__(512) sma_blend_kernel(char* P, const char* A, const __grid_constant__ SmaArgs a) {
+    const Hyper h = load_hyper(a.hyper);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t v = tid; v < a.nvec; v += stride) sma_blend_vec<T, KIND>(P, A, v, a, h);
+}
+
 template <typename T, int KIND, bool NVLS>
 __global__ void __launch_bounds__(512) sma_fused_kernel(const __grid_constant__ MeshArgs m,
                                                         const __grid_constant__ SmaArgs a) {
@@ -294,37 +339,12 @@ __global__ void __launch_bounds__(512) sma_fused_kernel(const __grid_constant__ 
     block_barrier<true>(m, seq);
     // phase 3: blend + local step. Block b touches, inside slice r, exactly the vectors that block b
     // of rank r read (phase 1) and wrote (phase 2) — the only blocks it has synchronised with.
-    const float alpha = h.v[kHpAlpha];
     char* P = reinterpret_cast<char*>(m.data[m.rank]) + a.param_off;
     const char* A = reinterpret_cast<const char*>(m.data[m.rank]) + a.avg_off;
     for (int r = 0; r < m.nranks; ++r) {
         size_t q0, q1;
         slice_bounds2(a.nvec, m.nranks, r, q0, q1);
-        for (size_t v = q0 + tid; v < q1; v += stride) {
-            const AccVec<T> p = unpack<T>(ld_plain(P + v * 16));
-            const AccVec<T> av = unpack<T>(ld_plain(A + v * 16));
-            const size_t idx = v * L;
-            float g[L];
-            if (a.grads) load_lanes_rt<L>(a.grads, a.grad_dtype, idx, g);
-            F32Lanes<L> m1, m2;
-            if (a.s1) m1.load(a.s1 + idx);
-            else m1.zero();
-            if (KIND == kOptAdam && a.s2) m2.load(a.s2 + idx);
-            else m2.zero();
-            AccVec<T> out;
-            float wf[L];
-#pragma unroll
-            for (int j = 0; j < L; ++j) {
-                float w = fmaf(alpha, (float)av.a[j] - (float)p.a[j], (float)p.a[j]);
-                if (a.grads) opt_update<KIND>(w, g[j] * h.v[kHpGradScale], m1.f[j], m2.f[j], h);
-                wf[j] = w;
-                out.a[j] = (typename Elem<T>::Acc)w;
-            }
-            st_plain(P + v * 16, pack<T>(out));
-            if (a.grads && a.s1) m1.store(a.s1 + idx);
-            if (a.grads && KIND == kOptAdam && a.s2) m2.store(a.s2 + idx);
-            if (a.model_out) store_lanes_rt<L>(a.model_out, a.model_dtype, idx, wf);
-        }
+        for (size_t v = q0 + tid; v < q1; v += stride) sma_blend_vec<T, KIND>(P, A, v, a, h);
     }
     store_seq(m, seq);
 }
@@ -359,37 +379,61 @@ void launch_sma_fused(int algo, const MeshArgs& m, size_t param_off, size_t avg_
     }
 }
 
+void launch_sma_blend(void* params, const void* avg, int dtype, size_t nbytes, const void* grads, int grad_dtype, float* s1, float* s2,
+                      const float* hyper, int opt_kind, int blocks, int threads, cudaStream_t st) {
+    if (nbytes % 16 != 0) throw std::runtime_error("kungfu_b200: region must be padded to 16 bytes");
+    if (blocks < 1 || threads < 32 || threads > 512) throw std::runtime_error("kungfu_b200: bad launch shape");
+    SmaArgs a{0, 0, nbytes / 16, grads, grad_dtype, s1, s2, nullptr, dtype, hyper};
+    char* P = reinterpret_cast<char*>(params);
+    const char* A = reinterpret_cast<const char*>(avg);
+    if (dtype == kF32) {
+        if (opt_kind == kOptSgd) sma_blend_kernel<float, kOptSgd><<<blocks, threads, 0, st>>>(P, A, a);
+        else sma_blend_kernel<float, kOptAdam><<<blocks, threads, 0, st>>>(P, A, a);
+    } else if (dtype == kBF16) {
+        if (opt_kind == kOptSgd) sma_blend_kernel<__nv_bfloat16, kOptSgd><<<blocks, threads, 0, st>>>(P, A, a);
+        else sma_blend_kernel<__nv_bfloat16, kOptAdam><<<blocks, threads, 0, st>>>(P, A, a);
+    } else {
+        throw std::runtime_error("kungfu_b200: SMA blend supports f32/bf16 parameters");
+    }
+    count_launch();
+    KF_CUDA_CHECK(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------------------------------------
 // PairAveraging: pull + average + step + publish
 // ------------------------------------------------------------------------------------------------
 struct PairArgs {
     int target;
-    size_t pub_off[2];
-    size_t ver_off; // uint32 words in the symmetric arena: [0] = published version, [1] = version being written
+    PubStore ps;
     void* params;
     size_t nvec;
     const void* grads;
     int grad_dtype;
     float* s1;
     float* s2;
+    float* master;              // pair_avg: fp32 master copy of 16-bit parameters (nullptr: update the parameters in place)
     const float* hyper;
     int do_step;
     uint32_t* done_counter;
-    void* dst;    // pull: destination
-    uint32_t* ok; // pull: [0] = version read, [1] += torn reads
+    void* dst;                  // pull: destination
+    uint32_t* ok;               // pull: [0] = version read, [1] += torn reads, [2] = this copy is torn
+    int retry;                  // pull: second attempt, runs only when ok[2] is set
+    const int* target_dev;      // device word holding the target rank (CUDA graphs: the target changes between replays); null: `target`
+    const void* pulled;         // pair_avg: private copy of the target's model (nullptr: read the target over NVLink)
+    const uint32_t* pulled_ok;  // pair_avg: the `ok` words of the pull that filled `pulled`
 };
+
+__device__ __forceinline__ uint32_t* ver_words(const MeshArgs& m, int rank, size_t ver_off) {
+    return reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(m.data[rank]) + ver_off);
+}
 
 // Marks the start of a publish (all blocks write the same value) and returns (version to read from
 // the target, version this rank is about to publish).
 __device__ __forceinline__ void pair_versions(const MeshArgs& m, int target, size_t ver_off, bool writer, uint32_t* sh) {
     if (threadIdx.x == 0) {
-        uint32_t* my_ver = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(m.data[m.rank]) + ver_off);
+        uint32_t* my_ver = ver_words(m, m.rank, ver_off);
         sh[0] = 0u;
-        if (target >= 0) {
-            const uint32_t* peer_ver =
-                reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(m.data[target]) + ver_off);
-            sh[0] = ld_acquire_sys(peer_ver);
-        }
+        if (target >= 0) sh[0] = ld_acquire_sys(ver_words(m, target, ver_off));
         if (writer) {
             sh[1] = ld_relaxed_sys(my_ver) + 1;
             st_release_sys(my_ver + 1, sh[1]);
@@ -408,16 +452,15 @@ __device__ __forceinline__ void pair_commit(const MeshArgs& m, size_t ver_off, u
         if (prev == gridDim.x - 1) {
             *done_counter = 0;
             __threadfence_system();
-            uint32_t* my_ver = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(m.data[m.rank]) + ver_off);
-            st_release_sys(my_ver, next);
+            st_release_sys(ver_words(m, m.rank, ver_off), next);
         }
     }
 }
 
-__device__ __forceinline__ bool pair_torn(const MeshArgs& m, int target, size_t ver_off, uint32_t vr) {
-    const uint32_t* peer_ver = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(m.data[target]) + ver_off);
-    const uint32_t wr = ld_acquire_sys(peer_ver + 1);
-    return (int32_t)(wr - (vr + 2)) >= 0; // the buffer we read was being rewritten
+// the buffer holding version vr has been handed back to the writer once it starts on version vr + nbuf
+__device__ __forceinline__ bool pair_torn(const MeshArgs& m, int target, const PubStore& ps, uint32_t vr) {
+    const uint32_t wr = ld_acquire_sys(ver_words(m, target, ps.ver_off) + 1);
+    return (int32_t)(wr - (vr + (uint32_t)ps.nbuf)) >= 0;
 }
 
 template <typename T, int KIND>
@@ -425,16 +468,21 @@ __global__ void __launch_bounds__(512) pair_avg_kernel(const __grid_constant__ M
                                                        const __grid_constant__ PairArgs a) {
     constexpr int L = Elem<T>::kLanes;
     __shared__ uint32_t sh[2];
-    pair_versions(m, a.target, a.ver_off, true, sh);
-    const uint32_t vr = sh[0], next = sh[1];
-    const char* src = reinterpret_cast<const char*>(m.data[a.target]) + a.pub_off[vr & 1];
-    char* pub = reinterpret_cast<char*>(m.data[m.rank]) + a.pub_off[next & 1];
+    const bool remote = a.pulled == nullptr;
+    const int target = a.target_dev ? *a.target_dev : a.target;
+    pair_versions(m, remote ? target : -1, a.ps.ver_off, true, sh);
+    uint32_t vr = sh[0];
+    if (!remote) vr = (a.pulled_ok[2] == 0u) ? a.pulled_ok[0] : 0u; // a torn private copy is not averaged in
+    const uint32_t next = sh[1];
+    const char* src = remote ? reinterpret_cast<const char*>(m.data[target]) + a.ps.pub_off[vr % (uint32_t)a.ps.nbuf]
+                             : reinterpret_cast<const char*>(a.pulled);
+    char* pub = reinterpret_cast<char*>(m.data[m.rank]) + a.ps.pub_off[next % (uint32_t)a.ps.nbuf];
     char* P = reinterpret_cast<char*>(a.params);
     const Hyper h = load_hyper(a.hyper);
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    // four NVLink reads are issued per thread before any of them is consumed: a peer load has ~2-3 us of latency, so the
-    // pull needs megabytes in flight to approach link bandwidth
+    // four reads of the other model are issued per thread before any of them is consumed: a peer load has ~2-3 us of
+    // latency, so the in-kernel pull needs megabytes in flight to approach link bandwidth
     constexpr int U = 4;
     for (size_t v0 = tid; v0 < a.nvec; v0 += stride * U) {
         Vec16 ovs[U];
@@ -451,11 +499,16 @@ __global__ void __launch_bounds__(512) pair_avg_kernel(const __grid_constant__ M
             const size_t idx = v * L;
             float g[L];
             if (a.do_step) load_lanes_rt<L>(a.grads, a.grad_dtype, idx, g);
-            F32Lanes<L> m1, m2;
+            F32Lanes<L> m1, m2, mw;
             if (a.do_step && a.s1) m1.load(a.s1 + idx);
             else m1.zero();
             if (a.do_step && KIND == kOptAdam && a.s2) m2.load(a.s2 + idx);
             else m2.zero();
+            if (a.master) { // the fp32 master is the model; the 16-bit parameters are its rounded image
+                mw.load(a.master + idx);
+#pragma unroll
+                for (int j = 0; j < L; ++j) p.a[j] = (typename Elem<T>::Acc)mw.f[j];
+            }
             if (vr != 0) {
                 const AccVec<T> o = unpack<T>(ovs[u]);
 #pragma unroll
@@ -471,37 +524,45 @@ __global__ void __launch_bounds__(512) pair_avg_kernel(const __grid_constant__ M
                 if (a.s1) m1.store(a.s1 + idx);
                 if (KIND == kOptAdam && a.s2) m2.store(a.s2 + idx);
             }
+            if (a.master) {
+#pragma unroll
+                for (int j = 0; j < L; ++j) mw.f[j] = (float)p.a[j];
+                mw.store(a.master + idx);
+            }
             const Vec16 res = pack<T>(p);
             st_plain(P + v * 16, res);
             st_stream(pub + v * 16, res);
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0 && vr != 0 && pair_torn(m, a.target, a.ver_off, vr) && m.status) *((volatile uint32_t*)&m.status[5]) = m.status[5] + 1u;
-    pair_commit(m, a.ver_off, next, a.done_counter);
+    if (remote && threadIdx.x == 0 && vr != 0 && pair_torn(m, target, a.ps, vr) && m.status)
+        *((volatile uint32_t*)&m.status[5]) = m.status[5] + 1u;
+    pair_commit(m, a.ps.ver_off, next, a.done_counter);
 }
 
 __global__ void __launch_bounds__(512) publish_kernel(const __grid_constant__ MeshArgs m,
                                                       const __grid_constant__ PairArgs a) {
     __shared__ uint32_t sh[2];
-    pair_versions(m, -1, a.ver_off, true, sh);
+    pair_versions(m, -1, a.ps.ver_off, true, sh);
     const uint32_t next = sh[1];
-    char* pub = reinterpret_cast<char*>(m.data[m.rank]) + a.pub_off[next & 1];
+    char* pub = reinterpret_cast<char*>(m.data[m.rank]) + a.ps.pub_off[next % (uint32_t)a.ps.nbuf];
     const char* S = reinterpret_cast<const char*>(a.params);
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t v = tid; v < a.nvec; v += stride) st_stream(pub + v * 16, ld_plain(S + v * 16));
-    pair_commit(m, a.ver_off, next, a.done_counter);
+    pair_commit(m, a.ps.ver_off, next, a.done_counter);
 }
 
 __global__ void __launch_bounds__(512) pull_kernel(const __grid_constant__ MeshArgs m,
                                                    const __grid_constant__ PairArgs a) {
+    if (a.retry && ld_relaxed_sys(a.ok + 2) == 0u) return; // the first attempt was clean
     __shared__ uint32_t sh[2];
-    pair_versions(m, a.target, a.ver_off, false, sh);
+    const int target = a.target_dev ? *a.target_dev : a.target;
+    pair_versions(m, target, a.ps.ver_off, false, sh);
     const uint32_t vr = sh[0];
     if (blockIdx.x == 0 && threadIdx.x == 0) a.ok[0] = vr;
     if (vr == 0) return;
-    const char* src = reinterpret_cast<const char*>(m.data[a.target]) + a.pub_off[vr & 1];
+    const char* src = reinterpret_cast<const char*>(m.data[target]) + a.ps.pub_off[vr % (uint32_t)a.ps.nbuf];
     char* D = reinterpret_cast<char*>(a.dst);
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -515,21 +576,44 @@ __global__ void __launch_bounds__(512) pull_kernel(const __grid_constant__ MeshA
             if (v0 + (size_t)u * stride < a.nvec) st_plain(D + (v0 + (size_t)u * stride) * 16, t[u]);
     }
     __syncthreads();
-    if (threadIdx.x == 0 && pair_torn(m, a.target, a.ver_off, vr)) atomicAdd(&a.ok[1], 1u);
+    if (threadIdx.x == 0) {
+        // ok[2] of a retry: set by the first attempt, cleared below only if EVERY block of this attempt was clean — blocks
+        // that see a torn copy again leave it set (and count), clean blocks never write it
+        if (pair_torn(m, target, a.ps, vr)) {
+            atomicAdd(&a.ok[1], 1u);
+            if (!a.retry) atomicExch(&a.ok[2], 1u);
+            else atomicExch(&a.ok[3], 1u);
+        }
+    }
 }
 
-void launch_pair_avg(const MeshArgs& m, int target, size_t pub_off0, size_t pub_off1, size_t ver_off, void* params,
-                     int dtype, size_t nbytes, const void* grads, int grad_dtype, float* s1, float* s2,
-                     const float* hyper, int opt_kind, int do_step, uint32_t* done_counter, int blocks, int threads,
-                     cudaStream_t st) {
+// After a retry: ok[2] <- ok[3] (still torn?), ok[3] <- 0. One thread; keeps the flag protocol free of inter-block races.
+__global__ void pull_settle_kernel(uint32_t* ok) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        ok[2] = ok[3];
+        ok[3] = 0u;
+    }
+}
+
+static void check_pub(const MeshArgs& m, const PubStore& ps) {
+    if (ps.nbuf < 2 || ps.nbuf > 3) throw std::runtime_error("kungfu_b200: the published-model store has 2 or 3 buffers");
+    for (int i = 0; i < ps.nbuf; ++i)
+        if (ps.pub_off[i] % 16) throw std::runtime_error("kungfu_b200: publish buffers must be 16-byte aligned");
+    if (ps.ver_off % 16) throw std::runtime_error("kungfu_b200: version words must be 16-byte aligned");
+}
+
+void launch_pair_avg(const MeshArgs& m, int target, const PubStore& ps, void* params, int dtype, size_t nbytes, const void* grads,
+                     int grad_dtype, float* s1, float* s2, const float* hyper, int opt_kind, int do_step, uint32_t* done_counter,
+                     const void* pulled, const uint32_t* pulled_ok, int blocks, int threads, cudaStream_t st, const int* target_dev,
+                     float* master) {
     check_launch_shape(m, nbytes, blocks, threads);
-    if (target < 0 || target >= m.nranks) throw std::runtime_error("kungfu_b200: bad pair-averaging target");
+    check_pub(m, ps);
+    if (!target_dev && (target < 0 || target >= m.nranks)) throw std::runtime_error("kungfu_b200: bad pair-averaging target");
     if (do_step && !grads) throw std::runtime_error("kungfu_b200: fused pair-averaging step needs gradients");
+    if (pulled && !pulled_ok) throw std::runtime_error("kungfu_b200: a private copy needs the status words of its pull");
     PairArgs a{};
     a.target = target;
-    a.pub_off[0] = pub_off0;
-    a.pub_off[1] = pub_off1;
-    a.ver_off = ver_off;
+    a.ps = ps;
     a.params = params;
     a.nvec = nbytes / 16;
     a.grads = grads;
@@ -539,6 +623,10 @@ void launch_pair_avg(const MeshArgs& m, int target, size_t pub_off0, size_t pub_
     a.hyper = hyper;
     a.do_step = do_step;
     a.done_counter = done_counter;
+    a.pulled = pulled;
+    a.pulled_ok = pulled_ok;
+    a.target_dev = target_dev;
+    a.master = dtype == kF32 ? nullptr : master;
     if (dtype == kF32) {
         if (opt_kind == kOptSgd) pair_avg_kernel<float, kOptSgd><<<blocks, threads, 0, st>>>(m, a);
         else pair_avg_kernel<float, kOptAdam><<<blocks, threads, 0, st>>>(m, a);
@@ -552,14 +640,13 @@ void launch_pair_avg(const MeshArgs& m, int target, size_t pub_off0, size_t pub_
     KF_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_publish(const MeshArgs& m, size_t pub_off0, size_t pub_off1, size_t ver_off, const void* src, size_t nbytes,
-                    uint32_t* done_counter, int blocks, int threads, cudaStream_t st) {
+void launch_publish(const MeshArgs& m, const PubStore& ps, const void* src, size_t nbytes, uint32_t* done_counter, int blocks,
+                    int threads, cudaStream_t st) {
     check_launch_shape(m, nbytes, blocks, threads);
+    check_pub(m, ps);
     PairArgs a{};
     a.target = -1;
-    a.pub_off[0] = pub_off0;
-    a.pub_off[1] = pub_off1;
-    a.ver_off = ver_off;
+    a.ps = ps;
     a.params = const_cast<void*>(src);
     a.nvec = nbytes / 16;
     a.done_counter = done_counter;
@@ -568,21 +655,29 @@ void launch_publish(const MeshArgs& m, size_t pub_off0, size_t pub_off1, size_t 
     KF_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_pull(const MeshArgs& m, int target, size_t pub_off0, size_t pub_off1, size_t ver_off, void* dst,
-                 size_t nbytes, uint32_t* ok, int blocks, int threads, cudaStream_t st) {
+void launch_pull_settle(uint32_t* ok, cudaStream_t st) {
+    pull_settle_kernel<<<1, 32, 0, st>>>(ok);
+    count_launch();
+    KF_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_pull(const MeshArgs& m, int target, const PubStore& ps, void* dst, size_t nbytes, uint32_t* ok, int retry, int blocks,
+                 int threads, cudaStream_t st, const int* target_dev) {
     check_launch_shape(m, nbytes, blocks, threads);
-    if (target < 0 || target >= m.nranks) throw std::runtime_error("kungfu_b200: bad pull target");
+    check_pub(m, ps);
+    if (!target_dev && (target < 0 || target >= m.nranks)) throw std::runtime_error("kungfu_b200: bad pull target");
     PairArgs a{};
     a.target = target;
-    a.pub_off[0] = pub_off0;
-    a.pub_off[1] = pub_off1;
-    a.ver_off = ver_off;
+    a.ps = ps;
     a.nvec = nbytes / 16;
     a.dst = dst;
     a.ok = ok;
+    a.retry = retry;
+    a.target_dev = target_dev;
     pull_kernel<<<blocks, threads, 0, st>>>(m, a);
     count_launch();
     KF_CUDA_CHECK(cudaGetLastError());
+    if (retry) launch_pull_settle(ok, st);
 }
 
 } // namespace kf

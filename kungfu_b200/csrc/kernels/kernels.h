@@ -13,7 +13,9 @@
 namespace kf {
 
 enum Algo : int { kAlgoAuto = 0, kAlgoOneShot = 1, kAlgoTwoShot = 2, kAlgoNvls = 3 };
-enum ArFlags : int { kArScale = 1, kArSumSq = 2 };
+// kArGated: split-phase launch (a gate kernel precedes, a wait kernel follows): no flag barriers inside the kernel,
+// its blocks signal completion on done word 0 and exit
+enum ArFlags : int { kArScale = 1, kArSumSq = 2, kArGated = 4 };
 enum OptKind : int { kOptSgd = 0, kOptAdam = 1 };
 
 // Device-resident optimizer hyper-parameters (16 floats). Kept in device memory so that a captured
@@ -25,8 +27,9 @@ enum HyperSlot : int {
 };
 
 // ---- allreduce.cu
+// `out_off`: arena offset the sliced algorithms deliver the result to on every rank (== off: in place)
 void launch_allreduce(int algo, const MeshArgs& m, size_t off, void* out, size_t nbytes, int dtype, int op, float scale,
-                      float* sumsq, int flags, int blocks, int threads, cudaStream_t st);
+                      float* sumsq, int flags, int blocks, int threads, cudaStream_t st, size_t out_off = (size_t)-1);
 bool nvls_supported(int dtype, int op);
 
 // ---- fused_step.cu
@@ -38,22 +41,41 @@ void launch_ssgd_fused(int algo, const MeshArgs& m, size_t grad_off, size_t para
 void launch_sma_fused(int algo, const MeshArgs& m, size_t param_off, size_t avg_off, int dtype, size_t nbytes,
                       const void* grads, int grad_dtype, float* s1, float* s2, void* model_out, int model_dtype,
                       const float* hyper, int opt_kind, int blocks, int threads, cudaStream_t st);
-// PairAveraging: pull the peer's published model over NVLink, v <- 0.5 (v + other), local optimizer step,
-// publish the new model (double buffer + version words).
-void launch_pair_avg(const MeshArgs& m, int target, size_t pub_off0, size_t pub_off1, size_t ver_off, void* params,
-                     int dtype, size_t nbytes, const void* grads, int grad_dtype, float* s1, float* s2,
-                     const float* hyper, int opt_kind, int do_step, uint32_t* done_counter, int blocks, int threads,
-                     cudaStream_t st);
+// SMA, overlapped form: the model average is produced by `launch_allreduce(param_off -> avg_off, scale 1/np)` while
+// forward/backward run; this LOCAL kernel then does blend + optimizer step in one pass (phase 3 of sma_fused).
+void launch_sma_blend(void* params, const void* avg, int dtype, size_t nbytes, const void* grads, int grad_dtype, float* s1, float* s2,
+                      const float* hyper, int opt_kind, int blocks, int threads, cudaStream_t st);
+// The published-model store: `nbuf` (2 or 3) buffers at pub_off[], version words at ver_off ([0] published, [1] being
+// written). Version v lives in buffer v % nbuf; a reader of version v is torn iff the owner started writing v + nbuf.
+struct PubStore {
+    size_t pub_off[3];
+    size_t ver_off;
+    int nbuf;
+};
+// PairAveraging: v <- 0.5 (v + other), local optimizer step, publish the new model. `other` is the target's published
+// model read over NVLink inside the kernel (pulled == nullptr), or a private copy pulled earlier on a side stream
+// (pulled_ok[0] = version it holds, 0: none; pulled_ok[2] != 0: that copy is torn, skip the averaging). `target_dev`
+// (pull, pull_tma, pair_avg): a device word holding the target rank, read by the kernel — one captured CUDA graph serves
+// every target.
+void launch_pair_avg(const MeshArgs& m, int target, const PubStore& ps, void* params, int dtype, size_t nbytes, const void* grads,
+                     int grad_dtype, float* s1, float* s2, const float* hyper, int opt_kind, int do_step, uint32_t* done_counter,
+                     const void* pulled, const uint32_t* pulled_ok, int blocks, int threads, cudaStream_t st,
+                     const int* target_dev = nullptr, float* master = nullptr);
 // publish(params) without averaging (step 0 of PairAveraging; `save_variable` on device)
-void launch_publish(const MeshArgs& m, size_t pub_off0, size_t pub_off1, size_t ver_off, const void* src, size_t nbytes,
-                    uint32_t* done_counter, int blocks, int threads, cudaStream_t st);
-// request(peer): copy the peer's latest published blob into dst; ok[0] = version read (0 = nothing published)
-void launch_pull(const MeshArgs& m, int target, size_t pub_off0, size_t pub_off1, size_t ver_off, void* dst,
-                 size_t nbytes, uint32_t* ok, int blocks, int threads, cudaStream_t st);
+void launch_publish(const MeshArgs& m, const PubStore& ps, const void* src, size_t nbytes, uint32_t* done_counter, int blocks,
+                    int threads, cudaStream_t st);
+// request(peer): copy the peer's latest published blob into dst. ok[0] = version read (0 = nothing published),
+// ok[1] += torn reads, ok[2] = 1 when this copy is torn (ok[3] is scratch; `ok` is 4 words, zeroed by the caller before
+// the first attempt). retry != 0: run only if ok[2] is set — a second attempt after a torn first one, followed by
+// `launch_pull_settle`, which leaves ok[2] = "still torn".
+void launch_pull(const MeshArgs& m, int target, const PubStore& ps, void* dst, size_t nbytes, uint32_t* ok, int retry, int blocks,
+                 int threads, cudaStream_t st, const int* target_dev = nullptr);
+
+void launch_pull_settle(uint32_t* ok, cudaStream_t st);
 
 // ---- tma_copy.cu: the same pull driven by the TMA engine (cp.async.bulk, 4-stage smem pipeline, one thread per CTA)
-void launch_pull_tma(const MeshArgs& m, int target, size_t pub_off0, size_t pub_off1, size_t ver_off, void* dst, size_t nbytes, uint32_t* ok,
-                     int blocks, cudaStream_t st);
+void launch_pull_tma(const MeshArgs& m, int target, const PubStore& ps, void* dst, size_t nbytes, uint32_t* ok, int retry, int blocks,
+                     cudaStream_t st, const int* target_dev = nullptr);
 
 // ---- misc.cu
 void launch_broadcast(int algo, const MeshArgs& m, size_t off, size_t nbytes, int root, int blocks, int threads,
@@ -61,6 +83,8 @@ void launch_broadcast(int algo, const MeshArgs& m, size_t off, size_t nbytes, in
 void launch_allgather(int algo, const MeshArgs& m, size_t in_off, size_t out_off, size_t nbytes_per_rank, int blocks,
                       int threads, cudaStream_t st);
 void launch_barrier(const MeshArgs& m, cudaStream_t st);
+// split-phase collectives: one warp waits until `add` more block completions have arrived on done word `word`
+void launch_wait_done(const MeshArgs& m, int word, uint32_t add, cudaStream_t st);
 
 // ---- optim.cu (single-GPU building blocks)
 void launch_hyper_tick(float* hyper, cudaStream_t st);
@@ -97,6 +121,19 @@ void launch_bn_bwd(const void* dy, const void* x, const uint8_t* mask, void* dx,
 // ---- pool.cu: 3x3 stride-2 pad-1 max pooling, channels_last, 1-byte arg-max indices, gather backward
 void launch_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* idx, int dtype, int N, int H, int W, int C, cudaStream_t st);
 void launch_maxpool3x3s2_bwd(const void* dy, const uint8_t* idx, void* dx, int dtype, int N, int H, int W, int C, cudaStream_t st);
+
+// ---- transformer.cu: fused residual + LayerNorm and bias + GELU (forward / backward), bf16 / f16 activations
+int add_ln_num_blocks(int rows);    // rows of the [blocks][2][H] fp32 scratch the backward needs
+int bias_gelu_num_blocks(int rows); // rows of the [blocks][I] fp32 scratch the backward needs
+// z = x + res (res may be null), y = LN(z) * gamma + beta; saves z (may be null: inference), mean, rstd
+void launch_add_ln_fwd(const void* x, const void* res, const void* gamma, const void* beta, void* z, void* y, float* mean, float* rstd, int dtype,
+                       int rows, int H, float eps, cudaStream_t st);
+// dz (= dx = dres), dgamma, dbeta from (dy, z, mean, rstd, gamma)
+void launch_add_ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const void* gamma, void* dz, void* dgamma, void* dbeta,
+                       float* partial, int dtype, int rows, int H, cudaStream_t st);
+void launch_bias_gelu_fwd(const void* x, const void* bias, void* y, int dtype, size_t rows, int I, cudaStream_t st);
+void launch_bias_gelu_bwd(const void* dy, const void* x, const void* bias, void* dx, void* dbias, float* partial, int dtype, int rows, int I,
+                          cudaStream_t st);
 
 // ---- gemm_sm100.cu: tcgen05 GEMM + bias (+GELU) epilogue (CUTLASS/CuTe sm100 collectives); act: 0 = identity, 1 = GELU
 bool gemm_sm100_available();

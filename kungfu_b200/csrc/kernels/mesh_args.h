@@ -8,9 +8,15 @@ namespace kf {
 constexpr int kMaxRanks = 8;    // one NVSwitch domain
 constexpr int kMaxBlocks = 160; // >= 148 SMs; signal pad rows per channel
 constexpr int kNumChannels = 8; // independent signal pads (concurrent streams)
-// bytes of one channel's signal pad: flags[kMaxBlocks][kMaxRanks] (peer-written) — the private
-// per-block sequence counters live in a separate, non-shared allocation.
-constexpr size_t kSignalPadBytes = (size_t)kMaxBlocks * kMaxRanks * sizeof(uint32_t);
+// One channel's signal pad: flags[kMaxBlocks][kMaxRanks] (peer-written barrier flags) followed by kDoneWords
+// peer-incremented completion counters (split-phase collectives: a body kernel's blocks add 1 to word 0 of every
+// rank's pad when their stores have been issued, a one-warp kernel waits for the total). The private per-block
+// sequence counters (and the expected completion totals) live in a separate, non-shared allocation of
+// kSeqWords words per channel.
+constexpr int kDoneWords = 64;
+constexpr size_t kFlagWords = (size_t)kMaxBlocks * kMaxRanks;
+constexpr size_t kSignalPadBytes = (kFlagWords + kDoneWords) * sizeof(uint32_t);
+constexpr int kSeqWords = kMaxBlocks + 16; // [0, kMaxBlocks): per-block barrier sequence; [kMaxBlocks + i]: expected total of done word i
 
 enum DType : int { kF32 = 0, kBF16 = 1, kF16 = 2, kI32 = 3, kI64 = 4, kU8 = 5, kF64 = 6, kI8 = 7, kU32 = 8, kU64 = 9, kI16 = 10, kU16 = 11 };
 enum RedOp : int { kSum = 0, kMin = 1, kMax = 2, kProd = 3 };

@@ -122,6 +122,18 @@ __global__ void __launch_bounds__(32) barrier_kernel(const __grid_constant__ Mes
     store_seq(m, seq);
 }
 
+// The tail of a split-phase collective: ONE thread waits for the body kernels' blocks (all ranks) to report completion.
+__global__ void __launch_bounds__(32) wait_done_kernel(const __grid_constant__ MeshArgs m, int word, uint32_t add) {
+    if (threadIdx.x == 0) wait_done(m, word, add);
+}
+
+void launch_wait_done(const MeshArgs& m, int word, uint32_t add, cudaStream_t st) {
+    if (word < 0 || word >= kDoneWords || word >= kSeqWords - kMaxBlocks) throw std::runtime_error("kungfu_b200: bad completion word");
+    wait_done_kernel<<<1, 32, 0, st>>>(m, word, add);
+    count_launch();
+    KF_CUDA_CHECK(cudaGetLastError());
+}
+
 void launch_barrier(const MeshArgs& m, cudaStream_t st) {
     barrier_kernel<<<1, 32, 0, st>>>(m);
     count_launch();

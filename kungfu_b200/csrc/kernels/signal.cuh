@@ -47,6 +47,9 @@ __device__ __forceinline__ unsigned long long global_ns() {
 __device__ __forceinline__ bool spin_ge(const uint32_t* p, uint32_t want, const MeshArgs& m, int peer) {
     uint32_t v = ld_acquire_sys(p);
     if ((int32_t)(v - want) >= 0) return true;
+    // a wait that already failed once on this mesh poisons every later wait: the job is lost, and each remaining kernel
+    // of the step would otherwise sit out its own full time-out (the host raises at its next `check()`)
+    if (m.status && *((volatile uint32_t*)&m.status[0]) != 0u) return false;
     const unsigned long long t0 = global_ns();
     uint32_t iters = 0;
     while (true) {
@@ -88,6 +91,28 @@ template <bool kRelease> __device__ __forceinline__ void block_barrier(const Mes
         spin_ge(src, seq, m, peer);
     }
     __syncthreads();
+}
+
+// ---- split-phase completion (gate kernel -> non-spinning body -> one-warp wait kernel) ----------------------------------
+// A body kernel launched between a gate (`barrier_kernel`: every rank has reached this point of its stream) and a wait
+// (`wait_done_kernel`) never spins: its CTAs do their loads/stores over NVLink, add 1 to done word `word` of EVERY rank's
+// pad and exit, so no SM is parked while a peer is late — the waiting is done by one warp. Called by all threads of the
+// block after their last store.
+__device__ __forceinline__ void red_release_sys_add(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void signal_done(const MeshArgs& m, int word) {
+    __syncthreads(); // every thread's stores are issued; the release below is cumulative over them
+    if (threadIdx.x < (unsigned)m.nranks) {
+        __threadfence_system();
+        red_release_sys_add(m.sig[threadIdx.x] + kFlagWords + word, 1u);
+    }
+}
+// One thread: wait until `add` more completions have arrived on local done word `word` (running total kept in m.seq).
+__device__ __forceinline__ void wait_done(const MeshArgs& m, int word, uint32_t add) {
+    const uint32_t want = m.seq[kMaxBlocks + word] + add;
+    spin_ge(m.sig[m.rank] + kFlagWords + word, want, m, 0xffff);
+    m.seq[kMaxBlocks + word] = want;
 }
 
 __device__ __forceinline__ uint32_t load_seq(const MeshArgs& m) { return m.seq[blockIdx.x]; }

@@ -52,18 +52,21 @@ __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wai
 
 struct TmaPullArgs {
     int target;
-    size_t pub_off[2];
-    size_t ver_off;
+    PubStore ps;
     void* dst;
     size_t nbytes;
-    uint32_t* ok; // [0] = version read (0: nothing published), [1] += torn reads
+    uint32_t* ok; // [0] = version read (0: nothing published), [1] += torn reads, [2] = this copy is torn, [3] scratch
+    int retry;    // second attempt: runs only when ok[2] is set
+    const int* target_dev; // device word holding the target rank (null: `target`)
 };
 
 __global__ void __launch_bounds__(32) pull_tma_kernel(const __grid_constant__ MeshArgs m, const __grid_constant__ TmaPullArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full[kStages];
     __shared__ uint32_t s_ver;
-    const uint32_t* peer_ver = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(m.data[a.target]) + a.ver_off);
+    if (a.retry && ld_relaxed_sys(a.ok + 2) == 0u) return; // the first attempt was clean
+    const int target = a.target_dev ? *a.target_dev : a.target;
+    const uint32_t* peer_ver = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(m.data[target]) + a.ps.ver_off);
     if (threadIdx.x == 0) {
         s_ver = ld_acquire_sys(peer_ver);
         for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(32) pull_tma_kernel(const __grid_constant__ Me
     const uint32_t vr = s_ver;
     if (blockIdx.x == 0 && threadIdx.x == 0) a.ok[0] = vr;
     if (vr == 0 || threadIdx.x != 0) return;
-    const char* src = reinterpret_cast<const char*>(m.data[a.target]) + a.pub_off[vr & 1];
+    const char* src = reinterpret_cast<const char*>(m.data[target]) + a.ps.pub_off[vr % (uint32_t)a.ps.nbuf];
     char* dst = reinterpret_cast<char*>(a.dst);
     const size_t nchunks = (a.nbytes + kChunk - 1) / kChunk;
     const size_t mine = nchunks > blockIdx.x ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -100,15 +103,19 @@ __global__ void __launch_bounds__(32) pull_tma_kernel(const __grid_constant__ Me
     }
     tma_wait_all();
     const uint32_t wr = ld_acquire_sys(peer_ver + 1);
-    if ((int32_t)(wr - (vr + 2)) >= 0) atomicAdd(&a.ok[1], 1u); // the buffer we copied was being rewritten
+    if ((int32_t)(wr - (vr + (uint32_t)a.ps.nbuf)) >= 0) { // the buffer we copied was being rewritten
+        atomicAdd(&a.ok[1], 1u);
+        atomicExch(a.retry ? &a.ok[3] : &a.ok[2], 1u);
+    }
 }
 
 } // namespace
 
-void launch_pull_tma(const MeshArgs& m, int target, size_t pub_off0, size_t pub_off1, size_t ver_off, void* dst, size_t nbytes, uint32_t* ok,
-                     int blocks, cudaStream_t st) {
+void launch_pull_tma(const MeshArgs& m, int target, const PubStore& ps, void* dst, size_t nbytes, uint32_t* ok, int retry, int blocks,
+                     cudaStream_t st, const int* target_dev) {
+    if (ps.nbuf < 2 || ps.nbuf > 3) throw std::runtime_error("kungfu_b200: the published-model store has 2 or 3 buffers");
     if (nbytes % 16) throw std::runtime_error("kungfu_b200: TMA pull needs a 16-byte multiple");
-    if (target < 0 || target >= m.nranks) throw std::runtime_error("kungfu_b200: bad pull target");
+    if (!target_dev && (target < 0 || target >= m.nranks)) throw std::runtime_error("kungfu_b200: bad pull target");
     if (blocks < 1) blocks = 1;
     static bool configured = false;
     const size_t smem = (size_t)kChunk * kStages;
@@ -116,10 +123,11 @@ void launch_pull_tma(const MeshArgs& m, int target, size_t pub_off0, size_t pub_
         KF_CUDA_CHECK(cudaFuncSetAttribute(pull_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    TmaPullArgs a{target, {pub_off0, pub_off1}, ver_off, dst, nbytes, ok};
+    TmaPullArgs a{target, ps, dst, nbytes, ok, retry, target_dev};
     pull_tma_kernel<<<blocks, 32, smem, st>>>(m, a);
     count_launch();
     KF_CUDA_CHECK(cudaGetLastError());
+    if (retry) launch_pull_settle(ok, st);
 }
 
 } // namespace kf

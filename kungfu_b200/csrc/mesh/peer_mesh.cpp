@@ -227,8 +227,8 @@ PeerMesh::PeerMesh(int device, size_t arena_bytes, const std::string& mode) : de
     if (mode_ == "auto") mode_ = drv().ok ? "vmm" : "ipc";
     if (mode_ == "vmm" && !drv().ok) throw std::runtime_error("kungfu_b200 PeerMesh: VMM driver API unavailable: " + drv().why);
     alloc_local();
-    KF_RT_CHECK(cudaMalloc(&seq_, sizeof(uint32_t) * kNumChannels * kMaxBlocks));
-    KF_RT_CHECK(cudaMemset(seq_, 0, sizeof(uint32_t) * kNumChannels * kMaxBlocks));
+    KF_RT_CHECK(cudaMalloc(&seq_, sizeof(uint32_t) * kNumChannels * kSeqWords));
+    KF_RT_CHECK(cudaMemset(seq_, 0, sizeof(uint32_t) * kNumChannels * kSeqWords));
     KF_RT_CHECK(cudaHostAlloc(&status_host_, 64 * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable));
     memset(status_host_, 0, 64 * sizeof(uint32_t));
     KF_RT_CHECK(cudaHostGetDevicePointer(&status_dev_, status_host_, 0));
@@ -346,7 +346,7 @@ void PeerMesh::disconnect() {
 
 void PeerMesh::reset_signals(cudaStream_t st) {
     KF_RT_CHECK(cudaMemsetAsync(reinterpret_cast<char*>(local_va_) + signal_off_, 0, (size_t)kNumChannels * kSignalPadBytes, st));
-    KF_RT_CHECK(cudaMemsetAsync(seq_, 0, sizeof(uint32_t) * kNumChannels * kMaxBlocks, st));
+    KF_RT_CHECK(cudaMemsetAsync(seq_, 0, sizeof(uint32_t) * kNumChannels * kSeqWords, st));
     KF_RT_CHECK(cudaStreamSynchronize(st));
 }
 
@@ -549,7 +549,7 @@ MeshArgs PeerMesh::args(int channel) const {
                         : nullptr;
     }
     m.mc = mc_va_;
-    m.seq = seq_ + (size_t)channel * kMaxBlocks;
+    m.seq = seq_ + (size_t)channel * kSeqWords;
     m.status = status_dev_;
     m.timeout_ns = timeout_ns_;
     m.rank = rank_;

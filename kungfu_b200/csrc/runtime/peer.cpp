@@ -113,6 +113,17 @@ void Peer::close() {
 
 void Peer::on_control(const PeerID& src, const std::string& name, const Bytes&) {
     if (name == "exit") { // fault injection / orderly removal (reference: rchannel/handler/control.go:17-21)
+        // only hosts that take part in the job (workers, runners) or this machine may ask a worker to leave
+        bool known = (src.ipv4 >> 24) == 127 || src.ipv4 == cfg_.self.ipv4;
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            for (auto& p : cluster_.workers) known = known || p.ipv4 == src.ipv4;
+            for (auto& p : cluster_.runners) known = known || p.ipv4 == src.ipv4;
+        }
+        if (!known && !getenv_bool("KUNGFU_ALLOW_REMOTE_EXIT", false)) {
+            KF_LOGW("ignoring exit request from %s: not a host of this job", src.str().c_str());
+            return;
+        }
         KF_LOGW("exit requested by %s", src.str().c_str());
         _exit(0);
     }

@@ -1,5 +1,7 @@
 #include "session.hpp"
 
+#include <atomic>
+
 #include <cstring>
 
 namespace kfrt {
@@ -106,8 +108,15 @@ void Session::run_strategies(const Workspace& w, const StratList& sl, bool monit
     const size_t chunk = Config::get().chunk_bytes;
     const size_t k = (bytes + chunk - 1) / chunk;
     const size_t esz = dtype_size(w.dtype);
-    std::string err = parallel_for((int)k, [&](int i) {
-        auto be = even_partition(w.count, k, (size_t)i);
+    // Chunks block on their peers (chunk i here waits for chunk i there) and fan out into nested parallel_for calls, so an
+    // unbounded chunk count per op could exhaust any thread budget (a 1 GiB tensor = 1024 chunks, each holding a worker while
+    // its recv/send tasks queue behind them). `kWindow` lanes pull chunk indices from a shared counter instead: chunks start in
+    // increasing order on every rank, so the lowest unfinished chunk is always in flight everywhere and the op makes progress
+    // with at most kWindow blocked workers (the reference relies on unbounded goroutines, session.go:304-317).
+    constexpr size_t kWindow = 64;
+    std::atomic<size_t> next{0};
+    auto run_chunk = [&](size_t i) {
+        auto be = even_partition(w.count, k, i);
         Workspace c = w;
         c.count = be.second - be.first;
         c.send = static_cast<const char*>(w.send) + be.first * esz;
@@ -115,11 +124,14 @@ void Session::run_strategies(const Workspace& w, const StratList& sl, bool monit
         // chunk i of the op, NOT its element range: two ranks that disagree on the tensor size must still rendezvous, so that the
         // receiver can report "chunk size mismatch" instead of both sides waiting forever for a name the other never uses
         c.name = "part::" + w.name + "#" + std::to_string(i);
-        const Strat& s = sl[strategy_hash((size_t)i, w.name) % sl.size()];
+        const Strat& s = sl[strategy_hash(i, w.name) % sl.size()];
         const Graph* gs[2] = {&s.g.reduce, &s.g.bcast};
         const double t0 = monitored ? now_s() : 0;
         run_graphs(c, gs, 2);
         if (monitored) s.stat->update(t0, now_s(), c.bytes());
+    };
+    std::string err = parallel_for((int)std::min(k, kWindow), [&](int) {
+        for (size_t i = next.fetch_add(1); i < k; i = next.fetch_add(1)) run_chunk(i);
     });
     if (!err.empty()) fail(err);
 }
@@ -347,10 +359,10 @@ bool Session::check_interference() {
         thr = st.throughput;
         ref = st.ref_throughput;
     }
-    int8_t vote = thr < 0.8 * ref ? 1 : 0, total = 0;
-    Workspace w{&vote, &total, 1, kI8, kSum, "StratMon::" + std::to_string(seq_++)};
+    int32_t vote = thr < 0.8 * ref ? 1 : 0, total = 0; // int32: an int8 sum wraps beyond 127 peers
+    Workspace w{&vote, &total, 1, kI32, kSum, "StratMon::" + std::to_string(seq_++)};
     all_reduce(w);
-    return total > (int8_t)(size() / 2);
+    return total > (int32_t)(size() / 2);
 }
 
 } // namespace kfrt

@@ -32,7 +32,9 @@ void Pool::submit(std::function<void()> fn) {
     // has been notified but has not yet woken up, hence the comparison with the queue length and not with zero — with
     // `idle_ == 0` as the test, two quick submits both "used" the same idle worker and the second task starved
     // (intermittent all-reduce deadlock with >= 7 chunks in flight).
-    if ((int)q_.size() > idle_ && nthreads_ < 1024) {
+    // No cap that could leave a task queued behind blocked workers: the per-op chunk window (Session::run_strategies) bounds
+    // how many workers one collective can hold, and a queued task that nobody can run is a deadlock, not back-pressure.
+    if ((int)q_.size() > idle_) {
         ++nthreads_;
         std::thread([this] { worker(); }).detach();
     } else {
@@ -811,6 +813,16 @@ void Server::serve(Socket s) {
         if (mh.name_len > kMaxNameLen) return;
         std::string name(mh.name_len, '\0');
         if (mh.name_len && !s.recv_all(&name[0], mh.name_len)) return;
+        // Lengths come from the wire: never allocate what an unauthenticated sender asks for. Control / ping messages are
+        // small by construction; data messages into a registered buffer are checked against that buffer's size, everything
+        // else is bounded by KUNGFU_MAX_MESSAGE_MB (default 4096).
+        static const uint64_t kMaxData = (uint64_t)std::max(1.0, parse_duration_s(getenv_str("KUNGFU_MAX_MESSAGE_MB", "4096"), 4096)) << 20;
+        const uint64_t cap = type == kConnControl ? (16ull << 20) : type == kConnPing ? (1ull << 20) : kMaxData;
+        if (mh.data_len > cap) {
+            KF_LOGW("dropping connection from %s: %llu-byte message on a type-%d connection exceeds the limit", src.str().c_str(),
+                    (unsigned long long)mh.data_len, (int)type);
+            return;
+        }
         NetMonitor::get().ingress(src, mh.data_len);
         switch (type) {
         case kConnCollective:

@@ -2,8 +2,10 @@
 async gossip"). The reference ships no BERT model — only a gradient-size list of BERT-base + Adam slots
 (srcs/python/kungfu/tensorflow/v1/benchmarks/model_sizes.py:27-81, tests/cpp/integration/bert.hpp) and a link to an external
 example (README.md:136-137); BERT-large shapes therefore come from this module: 24 layers, hidden 1024, 16 heads,
-≈335 M parameters. Attention uses `F.scaled_dot_product_attention` (library flash kernels); the gossip step over the
-1.3 GB parameter set is our `pair_avg_kernel`.
+≈335 M parameters. Attention uses `F.scaled_dot_product_attention` (library flash kernels), the projections are plain library
+GEMMs; everything between them runs on our fused kernels (`ops/transformer.py`: residual + LayerNorm in one pass, FFN bias +
+GELU in one pass, both with their parameter gradients produced inside the backward pass), and the gossip step over the
+parameter set is our TMA pull + `pair_avg_kernel`.
 """
 from __future__ import annotations
 
@@ -27,6 +29,7 @@ class BertConfig:
     num_labels: int = 2
     dropout: float = 0.0
     fused_mlp: bool = False  # FFN up-projection + GELU on the tcgen05 GEMM with a fused epilogue (ops/linear_act.py)
+    fused_ops: bool = True   # residual+LayerNorm and bias+GELU on our kernels (fall back to PyTorch off-GPU / in fp32)
 
     @staticmethod
     def large() -> "BertConfig":
@@ -58,13 +61,21 @@ class BertLayer(nn.Module):
         self.ff2 = nn.Linear(c.intermediate, c.hidden)
         self.ln2 = nn.LayerNorm(c.hidden, eps=1e-12)
 
+        self.fused_ops = c.fused_ops
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         B, S, H = x.shape
         q, k, v = self.qkv(x).view(B, S, 3, self.heads, H // self.heads).permute(2, 0, 3, 1, 4)
         a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H)
-        x = self.ln1(x + self.out(a))
-        h = self.ff1(x) if self.fused_mlp else F.gelu(self.ff1(x))
-        return self.ln2(x + self.ff2(h))
+        if not self.fused_ops:
+            x = self.ln1(x + self.out(a))
+            h = self.ff1(x) if self.fused_mlp else F.gelu(self.ff1(x))
+            return self.ln2(x + self.ff2(h))
+        from ..ops.transformer import add_layernorm, bias_gelu
+
+        x = add_layernorm(self.out(a), x, self.ln1.weight, self.ln1.bias, self.ln1.eps)
+        h = self.ff1(x) if self.fused_mlp else bias_gelu(F.linear(x, self.ff1.weight), self.ff1.bias)
+        return add_layernorm(self.ff2(h), x, self.ln2.weight, self.ln2.bias, self.ln2.eps)
 
 
 class Bert(nn.Module):
@@ -82,7 +93,13 @@ class Bert(nn.Module):
     def forward(self, ids: torch.Tensor) -> torch.Tensor:
         B, S = ids.shape
         pos = torch.arange(S, device=ids.device)
-        x = self.ln(self.word(ids) + self.pos(pos)[None] + self.typ.weight[0][None, None])
+        emb = self.word(ids) + self.pos(pos)[None] + self.typ.weight[0][None, None]
+        if self.cfg.fused_ops:
+            from ..ops.transformer import add_layernorm
+
+            x = add_layernorm(emb, None, self.ln.weight, self.ln.bias, self.ln.eps)
+        else:
+            x = self.ln(emb)
         for l in self.layers:
             x = l(x)
         return self.classifier(torch.tanh(self.pooler(x[:, 0])))

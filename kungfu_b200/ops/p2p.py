@@ -48,7 +48,7 @@ def save_variable(t: torch.Tensor, name: str, version: Optional[int] = None) -> 
         s = _gpu_slot(name, nb)
         st = torch.cuda.current_stream()
         s["stage"][:nb].copy_(t.detach().contiguous().view(-1).view(torch.uint8), non_blocking=True)
-        rt.gpu.ext.publish(s["arena"].mesh, 1, s["pub0"], s["pub1"], s["ver"], s["stage"].data_ptr(), s["nbytes"], s["done"].data_ptr(),
+        rt.gpu.ext.publish(s["arena"].mesh, 1, [s["pub0"], s["pub1"]], s["ver"], s["stage"].data_ptr(), s["nbytes"], s["done"].data_ptr(),
                            16, 512, st.cuda_stream)
         return
     f = getattr(rt.control, "save", None)
@@ -85,11 +85,11 @@ def request_variable(target: int, name: str, shape=None, dtype=None, version: Op
         if s["nbytes"] >= _TMA_MIN_BYTES:
             # large blobs: TMA bulk copies (cp.async.bulk through shared memory), one CTA per 32 KiB chunk up to one per SM
             blocks = min(148, (s["nbytes"] + 32767) // 32768)
-            rt.gpu.ext.pull_tma(s["arena"].mesh, 1, int(target), s["pub0"], s["pub1"], s["ver"], tmp.data_ptr(), s["nbytes"],
-                                s["ok"].data_ptr(), blocks, st.cuda_stream)
+            rt.gpu.ext.pull_tma(s["arena"].mesh, 1, int(target), [s["pub0"], s["pub1"]], s["ver"], tmp.data_ptr(), s["nbytes"],
+                                s["ok"].data_ptr(), 0, blocks, st.cuda_stream)
         else:
-            rt.gpu.ext.pull(s["arena"].mesh, 1, int(target), s["pub0"], s["pub1"], s["ver"], tmp.data_ptr(), s["nbytes"],
-                            s["ok"].data_ptr(), 16, 512, st.cuda_stream)
+            rt.gpu.ext.pull(s["arena"].mesh, 1, int(target), [s["pub0"], s["pub1"]], s["ver"], tmp.data_ptr(), s["nbytes"],
+                            s["ok"].data_ptr(), 0, 16, 512, st.cuda_stream)
         ok = int(s["ok"][0].item()) != 0
         if ok:
             out.view(-1).view(torch.uint8).copy_(tmp[:nb])

@@ -17,6 +17,22 @@ Modes
   grads   bucketed in-place all-reduce(avg) of gradients, then any torch optimizer  [K1]
   sma     all-reduce(model)/np -> blend -> local step                               [K8]
   pair    pull one peer's published model -> average -> local step -> publish       [K9]
+
+Split-phase launches (default, KUNGFU_GATED=0 restores the single-kernel form): every collective body is bracketed by two
+one-warp kernels — a gate (flag barrier: all ranks have reached this point of their comm streams) and a wait (all ranks'
+body blocks have reported completion) — and the body itself never spins, so a rank that is early does not park the body's
+CTAs on SMs its own backward still needs.
+
+Overlap
+  ssgd / grads : per bucket, from post-accumulate-grad hooks, under the rest of backward.
+  sma          : the model average does not depend on this step's gradients: `begin_step()` (called by `zero_grad()`)
+                 starts the out-of-place all-reduce params -> scratch on the comm stream under forward+backward; only the
+                 local blend+step kernel runs after backward.
+  pair         : `begin_step(target)` starts the TMA pull of the target's published model into a private buffer on the side
+                 stream under forward+backward; the local average+step+publish kernel runs after backward.
+
+`backend="nccl"` replaces OUR collective kernels by `torch.distributed` NCCL calls on the same streams, buckets, CUDA graph
+and local optimizer kernels — the same-box baseline arm of the benchmarks ("a path that only calls NCCL is the baseline").
 """
 from __future__ import annotations
 
@@ -56,7 +72,11 @@ class _Set:
         self.p_off = 0
         self.x_off = 0  # sma: avg scratch; pair: pub buffer 0
         self.x_off2 = 0  # pair: pub buffer 1
+        self.x_off3 = 0  # pair: pub buffer 2
         self.ver_off = 0
+        self.pulled: Optional[torch.Tensor] = None  # pair: private copy of the target's model (side-stream pull)
+        self.pull_ok: Optional[torch.Tensor] = None  # pair: [version, torn count, torn flag, scratch]
+        self.nccl_avg: Optional[torch.Tensor] = None  # sma over NCCL: the averaged model
         self.grads: Optional[torch.Tensor] = None
         self.params: Optional[torch.Tensor] = None
         self.hyper: Optional[torch.Tensor] = None
@@ -72,14 +92,24 @@ class _Set:
 class FlatEngine:
     def __init__(self, param_groups, named_parameters=None, mode: str = "ssgd", opt_kind: Optional[str] = None,
                  average: bool = True, overlap: bool = True, bucket_mb: Optional[float] = None, monitor: bool = False,
-                 alpha: float = 0.1, algo: Optional[str] = None, name: str = "engine") -> None:
+                 alpha: float = 0.1, algo: Optional[str] = None, name: str = "engine", backend: Optional[str] = None,
+                 master_weights: bool = True) -> None:
         self.rt = get_runtime()
         self.plane = self.rt.gpu
         self.ext = self.plane.ext
         self.mode = mode
         self.opt_kind = opt_kind  # "sgd" | "adam" | None (grads mode)
         self.average = average
+        self.backend = (backend or os.environ.get("KUNGFU_BACKEND", "kernels")).lower()  # "kernels" | "nccl" (baseline arm)
+        if self.backend not in ("kernels", "nccl"):
+            raise ValueError(f"kungfu_b200: unknown engine backend {self.backend!r}")
+        self.gated = os.environ.get("KUNGFU_GATED", "1") != "0"
+        if not master_weights:  # the wrapped torch optimizer updates the 16-bit parameters itself: no fp32 shadow to go stale
+            self._MASTER_MODES = ()
+        self.overlap_requested = overlap
         self.overlap = overlap and mode in ("ssgd", "grads")
+        self._defer = False  # inside no_sync(): hooks do not launch
+        self._early: Optional[str] = None  # sma / pair: what begin_step() has started for the current step
         self.monitor = monitor
         self.alpha = alpha
         self.algo = algo
@@ -92,7 +122,7 @@ class FlatEngine:
         self.threads = coll.CONFIG.threads
         named = list(named_parameters) if named_parameters is not None else None
         self.sets: List[_Set] = []
-        whole = mode in ("pair",)  # pair averaging works on the whole model at once
+        whole = mode in ("pair", "sma")  # model averaging works on the whole model at once
         for s in group_params(param_groups, named):
             bb = (1 << 62) if whole else self.bucket_bytes
             self.sets.append(_Set(s["group"], FlatLayout(s["items"], s["dtype"], bb)))
@@ -140,7 +170,7 @@ class FlatEngine:
         total = 1 << 20
         for s in self.sets:
             nb = (s.layout.nbytes + 4095) // 4096 * 4096
-            n_regions = {"ssgd": 2, "grads": 1, "sma": 3, "pair": 4}[self.mode]
+            n_regions = {"ssgd": 2, "grads": 1, "sma": 3, "pair": 5}[self.mode]
             total += n_regions * (nb + 4096) + 8192
         self.arena = self.plane.new_arena(total, name)
         for s in self.sets:
@@ -153,8 +183,11 @@ class FlatEngine:
             if self.mode == "pair":
                 s.x_off = self.arena.alloc(nb, align=4096)
                 s.x_off2 = self.arena.alloc(nb, align=4096)
+                s.x_off3 = self.arena.alloc(nb, align=4096)
                 s.ver_off = self.arena.alloc(256, align=256)
                 s.done_counter = torch.zeros(4, dtype=torch.int32, device=self.plane.device)
+                s.pull_ok = torch.zeros(4, dtype=torch.int32, device=self.plane.device)
+                self._target_dev = torch.zeros(1, dtype=torch.int32, device=self.plane.device)
             s.hyper = torch.zeros(16, dtype=torch.float32, device=self.plane.device)
 
     def _adopt_tensors(self) -> None:
@@ -191,7 +224,7 @@ class FlatEngine:
             v = [0.0] * 16
             v[HP["lr"]] = float(g.get("lr", 0.0))
             v[HP["weight_decay"]] = float(g.get("weight_decay", 0.0))
-            v[HP["grad_scale"]] = (1.0 / self.nranks) if (self.average and self.mode in ("ssgd",)) else 1.0
+            v[HP["grad_scale"]] = (1.0 / self.nranks) if (self.average and self.mode == "ssgd" and self.backend == "kernels") else 1.0
             v[HP["alpha"]] = float(self.alpha)
             if self.opt_kind == "adam":
                 b1, b2 = g.get("betas", (0.9, 0.999))
@@ -207,6 +240,11 @@ class FlatEngine:
             if s.hyper_cache is None or any(v[i] != s.hyper_cache[i] for i in idx):
                 s.hyper[idx] = torch.tensor([v[i] for i in idx], dtype=torch.float32, device=s.hyper.device)
                 s.hyper_cache = v
+
+    @property
+    def _sharded(self) -> bool:
+        """fp32 master weights / optimizer state are partitioned across ranks (fused S-SGD over our kernels only)."""
+        return self.mode == "ssgd" and self.nranks > 1 and self.backend == "kernels"
 
     def _needs_state(self, s: _Set):
         g = self.param_groups[s.group_index]
@@ -224,13 +262,13 @@ class FlatEngine:
             need1, need2 = self._needs_state(s)
             dev = self.plane.device
             for b in lay.buckets:
-                if self.mode == "ssgd" and self.nranks > 1:
+                if self._sharded:
                     n = lay.shard_elems(b, self.nranks)
                     lo, hi = lay.shard_range(b, self.nranks, self.rank)
                 else:
                     n = b.numel
                     lo, hi = b.start, b.start + b.numel
-                if lay.dtype != torch.float32 and self.mode == "ssgd":
+                if lay.dtype != torch.float32 and self.mode in self._MASTER_MODES:
                     m = torch.zeros(n, dtype=torch.float32, device=dev)
                     m[:hi - lo].copy_(s.params[lo:hi])
                     s.master[b.index] = m
@@ -240,13 +278,37 @@ class FlatEngine:
                     s.s2[b.index] = torch.zeros(n, dtype=torch.float32, device=dev)
             s.state_ready = True
 
+    _MASTER_MODES = ("ssgd", "pair")  # modes whose kernels keep fp32 master weights for 16-bit parameters
+
     # ---------------------------------------------------------------------------------------------
+    def no_sync(self):
+        """Context manager for gradient accumulation: backward passes inside it only accumulate (no bucket is launched);
+        the first backward outside it reduces and applies the accumulated gradients. Reference behaviour for comparison:
+        the torch SynchronousSGDOptimizer reduces inside step(), so plain accumulation loops work there."""
+        eng = self
+
+        class _NoSync:
+            def __enter__(self):
+                eng._defer = True
+
+            def __exit__(self, *a):
+                eng._defer = False
+
+        return _NoSync()
+
     def _install_hooks(self) -> None:
         for si, s in enumerate(self.sets):
             for ei, e in enumerate(s.layout.entries):
                 gv = _view_like(s.grads, e.offset, e.param)
 
                 def hook(p, si=si, bi=e.bucket, gv=gv, ei=ei):
+                    if self._defer:
+                        return  # gradient accumulation: autograd keeps adding into p.grad, nothing is launched
+                    if self._got[si][ei]:
+                        raise RuntimeError(
+                            "kungfu_b200: a second backward() reached a parameter whose bucket was already reduced (and, on the "
+                            "fused path, applied) in this step. Wrap all but the last backward of an accumulation loop in "
+                            "`with optimizer.no_sync():`, or build the optimizer with overlap=False.")
                     g = p.grad
                     if g is not None and g.data_ptr() != gv.data_ptr():
                         # autograd produced a fresh tensor (.grad was None): queue it for the bucket's multi-tensor copy
@@ -314,8 +376,23 @@ class FlatEngine:
         sumsq = self.sumsq.data_ptr() if self.monitor else 0
         kind = self.ext.OPT_ADAM if self.opt_kind == "adam" else self.ext.OPT_SGD
         ptr = lambda t: t.data_ptr() if t is not None else 0
+        mesh = self.arena.mesh
+        gate = self.gated and self.nranks > 1 and self.backend == "kernels"
+
+        def bracket(blocks, launch):
+            """gate -> body (never spins) -> wait, or the single self-synchronising kernel"""
+            if gate:
+                self.ext.barrier(mesh, 0, cs.cuda_stream)
+                launch(self.ext.FLAG_GATED)
+                self.ext.wait_done(mesh, 0, 0, self.nranks * blocks, cs.cuda_stream)
+                self.kernel_launches += 2
+            else:
+                launch(0)
+
         if self.mode == "ssgd":
-            if self.nranks == 1:
+            if self.nranks == 1 or self.backend == "nccl":
+                if self.nranks > 1:
+                    self._nccl_all_reduce(s.grads[b.start:b.start + b.numel], cs)
                 self.ext.flat_opt(s.params.data_ptr() + boff, dt, s.grads.data_ptr() + boff, dt, ptr(s.master[b.index]),
                                   ptr(s.s1[b.index]), ptr(s.s2[b.index]), s.hyper.data_ptr(), kind, b.numel, cs.cuda_stream)
                 if self.monitor:
@@ -325,17 +402,20 @@ class FlatEngine:
             else:
                 algo = self._algo_for(s, nbytes)
                 blocks = coll.pick_blocks(nbytes, self.nranks, True, self.max_blocks)
-                self.ext.ssgd_fused(self.arena.mesh, 0, algo, s.g_off + boff, s.p_off + boff, dt, nbytes,
-                                    ptr(s.master[b.index]), ptr(s.s1[b.index]), ptr(s.s2[b.index]), s.hyper.data_ptr(), kind,
-                                    sumsq, flags, blocks, self.threads, cs.cuda_stream)
+                bracket(blocks, lambda g: self.ext.ssgd_fused(
+                    mesh, 0, algo, s.g_off + boff, s.p_off + boff, dt, nbytes, ptr(s.master[b.index]), ptr(s.s1[b.index]),
+                    ptr(s.s2[b.index]), s.hyper.data_ptr(), kind, sumsq, flags | g, blocks, self.threads, cs.cuda_stream))
         elif self.mode == "grads":
-            if self.nranks > 1:
+            if self.nranks > 1 and self.backend == "nccl":
+                self._nccl_all_reduce(s.grads[b.start:b.start + b.numel], cs)
+                self.kernel_launches -= 1
+            elif self.nranks > 1:
                 algo = self._algo_for(s, nbytes)
                 blocks = coll.pick_blocks(nbytes, self.nranks, True, self.max_blocks)
                 scale = 1.0 / self.nranks if self.average else 1.0
                 f = flags | (self.ext.FLAG_SCALE if self.average else 0)
-                self.ext.allreduce(self.arena.mesh, 0, algo, s.g_off + boff, 0, nbytes, dt, dtypes.SUM, scale, sumsq, f, blocks,
-                                   self.threads, cs.cuda_stream)
+                bracket(blocks, lambda g: self.ext.allreduce(mesh, 0, algo, s.g_off + boff, 0, nbytes, dt, dtypes.SUM, scale, sumsq,
+                                                             f | g, blocks, self.threads, cs.cuda_stream))
             elif self.monitor:
                 self.ext.sumsq(s.grads.data_ptr() + boff, dt, b.numel, self.sumsq.data_ptr(), cs.cuda_stream)
                 self.ext.sumsq(s.grads.data_ptr() + boff, dt, b.numel, self.sumsq.data_ptr() + 4, cs.cuda_stream)
@@ -343,53 +423,158 @@ class FlatEngine:
             else:
                 self.kernel_launches -= 1
         elif self.mode == "sma":
+            grads = (s.grads.data_ptr() + boff) if self.opt_kind is not None else 0
             if self.nranks == 1:
                 self.ext.flat_opt(s.params.data_ptr() + boff, dt, s.grads.data_ptr() + boff, dt, 0, ptr(s.s1[b.index]),
                                   ptr(s.s2[b.index]), s.hyper.data_ptr(), kind, b.numel, cs.cuda_stream)
+            elif self._early == "sma" or self.backend == "nccl":
+                # the average is already in the scratch region (begin_step started it under forward/backward): local blend + step
+                if self._early != "sma":
+                    self._sma_average(si, cs)
+                avg = s.nccl_avg.data_ptr() + boff if self.backend == "nccl" else self.arena.view(s.x_off, lay.total, lay.dtype).data_ptr() + boff
+                self.ext.sma_blend(s.params.data_ptr() + boff, avg, dt, nbytes, grads, dt, ptr(s.s1[b.index]), ptr(s.s2[b.index]),
+                                   s.hyper.data_ptr(), kind, min(4 * self.plane.sm_count, max(1, nbytes // (16 * 512))), 512,
+                                   cs.cuda_stream)
             else:
                 algo = self._algo_for(s, nbytes)
                 blocks = coll.pick_blocks(nbytes, self.nranks, True, self.max_blocks)
-                grads = (s.grads.data_ptr() + boff) if self.opt_kind is not None else 0
-                self.ext.sma_fused(self.arena.mesh, 0, algo, s.p_off + boff, s.x_off + boff, dt, nbytes, grads, dt,
+                self.ext.sma_fused(mesh, 0, algo, s.p_off + boff, s.x_off + boff, dt, nbytes, grads, dt,
                                    ptr(s.s1[b.index]), ptr(s.s2[b.index]), 0, dt, s.hyper.data_ptr(), kind, blocks,
                                    self.threads, cs.cuda_stream)
         else:
             raise AssertionError(self.mode)
         self.kernel_launches += 1
 
+    # ---- NCCL baseline arm --------------------------------------------------------------------------
+    def _nccl_all_reduce(self, t: torch.Tensor, stream: torch.cuda.Stream) -> None:
+        """`ncclAllReduce` (average) of a flat arena view on the comm stream — what the reference's own NCCL path does per
+        tensor (srcs/cpp/src/nccl/gpu_collective.cpp:146-166), here per bucket and stream-ordered."""
+        import torch.distributed as dist
+
+        if not dist.is_initialized():
+            raise RuntimeError("kungfu_b200: backend='nccl' needs torch.distributed (NCCL) to be initialised")
+        with torch.cuda.stream(stream):
+            dist.all_reduce(t, op=dist.ReduceOp.AVG if self.average or self.mode == "sma" else dist.ReduceOp.SUM)
+
+    # ---- work that does not depend on this step's gradients -----------------------------------------
+    def _sma_average(self, si: int, cs: torch.cuda.Stream) -> None:
+        """scratch <- mean over ranks of the parameter region (out-of-place, split-phase, few CTAs: it has a whole
+        forward+backward to hide under)."""
+        s = self.sets[si]
+        lay = s.layout
+        dt = dtypes.dtype_code(lay.dtype)
+        nbytes = lay.nbytes
+        if self.backend == "nccl":
+            if s.nccl_avg is None:
+                s.nccl_avg = torch.empty_like(s.params)
+            with torch.cuda.stream(cs):
+                s.nccl_avg.copy_(s.params)
+            self._nccl_all_reduce(s.nccl_avg, cs)
+            return
+        mesh = self.arena.mesh
+        algo = self._algo_for(s, nbytes)
+        blocks = coll.pick_blocks(nbytes, self.nranks, True, int(os.environ.get("KUNGFU_SMA_BLOCKS", "16")))
+        self.ext.barrier(mesh, 0, cs.cuda_stream)
+        self.ext.allreduce_to(mesh, 0, algo, s.p_off, s.x_off, nbytes, dt, dtypes.SUM, 1.0 / self.nranks, 0,
+                              self.ext.FLAG_SCALE | self.ext.FLAG_GATED, blocks, self.threads, cs.cuda_stream)
+        self.ext.wait_done(mesh, 0, 0, self.nranks * blocks, cs.cuda_stream)
+        self.kernel_launches += 3
+
+    def begin_step(self, target: Optional[int] = None) -> None:
+        """Start, under the coming forward+backward, the part of the step that does not need its gradients
+        (sma: the model average; pair: the pull of `target`'s published model). Called by `optimizer.zero_grad()`;
+        without it `step()` does the same work after backward (correct, not overlapped)."""
+        if self._early is not None or self.nranks == 1 or not self.overlap_requested:
+            return
+        if self.mode == "sma":
+            self._open_step()
+            cs = self.plane.comm_stream
+            for si in range(len(self.sets)):
+                self._sma_average(si, cs)
+            self._early = "sma"
+        elif self.mode == "pair" and target is not None and self._pair_ready:
+            self._open_step()
+            ss = self.plane.side_stream
+            self._set_target(target)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            ss.wait_event(ev)
+            pull_blocks = int(os.environ.get("KUNGFU_PULL_BLOCKS", "24"))
+            for s in self.sets:
+                lay = s.layout
+                if s.pulled is None:
+                    s.pulled = torch.empty(lay.nbytes, dtype=torch.uint8, device=self.plane.device)
+                with torch.cuda.stream(ss):
+                    s.pull_ok[2:].zero_()
+                pubs = [s.x_off, s.x_off2, s.x_off3]
+                nb = min(pull_blocks, (lay.nbytes + 32767) // 32768)
+                for retry in (0, 1):  # the second attempt runs only if the first copy was torn
+                    self.ext.pull_tma(self.arena.mesh, 1, 0, pubs, s.ver_off, s.pulled.data_ptr(), lay.nbytes, s.pull_ok.data_ptr(),
+                                      retry, nb, ss.cuda_stream, self._target_dev.data_ptr())
+                self.kernel_launches += 3
+            self._early = "pair"
+
+    _pair_ready = False  # the first publish of this membership has happened (nothing to pull before it)
+
+    def _set_target(self, target: int) -> None:
+        """The target rank lives in a device word the kernels read, so that one captured graph serves every target.
+        Under capture the caller refreshes it before each replay (`set_pair_target`)."""
+        if not torch.cuda.is_current_stream_capturing():
+            self._target_dev.fill_(int(target))  # the value travels as a kernel argument: no host buffer to keep alive
+
+    def set_pair_target(self, target: int) -> None:
+        """Before replaying a captured pair-averaging step: choose whom this replay pulls from."""
+        self._set_target(target)
+
     # ---------------------------------------------------------------------------------------------
     def pair_step(self, target: int, do_step: bool) -> None:
-        """PairAveraging: one kernel per set on the side stream (whole model)."""
+        """PairAveraging: v <- 0.5 (v + other) -> local step -> publish, one kernel per set (whole model). `other` is the
+        private copy `begin_step(target)` pulled on the side stream under forward+backward; without it the kernel reads the
+        target's published model over NVLink itself (same result, the transfer is then exposed)."""
         self._open_step()
-        cs = self.plane.comm_stream
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
-        cs.wait_event(ev)
+        cur = torch.cuda.current_stream()
+        early = self._early == "pair"
+        tick = torch.cuda.Event()  # the hyper-parameter tick of _open_step went to the comm stream
+        tick.record(self.plane.comm_stream)
+        cur.wait_event(tick)
+        if early:
+            done = torch.cuda.Event()
+            done.record(self.plane.side_stream)
+            cur.wait_event(done)
+        else:
+            self._set_target(target)
         kind = self.ext.OPT_ADAM if self.opt_kind == "adam" else self.ext.OPT_SGD
         ptr = lambda t: t.data_ptr() if t is not None else 0
         for s in self.sets:
             lay = s.layout
             dt = dtypes.dtype_code(lay.dtype)
-            blocks = coll.pick_blocks(lay.nbytes, 1, False, 148)  # side stream at the end of a step: use every SM
-            self.ext.pair_avg(self.arena.mesh, 1, target, s.x_off, s.x_off2, s.ver_off, s.params.data_ptr(), dt, lay.nbytes,
+            blocks = coll.pick_blocks(lay.nbytes, 1, False, 148)  # after backward, nothing else runs: use every SM
+            self.ext.pair_avg(self.arena.mesh, 1, 0, [s.x_off, s.x_off2, s.x_off3], s.ver_off, s.params.data_ptr(), dt, lay.nbytes,
                               s.grads.data_ptr(), dt, ptr(s.s1[0]), ptr(s.s2[0]), s.hyper.data_ptr(), kind, 1 if do_step else 0,
-                              s.done_counter.data_ptr(), blocks, self.threads, cs.cuda_stream)
+                              s.done_counter.data_ptr(), s.pulled.data_ptr() if early else 0, s.pull_ok.data_ptr() if early else 0,
+                              blocks, self.threads, cur.cuda_stream, self._target_dev.data_ptr(), ptr(s.master[0]))
             self.kernel_launches += 1
 
     def publish(self) -> None:
         self._check_consensus()
         self.arena.ensure()
-        cs = self.plane.comm_stream
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
-        cs.wait_event(ev)
+        cur = torch.cuda.current_stream()
         for s in self.sets:
             lay = s.layout
             blocks = coll.pick_blocks(lay.nbytes, 1, False, max(self.max_blocks, 64))
-            self.ext.publish(self.arena.mesh, 1, s.x_off, s.x_off2, s.ver_off, s.params.data_ptr(), lay.nbytes,
-                             s.done_counter.data_ptr(), blocks, self.threads, cs.cuda_stream)
+            self.ext.publish(self.arena.mesh, 1, [s.x_off, s.x_off2, s.x_off3], s.ver_off, s.params.data_ptr(), lay.nbytes,
+                             s.done_counter.data_ptr(), blocks, self.threads, cur.cuda_stream)
             self.kernel_launches += 1
-        self.finish()
+        self._pair_ready = True
+
+    def torn_reads(self) -> int:
+        """PairAveraging: pulls whose source buffer was handed back to its owner while being read (after the retry).
+        Host-synchronising; for tests and end-of-run reports."""
+        n = int(self.arena.mesh.status()[5])
+        for s in self.sets:
+            if s.pull_ok is not None:
+                n += int(s.pull_ok[1].item())
+        return n
 
     # ---------------------------------------------------------------------------------------------
     def flush(self) -> None:
@@ -414,6 +599,9 @@ class FlatEngine:
         done.record(self.plane.comm_stream)
         torch.cuda.current_stream().wait_event(done)
         self._step_open = False
+        self._early = None
+        if self.nranks > 1 and self.arena.mesh.status()[0] != 0:
+            self.arena.check()  # a device-side wait timed out (host-mapped word: no synchronisation needed to read it)
         for si, s in enumerate(self.sets):
             self._launched[si] = 0
             for i in range(len(s.ready)):
@@ -457,6 +645,8 @@ class FlatEngine:
             s.state_ready = False
             s._saved_hyper = hp_step  # type: ignore[attr-defined]
         self._step_open = False
+        self._early = None
+        self._pair_ready = False
         self._launched = [0 for _ in self.sets]
 
     def sync_state_from_root(self, root: int = 0) -> None:
@@ -470,7 +660,7 @@ class FlatEngine:
         for si, s in enumerate(self.sets):
             lay = s.layout
             need1, need2 = self._needs_state(s)
-            keys = [("master", lay.dtype != torch.float32 and self.mode == "ssgd"), ("s1", need1), ("s2", need2)]
+            keys = [("master", lay.dtype != torch.float32 and self.mode in self._MASTER_MODES), ("s1", need1), ("s2", need2)]
             # the device-side step counter / bias corrections travel too
             coll.broadcast_(s.hyper, root)
             s.hyper_cache = None
@@ -488,24 +678,61 @@ class FlatEngine:
                     full = torch.zeros(sum(b.numel for b in lay.buckets), dtype=torch.float32, device=dev)
                 full = full.contiguous()
                 coll.broadcast_(full, root)
-                off = 0
-                shards = getattr(s, key)
-                for b in lay.buckets:
-                    if self.mode == "ssgd" and self.nranks > 1:
-                        n = lay.shard_elems(b, self.nranks)
-                        lo, hi = lay.shard_range(b, self.nranks, self.rank)
-                    else:
-                        n = b.numel
-                        lo, hi = b.start, b.start + b.numel
-                    t = torch.zeros(n, dtype=torch.float32, device=dev)
-                    t[:hi - lo].copy_(full[off + (lo - b.start):off + (hi - b.start)])
-                    shards[b.index] = t
-                    off += b.numel
-                setattr(s, "_have_" + key, True)
+                self._install_full(s, key, full)
             # anything not received is created lazily (zeros / from the broadcast parameters)
             s.state_ready = False
         self._ensure_state_keep_existing()
         self._full_state = None
+
+    def _install_full(self, s: _Set, key: str, full: torch.Tensor) -> None:
+        """Cut the un-sharded fp32 state `full` (all buckets, concatenated) into this rank's per-bucket shards."""
+        lay = s.layout
+        dev = self.plane.device
+        off = 0
+        shards = getattr(s, key)
+        for b in lay.buckets:
+            if self._sharded:
+                n = lay.shard_elems(b, self.nranks)
+                lo, hi = lay.shard_range(b, self.nranks, self.rank)
+            else:
+                n = b.numel
+                lo, hi = b.start, b.start + b.numel
+            t = torch.zeros(n, dtype=torch.float32, device=dev)
+            t[:hi - lo].copy_(full[off + (lo - b.start):off + (hi - b.start)])
+            shards[b.index] = t
+            off += b.numel
+
+    # ---- checkpointing -----------------------------------------------------------------------------
+    def state_dict(self) -> Dict[str, object]:
+        """COLLECTIVE when the state is sharded (every rank must call it): the un-sharded fp32 master weights and optimizer
+        state plus the device-side step counters, on the host. The reference has no optimizer checkpoint at all."""
+        torch.cuda.current_stream().synchronize()
+        full = self.gather_state() if all(s.state_ready for s in self.sets) else {}
+        return {"mode": self.mode, "opt_kind": self.opt_kind, "layout": [s.layout.digest().hex() for s in self.sets],
+                "state": {k: v.detach().cpu() for k, v in full.items()}, "hyper": [s.hyper.detach().cpu() for s in self.sets]}
+
+    def load_state_dict(self, sd: Dict[str, object]) -> None:
+        """Local (every rank reads the same file): re-shard the saved state for the CURRENT world size and restore the
+        device-side step counters. Call after the model parameters have been loaded."""
+        if sd.get("mode") != self.mode or sd.get("opt_kind") != self.opt_kind:
+            raise ValueError(f"kungfu_b200: checkpoint is for engine {sd.get('mode')}/{sd.get('opt_kind')}, this one is {self.mode}/{self.opt_kind}")
+        if list(sd.get("layout", [])) != [s.layout.digest().hex() for s in self.sets]:
+            raise ValueError("kungfu_b200: checkpoint was written for a different parameter/bucket layout")
+        dev = self.plane.device
+        state = sd.get("state", {})
+        for si, s in enumerate(self.sets):
+            for key in ("master", "s1", "s2"):
+                full = state.get(f"set{si}.{key}")
+                if full is not None:
+                    self._install_full(s, key, full.to(dev, torch.float32))
+            s.hyper.copy_(sd["hyper"][si].to(dev))
+            s.hyper_cache = None
+            s.state_ready = False
+        self._ensure_state_keep_existing()  # whatever the checkpoint did not contain (a run that never stepped)
+        self._step_open = False
+        self._early = None
+        self._pair_ready = False
+        torch.cuda.current_stream().synchronize()
 
     def _ensure_state_keep_existing(self) -> None:
         for s in self.sets:
@@ -513,14 +740,14 @@ class FlatEngine:
             need1, need2 = self._needs_state(s)
             dev = self.plane.device
             for b in lay.buckets:
-                if self.mode == "ssgd" and self.nranks > 1:
+                if self._sharded:
                     n = lay.shard_elems(b, self.nranks)
                     lo, hi = lay.shard_range(b, self.nranks, self.rank)
                 else:
                     n = b.numel
                     lo, hi = b.start, b.start + b.numel
                 ok = lambda t: t is not None and t.numel() == n
-                if lay.dtype != torch.float32 and self.mode == "ssgd" and not ok(s.master[b.index]):
+                if lay.dtype != torch.float32 and self.mode in self._MASTER_MODES and not ok(s.master[b.index]):
                     m = torch.zeros(n, dtype=torch.float32, device=dev)
                     m[:hi - lo].copy_(s.params[lo:hi])
                     s.master[b.index] = m
@@ -552,7 +779,7 @@ class FlatEngine:
                     t = shards[b.index]
                     if t is None:
                         continue
-                    if self.mode == "ssgd" and self.nranks > 1:
+                    if self._sharded:
                         g = coll.all_gather(t).view(-1)[:b.numel]
                     else:
                         g = t[:b.numel]

@@ -5,9 +5,13 @@ Reference (TF only): srcs/python/kungfu/tensorflow/optimizers/async_sgd.py:13-14
 first pull cannot miss), `v <- 0.5 (v + other)`, apply local gradients, `save_variable(new model)`. Legacy C++ ops with
 `RandomSelector` / `RoundRobinSelector`: srcs/cpp/src/tensorflow/ops/cpu/peer_to_peer.cpp:8-524.
 
-GPU: the model store is a double-buffered region of the symmetric arena with version words; one `pair_avg_kernel` reads
-the target's published model straight over NVLink, averages, applies the local optimizer step and publishes the result.
-The target is never blocked; a reader that overlaps two publishes is counted as `torn` in the mesh status.
+GPU: the model store is a TRIPLE-buffered region of the symmetric arena with version words (version v lives in buffer
+v % 3, so a reader of v is only disturbed once its owner starts on v + 3 — two full steps later). `zero_grad()` picks the
+step's target and starts `pull_tma_kernel` on the side stream: one elected thread per CTA drives the TMA engine and copies the
+target's published model over NVLink into a private buffer while forward+backward run (the reference's "the pull overlaps
+training", srcs/cpp/src/tensorflow/ops/cpu/peer_to_peer.cpp:212-254 AsyncModelAveraging); a copy that was torn anyway is
+pulled again from the then-current version. After backward ONE local kernel averages, applies the optimizer step and
+publishes. The target is never blocked. Without `zero_grad()` before backward the kernel reads the target over NVLink itself.
 CPU: the native runtime's versioned blob store + P2P request (`rt.control.save / request`).
 """
 from __future__ import annotations
@@ -31,7 +35,7 @@ def get_random_peer(cluster_size: int, self_rank: int, rng: random.Random = None
 
 
 class _PairAveraging(KungFuMixin):
-    def _kf_init_pair(self, named_parameters, fuse_requests, fused_model_name, fused, peer_selection, seed):
+    def _kf_init_pair(self, named_parameters, fuse_requests, fused_model_name, fused, peer_selection, seed, overlap=True):
         self._kf_setup(named_parameters, True)
         self._kf_fuse_requests = bool(fuse_requests)
         self._kf_model_name = fused_model_name or "kungfu::PairAveragingOptimizer::fused_model"
@@ -41,11 +45,40 @@ class _PairAveraging(KungFuMixin):
         kind = fusable_kind(self) if fused in (True, "auto") else None
         self._kf_kind = kind
         self._kf_published = False
+        self._kf_next_target = None
         if self._kf_gpu:
             from ...parallel.engine import FlatEngine
 
             self._kf_engine = FlatEngine(self.param_groups, self._kf_named, mode="pair", opt_kind=kind or "sgd", average=False,
-                                         overlap=False, name="pair")
+                                         overlap=overlap, name="pair", master_weights=kind is not None)
+
+    def _kf_begin_step(self) -> None:
+        """Choose this step's target and start pulling its model under forward+backward (GPU engine, after the first publish)."""
+        eng = self._kf_engine
+        if eng is None or self._kf_rt.size == 1 or not self._kf_published or self._kf_next_target is not None:
+            return
+        ver = getattr(self._kf_rt.control, "cluster_version", None)
+        if getattr(self, "_kf_membership", None) != ((ver() if ver else 0), self._kf_rt.size):
+            return  # membership changed: the next step() republishes first
+        self._kf_next_target = self._kf_pick_peer()
+        eng.begin_step(self._kf_next_target)
+
+    def prepare_replay(self) -> None:
+        """Before replaying a CUDA graph of a step that was captured with this optimizer: draw this replay's target and put
+        it into the device word the captured pull / averaging kernels read."""
+        eng = self._kf_engine
+        if eng is not None and self._kf_rt.size > 1:
+            eng.set_pair_target(self._kf_pick_peer())
+
+    def _kf_first_publish(self) -> None:
+        """First step of a membership (job start or right after a resize): every member publishes, then a barrier, so that no
+        pull can find an empty store — joiners and survivors meet here together (reference: async_sgd.py:106-123)."""
+        eng = self._kf_engine
+        eng._sync_hyper()
+        eng._ensure_state()
+        eng.publish()
+        coll.barrier()
+        self._kf_published = True
 
     # ---- peer selection (reference: async_sgd.py:71-75, peer_to_peer.cpp selectors) -----------------
     def _kf_pick_peer(self) -> int:
@@ -79,13 +112,11 @@ class _PairAveraging(KungFuMixin):
         rt = self._kf_rt
         eng = self._kf_engine
         if eng is not None:
-            if not self._kf_published:
-                eng._sync_hyper()
-                eng._ensure_state()
-                eng.publish()
-                coll.barrier()
-                self._kf_published = True
-            target = self._kf_pick_peer()
+            if self._kf_membership_changed() or not self._kf_published:
+                self._kf_next_target = None
+                self._kf_first_publish()
+            target = self._kf_next_target if self._kf_next_target is not None else self._kf_pick_peer()
+            self._kf_next_target = None
             if rt.size == 1:
                 target = rt.rank
             if self._kf_kind is not None:
@@ -121,8 +152,8 @@ class _PairAveraging(KungFuMixin):
 
 def PairAveragingOptimizer(optimizer: torch.optim.Optimizer, named_parameters=None, fuse_requests: bool = True,
                            fused_model_name: Optional[str] = None, fused="auto", peer_selection: str = "random",
-                           seed: Optional[int] = None):
+                           seed: Optional[int] = None, overlap: bool = True):
     """Wrap `optimizer` with asynchronous pairwise model averaging (reference signature:
     `(optimizer, fuse_requests=True, fused_model_name=None, name=None)`)."""
     return wrap_optimizer(optimizer, _PairAveraging,
-                          lambda o: o._kf_init_pair(named_parameters, fuse_requests, fused_model_name, fused, peer_selection, seed))
+                          lambda o: o._kf_init_pair(named_parameters, fuse_requests, fused_model_name, fused, peer_selection, seed, overlap))

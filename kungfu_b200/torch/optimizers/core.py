@@ -114,8 +114,22 @@ class KungFuMixin:
         eng = getattr(self, "_kf_engine", None)
         if eng is not None:
             eng.zero_grad()
+            self._kf_begin_step()
             return
         return self._kf_inner_cls.zero_grad(self, set_to_none=set_to_none)
+
+    def _kf_begin_step(self) -> None:
+        """Hook for optimizers that can start work before backward (SMA: model average, PairAveraging: the pull)."""
+
+    def no_sync(self):
+        """Gradient accumulation: `with opt.no_sync(): loss.backward()` for all but the last micro-batch (the overlapped
+        engines reduce — and on the fused path apply — a bucket as soon as backward has produced it)."""
+        eng = getattr(self, "_kf_engine", None)
+        if eng is not None:
+            return eng.no_sync()
+        import contextlib
+
+        return contextlib.nullcontext()
 
     @property
     def engine(self):

@@ -3,8 +3,11 @@
 Reference (TF only): srcs/python/kungfu/tensorflow/optimizers/sma_sgd.py:9-74 — every step all-reduce-sum the *model*,
 `avg = sum / np`, `v <- (1 - alpha) v + alpha avg` (alpha = 0.1), THEN apply the local gradients.
 
-GPU fused path: one `sma_fused_kernel` per bucket does reduce-scatter(params) -> 1/np -> all-gather into a scratch region
--> blend -> local SGD/Adam step in a single pass over the arena (csrc/kernels/fused_step.cu).
+GPU path (overlap=True, default): the model average does not depend on this step's gradients, so `zero_grad()` starts an
+out-of-place split-phase all-reduce (params -> scratch, 1/np folded in) on the comm stream and the whole transfer hides
+under forward+backward; after backward ONE local kernel does blend + SGD/Adam step over the arena. overlap=False (or no
+`zero_grad()` before backward): `sma_fused_kernel` does reduce-scatter -> 1/np -> all-gather -> blend -> step in a single
+kernel after backward (csrc/kernels/fused_step.cu).
 """
 from __future__ import annotations
 
@@ -17,7 +20,7 @@ from .core import KungFuMixin, fusable_kind, wrap_optimizer
 
 
 class _SynchronousAveraging(KungFuMixin):
-    def _kf_init_sma(self, named_parameters, alpha, fused, bucket_mb, algo):
+    def _kf_init_sma(self, named_parameters, alpha, fused, bucket_mb, algo, overlap=True, backend=None):
         self._kf_setup(named_parameters, True)
         self._kf_alpha = float(alpha)
         kind = fusable_kind(self) if fused in (True, "auto") else None
@@ -28,7 +31,12 @@ class _SynchronousAveraging(KungFuMixin):
             from ...parallel.engine import FlatEngine
 
             self._kf_engine = FlatEngine(self.param_groups, self._kf_named, mode="sma", opt_kind=kind, average=False,
-                                         overlap=False, bucket_mb=bucket_mb, alpha=self._kf_alpha, algo=algo, name="sma")
+                                         overlap=overlap, bucket_mb=bucket_mb, alpha=self._kf_alpha, algo=algo, name="sma",
+                                         backend=backend)
+
+    def _kf_begin_step(self) -> None:
+        if self._kf_engine is not None:
+            self._kf_engine.begin_step()
 
     def average_model(self):
         """v <- (1 - alpha) v + alpha mean_over_workers(v) (generic path)."""
@@ -65,6 +73,8 @@ class _SynchronousAveraging(KungFuMixin):
 
 
 def SynchronousAveragingOptimizer(optimizer: torch.optim.Optimizer, named_parameters=None, alpha: float = 0.1, fused="auto",
-                                  bucket_mb: Optional[float] = None, algo: Optional[str] = None):
+                                  bucket_mb: Optional[float] = None, algo: Optional[str] = None, overlap: bool = True,
+                                  backend: Optional[str] = None):
     """Wrap `optimizer` with synchronous model averaging (reference signature: `(optimizer, name, alpha=0.1)`)."""
-    return wrap_optimizer(optimizer, _SynchronousAveraging, lambda o: o._kf_init_sma(named_parameters, alpha, fused, bucket_mb, algo))
+    return wrap_optimizer(optimizer, _SynchronousAveraging,
+                          lambda o: o._kf_init_sma(named_parameters, alpha, fused, bucket_mb, algo, overlap, backend))

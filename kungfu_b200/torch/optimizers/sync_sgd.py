@@ -22,7 +22,7 @@ from .core import KungFuMixin, cpu_all_reduce_grads, fusable_kind, wrap_optimize
 
 
 class _SynchronousSGD(KungFuMixin):
-    def _kf_init_ssgd(self, named_parameters, op, fused, overlap, bucket_mb, monitor, algo, use_gpu_engine=True):
+    def _kf_init_ssgd(self, named_parameters, op, fused, overlap, bucket_mb, monitor, algo, use_gpu_engine=True, backend=None):
         self._kf_setup(named_parameters, use_gpu_engine)
         code, avg = dtypes.op_code(op if op is not None else "avg")
         if code != dtypes.SUM:
@@ -39,7 +39,7 @@ class _SynchronousSGD(KungFuMixin):
 
             self._kf_engine = FlatEngine(self.param_groups, self._kf_named, mode="ssgd" if kind else "grads", opt_kind=kind,
                                          average=avg, overlap=overlap, bucket_mb=bucket_mb, monitor=monitor, algo=algo,
-                                         name="ssgd")
+                                         name="ssgd", backend=backend)
 
     def sync_gradients(self):
         """Average (or sum) gradients across workers without stepping (generic path only)."""
@@ -71,10 +71,15 @@ class _SynchronousSGD(KungFuMixin):
 
 def SynchronousSGDOptimizer(optimizer: torch.optim.Optimizer, named_parameters=None, op: Optional[str] = None,
                             fused="auto", overlap: bool = True, bucket_mb: Optional[float] = None, monitor: bool = False,
-                            algo: Optional[str] = None):
+                            algo: Optional[str] = None, backend: Optional[str] = None):
     """Wrap `optimizer` so that `step()` applies the gradient averaged over all workers.
 
     `op`: None/'avg' (default, matches the TF optimizer and Horovod) or 'sum' (the reference torch binding).
+    `overlap=True` (default) reduces — and on the fused path applies — every bucket from autograd hooks while backward is
+    still running. Consequences: gradient accumulation needs `with opt.no_sync():` around all but the last backward;
+    `clip_grad_norm_` / AMP `unscale_` between backward() and step() see gradients that have already been consumed — build
+    the optimizer with `overlap=False` for those recipes (everything then happens inside step(), as in the reference).
+    `backend='nccl'`: same engine, buckets and local optimizer kernels, but the collective is `ncclAllReduce` (baseline arm).
     """
     return wrap_optimizer(optimizer, _SynchronousSGD,
-                          lambda o: o._kf_init_ssgd(named_parameters, op, fused, overlap, bucket_mb, monitor, algo))
+                          lambda o: o._kf_init_ssgd(named_parameters, op, fused, overlap, bucket_mb, monitor, algo, backend=backend))

@@ -36,7 +36,8 @@ class LossFuture:
 class ImageTrainer:
     def __init__(self, model: torch.nn.Module, optimizer, batch_size: int, image_size: int = 224,
                  dtype: torch.dtype = torch.bfloat16, loss_fn: Optional[Callable] = None, use_graph: bool = True,
-                 warmup_iters: int = 3, device: Optional[torch.device] = None) -> None:
+                 warmup_iters: int = 3, device: Optional[torch.device] = None, capture_error_mode: str = "global") -> None:
+        self.capture_error_mode = capture_error_mode
         rt = get_runtime()
         self.rt = rt
         self.device = device or (rt.gpu.device if rt.has_gpu() else torch.device("cpu"))
@@ -94,7 +95,7 @@ class ImageTrainer:
             return
         try:
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=s):
+            with torch.cuda.graph(g, stream=s, capture_error_mode=self.capture_error_mode):
                 self._train_body()
             torch.cuda.synchronize()
             self.graph = g
@@ -108,6 +109,9 @@ class ImageTrainer:
         """One training step on the resident device batch (kernel-only path)."""
         if self.graph is not None:
             self.graph.replay()
+            eng = getattr(self.optimizer, "engine", None)
+            if eng is not None and eng.nranks > 1 and eng.arena.mesh.status()[0] != 0:
+                eng.check()  # replays bypass the optimizer's python: poll the host-mapped status word of the device-side waits here
         else:
             self._train_body()
         return self.loss
@@ -164,3 +168,53 @@ class ImageTrainer:
     @property
     def d2h_bytes_per_step(self) -> int:
         return 4
+
+
+class GraphedStep:
+    """Capture one whole training step (zero_grad -> forward -> backward -> optimizer.step) of ANY model into a CUDA graph.
+
+        step = GraphedStep(lambda: train_body(), optimizer)   # eager warm-up, then capture
+        step()                                                 # replay (or eager when capture is disabled / failed)
+
+    `body` must use static input tensors (refill them in place between calls). What changes from step to step lives on the
+    device — learning rate / step counters (engine hyper block), the PairAveraging target (a device word) — so one graph serves
+    the whole run; `optimizer.prepare_replay()` (if present) refreshes those words before every replay.
+    """
+
+    def __init__(self, body: Callable[[], None], optimizer=None, warmup_iters: int = 3, use_graph: bool = True,
+                 capture_error_mode: str = "global") -> None:
+        self.body = body
+        self.optimizer = optimizer
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_error: Optional[str] = None
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(max(1, warmup_iters)):
+                body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if not use_graph:
+            return
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s, capture_error_mode=capture_error_mode):
+                body()
+            torch.cuda.synchronize()
+            self.graph = g
+        except Exception as e:  # capture is an optimisation; fall back to eager and say so
+            self.graph_error = f"{type(e).__name__}: {e}"
+            torch.cuda.synchronize()
+
+    def __call__(self) -> None:
+        if self.graph is None:
+            self.body()
+            return
+        prep = getattr(self.optimizer, "prepare_replay", None)
+        if prep is not None:
+            prep()
+        self.graph.replay()
+        eng = getattr(self.optimizer, "engine", None)
+        if eng is not None and eng.nranks > 1 and eng.arena.mesh.status()[0] != 0:
+            eng.check()

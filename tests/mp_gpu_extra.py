@@ -20,7 +20,7 @@ def loss_of(m, rank, step):
     return torch.nn.functional.cross_entropy(m(x), y)
 
 
-def check_sma(rt, log, algo):
+def check_sma(rt, log, algo, overlap=True):
     N, me = rt.size, rt.rank
     alpha, lr, mom = 0.1, 0.05, 0.9
     # replicas start DIFFERENT (seed = rank) so that averaging matters
@@ -28,7 +28,8 @@ def check_sma(rt, log, algo):
     sim_opts = [torch.optim.SGD(s.parameters(), lr=lr, momentum=mom) for s in sims]
     m = mlp(100 + me)
     opt = kf.optimizers.SynchronousAveragingOptimizer(torch.optim.SGD(m.parameters(), lr=lr, momentum=mom),
-                                                      named_parameters=m.named_parameters(), alpha=alpha, bucket_mb=0.01, algo=algo)
+                                                      named_parameters=m.named_parameters(), alpha=alpha, bucket_mb=0.01, algo=algo,
+                                                      overlap=overlap)
     assert opt.engine is not None and opt.engine.mode == "sma"
     fails = 0
     for step in range(5):
@@ -51,7 +52,7 @@ def check_sma(rt, log, algo):
     for a, b in zip(sims[me].parameters(), m.parameters()):
         if not torch.allclose(a, b, atol=2e-5, rtol=2e-5):
             fails += 1
-            log(f"FAIL sma algo={algo} maxdiff={(a - b).abs().max().item()}")
+            log(f"FAIL sma algo={algo} overlap={overlap} maxdiff={(a - b).abs().max().item()}")
             break
     return fails
 
@@ -88,7 +89,8 @@ def check_pair(rt, log):
                 torch.cuda.synchronize()
             elif step == 0 and not opt._kf_published:
                 # every rank must take part in the first publish + barrier
-                eng._sync_hyper(); eng._ensure_state(); eng.publish(); coll.barrier(); opt._kf_published = True
+                opt._kf_membership_changed()
+                opt._kf_first_publish()
             coll.barrier()
     for a, b in zip(sims[me].parameters(), m.parameters()):
         if not torch.allclose(a, b, atol=2e-5, rtol=2e-5):
@@ -118,7 +120,7 @@ def check_pair(rt, log):
     if not (s1 < 0.05 * s0 + 1e-12):
         fails += 1
         log(f"FAIL pair gossip did not contract: {s0} -> {s1}")
-    log(f"pair gossip spread {s0:.3e} -> {s1:.3e}, torn={st[5]}")
+    log(f"pair gossip spread {s0:.3e} -> {s1:.3e}, torn={eng.torn_reads()} (status word {st[5]})")
     return fails
 
 
@@ -136,7 +138,7 @@ def check_pull_publish(rt, log):
     st = torch.cuda.current_stream().cuda_stream
     fails = 0
     target = (me + 1) % N
-    ext.pull(arena.mesh, 1, target, pub0, pub1, ver, dst.data_ptr(), n * 4, ok.data_ptr(), 8, 512, st)
+    ext.pull(arena.mesh, 1, target, [pub0, pub1], ver, dst.data_ptr(), n * 4, ok.data_ptr(), 0, 8, 512, st)
     torch.cuda.synchronize()
     if ok[0].item() != 0:
         fails += 1
@@ -144,10 +146,10 @@ def check_pull_publish(rt, log):
     coll.barrier()  # nobody publishes before every rank has done its "nothing there yet" pull
     for v in range(1, 4):
         src = torch.full((n,), float(100 * me + v), device="cuda")
-        ext.publish(arena.mesh, 1, pub0, pub1, ver, src.data_ptr(), n * 4, done.data_ptr(), 8, 512, st)
+        ext.publish(arena.mesh, 1, [pub0, pub1], ver, src.data_ptr(), n * 4, done.data_ptr(), 8, 512, st)
         torch.cuda.synchronize()
         coll.barrier()
-        ext.pull(arena.mesh, 1, target, pub0, pub1, ver, dst.data_ptr(), n * 4, ok.data_ptr(), 8, 512, st)
+        ext.pull(arena.mesh, 1, target, [pub0, pub1], ver, dst.data_ptr(), n * 4, ok.data_ptr(), 0, 8, 512, st)
         torch.cuda.synchronize()
         if ok[0].item() != v or not torch.all(dst == float(100 * target + v)):
             fails += 1
@@ -156,7 +158,7 @@ def check_pull_publish(rt, log):
         for nb in (n * 4, n * 4 - 48, 4096):
             dst.zero_()
             ok.zero_()
-            ext.pull_tma(arena.mesh, 1, target, pub0, pub1, ver, dst.data_ptr(), nb, ok.data_ptr(), 148, st)
+            ext.pull_tma(arena.mesh, 1, target, [pub0, pub1], ver, dst.data_ptr(), nb, ok.data_ptr(), 0, 148, st)
             torch.cuda.synchronize()
             k = nb // 4
             if ok[0].item() != v or not torch.all(dst[:k] == float(100 * target + v)) or not torch.all(dst[k:] == 0):
@@ -166,14 +168,112 @@ def check_pull_publish(rt, log):
     return fails
 
 
+def check_checkpoint(rt, log):
+    """Fused S-SGD (bf16 params, fp32 master shards, momentum): train -> save -> {keep going | fresh model + load} must give
+    bit-identical parameters (the sharded state, the master weights and the device-side step counter all survive)."""
+    import os
+    import tempfile
+
+    from kungfu_b200 import checkpoint as ckpt
+
+    me = rt.rank
+    path = os.path.join(tempfile.gettempdir(), "kf_ckpt_roundtrip.pt")
+
+    def make(seed):
+        m = mlp(seed, torch.bfloat16)
+        o = kf.optimizers.SynchronousSGDOptimizer(torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9), named_parameters=m.named_parameters(),
+                                                  bucket_mb=0.005)
+        return m, o
+
+    def train(m, o, steps):
+        for st in steps:
+            o.zero_grad()
+            x, y = batch(me, st)
+            torch.nn.functional.cross_entropy(m(x.to(torch.bfloat16)).float(), y).backward()
+            o.step()
+        torch.cuda.synchronize()
+
+    m1, o1 = make(300)
+    train(m1, o1, range(3))
+    ckpt.save(path, m1, o1, step=3)  # collective: every rank calls it, rank 0 writes
+    coll.barrier()
+    m2, o2 = make(999)  # different initial weights: everything must come from the file
+    meta = ckpt.load(path, m2, o2)
+    train(m1, o1, range(3, 5))
+    train(m2, o2, range(3, 5))
+    fails = 0
+    if meta.get("step") != 3:
+        fails += 1
+        log(f"FAIL checkpoint meta {meta}")
+    for a, b in zip(m1.parameters(), m2.parameters()):
+        if not torch.equal(a, b):
+            fails += 1
+            log(f"FAIL checkpoint resume differs: maxdiff={(a.float() - b.float()).abs().max().item()}")
+            break
+    sd1, sd2 = o1.engine.state_dict(), o2.engine.state_dict()
+    for k in sd1["state"]:
+        if not torch.equal(sd1["state"][k], sd2["state"][k]):
+            fails += 1
+            log(f"FAIL checkpoint resume: optimizer state {k} differs")
+    if me == 0:
+        os.remove(path)
+    return fails
+
+
+def check_accumulation(rt, log):
+    """Gradient accumulation with the overlapped engine: two micro-batches under no_sync() + one outside == one backward on the
+    summed loss; a second backward WITHOUT no_sync() must raise instead of silently dropping gradients."""
+    me = rt.rank
+    fails = 0
+
+    def make():
+        m = mlp(400)
+        o = kf.optimizers.SynchronousSGDOptimizer(torch.optim.SGD(m.parameters(), lr=0.05), named_parameters=m.named_parameters(), bucket_mb=0.005)
+        return m, o
+
+    ma, oa = make()
+    mb, ob = make()
+    oa.zero_grad()
+    with oa.no_sync():
+        loss_of(ma, me, 1).backward()
+        loss_of(ma, me, 2).backward()
+    loss_of(ma, me, 3).backward()
+    oa.step()
+    ob.zero_grad()
+    (loss_of(mb, me, 1) + loss_of(mb, me, 2) + loss_of(mb, me, 3)).backward()
+    ob.step()
+    torch.cuda.synchronize()
+    for a, b in zip(ma.parameters(), mb.parameters()):
+        if not torch.allclose(a, b, atol=1e-5, rtol=1e-5):
+            fails += 1
+            log(f"FAIL accumulation under no_sync differs: {(a - b).abs().max().item()}")
+            break
+    ob.zero_grad()
+    loss_of(mb, me, 4).backward()
+    try:
+        loss_of(mb, me, 5).backward()
+        fails += 1
+        log("FAIL a second backward without no_sync() was accepted")
+    except RuntimeError:
+        pass
+    ob.step()  # finish the step on every rank so that the kernel sequences stay matched
+    torch.cuda.synchronize()
+    return fails
+
+
 def run(rt, log):
     fails = 0
     fails += check_pull_publish(rt, log)
     log("pull/publish done, fails =", fails)
     arena = rt.gpu.staging()[0]
     for algo in ["twoshot"] + (["nvls"] if arena.has_multicast else []):
-        fails += check_sma(rt, log, algo)
+        fails += check_sma(rt, log, algo, overlap=True)   # average started by zero_grad(), local blend kernel after backward
+        fails += check_sma(rt, log, algo, overlap=False)  # single fused kernel after backward
     log("sma done, fails =", fails)
+    fails += check_checkpoint(rt, log)
+    log("checkpoint done, fails =", fails)
+    fails += check_accumulation(rt, log)
+    log("accumulation done, fails =", fails)
     fails += check_pair(rt, log)
     log("pair done, fails =", fails)
     return fails

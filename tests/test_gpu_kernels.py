@@ -392,3 +392,84 @@ def test_maxpool3x3s2_matches_torch(plane, N, C, H, W):
     yr.backward(dy)
     assert y.shape == yr.shape and torch.equal(y, yr)
     assert torch.allclose(x.grad.float(), xr.grad.float(), atol=1e-2, rtol=1e-2), (x.grad.float() - xr.grad.float()).abs().max()
+
+
+def test_collective_kernels_on_one_rank_mesh(plane):
+    """all-reduce (one-shot / two-shot / split-phase), fused S-SGD / SMA / PairAveraging, publish / pull (LDG + TMA + retry),
+    broadcast, all-gather, barrier, completion wait: each launched on a one-rank mesh and compared with fp32 PyTorch math."""
+    from kungfu_b200.selftest import run_single_rank_kernels
+
+    res = run_single_rank_kernels(plane, verbose=True)
+    assert not res["fails"], res["fails"]
+    assert len(res["launched"]) >= 14
+
+
+@pytest.mark.parametrize("H", [64, 768, 1024])
+@pytest.mark.parametrize("with_res", [True, False])
+def test_add_layernorm_matches_fp32(H, with_res):
+    """Fused residual + LayerNorm forward/backward vs an fp32 PyTorch reference of the same op."""
+    from kungfu_b200.ops.transformer import add_layernorm
+
+    torch.manual_seed(1)
+    rows = 515
+    x = torch.randn(rows, H, device="cuda").bfloat16().requires_grad_()
+    r = torch.randn(rows, H, device="cuda").bfloat16().requires_grad_() if with_res else None
+    w = (1 + 0.1 * torch.randn(H, device="cuda")).bfloat16().requires_grad_()
+    b = (0.1 * torch.randn(H, device="cuda")).bfloat16().requires_grad_()
+    dy = torch.randn(rows, H, device="cuda").bfloat16()
+    y = add_layernorm(x, r, w, b, 1e-5)
+    y.backward(dy)
+    xf, wf, bf = x.detach().float().requires_grad_(), w.detach().float().requires_grad_(), b.detach().float().requires_grad_()
+    rf = r.detach().float().requires_grad_() if with_res else None
+    zf = ((xf + rf) if with_res else xf).bfloat16().float()  # the kernel rounds the saved sum to storage precision
+    zf = zf + ((xf + rf) if with_res else xf) - ((xf + rf) if with_res else xf).detach()  # keep the graph, use the rounded value
+    yf = torch.nn.functional.layer_norm(zf, (H,), wf, bf, 1e-5)
+    yf.backward(dy.float())
+    assert torch.allclose(y.float(), yf, atol=3e-2, rtol=3e-2)
+    assert torch.allclose(x.grad.float(), xf.grad, atol=3e-2, rtol=3e-2)
+    if with_res:
+        assert torch.equal(x.grad, r.grad)
+    # parameter gradients are sums over 515 rows: compare relative to their scale
+    for got, ref in ((w.grad, wf.grad), (b.grad, bf.grad)):
+        assert (got.float() - ref).abs().max() <= 2e-2 * ref.abs().max() + 1e-2
+
+
+@pytest.mark.parametrize("I", [128, 3072, 4096])
+def test_bias_gelu_matches_fp32(I):
+    from kungfu_b200.ops.transformer import bias_gelu
+
+    torch.manual_seed(2)
+    rows = 300
+    x = torch.randn(rows, I, device="cuda").bfloat16().requires_grad_()
+    b = (0.5 * torch.randn(I, device="cuda")).bfloat16().requires_grad_()
+    dy = torch.randn(rows, I, device="cuda").bfloat16()
+    y = bias_gelu(x, b)
+    y.backward(dy)
+    xf, bf = x.detach().float().requires_grad_(), b.detach().float().requires_grad_()
+    yf = torch.nn.functional.gelu(xf + bf)
+    yf.backward(dy.float())
+    assert torch.allclose(y.float(), yf, atol=2e-2, rtol=2e-2)
+    assert torch.allclose(x.grad.float(), xf.grad, atol=2e-2, rtol=2e-2)
+    assert (b.grad.float() - bf.grad).abs().max() <= 2e-2 * bf.grad.abs().max() + 1e-2
+
+
+def test_bert_fused_ops_match_unfused():
+    """BERT (tiny config, bf16) with the fused residual+LayerNorm / bias+GELU kernels == the same weights through the PyTorch ops."""
+    from kungfu_b200.models import bert
+
+    torch.manual_seed(3)
+    cfg = bert.BertConfig.tiny()
+    m = bert.Bert(cfg).cuda().bfloat16()
+    ids = torch.randint(0, cfg.vocab_size, (4, 32), device="cuda")
+    y = torch.randint(0, 2, (4,), device="cuda")
+    out = {}
+    for fused in (True, False):
+        cfg.fused_ops = fused
+        for l in m.layers:
+            l.fused_ops = fused
+        m.zero_grad()
+        logits = m(ids)
+        torch.nn.functional.cross_entropy(logits.float(), y).backward()
+        out[fused] = (logits.float().clone(), m.layers[0].ff1.bias.grad.float().clone(), m.layers[1].ln2.weight.grad.float().clone())
+    for a, b in zip(out[True], out[False]):
+        assert (a - b).abs().max() <= 5e-2 * b.abs().max() + 2e-2
