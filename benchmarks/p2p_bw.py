@@ -18,7 +18,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 from kungfu_b200.ops import collective as coll  # noqa: E402
 from kungfu_b200.runtime import get_runtime  # noqa: E402
-from kungfu_b200.utils.timing import max_over_ranks  # noqa: E402
+from kungfu_b200.utils.timing import ClockSampler, max_over_ranks  # noqa: E402
 
 
 def main():
@@ -44,6 +44,7 @@ def main():
     torch.cuda.synchronize()
     coll.barrier()
     target = (rt.rank + 1) % N
+    sampler = ClockSampler(rt.cuda_index()).start() if rt.rank == 0 else None
     rows = []
 
     def timed(fn):
@@ -85,7 +86,7 @@ def main():
               f"peak pull bandwidth ldg {max(r['ldg_GBs'] for r in rows)} GB/s, tma {max(r['tma_GBs'] for r in rows)} GB/s", flush=True)
         if args.out:
             with open(args.out, "w") as f:
-                json.dump({"n_gpus": N, "rows": rows}, f, indent=1)
+                json.dump({"n_gpus": N, "rows": rows, "clocks": sampler.stop() if sampler is not None else None}, f, indent=1)
     coll.barrier()
 
 

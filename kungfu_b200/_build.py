@@ -114,8 +114,8 @@ def _compile(src: Path, obj: Path, cmd: list[str], deps: list[Path]) -> bool:
 def build_cuda(verbose: bool = False, force: bool = False) -> Path:
     """Compile every .cu for sm_100a and link `_kfcuda`."""
     out = PKG / ("_kfcuda" + _ext_suffix())
-    kdir, mdir, bdir = CSRC / "kernels", CSRC / "mesh", CSRC / "bindings"
-    hdrs = _headers(kdir, mdir)
+    kdir, mdir, bdir, edir = CSRC / "kernels", CSRC / "mesh", CSRC / "bindings", CSRC / "engine"
+    hdrs = _headers(kdir, mdir, edir)
     jobs = []
     objs = []
     for cu in sorted(kdir.glob("*.cu")):
@@ -129,7 +129,7 @@ def build_cuda(verbose: bool = False, force: bool = False) -> Path:
         jobs.append((cu, obj, cmd))
         objs.append(obj)
     host_inc = ["-I" + str(kdir), "-I" + str(mdir), "-I" + CUDA_HOME + "/include"] + _pybind_includes()
-    for cpp in [mdir / "peer_mesh.cpp", bdir / "cuda_ext.cpp"]:
+    for cpp in [mdir / "peer_mesh.cpp", edir / "grad_engine.cpp", bdir / "cuda_ext.cpp"]:
         obj = OBJ / "cuda" / (cpp.stem + ".o")
         cmd = [CXX] + CXX_FLAGS + host_inc + ["-c", str(cpp), "-o", str(obj)]
         jobs.append((cpp, obj, cmd))
@@ -179,7 +179,8 @@ def build_runtime(verbose: bool = False, force: bool = False) -> Path | None:
     # launcher + tools: every launcher/*.cpp with a main() links against the runtime objects (minus bindings)
     BIN.mkdir(exist_ok=True)
     lib_objs = [str(o) for o in objs if o.stem != "bindings"]
-    for cpp in sorted(ldir.glob("*.cpp")):
+    tdir = CSRC / "tests"
+    for cpp in sorted(ldir.glob("*.cpp")) + sorted(tdir.glob("*.cpp")):
         exe = BIN / cpp.stem.replace("_", "-")
         obj = OBJ / "launcher" / (cpp.stem + ".o")
         c = _compile(cpp, obj, [CXX] + CXX_FLAGS + ["-I" + str(rdir), "-I" + str(ldir), "-c", str(cpp), "-o", str(obj)], hdrs)

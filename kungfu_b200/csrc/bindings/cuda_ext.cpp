@@ -8,6 +8,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include "../engine/grad_engine.h"
 #include "../kernels/kernels.h"
 #include "../mesh/peer_mesh.h"
 
@@ -86,6 +87,32 @@ PYBIND11_MODULE(_kfcuda, m) {
             return d;
         });
 
+    py::class_<GradEngine>(m, "GradEngine")
+        .def(py::init<PeerMesh*, int, bool, bool, int, int, int>(), py::arg("mesh"), py::arg("mode"), py::arg("average"), py::arg("gated"),
+             py::arg("max_blocks"), py::arg("threads"), py::arg("algo"), py::keep_alive<1, 2>())
+        .def("add_set", &GradEngine::add_set)
+        .def("add_bucket", &GradEngine::add_bucket)
+        .def("add_entry", &GradEngine::add_entry)
+        .def("set_bucket_state", &GradEngine::set_bucket_state)
+        .def("set_monitor", &GradEngine::set_monitor)
+        .def("set_comm_stream", &GradEngine::set_comm_stream)
+        .def("set_deferred", &GradEngine::set_deferred)
+        .def("open_step", [](GradEngine& e, uintptr_t st) { e.open_step(S(st)); })
+        .def("grad_ready", [](GradEngine& e, int set, int entry, uintptr_t grad, uintptr_t st) { return e.grad_ready(set, entry, P<const void>(grad), S(st)); })
+        .def("flush", [](GradEngine& e, uintptr_t st, bool zero_missing) { e.flush(S(st), zero_missing); })
+        .def("finish", [](GradEngine& e, uintptr_t st) { return e.finish(S(st)); })
+        .def_property_readonly("launches", &GradEngine::launches)
+        .def_property_readonly("nranks", &GradEngine::nranks);
+    m.attr("MODE_SSGD") = (int)kModeSsgd;
+    m.attr("MODE_GRADS") = (int)kModeGrads;
+    m.def("multi_copy", [](const std::vector<uintptr_t>& src, const std::vector<uintptr_t>& dst, const std::vector<size_t>& nbytes, uintptr_t st) {
+        if (src.size() != dst.size() || src.size() != nbytes.size()) throw std::runtime_error("kungfu_b200: multi_copy lists differ in length");
+        std::vector<const void*> s(src.size());
+        std::vector<void*> d(dst.size());
+        for (size_t i = 0; i < src.size(); ++i) s[i] = P<const void>(src[i]), d[i] = P<void>(dst[i]);
+        launch_multi_copy(s.data(), d.data(), nbytes.data(), (int)src.size(), S(st));
+    });
+
     m.def("launch_count", &launch_count);
     m.def("nvls_supported", &nvls_supported);
 
@@ -101,6 +128,12 @@ PYBIND11_MODULE(_kfcuda, m) {
              float scale, uintptr_t sumsq, int flags, int blocks, int threads, uintptr_t st) {
               launch_allreduce(algo, mesh.args(channel), off, nullptr, nbytes, dtype, op, scale, P<float>(sumsq), flags, blocks,
                                threads, S(st), out_off);
+          });
+    m.def("allreduce_ll_slot_bytes", &allreduce_ll_slot_bytes);
+    m.def("allreduce_ll",
+          [](const PeerMesh& mesh, int channel, uintptr_t in, uintptr_t out, size_t nbytes, size_t slot_off, size_t max_payload, int dtype, int op,
+             float scale, int flags, uintptr_t st) {
+              launch_allreduce_ll(mesh.args(channel), P<const void>(in), P<void>(out), nbytes, slot_off, max_payload, dtype, op, scale, flags, S(st));
           });
     m.def("wait_done", [](const PeerMesh& mesh, int channel, int word, uint32_t add, uintptr_t st) {
         launch_wait_done(mesh.args(channel), word, add, S(st));

@@ -223,6 +223,174 @@ __global__ void __launch_bounds__(512) allreduce_nvls_kernel(const __grid_consta
     store_seq(m, seq);
 }
 
+
+// --------------------------------------------------------------------------------------------
+// LL one-shot: flag-carrying pushes, no barrier at all (latency path for small messages)
+// --------------------------------------------------------------------------------------------
+// Every rank PUSHES its message into a slot of every peer as 16-byte lines {data, flag, data, flag} (8 payload bytes per
+// line, each 8-byte half validated by its own flag word — no reliance on 16-byte store atomicity), then polls its own slots
+// until the lines of all N ranks carry this operation's flag, reduces them in rank order (bit-identical results everywhere)
+// and writes the result straight into the user tensor. One NVLink one-way trip instead of barrier + load round trip + barrier.
+// Two slot sets alternate by operation parity: a rank can start operation k+2 (which reuses the slots of k) only after it has
+// received every peer's data of k+1, and a peer sends that only after it has finished reading k — so no trailing barrier is
+// needed either. The operation counter lives in m.seq[kMaxBlocks + 1]; the last block to finish bumps it (ticket in +2), the
+// next launch on the stream reads the new value.
+struct LlArgs {
+    const void* in;   // local input (any device memory, 8-byte aligned)
+    void* out;        // local output
+    size_t slot_off;  // arena offset of the slot area: [2 parities][kMaxRanks][max_lines] 16-byte lines
+    size_t max_lines; // capacity of one (parity, rank) slot
+    size_t nlines;    // 8-byte payload groups in this message
+    float scale;
+    int flags;
+};
+
+__device__ __forceinline__ void st_volatile_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void ld_volatile_v4(const void* p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+}
+
+template <typename T> struct Half8 { // 8 payload bytes as elements of T with their accumulator type
+    static constexpr int kN = 8 / sizeof(T);
+    typename Elem<T>::Acc a[kN];
+};
+template <typename T> __device__ __forceinline__ Half8<T> unpack_half(uint32_t lo, uint32_t hi) {
+    uint32_t w[2] = {lo, hi};
+    Half8<T> r;
+    const T* e = reinterpret_cast<const T*>(w);
+#pragma unroll
+    for (int i = 0; i < Half8<T>::kN; ++i) r.a[i] = Elem<T>::up(e[i]);
+    return r;
+}
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(512) allreduce_ll_kernel(const __grid_constant__ MeshArgs m, const __grid_constant__ LlArgs a) {
+    const uint32_t op = m.seq[kMaxBlocks + 1] + 1u; // flag of this operation (never 0: slots start zeroed)
+    const size_t par = op & 1u;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t slot_lines = a.max_lines;
+    // ---- push my lines to every rank (own slot included: the reduce below treats all N sources alike)
+    const uint2* in = reinterpret_cast<const uint2*>(a.in);
+    for (size_t i = tid; i < a.nlines; i += stride) {
+        const uint2 d = in[i];
+#pragma unroll
+        for (int k = 0; k < kMaxRanks; ++k) {
+            if (k < m.nranks) {
+                int r = m.rank + k;
+                if (r >= m.nranks) r -= m.nranks;
+                char* dst = reinterpret_cast<char*>(m.data[r]) + a.slot_off + ((par * kMaxRanks + (size_t)m.rank) * slot_lines + i) * 16;
+                st_volatile_v4(dst, d.x, op, d.y, op);
+            }
+        }
+    }
+    // ---- poll + reduce in rank order
+    uint2* out = reinterpret_cast<uint2*>(a.out);
+    const char* mine = reinterpret_cast<const char*>(m.data[m.rank]) + a.slot_off + par * kMaxRanks * slot_lines * 16;
+    for (size_t i = tid; i < a.nlines; i += stride) {
+        Half8<T> acc;
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r) {
+            if (r < m.nranks) {
+                const char* src = mine + ((size_t)r * slot_lines + i) * 16;
+                uint32_t d0, f0, d1, f1;
+                ld_volatile_v4(src, d0, f0, d1, f1);
+                if (f0 != op || f1 != op) {
+                    const unsigned long long t0 = global_ns();
+                    uint32_t iters = 0;
+                    bool dead = m.status && *((volatile uint32_t*)&m.status[0]) != 0u;
+                    while (!dead) {
+                        ld_volatile_v4(src, d0, f0, d1, f1);
+                        if (f0 == op && f1 == op) break;
+                        if (((++iters) & 0x3ff) == 0 && global_ns() - t0 > m.timeout_ns) {
+                            if (m.status) {
+                                m.status[1] = ((uint32_t)m.rank << 16) | (uint32_t)r;
+                                m.status[3] = op;
+                                m.status[4] = f0;
+                                m.status[2] = m.status[2] + 1u;
+                                *((volatile uint32_t*)&m.status[0]) = kErrBarrierTimeout;
+                                __threadfence_system();
+                            }
+                            dead = true;
+                        }
+                    }
+                }
+                const Half8<T> x = unpack_half<T>(d0, d1);
+                if (r == 0) acc = x;
+                else {
+#pragma unroll
+                    for (int j = 0; j < Half8<T>::kN; ++j) acc.a[j] = red_apply<OP>(acc.a[j], x.a[j]);
+                }
+            }
+        }
+        if constexpr (IsFloatAcc<T>::value) {
+            if (a.flags & kArScale) {
+#pragma unroll
+                for (int j = 0; j < Half8<T>::kN; ++j) acc.a[j] = (typename Elem<T>::Acc)(acc.a[j] * a.scale);
+            }
+        }
+        uint32_t w[2];
+        T* e = reinterpret_cast<T*>(w);
+#pragma unroll
+        for (int j = 0; j < Half8<T>::kN; ++j) e[j] = Elem<T>::down(acc.a[j]);
+        out[i] = make_uint2(w[0], w[1]);
+    }
+    // ---- last block out advances the operation counter
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t prev = atomicAdd(&m.seq[kMaxBlocks + 2], 1u);
+        if (prev == gridDim.x - 1) {
+            m.seq[kMaxBlocks + 2] = 0u;
+            m.seq[kMaxBlocks + 1] = op;
+        }
+    }
+}
+
+template <typename T> static void launch_ll_op(int op, const MeshArgs& m, const LlArgs& a, int blocks, int threads, cudaStream_t st) {
+    switch (op) {
+    case kSum: allreduce_ll_kernel<T, kSum><<<blocks, threads, 0, st>>>(m, a); break;
+    case kMin: allreduce_ll_kernel<T, kMin><<<blocks, threads, 0, st>>>(m, a); break;
+    case kMax: allreduce_ll_kernel<T, kMax><<<blocks, threads, 0, st>>>(m, a); break;
+    case kProd: allreduce_ll_kernel<T, kProd><<<blocks, threads, 0, st>>>(m, a); break;
+    default: throw std::runtime_error("kungfu_b200: bad reduce op");
+    }
+}
+
+size_t allreduce_ll_slot_bytes(size_t max_payload_bytes) { return 2 * (size_t)kMaxRanks * ((max_payload_bytes + 7) / 8) * 16; }
+
+void launch_allreduce_ll(const MeshArgs& m, const void* in, void* out, size_t nbytes, size_t slot_off, size_t max_payload_bytes, int dtype,
+                         int op, float scale, int flags, cudaStream_t st) {
+    if (nbytes == 0) return;
+    if (nbytes % 8 != 0 || ((uintptr_t)in % 8) || ((uintptr_t)out % 8)) throw std::runtime_error("kungfu_b200: LL all-reduce needs 8-byte aligned, 8-byte padded messages");
+    if (nbytes > max_payload_bytes) throw std::runtime_error("kungfu_b200: message exceeds the LL slot");
+    if (slot_off % 16) throw std::runtime_error("kungfu_b200: LL slot area must be 16-byte aligned");
+    LlArgs a{in, out, slot_off, (max_payload_bytes + 7) / 8, nbytes / 8, scale, flags};
+    const int threads = a.nlines <= 128 ? 128 : 512;
+    int blocks = (int)((a.nlines + threads - 1) / threads);
+    if (blocks > 16) blocks = 16; // enough stores in flight for 64 KiB; more CTAs only add scheduling latency
+    if (blocks < 1) blocks = 1;
+    switch (dtype) {
+    case kF32: launch_ll_op<float>(op, m, a, blocks, threads, st); break;
+    case kBF16: launch_ll_op<__nv_bfloat16>(op, m, a, blocks, threads, st); break;
+    case kF16: launch_ll_op<__half>(op, m, a, blocks, threads, st); break;
+    case kF64: launch_ll_op<double>(op, m, a, blocks, threads, st); break;
+    case kI32: launch_ll_op<int32_t>(op, m, a, blocks, threads, st); break;
+    case kI64: launch_ll_op<int64_t>(op, m, a, blocks, threads, st); break;
+    case kU8: launch_ll_op<uint8_t>(op, m, a, blocks, threads, st); break;
+    case kI8: launch_ll_op<int8_t>(op, m, a, blocks, threads, st); break;
+    case kU32: launch_ll_op<uint32_t>(op, m, a, blocks, threads, st); break;
+    case kU64: launch_ll_op<uint64_t>(op, m, a, blocks, threads, st); break;
+    case kI16: launch_ll_op<int16_t>(op, m, a, blocks, threads, st); break;
+    case kU16: launch_ll_op<uint16_t>(op, m, a, blocks, threads, st); break;
+    default: throw std::runtime_error("kungfu_b200: unsupported dtype");
+    }
+    count_launch();
+    KF_CUDA_CHECK(cudaGetLastError());
+}
+
 // --------------------------------------------------------------------------------------------
 // host dispatch
 // --------------------------------------------------------------------------------------------

@@ -31,6 +31,10 @@ enum HyperSlot : int {
 void launch_allreduce(int algo, const MeshArgs& m, size_t off, void* out, size_t nbytes, int dtype, int op, float scale,
                       float* sumsq, int flags, int blocks, int threads, cudaStream_t st, size_t out_off = (size_t)-1);
 bool nvls_supported(int dtype, int op);
+// LL one-shot (flag-carrying pushes, no barrier): reads `in` / writes `out` (local tensors) directly, slot area in the arena
+size_t allreduce_ll_slot_bytes(size_t max_payload_bytes);
+void launch_allreduce_ll(const MeshArgs& m, const void* in, void* out, size_t nbytes, size_t slot_off, size_t max_payload_bytes, int dtype,
+                         int op, float scale, int flags, cudaStream_t st);
 
 // ---- fused_step.cu
 // S-SGD: reduce-scatter(grads) -> optimizer on the owned shard (fp32 master/state) -> all-gather(params).
@@ -103,6 +107,9 @@ void launch_gns_finalize(const float* sums, float* state, float* out, float batc
 void launch_u8_normalize(const uint8_t* src, void* dst, int dst_dtype, size_t npix, const float* mean3,
                          const float* invstd3, cudaStream_t st);
 void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t st);
+// n (src -> dst, nbytes) copies in one launch per 48 tensors (gradient hand-over into the flat arena)
+constexpr int kMaxCopyBatch = 48;
+void launch_multi_copy(const void* const* src, void* const* dst, const size_t* nbytes, int n, cudaStream_t st);
 
 // ---- bn_act.cu: fused BatchNorm (+residual) + ReLU on channels_last activations
 int bn_num_blocks(size_t rows, int C);

@@ -309,3 +309,54 @@ void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t st) {
 }
 
 } // namespace kf
+
+// ---- multi-tensor copy: the stolen gradients of one bucket -> their slots of the flat arena, ONE launch ----------------
+// (reference: gradient `fuse` = tf.concat of every gradient, srcs/python/kungfu/tensorflow/ops/__init__.py:29-46)
+namespace kf {
+
+struct CopyBatch {
+    const void* src[kMaxCopyBatch];
+    void* dst[kMaxCopyBatch];
+    unsigned long long nbytes[kMaxCopyBatch];
+    int n;
+};
+
+__global__ void __launch_bounds__(256) multi_copy_kernel(const __grid_constant__ CopyBatch b) {
+    // blockIdx.y = tensor, blockIdx.x strides over its 16-byte vectors; ragged heads/tails go byte-wise
+    const int t = blockIdx.y;
+    if (t >= b.n) return;
+    const char* s = reinterpret_cast<const char*>(b.src[t]);
+    char* d = reinterpret_cast<char*>(b.dst[t]);
+    const size_t nb = b.nbytes[t];
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+        const size_t nv = nb / 16;
+        for (size_t v = tid; v < nv; v += stride) st_plain(d + v * 16, ld_ro_stream(s + v * 16));
+        for (size_t i = nv * 16 + tid; i < nb; i += stride) d[i] = s[i];
+    } else {
+        for (size_t i = tid; i < nb; i += stride) d[i] = s[i];
+    }
+}
+
+void launch_multi_copy(const void* const* src, void* const* dst, const size_t* nbytes, int n, cudaStream_t st) {
+    for (int base = 0; base < n; base += kMaxCopyBatch) {
+        CopyBatch b{};
+        b.n = n - base < kMaxCopyBatch ? n - base : kMaxCopyBatch;
+        size_t big = 0;
+        for (int i = 0; i < b.n; ++i) {
+            b.src[i] = src[base + i];
+            b.dst[i] = dst[base + i];
+            b.nbytes[i] = nbytes[base + i];
+            if (nbytes[base + i] > big) big = nbytes[base + i];
+        }
+        int gx = (int)((big / 16 + 255) / 256);
+        if (gx < 1) gx = 1;
+        if (gx > 64) gx = 64;
+        multi_copy_kernel<<<dim3(gx, b.n), 256, 0, st>>>(b);
+        count_launch();
+    }
+    KF_CUDA_CHECK(cudaGetLastError());
+}
+
+} // namespace kf

@@ -1,0 +1,309 @@
+// kungfu_b200 — C++ unit tests of the native runtime, independent of Python (the pybind layer is tested by pytest).
+//
+// Counterpart of the reference's gtest suite (tests/cpp/unit/test_{kungfu,kungfu_world,operations,mst,placement}.cpp,
+// srcs/cmake/tests.cmake:58-63) and of its Go unit tests for the pieces that are C++ here (plan/topology_test.go,
+// plan/{cluster,hostspec}_test.go, plan/hostfile/hostfile_test.go, plan/graph/graph_test.go, store/versionedstore_test.go).
+// No framework dependency: CHECK records a failure with file:line, main() prints a summary and returns the failure count.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <numeric>
+#include <random>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "base.hpp"
+#include "graph.hpp"
+#include "numa.hpp"
+#include "peer.hpp"
+#include "plan.hpp"
+#include "reduce.hpp"
+#include "store.hpp"
+
+using namespace kfrt;
+
+static int g_fail = 0, g_checks = 0;
+#define CHECK(cond)                                                                  \
+    do {                                                                             \
+        ++g_checks;                                                                  \
+        if (!(cond)) {                                                               \
+            ++g_fail;                                                                \
+            std::fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond);     \
+        }                                                                            \
+    } while (0)
+#define CHECK_THROWS(expr)                                                           \
+    do {                                                                             \
+        ++g_checks;                                                                  \
+        bool threw = false;                                                          \
+        try {                                                                        \
+            (void)(expr);                                                            \
+        } catch (const std::exception&) {                                            \
+            threw = true;                                                            \
+        }                                                                            \
+        if (!threw) {                                                                \
+            ++g_fail;                                                                \
+            std::fprintf(stderr, "FAIL %s:%d: expected an exception: %s\n", __FILE__, __LINE__, #expr); \
+        }                                                                            \
+    } while (0)
+
+static PeerList peers_on(std::vector<std::pair<const char*, int>> hosts) {
+    PeerList pl;
+    for (auto& h : hosts)
+        for (int i = 0; i < h.second; ++i) pl.push_back(PeerID{parse_ipv4(h.first), (uint16_t)(10000 + i)});
+    return pl;
+}
+
+// ---- dtype sizes / reduce kernels (test_operations.cpp) ---------------------------------------------------------------
+static void test_dtypes_and_transform2() {
+    CHECK(dtype_size(kF32) == 4 && dtype_size(kBF16) == 2 && dtype_size(kF16) == 2 && dtype_size(kI64) == 8 && dtype_size(kU8) == 1 &&
+          dtype_size(kF64) == 8 && dtype_size(kI16) == 2);
+    std::mt19937 rng(7);
+    for (size_t n : {1, 7, 64, 1000, 4099}) {
+        std::vector<float> x(n), y(n), z(n);
+        for (size_t i = 0; i < n; ++i) x[i] = (float)(rng() % 100) / 7.f, y[i] = (float)(rng() % 100) / 3.f;
+        transform2(z.data(), x.data(), y.data(), n, kF32, kSum);
+        bool ok = true;
+        for (size_t i = 0; i < n; ++i) ok = ok && z[i] == x[i] + y[i];
+        CHECK(ok);
+        transform2(z.data(), x.data(), y.data(), n, kF32, kMax);
+        ok = true;
+        for (size_t i = 0; i < n; ++i) ok = ok && z[i] == std::max(x[i], y[i]);
+        CHECK(ok);
+        std::vector<int32_t> a(n), b(n), c(n);
+        for (size_t i = 0; i < n; ++i) a[i] = (int32_t)(rng() % 1000) - 500, b[i] = (int32_t)(rng() % 1000) - 500;
+        transform2(c.data(), a.data(), b.data(), n, kI32, kMin);
+        ok = true;
+        for (size_t i = 0; i < n; ++i) ok = ok && c[i] == std::min(a[i], b[i]);
+        CHECK(ok);
+        transform2(c.data(), a.data(), b.data(), n, kI32, kProd);
+        ok = true;
+        for (size_t i = 0; i < n; ++i) ok = ok && c[i] == a[i] * b[i];
+        CHECK(ok);
+        // 16-bit floats: sum in fp32, rounded once (the reference sums bf16 as IEEE half by mistake, tensorflow/ops.h:21-22)
+        std::vector<uint16_t> hx(n), hy(n), hz(n), bx(n), by(n), bz(n);
+        for (size_t i = 0; i < n; ++i) {
+            hx[i] = float_to_half(x[i]), hy[i] = float_to_half(y[i]);
+            bx[i] = float_to_bf16(x[i]), by[i] = float_to_bf16(y[i]);
+        }
+        transform2(hz.data(), hx.data(), hy.data(), n, kF16, kSum);
+        transform2(bz.data(), bx.data(), by.data(), n, kBF16, kSum);
+        ok = true;
+        for (size_t i = 0; i < n; ++i) {
+            ok = ok && hz[i] == float_to_half(half_to_float(hx[i]) + half_to_float(hy[i]));
+            ok = ok && bz[i] == float_to_bf16(bf16_to_float(bx[i]) + bf16_to_float(by[i]));
+        }
+        CHECK(ok);
+    }
+    CHECK(half_to_float(float_to_half(1.5f)) == 1.5f && bf16_to_float(float_to_bf16(-2.0f)) == -2.0f);
+}
+
+// ---- plan: ids, host specs, peer lists, cluster resize (plan/*_test.go) ----------------------------------------------
+static void test_plan() {
+    CHECK(format_ipv4(parse_ipv4("10.1.2.3")) == "10.1.2.3");
+    CHECK_THROWS(parse_ipv4("10.1.2"));
+    const PeerID p = PeerID::parse("192.168.1.7:10003");
+    CHECK(p.port == 10003 && p.str() == "192.168.1.7:10003");
+    const HostList hl = HostList::parse("10.0.0.1:4,10.0.0.2:2:pub.example");
+    CHECK(hl.size() == 2 && hl.cap() == 6 && hl[1].public_addr == "pub.example");
+    const PeerList pl = hl.gen_peer_list(5, PortRange{});
+    CHECK(pl.size() == 5 && pl[0].port == 10000 && pl[3].port == 10003 && pl[4].ipv4 == parse_ipv4("10.0.0.2") && pl[4].port == 10000);
+    CHECK_THROWS(hl.gen_peer_list(7, PortRange{}));
+    CHECK(pl.rank_of(pl[4]) == 4 && pl.local_rank_of(pl[4]) == 0 && pl.local_size_of(pl[0]) == 4 && pl.host_count() == 2);
+    std::vector<int> masters, parents;
+    pl.partition_by_host(masters, parents);
+    CHECK(masters == std::vector<int>({0, 4}) && parents == std::vector<int>({0, 0, 0, 0, 4}));
+    CHECK(PeerList::parse(pl.str()) == pl);
+    const HostList hf = HostList::parse_hostfile("# comment\n10.0.0.1 slots=4\n\n10.0.0.2 slots=2\n");
+    CHECK(hf.size() == 2 && hf.cap() == 6);
+    const PortRange pr = PortRange::parse("20000-20009");
+    CHECK(pr.cap() == 10 && pr.str() == "20000-20009");
+    // cluster: validate, shrink keeps the prefix, grow lands on the least-loaded host with port = max + 1
+    Cluster c;
+    c.runners = hl.gen_runner_list(kDefaultRunnerPort);
+    c.workers = hl.gen_peer_list(3, PortRange{});
+    c.validate();
+    const Cluster shr = c.resized(2);
+    CHECK(shr.workers.size() == 2 && shr.workers[0] == c.workers[0] && shr.workers[1] == c.workers[1]);
+    const Cluster gr = c.resized(5);
+    CHECK(gr.workers.size() == 5);
+    CHECK(gr.workers[3].ipv4 == parse_ipv4("10.0.0.2") && gr.workers[4].ipv4 == parse_ipv4("10.0.0.2")); // host 2 had 0 workers
+    gr.validate();
+    CHECK(Cluster::from_json(gr.to_json()) == gr);
+    CHECK(c.digest() != gr.digest());
+    Cluster bad = c;
+    bad.workers.push_back(bad.workers[0]); // duplicate worker
+    CHECK_THROWS(bad.validate());
+    Stage st{3, gr};
+    CHECK(Stage::from_json(st.to_json()).version == 3 && Stage::from_json(st.to_json()).cluster == gr);
+    // even partition covers [0, n) exactly
+    for (size_t n : {0, 1, 10, 1023}) {
+        for (size_t k : {1, 3, 8}) {
+            size_t at = 0;
+            bool ok = true;
+            for (size_t i = 0; i < k; ++i) {
+                auto be = even_partition(n, k, i);
+                ok = ok && be.first == at && be.second >= be.first;
+                at = be.second;
+            }
+            CHECK(ok && at == n);
+        }
+    }
+}
+
+// ---- topology generators yield rooted trees (plan/topology_test.go:14-98) ---------------------------------------------
+static void test_topologies() {
+    const std::vector<PeerList> shapes = {peers_on({{"10.0.0.1", 1}}), peers_on({{"10.0.0.1", 4}}), peers_on({{"10.0.0.1", 3}, {"10.0.0.2", 3}}),
+                                          peers_on({{"10.0.0.1", 4}, {"10.0.0.2", 2}, {"10.0.0.3", 1}}),
+                                          peers_on({{"10.0.0.1", 2}, {"10.0.0.2", 2}, {"10.0.0.3", 2}, {"10.0.0.4", 2}})};
+    for (auto& pl : shapes) {
+        const int n = (int)pl.size();
+        for (auto& name : strategy_names()) {
+            const Strategy s = parse_strategy(name);
+            auto sl = gen_global_strategies(pl, s);
+            CHECK(!sl.empty());
+            for (auto& gp : sl) {
+                CHECK(gp.bcast.size() == n && gp.reduce.size() == n);
+                // the broadcast graph is a tree rooted somewhere that reaches everybody; the reduce graph is its reverse + self loops
+                int roots = 0, root = -1;
+                for (int i = 0; i < n; ++i)
+                    if (gp.bcast.prevs(i).empty()) ++roots, root = i;
+                CHECK(roots == 1);
+                if (roots == 1) CHECK(gp.bcast.is_rooted_tree(root));
+                // the reduce graph funnels every node into the SAME root (reversed: a tree rooted there) and every node folds
+                // its own contribution in (self loop)
+                bool loops = true;
+                for (int i = 0; i < n; ++i) loops = loops && gp.reduce.is_self_loop(i);
+                CHECK(loops);
+                if (roots == 1) CHECK(gp.reduce.reversed().is_rooted_tree(root));
+            }
+            CHECK(digest_strategies(sl) == digest_strategies(gen_global_strategies(pl, s)));
+        }
+        CHECK(auto_select(pl) == (pl.host_count() == 1 ? Strategy::Star : Strategy::BinaryTreeStar));
+    }
+    CHECK_THROWS(parse_strategy("NO_SUCH_STRATEGY"));
+    // forest arrays (set_tree): valid forest, cycle, out of range
+    Graph g;
+    int roots = 0;
+    CHECK(Graph::from_forest_array({0, 0, 1, 1, 0}, g, roots) && roots == 1 && g.is_rooted_tree(0));
+    CHECK(Graph::from_forest_array({0, 1, 0, 1}, g, roots) && roots == 2);
+    CHECK(!Graph::from_forest_array({1, 0}, g, roots));
+    CHECK(!Graph::from_forest_array({0, 7}, g, roots));
+}
+
+// ---- MST (test_mst.cpp): Prim on random symmetric weights equals the brute-force optimum for small n ----------------
+static double tree_weight(const std::vector<std::pair<int, int>>& edges, const std::vector<double>& w, int n) {
+    double t = 0;
+    for (auto& e : edges) t += w[(size_t)e.first * n + e.second];
+    return t;
+}
+static void test_mst() {
+    std::mt19937 rng(11);
+    for (int n = 1; n <= 7; ++n) {
+        std::vector<double> w((size_t)n * n, 0.0);
+        for (int i = 0; i < n; ++i)
+            for (int j = i + 1; j < n; ++j) w[(size_t)i * n + j] = w[(size_t)j * n + i] = 1.0 + (double)(rng() % 1000) / 10.0;
+        auto edges = minimum_spanning_tree(w, n);
+        CHECK((int)edges.size() == n - 1);
+        // spanning: union-find
+        std::vector<int> uf(n);
+        std::iota(uf.begin(), uf.end(), 0);
+        std::function<int(int)> find = [&](int x) { return uf[x] == x ? x : uf[x] = find(uf[x]); };
+        for (auto& e : edges) uf[find(e.first)] = find(e.second);
+        bool spanning = true;
+        for (int i = 0; i < n; ++i) spanning = spanning && find(i) == find(0);
+        CHECK(spanning);
+        // optimal: compare with Kruskal
+        std::vector<std::tuple<double, int, int>> all;
+        for (int i = 0; i < n; ++i)
+            for (int j = i + 1; j < n; ++j) all.emplace_back(w[(size_t)i * n + j], i, j);
+        std::sort(all.begin(), all.end());
+        std::iota(uf.begin(), uf.end(), 0);
+        double best = 0;
+        for (auto& t : all) {
+            int a = find(std::get<1>(t)), b = find(std::get<2>(t));
+            if (a != b) uf[a] = b, best += std::get<0>(t);
+        }
+        CHECK(std::fabs(tree_weight(edges, w, n) - best) < 1e-9);
+        auto fa = mst_forest_array(w, n, 0);
+        Graph g;
+        int roots = 0;
+        CHECK((int)fa.size() == n && Graph::from_forest_array(fa, g, roots) && roots == 1 && fa[0] == 0);
+    }
+}
+
+// ---- NUMA placement (test_placement.cpp) ----------------------------------------------------------------------------
+static void test_placement() {
+    std::vector<std::vector<int>> numa = {{0, 1, 2, 3, 4, 5, 6, 7}, {8, 9, 10, 11, 12, 13, 14, 15}};
+    std::set<int> seen;
+    for (int r = 0; r < 4; ++r) {
+        auto cpus = select_cpus(numa, r, 4);
+        CHECK(cpus.size() == 4);
+        // contiguous slice inside ONE node, disjoint from the other ranks
+        bool one_node = true;
+        for (int c : cpus) one_node = one_node && (c / 8 == cpus[0] / 8);
+        CHECK(one_node);
+        for (int c : cpus) CHECK(seen.insert(c).second);
+    }
+    CHECK(seen.size() == 16);
+    CHECK(select_cpus(numa, 0, 1).size() == 16 || select_cpus(numa, 0, 1).size() == 8);
+    CHECK(!numa_topology().empty());
+}
+
+// ---- stores (store/versionedstore_test.go) ---------------------------------------------------------------------------
+static void test_stores() {
+    Store s;
+    const char a[] = "hello", b[] = "world";
+    s.save("x", a, 5);
+    CHECK(s.get("x") && s.get("x")->data.size() == 5 && std::memcmp(s.get("x")->data.data(), a, 5) == 0);
+    s.save("x", b, 5);
+    CHECK(std::memcmp(s.get("x")->data.data(), b, 5) == 0);
+    CHECK_THROWS(s.save("x", a, 3)); // size conflict
+    CHECK(s.get("missing") == nullptr && s.size() == 1);
+    VersionedStore vs(3);
+    for (int v = 0; v < 5; ++v) vs.save(std::to_string(v), "m", a, 5);
+    CHECK(vs.versions().size() == 3 && vs.get("0", "m") == nullptr && vs.get("1", "m") == nullptr && vs.get("4", "m") != nullptr);
+    CHECK(vs.get("4", "other") == nullptr);
+}
+
+// ---- a Peer in single-process mode can be built and torn down twice, collectives with np=1 are identities (test_kungfu.cpp) ----
+static void test_single_process_peer() {
+    for (int round = 0; round < 2; ++round) {
+        for (const char* k : {"KUNGFU_SELF_SPEC", "KUNGFU_INIT_PEERS", "RANK", "WORLD_SIZE", "LOCAL_RANK"}) unsetenv(k);
+        PeerConfig cfg = PeerConfig::from_env(); // nothing in the environment: single-process mode
+        CHECK(cfg.single);
+        Peer p(cfg);
+        p.start();
+        auto sess = p.session();
+        CHECK(sess->rank() == 0 && sess->size() == 1 && !p.detached());
+        std::vector<float> x = {1.f, 2.f, 3.f}, y(3, 0.f);
+        Workspace w{x.data(), y.data(), 3, kF32, kSum, "t"};
+        sess->all_reduce(w);
+        CHECK(y == x);
+        sess->barrier();
+        p.close();
+    }
+}
+
+int main() {
+    struct {
+        const char* name;
+        void (*fn)();
+    } tests[] = {{"dtypes_and_transform2", test_dtypes_and_transform2}, {"plan", test_plan}, {"topologies", test_topologies}, {"mst", test_mst},
+                 {"placement", test_placement}, {"stores", test_stores}, {"single_process_peer", test_single_process_peer}};
+    for (auto& t : tests) {
+        const int before = g_fail;
+        try {
+            t.fn();
+        } catch (const std::exception& e) {
+            ++g_fail;
+            std::fprintf(stderr, "FAIL %s: uncaught exception: %s\n", t.name, e.what());
+        }
+        std::printf("[%s] %s\n", g_fail == before ? " OK " : "FAIL", t.name);
+    }
+    std::printf("%d checks, %d failures\n", g_checks, g_fail);
+    return g_fail ? 1 : 0;
+}

@@ -5,7 +5,8 @@ API parity: `kungfu.torch.ops.{all_reduce_fn,inplace_all_reduce_op,inplace_all_r
 wait_all_handles,all_gather,broadcast_parameters}` (srcs/python/kungfu/torch/ops/collective.py:8-55) and the TF
 ops `barrier/consensus/broadcast/all_reduce/all_gather` (srcs/python/kungfu/tensorflow/ops/collective.py:8-133).
 
-Algorithm table (KUNGFU_CONFIG_ALGO = auto | oneshot | twoshot | nvls):
+Algorithm table (KUNGFU_CONFIG_ALGO = auto | ll | oneshot | twoshot | nvls):
+  <= 64 KiB (8-byte aligned) : LL one-shot — flag-carrying pushes straight from / into the user tensor, no barrier, no staging
   <= oneshot_max bytes  : one-shot (every rank reduces the whole message; latency path)
   larger                : NVLS multimem reduce+multicast when the mesh has a multicast mapping and the
                           dtype/op is switch-reducible, else two-shot P2P.
@@ -40,7 +41,7 @@ def pick_algo(arena, nbytes: int, dtype_code: int, op_code: int, inplace: bool, 
     """Returns the kernel algorithm code for a message."""
     ext = arena.ext
     name = (force or CONFIG.algo).lower()
-    if name == "nccl":
+    if name in ("nccl", "ll"):
         name = "auto"
     if name != "auto":
         code = _ALGO_CODE[name]
@@ -124,6 +125,13 @@ def _gpu_all_reduce_(x: torch.Tensor, op_code: int, average: bool, stream: Optio
     _count_gpu_bytes("all_reduce", n * esize)
     if plane.spans_hosts:
         _gpu_all_reduce_hier_(plane, flat, op_code, average, st, algo)
+        return
+    nbytes = n * esize
+    if (nbytes <= plane.ll_max and nbytes % 8 == 0 and flat.data_ptr() % 8 == 0 and (algo or CONFIG.algo).lower() in ("auto", "ll")
+            and os.environ.get("KUNGFU_DISABLE_LL", "0") != "1"):
+        # latency path: flag-carrying pushes straight from / into the user tensor — no staging copy, no barrier
+        ext.allreduce_ll(arena.mesh, 0, flat.data_ptr(), flat.data_ptr(), nbytes, plane.ll_off, plane.ll_max, dt, op_code, scale, flags,
+                         st.cuda_stream)
         return
     with torch.cuda.stream(st):
         for lo in range(0, n, chunk_elems):

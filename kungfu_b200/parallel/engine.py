@@ -146,10 +146,40 @@ class FlatEngine:
         self._pending = [[[] for _ in s.layout.buckets] for s in self.sets]
         self._got = [[False] * len(s.layout.entries) for s in self.sets]
         self.plane.engines.append(self)
+        # The native GradEngine (csrc/engine/grad_engine.cpp) owns the hot path of the bucketed modes: hand-over of stolen
+        # gradients (one multi-tensor copy per bucket), bucket counting, in-order launches, stream/event wiring. Python keeps
+        # what needs Python objects (re-pointing .grad), the NCCL baseline arm and the membership / state management.
+        self._native = None
+        if self.mode in ("ssgd", "grads") and self.backend == "kernels" and os.environ.get("KUNGFU_NATIVE_ENGINE", "1") != "0":
+            self._build_native()
         if self.overlap:
             self._install_hooks()
 
     # ---------------------------------------------------------------------------------------------
+    def _build_native(self) -> None:
+        ext = self.ext
+        algo = {"twoshot": ext.ALGO_TWOSHOT, "nvls": ext.ALGO_NVLS}.get((self.algo or coll.CONFIG.algo).lower(), ext.ALGO_AUTO)
+        kind = ext.OPT_ADAM if self.opt_kind == "adam" else ext.OPT_SGD
+        ne = ext.GradEngine(self.arena.mesh, ext.MODE_SSGD if self.mode == "ssgd" else ext.MODE_GRADS, bool(self.average), bool(self.gated),
+                            self.max_blocks, self.threads, algo)
+        ne.set_comm_stream(self.plane.comm_stream.cuda_stream)
+        for s in self.sets:
+            lay = s.layout
+            si = ne.add_set(s.g_off, s.p_off, dtypes.dtype_code(lay.dtype), s.hyper.data_ptr() if self.opt_kind is not None else 0, kind)
+            for b in lay.buckets:
+                ne.add_bucket(si, b.start * lay.esize, b.nbytes(lay.esize), b.numel)
+            for e in lay.entries:
+                ne.add_entry(si, e.bucket, e.offset * lay.esize, e.numel * lay.esize)
+        if self.monitor:
+            ne.set_monitor(self.sumsq.data_ptr())
+        self._native = ne
+
+    def _push_native_state(self) -> None:
+        ptr = lambda t: t.data_ptr() if t is not None else 0
+        for si, s in enumerate(self.sets):
+            for b in s.layout.buckets:
+                self._native.set_bucket_state(si, b.index, ptr(s.master[b.index]), ptr(s.s1[b.index]), ptr(s.s2[b.index]))
+
     def _check_consensus(self) -> None:
         key = self.plane.membership_key()
         if self._consensus_key == key:
@@ -290,13 +320,34 @@ class FlatEngine:
         class _NoSync:
             def __enter__(self):
                 eng._defer = True
+                if eng._native is not None:
+                    eng._native.set_deferred(True)
 
             def __exit__(self, *a):
                 eng._defer = False
+                if eng._native is not None:
+                    eng._native.set_deferred(False)
 
         return _NoSync()
 
     def _install_hooks(self) -> None:
+        if self._native is not None:
+            ne = self._native
+            cur = torch.cuda.current_stream
+            for si, s in enumerate(self.sets):
+                for ei, e in enumerate(s.layout.entries):
+                    gv = _view_like(s.grads, e.offset, e.param)
+
+                    def nhook(p, si=si, ei=ei, gv=gv):  # ONE native call per parameter
+                        if self._defer:
+                            return
+                        if not self._step_open:
+                            self._open_step()
+                        g = p.grad
+                        if ne.grad_ready(si, ei, g.data_ptr() if g is not None else 0, cur().cuda_stream):
+                            p.grad = gv
+                    self._hooks.append(e.param.register_post_accumulate_grad_hook(nhook))
+            return
         for si, s in enumerate(self.sets):
             for ei, e in enumerate(s.layout.entries):
                 gv = _view_like(s.grads, e.offset, e.param)
@@ -342,6 +393,10 @@ class FlatEngine:
         self.arena.ensure()
         self._sync_hyper()
         self._ensure_state()
+        if self._native is not None:
+            self._push_native_state()
+            self._native.open_step(torch.cuda.current_stream().cuda_stream)  # stream ordering + device-side hyper tick
+            return
         cs = self.plane.comm_stream
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream())
@@ -579,6 +634,11 @@ class FlatEngine:
     # ---------------------------------------------------------------------------------------------
     def flush(self) -> None:
         """Launch every bucket that the hooks have not launched yet (unused params, overlap disabled)."""
+        if self._native is not None:
+            if not self._step_open:
+                self._open_step()
+            self._native.flush(torch.cuda.current_stream().cuda_stream, bool(self._steal))
+            return
         if self._steal:
             for si, s in enumerate(self.sets):
                 for ei, e in enumerate(s.layout.entries):
@@ -595,6 +655,14 @@ class FlatEngine:
 
     def finish(self) -> None:
         """Make the current stream wait for the comm stream and reset the per-step bookkeeping."""
+        if self._native is not None:
+            status = self._native.finish(torch.cuda.current_stream().cuda_stream)
+            self._step_open = False
+            self._early = None
+            self.steps += 1
+            if status != 0:
+                self.arena.check()
+            return
         done = torch.cuda.Event()
         done.record(self.plane.comm_stream)
         torch.cuda.current_stream().wait_event(done)

@@ -58,6 +58,7 @@ class SymmetricArena:
         self.mesh.set_timeout_ms(float(os.environ.get("KUNGFU_DEVICE_TIMEOUT_MS", "20000")))
         self._cursor = 0
         self._regions: Dict[str, Tuple[int, int]] = {}
+        self._zero_on_connect: List[Tuple[int, int]] = []
         self._want_multicast = want_multicast
         self._epoch = None  # membership this arena is connected for; connection is lazy (see `ensure`)
         base = _CudaView(self.mesh.local_ptr, self.mesh.arena_bytes, self)
@@ -78,6 +79,11 @@ class SymmetricArena:
         their objects without the survivors taking part. Local memory and every tensor viewing it survive."""
         key = self.plane.membership_key()
         if self._epoch != key:
+            torch.cuda.synchronize(self.plane.device_index)
+            for off, size in self._zero_on_connect:
+                # regions validated by operation numbers that restart with the membership (LL slots): stale flags must be gone
+                # before the connect's closing barrier lets any peer push again
+                self._bytes[off:off + size].zero_()
             torch.cuda.synchronize(self.plane.device_index)
             self._connect(self._want_multicast)
             self._epoch = key
@@ -217,9 +223,13 @@ class GpuPlane:
         """Default arena used to stage arbitrary tensors for the generic collectives."""
         if self._staging is None:
             mb = int(os.environ.get("KUNGFU_STAGING_MB", "64"))
-            self._staging = self.new_arena((mb + 2) << 20, "staging")
+            self.ll_max = int(os.environ.get("KUNGFU_LL_MAX", str(64 << 10)))  # payload bytes of the barrier-free LL one-shot
+            ll_bytes = self.ext.allreduce_ll_slot_bytes(self.ll_max)
+            self._staging = self.new_arena(((mb + 2) << 20) + ll_bytes + (1 << 16), "staging")
             self._staging_bytes = mb << 20
             self._staging_off = self._staging.alloc(self._staging_bytes, name="stage")
+            self.ll_off = self._staging.alloc(ll_bytes, align=4096, name="ll")
+            self._staging._zero_on_connect.append((self.ll_off, ll_bytes))
         self._staging.ensure()
         return self._staging, self._staging_off, self._staging_bytes
 

@@ -28,7 +28,7 @@ def run_single_rank_kernels(plane=None, verbose: bool = False) -> Dict[str, obje
     st = torch.cuda.current_stream().cuda_stream
     n = 1 << 16  # bf16 elements: 128 KiB regions
     nb = n * 2
-    arena = plane.new_arena(16 * nb + (1 << 20), "selftest")
+    arena = plane.new_arena(16 * nb + (4 << 20), "selftest")
     arena.ensure()
     mesh = arena.mesh
     launched: List[str] = []
@@ -57,6 +57,16 @@ def run_single_rank_kernels(plane=None, verbose: bool = False) -> Dict[str, obje
     out = torch.zeros_like(x)
     ext.allreduce(mesh, 0, ext.ALGO_ONESHOT, a_off, out.data_ptr(), nb, BF16, dtypes.SUM, 1.0, 0, 0, BLOCKS, THREADS, st)
     expect("allreduce_oneshot", torch.equal(out, x))
+    ll_max = 64 << 10
+    ll_off = arena.alloc(ext.allreduce_ll_slot_bytes(ll_max), align=4096)
+    for it in range(3):  # three operations: both slot parities and the counter hand-over
+        src = (x[:ll_max // 2].float() + it).to(torch.bfloat16)
+        out2 = torch.zeros_like(src)
+        ext.allreduce_ll(mesh, 0, src.data_ptr(), out2.data_ptr(), ll_max, ll_off, ll_max, BF16, dtypes.SUM, 0.5, ext.FLAG_SCALE, st)
+        good = torch.equal(out2, (src.float() * 0.5).to(torch.bfloat16))
+        if it == 2 or not good:
+            expect("allreduce_ll(flag-carrying pushes)", good)
+            break
     acc = torch.zeros(2, device=dev)
     ext.allreduce(mesh, 0, ext.ALGO_TWOSHOT, a_off, 0, nb, BF16, dtypes.SUM, 0.5, acc.data_ptr(), ext.FLAG_SCALE | ext.FLAG_SUMSQ, BLOCKS,
                   THREADS, st)

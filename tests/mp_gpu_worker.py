@@ -44,7 +44,7 @@ def check_allreduce(rt):
         for op in ("sum", "min", "max", "prod"):
             cases.append((dtype, op))
     sizes = [1, 7, 1024, 65536 + 3, (1 << 20) + 5]
-    algos = ["oneshot", "twoshot"] + (["nvls"] if arena.has_multicast else [])
+    algos = ["ll", "oneshot", "twoshot"] + (["nvls"] if arena.has_multicast else [])
     for algo in algos:
         for dtype, op in cases:
             for n in sizes:

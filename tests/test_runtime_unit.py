@@ -259,3 +259,19 @@ def test_s2d_stem_equals_plain_conv():
     (g0,) = torch.autograd.grad(y0, w, g, retain_graph=True)
     (g1,) = torch.autograd.grad(y1, w, g)
     assert torch.allclose(g0, g1, atol=1e-3)
+
+
+def test_cpp_unit_test_binary():
+    """The native runtime has its own C++ unit tests (csrc/tests/kungfu_unit_tests.cpp: reducers, plan, topology generators,
+    MST, NUMA placement, stores, single-process Peer) — the counterpart of the reference's gtest suite; run the binary."""
+    import subprocess
+
+    from kungfu_b200 import _build
+
+    _build.build_runtime()
+    exe = _build.BIN / "kungfu-unit-tests"
+    assert exe.exists()
+    r = subprocess.run([str(exe)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "0 failures" in r.stdout
