@@ -153,6 +153,11 @@ def main() -> int:
         opt = kf.optimizers.SynchronousAveragingOptimizer(base_opt, named_parameters=model.named_parameters(), backend=backend)
     kf.broadcast_parameters(model.state_dict())
     train_model = model
+    if os.environ.get("KUNGFU_BENCH_NO_COMM") == "1" and N > 1:
+        # diagnostic arm: N processes with their arenas connected and peer-mapped, but every rank trains on its own (the engine is
+        # told it is alone) — separates "what the collectives cost" from "what having peer mappings / N busy GPUs costs"
+        opt.engine.nranks = 1
+        opt.engine._native = None
 
     trainer = ImageTrainer(train_model, opt, B, 224, torch.bfloat16, use_graph=not args.no_graph, warmup_iters=3 if backend is None else 12,
                            device=device, capture_error_mode="thread_local" if backend == "nccl" else "global")

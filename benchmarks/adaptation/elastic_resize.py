@@ -28,6 +28,10 @@ def main():
     ap.add_argument("--schedule", default="4:10,8:10,4:10")
     ap.add_argument("--model", default="resnet50")
     ap.add_argument("--batch-size", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=0, help="with --follow-config-server: how many steps to run")
+    ap.add_argument("--follow-config-server", action="store_true",
+                    help="do not drive the size from --schedule: after every step adopt whatever cluster the config server holds "
+                         "(an external client / operator resizes the job; reference: benchmark_kungfu_elastic.py:160-196)")
     a = ap.parse_args()
     from kungfu_b200.ops.adapt import StepBasedSchedule
 
@@ -49,12 +53,23 @@ def main():
         x = x.contiguous(memory_format=torch.channels_last)
     y = torch.randint(0, 1000, (a.batch_size,), device=dev)
     t_phase, n_phase = time.time(), 0
-    while state.step < sch.total_steps:
+    total_steps = a.steps if a.follow_config_server and a.steps > 0 else sch.total_steps
+    while state.step < total_steps:
         opt.zero_grad()
         F.cross_entropy(model(x).float(), y).backward()
         opt.step()
         state.step += 1
         n_phase += 1
+        if a.follow_config_server:
+            t0 = time.time()
+            changed, detached = kfp.resize()  # consensus on the server's current cluster, adopt it if it differs
+            if detached:
+                return
+            if changed:
+                state = sync_after_resize(state, model, opt)
+                if kf.current_rank() == 0:
+                    print(json.dumps({"resize_to": kf.current_cluster_size(), "latency_s": round(time.time() - t0, 3), "step": state.step}), flush=True)
+            continue
         want = sch(state.step) if state.step < sch.total_steps else kf.current_cluster_size()
         if want != kf.current_cluster_size():
             if use_gpu:

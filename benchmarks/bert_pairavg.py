@@ -45,6 +45,7 @@ class NcclGossip:
         self.k = 0
         s = self.eng.sets[0]
         self.recv = torch.empty_like(s.params)
+        self.send = torch.empty_like(s.params)  # NCCL sends from an ordinary allocation (the parameters live in VMM-mapped arena memory)
         self.ok = torch.tensor([1, 0, 0, 0], dtype=torch.int32, device=s.params.device)  # "version 1, clean": average it in
 
     def zero_grad(self):
@@ -57,7 +58,8 @@ class NcclGossip:
         s = eng.sets[0]
         N = rt.size
         self.k = self.k % (N - 1) + 1
-        ops = [dist.P2POp(dist.isend, s.params, (rt.rank + self.k) % N), dist.P2POp(dist.irecv, self.recv, (rt.rank - self.k) % N)]
+        self.send.copy_(s.params)
+        ops = [dist.P2POp(dist.isend, self.send, (rt.rank + self.k) % N), dist.P2POp(dist.irecv, self.recv, (rt.rank - self.k) % N)]
         for w in dist.batch_isend_irecv(ops):
             w.wait()
         from kungfu_b200.utils import dtypes

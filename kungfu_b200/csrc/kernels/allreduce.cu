@@ -204,15 +204,29 @@ __global__ void __launch_bounds__(512) allreduce_nvls_kernel(const __grid_consta
     slice_bounds(a.nvec, m.nranks, m.rank, s0, s1);
     char* mc = reinterpret_cast<char*>(m.mc) + a.off;
     char* mco = reinterpret_cast<char*>(m.mc) + a.out_off;
-    for (size_t v = s0 + tid; v < s1; v += stride) {
-        Vec16 x = Multimem<T, OP>::ld_reduce(mc + v * 16);
-        if ((a.flags & kArScale) || SUMSQ) {
-            AccVec<T> acc = unpack<T>(x);
-            if (a.flags & kArScale) apply_scale<T>(acc, a.scale);
-            if constexpr (SUMSQ) post += vec_sumsq<T>(acc);
-            x = pack<T>(acc);
+    // kU switch reductions in flight per thread: a multimem.ld_reduce is a ~3 us round trip through the NVSwitch, so the bytes
+    // in flight (threads x kU x 16 B), not the instruction rate, set the bandwidth — one load at a time left 32 CTAs at ~90 GB/s
+    constexpr int kU = 4;
+    for (size_t v0 = s0 + tid; v0 < s1; v0 += stride * kU) {
+        Vec16 xs[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const size_t v = v0 + (size_t)u * stride;
+            if (v < s1) xs[u] = Multimem<T, OP>::ld_reduce(mc + v * 16);
         }
-        multimem_st(mco + v * 16, x);
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const size_t v = v0 + (size_t)u * stride;
+            if (v >= s1) break;
+            Vec16 x = xs[u];
+            if ((a.flags & kArScale) || SUMSQ) {
+                AccVec<T> acc = unpack<T>(x);
+                if (a.flags & kArScale) apply_scale<T>(acc, a.scale);
+                if constexpr (SUMSQ) post += vec_sumsq<T>(acc);
+                x = pack<T>(acc);
+            }
+            multimem_st(mco + v * 16, x);
+        }
     }
     flush_sumsq<SUMSQ>(a, pre, post);
     if (gated) {

@@ -167,39 +167,54 @@ __global__ void __launch_bounds__(512) ssgd_fused_kernel(const __grid_constant__
     }
     if (!gated) block_barrier<false>(m, seq);
     const Hyper h = load_hyper(a.hyper);
-    const float gs = h.v[kHpGradScale];
+    const float gs_scale = h.v[kHpGradScale];
     size_t s0, s1;
     slice_bounds2(a.nvec, m.nranks, m.rank, s0, s1);
-    for (size_t v = s0 + tid; v < s1; v += stride) {
-        AccVec<T> g;
-        if constexpr (NVLS) g = unpack<T>(Multimem<T, kSum>::ld_reduce(reinterpret_cast<const char*>(m.mc) + a.grad_off + v * 16));
-        else g = gather_sum<T>(m, a.grad_off + v * 16, sumsq ? &pre : nullptr);
-        const size_t idx = (v - s0) * L;
-        F32Lanes<L> w, m1, m2;
-        if (a.master) w.load(a.master + idx);
-        else {
-            const AccVec<T> p = unpack<T>(ld_plain(reinterpret_cast<const char*>(m.data[m.rank]) + a.param_off + v * 16));
+    // kU gradient reductions in flight per thread (switch round trip ~3 us: bytes in flight set the bandwidth), then the
+    // optimizer math on each of them while the next batch's loads are already queued behind
+    constexpr int kU = NVLS ? 4 : 2;
+    for (size_t v0 = s0 + tid; v0 < s1; v0 += stride * kU) {
+        AccVec<T> gs[kU];
 #pragma unroll
-            for (int j = 0; j < L; ++j) w.f[j] = (float)p.a[j];
+        for (int u = 0; u < kU; ++u) {
+            const size_t v = v0 + (size_t)u * stride;
+            if (v < s1) {
+                if constexpr (NVLS) gs[u] = unpack<T>(Multimem<T, kSum>::ld_reduce(reinterpret_cast<const char*>(m.mc) + a.grad_off + v * 16));
+                else gs[u] = gather_sum<T>(m, a.grad_off + v * 16, sumsq ? &pre : nullptr);
+            }
         }
-        if (a.s1) m1.load(a.s1 + idx);
-        else m1.zero();
-        if (KIND == kOptAdam && a.s2) m2.load(a.s2 + idx);
-        else m2.zero();
-        AccVec<T> out;
 #pragma unroll
-        for (int j = 0; j < L; ++j) {
-            const float gj = (float)g.a[j] * gs;
-            post = fmaf(gj, gj, post);
-            opt_update<KIND>(w.f[j], gj, m1.f[j], m2.f[j], h);
-            out.a[j] = (typename Elem<T>::Acc)w.f[j];
+        for (int u = 0; u < kU; ++u) {
+            const size_t v = v0 + (size_t)u * stride;
+            if (v >= s1) break;
+            const AccVec<T>& g = gs[u];
+            const size_t idx = (v - s0) * L;
+            F32Lanes<L> w, m1, m2;
+            if (a.master) w.load(a.master + idx);
+            else {
+                const AccVec<T> p = unpack<T>(ld_plain(reinterpret_cast<const char*>(m.data[m.rank]) + a.param_off + v * 16));
+#pragma unroll
+                for (int j = 0; j < L; ++j) w.f[j] = (float)p.a[j];
+            }
+            if (a.s1) m1.load(a.s1 + idx);
+            else m1.zero();
+            if (KIND == kOptAdam && a.s2) m2.load(a.s2 + idx);
+            else m2.zero();
+            AccVec<T> out;
+#pragma unroll
+            for (int j = 0; j < L; ++j) {
+                const float gj = (float)g.a[j] * gs_scale;
+                post = fmaf(gj, gj, post);
+                opt_update<KIND>(w.f[j], gj, m1.f[j], m2.f[j], h);
+                out.a[j] = (typename Elem<T>::Acc)w.f[j];
+            }
+            if (a.master) w.store(a.master + idx);
+            if (a.s1) m1.store(a.s1 + idx);
+            if (KIND == kOptAdam && a.s2) m2.store(a.s2 + idx);
+            const Vec16 res = pack<T>(out);
+            if constexpr (NVLS) multimem_st(reinterpret_cast<char*>(m.mc) + a.param_off + v * 16, res);
+            else scatter_store(m, a.param_off + v * 16, res);
         }
-        if (a.master) w.store(a.master + idx);
-        if (a.s1) m1.store(a.s1 + idx);
-        if (KIND == kOptAdam && a.s2) m2.store(a.s2 + idx);
-        const Vec16 res = pack<T>(out);
-        if constexpr (NVLS) multimem_st(reinterpret_cast<char*>(m.mc) + a.param_off + v * 16, res);
-        else scatter_store(m, a.param_off + v * 16, res);
     }
     if (sumsq) {
         __shared__ float red[32];

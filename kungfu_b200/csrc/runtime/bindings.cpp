@@ -220,6 +220,7 @@ PYBIND11_MODULE(_kfrt, m) {
 
     // ---- numa
     m.def("numa_topology", &numa_topology);
+    m.def("numa_topology_ordered", &numa_topology_ordered);
     m.def("select_cpus", &select_cpus);
     m.def("apply_affinity_from_env", &apply_affinity_from_env);
 

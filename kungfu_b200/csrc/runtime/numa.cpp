@@ -3,6 +3,8 @@
 
 #include <sched.h>
 
+#include <algorithm>
+#include <array>
 #include <fstream>
 #include <sstream>
 #include <string>
@@ -47,6 +49,31 @@ std::vector<std::vector<int>> numa_topology() {
     return nodes;
 }
 
+// Topology (hwloc-like) order of the PUs of every NUMA node: package -> core -> hardware thread, i.e. the depth-first order of
+// the machine tree that the reference takes from hwloc (srcs/cpp/src/numa/hwloc.cpp:8-63 `get_pu_numa_order`), read from sysfs
+// instead of a library. With Linux' OS numbering the two hyper-threads of a core are N/2 apart, so a contiguous OS-order
+// slice hands a worker one thread of many cores that it then shares with another worker; in topology order a slice is a
+// set of whole cores.
+std::vector<std::vector<int>> numa_topology_ordered() {
+    auto nodes = numa_topology();
+    auto read_int = [](const std::string& path, int dflt) {
+        std::ifstream f(path);
+        int v = dflt;
+        if (f) f >> v;
+        return v;
+    };
+    for (auto& cpus : nodes) {
+        std::vector<std::array<int, 4>> keyed; // package, core, position among the core's threads (os order), cpu
+        for (int c : cpus) {
+            const std::string base = "/sys/devices/system/cpu/cpu" + std::to_string(c) + "/topology/";
+            keyed.push_back({read_int(base + "physical_package_id", 0), read_int(base + "core_id", c), c, c});
+        }
+        std::sort(keyed.begin(), keyed.end());
+        for (size_t i = 0; i < cpus.size(); ++i) cpus[i] = keyed[i][3];
+    }
+    return nodes;
+}
+
 std::vector<int> select_cpus(const std::vector<std::vector<int>>& numa_cpus, int local_rank, int local_size) {
     if (numa_cpus.empty() || local_size <= 0 || local_rank < 0 || local_rank >= local_size) return {};
     const int nn = (int)numa_cpus.size();
@@ -76,7 +103,9 @@ bool set_affinity(const std::vector<int>& cpus) {
 
 std::vector<int> apply_affinity_from_env(int local_rank, int local_size) {
     if (!getenv_bool("KUNGFU_USE_AFFINITY", false)) return {};
-    auto cpus = select_cpus(numa_topology(), local_rank, local_size);
+    // KUNGFU_AFFINITY_ORDER=topology (default: whole cores per worker, the reference's hwloc build) | os (plain OS numbering)
+    const bool topo = getenv_str("KUNGFU_AFFINITY_ORDER", "topology") != "os";
+    auto cpus = select_cpus(topo ? numa_topology_ordered() : numa_topology(), local_rank, local_size);
     if (!set_affinity(cpus)) KF_LOGW("failed to set CPU affinity");
     return cpus;
 }

@@ -10,6 +10,7 @@ namespace kfrt {
 
 // CPUs grouped by NUMA node, read from sysfs (one group with every online CPU when sysfs has no NUMA info)
 std::vector<std::vector<int>> numa_topology();
+std::vector<std::vector<int>> numa_topology_ordered(); // per node: package -> core -> thread (hwloc-like PU order from sysfs)
 // pure placement function (unit-testable): CPUs for `local_rank` out of `local_size` workers
 std::vector<int> select_cpus(const std::vector<std::vector<int>>& numa_cpus, int local_rank, int local_size);
 bool set_affinity(const std::vector<int>& cpus);

@@ -251,6 +251,15 @@ static void test_placement() {
     CHECK(seen.size() == 16);
     CHECK(select_cpus(numa, 0, 1).size() == 16 || select_cpus(numa, 0, 1).size() == 8);
     CHECK(!numa_topology().empty());
+    // topology (hwloc-like) order: a permutation of the OS order per node
+    auto os = numa_topology(), topo = numa_topology_ordered();
+    CHECK(os.size() == topo.size());
+    for (size_t i = 0; i < os.size() && i < topo.size(); ++i) {
+        auto a = os[i], b = topo[i];
+        std::sort(a.begin(), a.end());
+        std::sort(b.begin(), b.end());
+        CHECK(a == b);
+    }
 }
 
 // ---- stores (store/versionedstore_test.go) ---------------------------------------------------------------------------

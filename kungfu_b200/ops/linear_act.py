@@ -1,9 +1,10 @@
 """Linear + bias (+ GELU) on the tcgen05 tensor cores with the activation fused into the GEMM epilogue
-(csrc/kernels/gemm_sm100.cu: CUTLASS/CuTe sm100 collectives — TMA loads, `tcgen05.mma` cta_group::2, TMEM accumulator).
+(csrc/kernels/gemm_tc5.cu: a hand-written persistent kernel — TMA-fed 4-stage ring, `tcgen05.mma` 128x256x16 issued by one
+thread, two TMEM accumulators so that the bias+GELU epilogue of one tile overlaps the mainloop of the next).
 
-`linear_act(x, weight, bias, act)` == `gelu(F.linear(x, weight, bias))` / `F.linear(...)` for bf16 CUDA tensors whose sizes
-are multiples of 8; anything else falls back to the PyTorch ops. Backward recomputes the pre-activation (one cuBLAS GEMM)
-instead of storing it.
+`linear_act(x, weight, bias, act)` == `gelu(F.linear(x, weight, bias))` / `F.linear(...)` for bf16 CUDA tensors with
+in_features % 64 == 0 and out_features % 8 == 0; anything else falls back to the PyTorch ops. Backward recomputes the
+pre-activation (one library GEMM) instead of storing it.
 """
 from __future__ import annotations
 
@@ -25,8 +26,7 @@ def _ext():
 def supported(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> bool:
     if not (x.is_cuda and x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and bias is not None and bias.dtype == torch.bfloat16):
         return False
-    tokens = x.numel() // x.shape[-1]
-    if tokens % 8 or x.shape[-1] % 8 or weight.shape[0] % 8 or not weight.is_contiguous():
+    if x.shape[-1] % 64 or weight.shape[0] % 8 or not weight.is_contiguous() or x.numel() == 0:
         return False
     try:
         return bool(_ext().gemm_sm100_available())

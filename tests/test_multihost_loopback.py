@@ -170,3 +170,29 @@ def test_hostfile_and_nic_discovery(tmp_path):
     text = a.stdout + out_b
     for k in range(4):
         assert f"rank {k}/4: [4.0" in text, text[-3000:]
+
+
+def test_native_rrun_fans_out_to_every_host_and_fails_fast():
+    """`kungfu-rrun` (C++: fork/exec + pipes + poll; the reference's is Go over an SSH library) starts one launcher per host —
+    here with -local on loopback-alias hosts — prefixes their output, and cancels the other hosts when one fails."""
+    from kungfu_b200 import _build
+
+    _build.build_runtime()
+    rrun = str(_build.BIN / "kungfu-rrun")
+    rport, prange = ports()
+    env = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN")
+    r = subprocess.run([rrun, "-local", "-q", "-np", "4", "-H", "127.0.0.1:2,127.0.0.2:2", "-kungfu-run", kungfu_run(), "-port", str(rport),
+                        "-port-range", prange, sys.executable, WORKER, "collectives"], cwd=ROOT, env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-4000:]
+    assert r.stdout.count('"ok": true') == 4 and "[127.0.0.1]" in r.stdout and "[127.0.0.2]" in r.stdout, r.stdout[-4000:]
+    # dry run prints the SSH command lines of a real multi-host launch
+    d = subprocess.run([rrun, "-dry-run", "-np", "16", "-H", "10.0.0.1:8,10.0.0.2:8", "-u", "me", "-w", "-config-server", "http://10.0.0.1:9100/config",
+                        "python3", "train.py"], stdout=subprocess.PIPE, text=True)
+    lines = d.stdout.strip().splitlines()
+    assert len(lines) == 2 and all(l.startswith("ssh ") and "kungfu-run -self 10.0.0." in l and " -w " in l for l in lines), d.stdout
+    # kungfu-distribute: the same binary under its second name; one failing host cancels the rest and the exit code is non-zero
+    dist = str(_build.BIN / "kungfu-distribute")
+    f = subprocess.run([dist, "-local", "-H", "127.0.0.1,127.0.0.2", "sh", "-c", "exit 3"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=60)
+    assert f.returncode == 1 and "cancelling" in f.stdout
