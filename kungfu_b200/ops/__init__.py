@@ -10,7 +10,8 @@ from .adapt import StepBasedSchedule, resize, resize_cluster, resize_cluster_fro
 from .collective import (Handle, all_gather, all_gather_transform, all_reduce, all_reduce_, all_reduce_async_, barrier, broadcast_, consensus, subset_all_reduce,
                          wait_all_handles, wait_handle)
 from .monitor import NoiseScale, egress_rates, global_noise_scale
-from .p2p import request_variable, request_variable_with_template, save_variable, save_variables
+from .p2p import (AsyncModelAveraging, ModelAveraging, RandomSelector, RoundRobinSelector, request_variable, request_variable_with_template,
+                  save_variable, save_variables)
 from .state import Counter, ExponentialMovingAverage, counter, exponential_moving_average
 from .topology import (cluster_size, get_neighbour_mask, get_peer_latencies, global_minimum_spanning_tree,
                        minimum_spanning_tree_father, peer_info, rank, round_robin)
@@ -42,9 +43,10 @@ def group_nccl_all_reduce(ts: Sequence[torch.Tensor], op="sum") -> List[torch.Te
     """All-reduce a list of device tensors concurrently. The reference schedules one NCCL all-reduce per tensor in a
     negotiated order (ops/collective.py:96-106); here each tensor goes to the sm_100a kernels on the comm stream (their order is
     the list order on every rank), host tensors to the native runtime. None entries pass through."""
-    outs = [None if t is None else t.detach().clone() for t in ts]
-    hs = [all_reduce_async_(t, f"group::{i}", op) for i, t in enumerate(outs) if t is not None]
-    wait_all_handles(hs)
+    outs = [None if t is None else t.detach().clone().contiguous() for t in ts]
+    from .collective import all_reduce_group_async_
+
+    all_reduce_group_async_([t for t in outs if t is not None], op).wait()
     return outs
 
 

@@ -127,11 +127,16 @@ def _gpu_all_reduce_(x: torch.Tensor, op_code: int, average: bool, stream: Optio
         _gpu_all_reduce_hier_(plane, flat, op_code, average, st, algo)
         return
     nbytes = n * esize
-    if (nbytes <= plane.ll_max and nbytes % 8 == 0 and flat.data_ptr() % 8 == 0 and (algo or CONFIG.algo).lower() in ("auto", "ll")
+    if (nbytes <= plane.ll_max and nbytes % 8 == 0 and (algo or CONFIG.algo).lower() in ("auto", "ll")
             and os.environ.get("KUNGFU_DISABLE_LL", "0") != "1"):
-        # latency path: flag-carrying pushes straight from / into the user tensor — no staging copy, no barrier
-        ext.allreduce_ll(arena.mesh, 0, flat.data_ptr(), flat.data_ptr(), nbytes, plane.ll_off, plane.ll_max, dt, op_code, scale, flags,
-                         st.cuda_stream)
+        # latency path: flag-carrying pushes straight from / into the user tensor — no staging copy, no barrier. The choice
+        # depends on the message size only (identical on every rank); a misaligned view goes through an aligned temporary.
+        with torch.cuda.stream(st):
+            buf = flat if flat.data_ptr() % 8 == 0 else flat.clone()
+            ext.allreduce_ll(arena.mesh, 0, buf.data_ptr(), buf.data_ptr(), nbytes, plane.ll_off, plane.ll_max, dt, op_code, scale, flags,
+                             st.cuda_stream)
+            if buf is not flat:
+                flat.copy_(buf)
         return
     with torch.cuda.stream(st):
         for lo in range(0, n, chunk_elems):
@@ -384,6 +389,28 @@ def _async_name(rt) -> str:
         _async_seq["version"], _async_seq["n"] = v, 0
     _async_seq["n"] += 1
     return f"async-allreduce::v{v}::{_async_seq['n']}"
+
+
+def all_reduce_group_async_(ts: List[torch.Tensor], op=None) -> Handle:
+    """All-reduce a LIST of CUDA tensors in place with ONE hop onto the comm stream and one completion event: the per-tensor
+    cost is one kernel launch (small tensors: the barrier-free LL kernel reading / writing the user tensor directly). The
+    reference's `group_all_reduce` issues one named op per tensor (ops/collective.py:67-69); their list order is the order on
+    every rank here too. Host tensors fall back to per-tensor ops."""
+    code, avg = dtypes.op_code(op)
+    rt = get_runtime()
+    ts = [t for t in ts if t is not None]
+    if rt.size == 1 or not ts:
+        return Handle()
+    if not all(t.is_cuda and t.is_contiguous() for t in ts):
+        hs = [all_reduce_async_(t, f"group::{i}", op) for i, t in enumerate(ts)]
+        return Handle(post=lambda: wait_all_handles(hs))
+    plane = rt.gpu
+
+    def run(st):
+        for t in ts:
+            _gpu_all_reduce_(t, code, avg, stream=st)
+
+    return Handle(event=_run_on_comm(plane, run, ts, wait=False))
 
 
 def wait_handle(h: Handle) -> None:

@@ -112,3 +112,118 @@ def request_variable_with_template(target: int, template: torch.Tensor, name: st
 def save_variables(tensors, names, version: Optional[int] = None) -> None:
     for t, n in zip(tensors, names):
         save_variable(t, n, version)
+
+
+# ---- legacy fused-model ops (reference: ModelAveraging / AsyncModelAveraging / SaveModel / RequestModel / AsyncRequestModel with
+# RandomSelector / RoundRobinSelector, srcs/cpp/src/tensorflow/ops/cpu/peer_to_peer.cpp:8-524) -----------------------------------------
+class RoundRobinSelector:
+    """Next peer in rank order, skipping oneself (peer_to_peer.cpp `RoundRobinSelector`)."""
+
+    def __init__(self, size: int, rank: int) -> None:
+        self.peers = [r for r in range(size) if r != rank] or [rank]
+        self.i = 0
+
+    def next(self) -> int:
+        p = self.peers[self.i % len(self.peers)]
+        self.i += 1
+        return p
+
+
+class RandomSelector:
+    """A uniformly drawn peer other than oneself (peer_to_peer.cpp `RandomSelector`)."""
+
+    def __init__(self, size: int, rank: int, seed: Optional[int] = None) -> None:
+        import random
+
+        self.peers = [r for r in range(size) if r != rank] or [rank]
+        self.rng = random.Random(seed if seed is not None else 0xA11CE + rank)
+
+    def next(self) -> int:
+        return self.rng.choice(self.peers)
+
+
+def _fuse(vs):
+    return torch.cat([v.detach().reshape(-1) for v in vs])
+
+
+def _blend_in(vs, flat: torch.Tensor) -> None:
+    off = 0
+    with torch.no_grad():
+        for v in vs:
+            n = v.numel()
+            v.mul_(0.5).add_(flat[off:off + n].view_as(v).to(v.dtype), alpha=0.5)
+            off += n
+
+
+class ModelAveraging:
+    """`model_averaging(variables)`: pull the fused model of a selected peer NOW and average it in (`v <- 0.5 (v + other)`);
+    the requester waits for the transfer. Call `save_model` after each local update so that peers find something to pull."""
+
+    def __init__(self, variables, strategy: str = "random", name: str = "kungfu::legacy_model", seed: Optional[int] = None) -> None:
+        rt = get_runtime()
+        self.vs = list(variables)
+        self.name = name
+        self.sel = RoundRobinSelector(rt.size, rt.rank) if strategy == "roundrobin" else RandomSelector(rt.size, rt.rank, seed)
+
+    def save(self) -> None:
+        save_variable(_fuse(self.vs), self.name)
+
+    def __call__(self) -> bool:
+        if get_runtime().size == 1:
+            return False
+        ok, flat = request_variable_with_template(self.sel.next(), _fuse(self.vs), self.name)
+        if ok:
+            _blend_in(self.vs, flat)
+        return bool(ok)
+
+
+class AsyncModelAveraging(ModelAveraging):
+    """`async_model_averaging(variables)`: double-buffered PREFETCH — every call averages in the model that was fetched while the
+    previous training step ran and starts fetching the next peer's model; the caller never waits for a transfer (reference:
+    peer_to_peer.cpp:212-254, whose prefetch callback races with the averaging — `is_requesting_` is read unlocked; here the
+    hand-over is a stream event on GPUs and a joined future on the host)."""
+
+    def __init__(self, variables, strategy: str = "random", name: str = "kungfu::legacy_model", seed: Optional[int] = None) -> None:
+        super().__init__(variables, strategy, name, seed)
+        self._pending = None  # (ok_or_future, buffer, event)
+        self._pool = None
+
+    def _start_prefetch(self) -> None:
+        target = self.sel.next()
+        template = _fuse(self.vs)
+        if template.is_cuda:
+            rt = get_runtime()
+            side = rt.gpu.side_stream
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                ok, flat = request_variable_with_template(target, template, self.name)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            self._pending = (ok, flat, ev)
+        else:
+            if self._pool is None:
+                from concurrent.futures import ThreadPoolExecutor
+
+                self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="kf-prefetch")
+            self._pending = (self._pool.submit(request_variable_with_template, target, template, self.name), None, None)
+
+    def __call__(self) -> bool:
+        if get_runtime().size == 1:
+            return False
+        averaged = False
+        if self._pending is not None:
+            ok, flat, ev = self._pending
+            if ev is None:  # host: the future holds (ok, tensor)
+                ok, flat = ok.result()
+            else:
+                torch.cuda.current_stream().wait_event(ev)
+            if ok:
+                _blend_in(self.vs, flat)
+                averaged = True
+        self._start_prefetch()
+        return averaged
+
+
+def save_model_legacy(variables, name: str = "kungfu::legacy_model") -> None:
+    """`SaveModel`: publish the fused model under `name`."""
+    save_variable(_fuse(list(variables)), name)

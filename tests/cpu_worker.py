@@ -153,6 +153,26 @@ def cmd_p2p(args):
     ok, _ = ops.request_variable(tgt, "vmodel", (1024,), torch.float32, version=0)
     check(ok is False, "versioned store keeps a sliding window of 3")
     coll.barrier()
+    # legacy fused-model ops: synchronous averaging pulls now; the asynchronous form averages in what it prefetched during the
+    # previous call (first call: nothing yet) and never waits for a transfer
+    if n > 1:
+        w = [torch.full((8,), float(r)), torch.full((3, 3), float(r))]
+        ma = ops.ModelAveraging(w, strategy="roundrobin", name="legacy")
+        ma.save()
+        coll.barrier()
+        check(ma() is True, "model_averaging pulled a model")
+        peer = (r + 1) % n if r + 1 != r else r
+        first = [q for q in range(n) if q != r][0]
+        check(bool(torch.all(w[0] == 0.5 * (r + first))) and bool(torch.all(w[1] == 0.5 * (r + first))), "model_averaging averaged with the selected peer")
+        coll.barrier()
+        v = [torch.full((16,), float(10 * r))]
+        ama = ops.AsyncModelAveraging(v, strategy="roundrobin", name="legacy-async")
+        ama.save()
+        coll.barrier()
+        check(ama() is False, "async_model_averaging: the first call only starts the prefetch")
+        check(ama() is True, "async_model_averaging: the second call averages the prefetched model in")
+        check(bool(torch.all(v[0] == 0.5 * (10 * r + 10 * first))), "async_model_averaging value")
+        coll.barrier()
     print(json.dumps({"ok": True}), flush=True)
 
 
