@@ -314,11 +314,14 @@ __global__ void __launch_bounds__(512) allreduce_ll_kernel(const __grid_constant
                 if (f0 != op || f1 != op) {
                     const unsigned long long t0 = global_ns();
                     uint32_t iters = 0;
-                    bool dead = m.status && *((volatile uint32_t*)&m.status[0]) != 0u;
+                    bool dead = false;
                     while (!dead) {
                         ld_volatile_v4(src, d0, f0, d1, f1);
                         if (f0 == op && f1 == op) break;
-                        if (((++iters) & 0x3ff) == 0 && global_ns() - t0 > m.timeout_ns) {
+                        if (((++iters) & 0x3ff) != 0) continue;
+                        // (host-mapped status word: a PCIe read, so only every 1024 polls)
+                        if (m.status && *((volatile uint32_t*)&m.status[0]) != 0u) dead = true;
+                        else if (global_ns() - t0 > m.timeout_ns) {
                             if (m.status) {
                                 m.status[1] = ((uint32_t)m.rank << 16) | (uint32_t)r;
                                 m.status[3] = op;

@@ -47,15 +47,17 @@ __device__ __forceinline__ unsigned long long global_ns() {
 __device__ __forceinline__ bool spin_ge(const uint32_t* p, uint32_t want, const MeshArgs& m, int peer) {
     uint32_t v = ld_acquire_sys(p);
     if ((int32_t)(v - want) >= 0) return true;
-    // a wait that already failed once on this mesh poisons every later wait: the job is lost, and each remaining kernel
-    // of the step would otherwise sit out its own full time-out (the host raises at its next `check()`)
-    if (m.status && *((volatile uint32_t*)&m.status[0]) != 0u) return false;
     const unsigned long long t0 = global_ns();
     uint32_t iters = 0;
     while (true) {
         v = ld_acquire_sys(p);
         if ((int32_t)(v - want) >= 0) return true;
         if (((++iters) & 0x3ff) == 0) {
+            // a wait that already failed once on this mesh poisons every later wait: the job is lost, and each remaining
+            // kernel of the step would otherwise sit out its own full time-out (the host raises at its next `check()`). The
+            // status word lives in host memory (a PCIe round trip), so it is looked at here — every 1024 polls — and not on
+            // the way into the loop, where it cost every barrier ~2 us.
+            if (m.status && *((volatile uint32_t*)&m.status[0]) != 0u) return false;
             if (global_ns() - t0 > m.timeout_ns) {
                 if (m.status) {
                     m.status[1] = ((uint32_t)m.rank << 16) | (uint32_t)peer;

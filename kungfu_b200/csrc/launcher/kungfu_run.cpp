@@ -68,6 +68,7 @@ struct Flags {
     std::string strategy = "BINARY_TREE_STAR";
     int port = kDefaultRunnerPort;
     int debug_port = 0;
+    int standby = 0; // -standby N (watch mode): warmed-up processes kept ready to become workers at the next grow
     bool watch = false;
     bool keep = false;
     int init_version = 0;
@@ -87,7 +88,7 @@ struct Flags {
             "usage: kungfu-run [-np N] [-H ip:slots,...] [-hostfile f] [-self ip] [-nic name] [-strategy S]\n"
             "                  [-port-range a-b] [-port p] [-w] [-k] [-config-server URL] [-builtin-config-port p]\n"
             "                  [-init-version v] [-timeout d] [-logdir d] [-logfile f] [-q] [-v] [-allow-nvlink]\n"
-            "                  [-auto-recover d] [-delay d] [-debug-port p] prog args...\n"
+            "                  [-auto-recover d] [-delay d] [-debug-port p] [-standby n] prog args...\n"
             "strategies: ");
     for (auto& s : strategy_names()) fprintf(stderr, "%s ", s.c_str());
     fprintf(stderr, "\n");
@@ -136,6 +137,7 @@ Flags parse_flags(int argc, char** argv) {
         else if (k == "strategy") f.strategy = v;
         else if (k == "port") f.port = atoi(v.c_str());
         else if (k == "debug-port") f.debug_port = atoi(v.c_str());
+        else if (k == "standby") f.standby = atoi(v.c_str());
         else if (k == "w") f.watch = parse_bool(v);
         else if (k == "k") f.keep = parse_bool(v);
         else if (k == "init-version") f.init_version = atoi(v.c_str());
@@ -324,14 +326,21 @@ void pump(int fd, const std::string& tag, const char* color, bool verbose, FILE*
     if (lf) fclose(lf);
 }
 
-// returns the exit code (128+signal when killed)
-int run_proc(const Proc& p, bool verbose, const std::string& logdir, Cancel* cancel, int color_idx) {
+// A started child with its output pumps. `stdin_fd` >= 0: the child reads its activation (environment) from a pipe (standby workers).
+struct Child {
+    pid_t pid = -1;
+    int stdin_fd = -1;
+    std::thread out, err;
+};
+
+Child spawn_proc(const Proc& p, bool verbose, const std::string& logdir, Cancel* cancel, int color_idx, bool want_stdin) {
     // O_CLOEXEC: workers are spawned from several threads at once; a plain pipe() leaks this worker's write ends into every
     // sibling forked meanwhile, the pumps then never see EOF when this worker exits, its waiter thread never returns, and the
-    // watch loop (which joins the waiter of a removed worker before it handles the next stage) wedges. dup2 onto 1 / 2 in
+    // watch loop (which joins the waiter of a removed worker before it handles the next stage) wedges. dup2 onto 0 / 1 / 2 in
     // the child clears the flag on the copies that matter.
-    int out_pipe[2], err_pipe[2];
+    int out_pipe[2], err_pipe[2], in_pipe[2] = {-1, -1};
     if (pipe2(out_pipe, O_CLOEXEC) != 0 || pipe2(err_pipe, O_CLOEXEC) != 0) fail("pipe() failed");
+    if (want_stdin && pipe2(in_pipe, O_CLOEXEC) != 0) fail("pipe() failed");
     std::vector<std::string> envs;
     for (char** e = environ; *e; ++e) {
         std::string kv = *e;
@@ -348,33 +357,53 @@ int run_proc(const Proc& p, bool verbose, const std::string& logdir, Cancel* can
     pid_t pid = fork();
     if (pid < 0) fail("fork() failed");
     if (pid == 0) {
+        if (want_stdin) dup2(in_pipe[0], 0);
         dup2(out_pipe[1], 1);
         dup2(err_pipe[1], 2);
         close(out_pipe[0]);
         close(out_pipe[1]);
         close(err_pipe[0]);
         close(err_pipe[1]);
+        if (want_stdin) {
+            close(in_pipe[0]);
+            close(in_pipe[1]);
+        }
         execvpe(p.prog.c_str(), argv.data(), envp.data());
         fprintf(stderr, "kungfu-run: cannot exec %s: %s\n", p.prog.c_str(), strerror(errno));
         _exit(127);
     }
     close(out_pipe[1]);
     close(err_pipe[1]);
+    if (want_stdin) close(in_pipe[0]);
     if (cancel) cancel->add(pid);
     if (!logdir.empty()) mkdir(logdir.c_str(), 0755);
     const std::string base = logdir.empty() ? "" : logdir + "/" + p.log_prefix;
     const char* color = kColors[color_idx % 6];
-    std::thread t1(pump, out_pipe[0], p.name + "::stdout", color, verbose, stdout, base.empty() ? "" : base + ".stdout.log");
-    std::thread t2(pump, err_pipe[0], p.name + "::stderr", color, verbose, stderr, base.empty() ? "" : base + ".stderr.log");
+    Child c;
+    c.pid = pid;
+    c.stdin_fd = want_stdin ? in_pipe[1] : -1;
+    c.out = std::thread(pump, out_pipe[0], p.name + "::stdout", color, verbose, stdout, base.empty() ? "" : base + ".stdout.log");
+    c.err = std::thread(pump, err_pipe[0], p.name + "::stderr", color, verbose, stderr, base.empty() ? "" : base + ".stderr.log");
+    return c;
+}
+
+// returns the exit code (128+signal when killed)
+int wait_proc(Child& c, Cancel* cancel) {
     int status = 0;
-    while (waitpid(pid, &status, 0) < 0 && errno == EINTR) {
+    while (waitpid(c.pid, &status, 0) < 0 && errno == EINTR) {
     }
-    if (cancel) cancel->remove(pid);
-    t1.join();
-    t2.join();
+    if (cancel) cancel->remove(c.pid);
+    if (c.stdin_fd >= 0) close(c.stdin_fd), c.stdin_fd = -1;
+    c.out.join();
+    c.err.join();
     if (WIFEXITED(status)) return WEXITSTATUS(status);
     if (WIFSIGNALED(status)) return 128 + WTERMSIG(status);
     return 1;
+}
+
+int run_proc(const Proc& p, bool verbose, const std::string& logdir, Cancel* cancel, int color_idx) {
+    Child c = spawn_proc(p, verbose, logdir, cancel, color_idx, false);
+    return wait_proc(c, cancel);
 }
 
 // run all procs concurrently; the first failure cancels the rest (fail-fast). Returns 0 iff all succeeded.
@@ -457,8 +486,66 @@ struct Watcher {
     bool failed = false;
     int fail_code = 0;
     Cluster current;
+    // -standby N: warmed-up processes (interpreter, torch, CUDA context on a reserved GPU slot) waiting on a pipe for an identity
+    struct Standby {
+        Child child;
+        int gpu = -1;
+        int seq = 0;
+    };
+    std::deque<std::shared_ptr<Standby>> standbys;
+    int standby_seq = 0;
 
     Watcher(const Flags& fl, const Job& j, const PeerID& s) : f(fl), job(j), self(s), gpus(j.hosts.slots_of(s.ipv4)) {}
+
+    bool standby_supported() const {
+        const std::string base = job.prog.substr(job.prog.find_last_of('/') == std::string::npos ? 0 : job.prog.find_last_of('/') + 1);
+        return f.standby > 0 && base.rfind("python", 0) == 0 && !job.args.empty() && job.args[0].rfind("-", 0) != 0;
+    }
+
+    // keep up to f.standby warm processes around while GPU slots are free
+    void replenish_standbys() {
+        if (!standby_supported()) return;
+        while (true) {
+            {
+                std::lock_guard<std::mutex> g(mu);
+                if ((int)standbys.size() >= f.standby) return;
+            }
+            const int slots = job.hosts.slots_of(self.ipv4);
+            const int gpu = gpus.get();
+            if (gpu < 0 && slots > 0) return; // every slot of this host is taken by a worker or a standby
+            Proc p;
+            auto sb = std::make_shared<Standby>();
+            sb->gpu = gpu;
+            sb->seq = ++standby_seq;
+            p.name = "standby-" + std::to_string(sb->seq);
+            p.log_prefix = p.name;
+            p.prog = job.prog;
+            p.args = {"-m", "kungfu_b200.cmd.standby"};
+            p.args.insert(p.args.end(), job.args.begin(), job.args.end());
+            const std::string idx = Job::cuda_index(gpu);
+            p.envs[envkeys::kCudaVisibleDevices] = idx;
+            if (job.allow_nvlink) p.envs[envkeys::kAllowNvlink] = "1";
+            else p.envs["CUDA_VISIBLE_DEVICES"] = idx;
+            p.envs["PYTHONUNBUFFERED"] = "1";
+            p.envs["KUNGFU_STANDBY"] = "1";
+            sb->child = spawn_proc(p, true, job.logdir, &cancel, sb->seq, true);
+            std::lock_guard<std::mutex> g(mu);
+            standbys.push_back(sb);
+        }
+    }
+
+    void stop_standbys() {
+        std::deque<std::shared_ptr<Standby>> all;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            all.swap(standbys);
+        }
+        for (auto& sb : all) {
+            if (sb->child.stdin_fd >= 0) close(sb->child.stdin_fd), sb->child.stdin_fd = -1; // EOF without activation: it exits
+            wait_proc(sb->child, &cancel);
+            gpus.put(sb->gpu);
+        }
+    }
 
     void push(const Stage& st) {
         std::lock_guard<std::mutex> g(mu);
@@ -473,17 +560,40 @@ struct Watcher {
     }
 
     void create(const PeerID& id, const Stage& st) {
-        const int gpu = gpus.get();
+        std::shared_ptr<Standby> sb;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (!standbys.empty()) {
+                sb = standbys.front();
+                standbys.pop_front();
+            }
+        }
+        const int gpu = sb ? sb->gpu : gpus.get();
         if (gpu < 0) KF_LOGW("no free GPU slot for %s", id.str().c_str());
         Proc p = job.new_proc(id, gpu, st.version, st.cluster);
+        if (sb) {
+            // activate the warm process: its identity is the environment a cold worker would have been exec'ed with
+            std::string msg;
+            for (auto& kv : p.envs) msg += kv.first + "=" + kv.second + "\n";
+            msg += "\n";
+            size_t off = 0;
+            while (off < msg.size()) {
+                const ssize_t n = write(sb->child.stdin_fd, msg.data() + off, msg.size() - off);
+                if (n <= 0 && errno != EINTR) break;
+                if (n > 0) off += (size_t)n;
+            }
+            close(sb->child.stdin_fd);
+            sb->child.stdin_fd = -1;
+            fprintf(stderr, "[kungfu-run] standby-%d becomes %s\n", sb->seq, p.name.c_str());
+        }
         {
             std::lock_guard<std::mutex> g(mu);
             ++n_running;
             finished[id.key()] = false;
         }
         const int color = (int)(id.port % 6);
-        std::thread t([this, p, gpu, id, color] {
-            const int rc = run_proc(p, true, job.logdir, &cancel, color);
+        std::thread t([this, p, gpu, id, color, sb] {
+            const int rc = sb ? wait_proc(sb->child, &cancel) : run_proc(p, true, job.logdir, &cancel, color);
             gpus.put(gpu);
             std::lock_guard<std::mutex> g(mu);
             --n_running;
@@ -520,6 +630,7 @@ struct Watcher {
         for (auto& id : del) remove(id);
         for (auto& id : add) create(id, st);
         current = st.cluster;
+        replenish_standbys();
     }
 
     int loop(Server& server) {
@@ -560,6 +671,7 @@ struct Watcher {
     }
 
     void join_all() {
+        stop_standbys();
         std::map<uint64_t, std::thread> ts;
         {
             std::lock_guard<std::mutex> g(mu);

@@ -150,6 +150,7 @@ class FlatEngine:
         # gradients (one multi-tensor copy per bucket), bucket counting, in-order launches, stream/event wiring. Python keeps
         # what needs Python objects (re-pointing .grad), the NCCL baseline arm and the membership / state management.
         self._native = None
+        self._held: List[torch.Tensor] = []  # stolen gradients whose bucket copy has not been enqueued yet (released in finish())
         if self.mode in ("ssgd", "grads") and self.backend == "kernels" and os.environ.get("KUNGFU_NATIVE_ENGINE", "1") != "0":
             self._build_native()
         if self.overlap:
@@ -338,14 +339,28 @@ class FlatEngine:
                 for ei, e in enumerate(s.layout.entries):
                     gv = _view_like(s.grads, e.offset, e.param)
 
-                    def nhook(p, si=si, ei=ei, gv=gv):  # ONE native call per parameter
+                    gv_ptr, gv_stride = gv.data_ptr(), gv.stride()
+
+                    def nhook(p, si=si, ei=ei, gv=gv, gv_ptr=gv_ptr, gv_stride=gv_stride):  # ONE native call per parameter
                         if self._defer:
                             return
                         if not self._step_open:
                             self._open_step()
                         g = p.grad
-                        if ne.grad_ready(si, ei, g.data_ptr() if g is not None else 0, cur().cuda_stream):
-                            p.grad = gv
+                        st = cur().cuda_stream
+                        if g is None or g.data_ptr() == gv_ptr:
+                            ne.grad_ready(si, ei, 0, st)  # already in its arena slot (or absent: flush() zero-fills)
+                            return
+                        if g.stride() == gv_stride and g.dtype == gv.dtype:
+                            # a fresh autograd tensor with the slot's memory layout: the engine copies it with the rest of the
+                            # bucket in ONE launch; keep it alive until then (the allocator must not hand its block to a later
+                            # backward kernel before the copy has been enqueued)
+                            self._held.append(g)
+                            ne.grad_ready(si, ei, g.data_ptr(), st)
+                        else:
+                            gv.copy_(g)  # different layout (e.g. an expanded or transposed gradient): let torch convert it
+                            ne.grad_ready(si, ei, 0, st)
+                        p.grad = gv
                     self._hooks.append(e.param.register_post_accumulate_grad_hook(nhook))
             return
         for si, s in enumerate(self.sets):
@@ -657,6 +672,7 @@ class FlatEngine:
         """Make the current stream wait for the comm stream and reset the per-step bookkeeping."""
         if self._native is not None:
             status = self._native.finish(torch.cuda.current_stream().cuda_stream)
+            self._held.clear()
             self._step_open = False
             self._early = None
             self.steps += 1

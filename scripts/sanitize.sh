@@ -7,10 +7,16 @@ set -euo pipefail
 cd "$(dirname "$0")/.."
 mode="${1:-thread}"
 if [ "$mode" = "cuda" ]; then
+    # one-rank forms of every collective / fused kernel (kungfu_b200/selftest.py), the optimizer, BN and transformer kernels
+    sel="one_rank_mesh or allreduce_single_rank or flat_opt or cast or add_layernorm or bias_gelu or bn_"
+    out="${2:-gpurun_out/compute_sanitizer}"
+    mkdir -p "$(dirname "$out")"
+    rc=0
     for tool in memcheck racecheck synccheck; do
-        compute-sanitizer --tool "$tool" --error-exitcode 1 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "allreduce or flat_opt or cast or bn"
+        compute-sanitizer --tool "$tool" --error-exitcode 1 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "$sel" > "$out.$tool.log" 2>&1 || rc=1
+        echo "compute-sanitizer $tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' "$out.$tool.log" | tail -1) | $(tail -1 "$out.$tool.log")"
     done
-    exit 0
+    exit $rc
 fi
 KUNGFU_SANITIZE="$mode" python -c "from kungfu_b200 import _build; _build.build_runtime(verbose=True)"
 bin="kungfu_b200/bin-$mode"

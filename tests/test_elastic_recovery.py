@@ -72,10 +72,10 @@ def test_standalone_config_server(tmp_path):
             p.kill()
 
 
-def _watch(np, slots, what, extra, cfg_port, timeout=240, env=None):
+def _watch(np, slots, what, extra, cfg_port, timeout=240, env=None, flags=()):
     rport, prange = ports()
     cmd = [kungfu_run(), "-q", "-w", "-np", str(np), "-H", f"127.0.0.1:{slots}", "-port", str(rport), "-port-range", prange,
-           "-builtin-config-port", str(cfg_port), sys.executable, WORKER, what, *extra]
+           "-builtin-config-port", str(cfg_port), *flags, sys.executable, WORKER, what, *extra]
     e = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN")
     e.update(env or {})
     return subprocess.run(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
@@ -94,6 +94,19 @@ def test_elastic_step_schedule_grow_and_shrink():
     assert final[0]["sizes"] == [1, 2, 4, 8]
     assert len([j for j in js if j.get("detached")]) == 7  # 4 leave at 8->4, 2 at 4->2, 1 at 2->1
     assert "resize 1 -> 2 took" in r.stdout and "resize 8 -> 4 took" in r.stdout
+
+
+def test_elastic_grow_uses_warm_standby_workers():
+    """`kungfu-run -w -standby 2`: added workers are pre-started processes (interpreter, torch, native extensions loaded) that
+    receive their identity over a pipe — same training result as with cold starts, and the launcher reports the hand-overs."""
+    cfg_port = 9300 + os.getpid() % 200
+    r = _watch(1, 4, "elastic", ["--schedule", "1:3,2:3,4:3,2:3,1:3", "--max-step", "15"], cfg_port, timeout=300, flags=("-standby", "2"),
+               env={"KUNGFU_CONFIG_LOG_LEVEL": "INFO"})
+    assert r.returncode == 0, r.stdout[-5000:]
+    final = [j for j in json_lines(r.stdout) if j.get("elastic")]
+    assert len(final) == 1 and final[0]["final_step"] == 15 and final[0]["sizes"] == [1, 2, 4], r.stdout[-5000:]
+    assert r.stdout.count("becomes 127.0.0.1.") >= 3, r.stdout[-5000:]  # 1 worker at 1->2, 2 at 2->4: all from the standby pool
+    assert "[standby] ready" in r.stdout
 
 
 def test_elastic_churn_with_sibling_survivors():
