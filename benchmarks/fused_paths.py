@@ -27,7 +27,7 @@ from kungfu_b200.benchmarks import model_sizes  # noqa: E402
 from kungfu_b200.ops import collective as coll  # noqa: E402
 from kungfu_b200.runtime import get_runtime  # noqa: E402
 from kungfu_b200.utils import dtypes  # noqa: E402
-from kungfu_b200.utils.timing import ClockSampler, max_over_ranks  # noqa: E402
+from kungfu_b200.utils.timing import ClockSampler, max_over_ranks, nvlink_counters  # noqa: E402
 
 
 def hbm_peak():
@@ -57,17 +57,25 @@ def main():
     rows = []
     sampler = ClockSampler(rt.cuda_index()).start() if me == 0 else None
 
+    last_links = {}
+
     def timeit(fn, iters):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
         rt.control.barrier()
+        c0 = nvlink_counters(rt.cuda_index()) if me == 0 else None
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(iters):
             fn()
         t1.record()
         torch.cuda.synchronize()
+        rt.control.barrier()  # every rank's traffic of this loop has crossed the links before they are read again
+        c1 = nvlink_counters(rt.cuda_index()) if me == 0 else None
+        last_links.clear()
+        if c0 and c1:
+            last_links.update({"nvlink_tx_bytes_per_iter_counted": round((c1["tx"] - c0["tx"]) / iters), "nvlink_rx_bytes_per_iter_counted": round((c1["rx"] - c0["rx"]) / iters)})
         return max_over_ranks(t0.elapsed_time(t1) / iters) * 1e3  # us
 
     for model in a.models.split(","):
@@ -146,7 +154,7 @@ def main():
                          ext.OPT_ADAM, n, st.cuda_stream)
 
         def add(path, us, nvlink_bytes=0, hbm_bytes=0, note=""):
-            row = {"model": model, "params": n, "path": path, "us": round(us, 1), "note": note}
+            row = {"model": model, "params": n, "path": path, "us": round(us, 1), "note": note, **last_links}
             if nvlink_bytes:
                 gbs = nvlink_bytes / (us * 1e-6) / 1e9
                 row.update({"nvlink_bytes_per_dir": int(nvlink_bytes), "nvlink_gbs": round(gbs, 1), "frac_of_770_measured": round(gbs / 770, 3),

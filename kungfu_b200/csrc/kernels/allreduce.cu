@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(512) allreduce_nvls_kernel(const __grid_consta
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     float pre = 0.f, post = 0.f;
-    if constexpr (SUMSQ) {
+    if (SUMSQ && !(a.flags & kArSumSqPost)) {
         // |x_local|^2 over the whole local message. Block b touches exactly the vectors that the
         // peers' block b will later overwrite, and does so before it signals — no race with the
         // in-place multicast stores.

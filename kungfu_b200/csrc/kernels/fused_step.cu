@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(512) ssgd_fused_kernel(const __grid_constant__
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const bool sumsq = (a.flags & kArSumSq) != 0;
     float pre = 0.f, post = 0.f;
-    if (NVLS && sumsq) {
+    if (NVLS && sumsq && !(a.flags & kArSumSqPost)) {
         for (int r = 0; r < m.nranks; ++r) {
             size_t q0, q1;
             slice_bounds2(a.nvec, m.nranks, r, q0, q1);
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(512) ssgd_fused_kernel(const __grid_constant__
             const size_t v = v0 + (size_t)u * stride;
             if (v < s1) {
                 if constexpr (NVLS) gs[u] = unpack<T>(Multimem<T, kSum>::ld_reduce(reinterpret_cast<const char*>(m.mc) + a.grad_off + v * 16));
-                else gs[u] = gather_sum<T>(m, a.grad_off + v * 16, sumsq ? &pre : nullptr);
+                else gs[u] = gather_sum<T>(m, a.grad_off + v * 16, (sumsq && !(a.flags & kArSumSqPost)) ? &pre : nullptr);
             }
         }
 #pragma unroll

@@ -38,7 +38,8 @@ constexpr int kThreads = 192;
 constexpr uint32_t kABytes = kBM * kBK * 2;          // 16 KiB
 constexpr uint32_t kBBytes = kBN * kBK * 2;          // 32 KiB
 constexpr uint32_t kStageBytes = kABytes + kBBytes;  // 48 KiB
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr uint32_t kBiasBytes = 2 * kBN * 4;          // the bias of the current / next tile as fp32, staged once per tile
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /* alignment slack */ + 256 /* barriers */ + kBiasBytes;
 constexpr uint32_t kTmemCols = 512;                  // 2 accumulators x 256 fp32 columns
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -140,7 +141,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // erf(x) by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7): one reciprocal, one exponential, five FMAs
 __device__ __forceinline__ float erf_fast(float x) {
     const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+    const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f)); // MUFU.RCP, no IEEE slow path: |error| stays far below bf16 resolution
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);
@@ -241,52 +242,57 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc5_kernel(const __grid_cons
         }
     } else {
         // ================= epilogue: TMEM -> registers -> bias/GELU -> bf16 -> global =================
-        const int q = warp & 3; // the TMEM lane quarter this warp may read: lanes [32 q, 32 q + 32)
+        const int q = warp & 3;            // the TMEM lane quarter this warp may read: lanes [32 q, 32 q + 32)
+        const int et = threadIdx.x - 64;   // 0..127 among the epilogue threads
+        float* sbias = reinterpret_cast<float*>(smem_raw + (bars + 256 - raw));
         uint32_t acc = 0, acc_phase = 0;
+        // one 32-column chunk: bias (shared memory, staged per tile) + activation + bf16 pack + 16-byte row-contiguous stores
+        auto emit = [&](const uint32_t* r, int c, int row, int n0, const float* sb, __nv_bfloat16* yrow) {
+            if (row >= a.M || n0 + c >= a.N) return;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                if (n0 + c + j < a.N) { // N % 8 == 0: a 16-byte chunk is entirely inside or outside
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]) + sb[c + j + i];
+                    if (a.act == 1) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
+                    }
+                    uint4 o;
+                    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                        ow[i] = *reinterpret_cast<const uint32_t*>(&h);
+                    }
+                    *reinterpret_cast<uint4*>(yrow + c + j) = o;
+                }
+            }
+        };
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int m0 = (t % a.tiles_m) * kBM, n0 = (t / a.tiles_m) * kBN;
+            // the tile's bias, once, as fp32 in shared memory (a global load per 8 columns inside the loop was the epilogue's
+            // critical path: 32 dependent L2 round trips per tile, ncu: long-scoreboard stalls on the bias unpack)
+            float* sb = sbias + acc * kBN;
+            for (int i = et; i < kBN; i += 128) sb[i] = (a.bias && n0 + i < a.N) ? __bfloat162float(a.bias[n0 + i]) : 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory"); // the four epilogue warps only
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const int row = m0 + q * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kBN;
             __nv_bfloat16* yrow = a.y + (size_t)row * a.N + n0;
+            // software pipeline over the 8 chunks: the TMEM load of chunk c+1 is in flight while chunk c is computed
+            uint32_t ra[32], rb[32];
+            tmem_ld32(taddr, ra);
 #pragma unroll 1
-            for (int c = 0; c < kBN; c += 32) {
-                uint32_t r[32];
-                tmem_ld32(taddr + c, r);
+            for (int c = 0; c < kBN; c += 64) {
                 tmem_ld_wait();
-                if (row < a.M && n0 + c < a.N) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        if (n0 + c + j < a.N) { // N % 8 == 0: a 16-byte chunk is entirely inside or outside
-                            float v[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]);
-                            if (a.bias) {
-                                const uint4 bq = __ldg(reinterpret_cast<const uint4*>(a.bias + n0 + c + j));
-                                const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&bw[i]);
-                                    v[2 * i] += __low2float(b2);
-                                    v[2 * i + 1] += __high2float(b2);
-                                }
-                            }
-                            if (a.act == 1) {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
-                            }
-                            uint4 o;
-                            uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                                ow[i] = *reinterpret_cast<const uint32_t*>(&h);
-                            }
-                            *reinterpret_cast<uint4*>(yrow + c + j) = o;
-                        }
-                    }
-                }
+                tmem_ld32(taddr + c + 32, rb);
+                emit(ra, c, row, n0, sb, yrow);
+                tmem_ld_wait();
+                if (c + 64 < kBN) tmem_ld32(taddr + c + 64, ra);
+                emit(rb, c + 32, row, n0, sb, yrow);
             }
             tc_fence_before();
             __syncwarp();

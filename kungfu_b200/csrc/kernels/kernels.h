@@ -15,7 +15,9 @@ namespace kf {
 enum Algo : int { kAlgoAuto = 0, kAlgoOneShot = 1, kAlgoTwoShot = 2, kAlgoNvls = 3 };
 // kArGated: split-phase launch (a gate kernel precedes, a wait kernel follows): no flag barriers inside the kernel,
 // its blocks signal completion on done word 0 and exit
-enum ArFlags : int { kArScale = 1, kArSumSq = 2, kArGated = 4 };
+// kArSumSqPost: with kArSumSq, only [1] (|result|^2) is accumulated — the caller already has sum_r |x_r|^2 (the gradient
+// hand-over copy computes it on the way into the arena)
+enum ArFlags : int { kArScale = 1, kArSumSq = 2, kArGated = 4, kArSumSqPost = 8 };
 enum OptKind : int { kOptSgd = 0, kOptAdam = 1 };
 
 // Device-resident optimizer hyper-parameters (16 floats). Kept in device memory so that a captured
@@ -109,7 +111,8 @@ void launch_u8_normalize(const uint8_t* src, void* dst, int dst_dtype, size_t np
 void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t st);
 // n (src -> dst, nbytes) copies in one launch per 48 tensors (gradient hand-over into the flat arena)
 constexpr int kMaxCopyBatch = 48;
-void launch_multi_copy(const void* const* src, void* const* dst, const size_t* nbytes, int n, cudaStream_t st);
+// sumsq != nullptr: sumsq[0] += sum of squares of everything copied, elements of `dtype` (f32 / bf16 / f16)
+void launch_multi_copy(const void* const* src, void* const* dst, const size_t* nbytes, int n, cudaStream_t st, float* sumsq = nullptr, int dtype = 0);
 
 // ---- bn_act.cu: fused BatchNorm (+residual) + ReLU on channels_last activations
 int bn_num_blocks(size_t rows, int C);

@@ -319,7 +319,34 @@ struct CopyBatch {
     void* dst[kMaxCopyBatch];
     unsigned long long nbytes[kMaxCopyBatch];
     int n;
+    float* sumsq; // optional: [0] += sum of squares of the copied elements
+    int dtype;
 };
+
+__device__ __forceinline__ float vec16_sumsq(const Vec16& v, int dtype) {
+    float s = 0.f;
+    if (dtype == kF32) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float f = __uint_as_float(v.w[i]);
+            s = fmaf(f, f, s);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float a, c;
+            if (dtype == kBF16) {
+                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&v.w[i]);
+                a = __low2float(h), c = __high2float(h);
+            } else {
+                const __half2 h = *reinterpret_cast<const __half2*>(&v.w[i]);
+                a = __low2float(h), c = __high2float(h);
+            }
+            s = fmaf(a, a, fmaf(c, c, s));
+        }
+    }
+    return s;
+}
 
 __global__ void __launch_bounds__(256) multi_copy_kernel(const __grid_constant__ CopyBatch b) {
     // blockIdx.y = tensor, blockIdx.x strides over its 16-byte vectors; ragged heads/tails go byte-wise
@@ -330,18 +357,56 @@ __global__ void __launch_bounds__(256) multi_copy_kernel(const __grid_constant__
     const size_t nb = b.nbytes[t];
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    float sq = 0.f;
     if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
         const size_t nv = nb / 16;
-        for (size_t v = tid; v < nv; v += stride) st_plain(d + v * 16, ld_ro_stream(s + v * 16));
-        for (size_t i = nv * 16 + tid; i < nb; i += stride) d[i] = s[i];
+        for (size_t v = tid; v < nv; v += stride) {
+            const Vec16 x = ld_ro_stream(s + v * 16);
+            if (b.sumsq) sq += vec16_sumsq(x, b.dtype);
+            st_plain(d + v * 16, x);
+        }
+        const size_t esz = b.dtype == kF32 ? 4 : 2;
+        for (size_t i = nv * 16 + tid * esz; i + esz <= nb; i += stride * esz) { // ragged tail, element-wise
+            float f;
+            if (esz == 4) {
+                f = *reinterpret_cast<const float*>(s + i);
+                *reinterpret_cast<float*>(d + i) = f;
+            } else {
+                const uint16_t h = *reinterpret_cast<const uint16_t*>(s + i);
+                *reinterpret_cast<uint16_t*>(d + i) = h;
+                f = b.dtype == kBF16 ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&h)) : __half2float(*reinterpret_cast<const __half*>(&h));
+            }
+            sq = fmaf(f, f, sq);
+        }
     } else {
         for (size_t i = tid; i < nb; i += stride) d[i] = s[i];
+        if (b.sumsq && blockIdx.x == 0 && threadIdx.x == 0) { // unaligned hand-over (never seen from autograd): correct, not fast
+            const size_t esz = b.dtype == kF32 ? 4 : 2;
+            for (size_t i = 0; i + esz <= nb; i += esz) {
+                float f;
+                if (esz == 4) memcpy(&f, s + i, 4);
+                else {
+                    uint16_t h;
+                    memcpy(&h, s + i, 2);
+                    f = b.dtype == kBF16 ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&h)) : __half2float(*reinterpret_cast<const __half*>(&h));
+                }
+                sq = fmaf(f, f, sq);
+            }
+        }
+    }
+    if (b.sumsq) {
+        __shared__ float red[32];
+        const float t0 = block_sum(sq, red);
+        if (threadIdx.x == 0 && t0 != 0.f) atomicAdd(b.sumsq, t0);
     }
 }
 
-void launch_multi_copy(const void* const* src, void* const* dst, const size_t* nbytes, int n, cudaStream_t st) {
+void launch_multi_copy(const void* const* src, void* const* dst, const size_t* nbytes, int n, cudaStream_t st, float* sumsq, int dtype) {
+    if (sumsq && dtype != kF32 && dtype != kBF16 && dtype != kF16) throw std::runtime_error("kungfu_b200: multi_copy sum of squares needs a float dtype");
     for (int base = 0; base < n; base += kMaxCopyBatch) {
         CopyBatch b{};
+        b.sumsq = sumsq;
+        b.dtype = dtype;
         b.n = n - base < kMaxCopyBatch ? n - base : kMaxCopyBatch;
         size_t big = 0;
         for (int i = 0; i < b.n; ++i) {

@@ -123,3 +123,34 @@ def flush_l2(buf: Optional[torch.Tensor] = None) -> torch.Tensor:
         buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     buf.fill_(1)
     return buf
+
+
+def nvlink_counters(gpu_index: int = 0) -> Optional[Dict[str, float]]:
+    """Cumulative NVLink data counters of one GPU, summed over its links, in bytes: {"tx": ..., "rx": ...} from
+    `nvidia-smi nvlink -gt d` (None if the tool or the counters are unavailable). Read them before and after a loop of K
+    launches: (after - before) / K is what one launch really moved over the links — the hardware's own byte count next to the
+    algorithmic one (Nsight Compute cannot attach to kernels that touch peer-mapped / multicast memory: `ncu` aborts with
+    "UnknownError" on them, see profiles/collectives_ncu.md)."""
+    import re
+
+    exe = shutil.which("nvidia-smi")
+    if exe is None:
+        return None
+    try:
+        out = subprocess.run([exe, "nvlink", "-gt", "d", "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=20).stdout
+    except Exception:
+        return None
+    tx = rx = 0.0
+    seen = False
+    for line in out.splitlines():
+        m = re.search(r"Data\s+(Tx|Rx):\s*([0-9]+)\s*(KiB|MiB|GiB|B)?", line, re.I)
+        if not m:
+            continue
+        mult = {"b": 1.0, "kib": 1024.0, "mib": 1048576.0, "gib": 1073741824.0}.get((m.group(3) or "KiB").lower(), 1024.0)
+        v = float(m.group(2)) * mult
+        seen = True
+        if m.group(1).lower() == "tx":
+            tx += v
+        else:
+            rx += v
+    return {"tx": tx, "rx": rx} if seen else None
