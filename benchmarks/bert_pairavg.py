@@ -92,6 +92,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--eager-ops", action="store_true", help="PyTorch LayerNorm / GELU instead of the fused kernels")
     ap.add_argument("--out", default="")
+    ap.add_argument("--breakdown", default="", help="rank 0: CUPTI kernel-time breakdown of 3 steps -> this markdown file")
     a = ap.parse_args()
     rt = get_runtime()
     N = rt.size
@@ -164,6 +165,29 @@ def main():
         g1.record(ss)
         torch.cuda.synchronize()
         pull_ms = max_over_ranks(g0.elapsed_time(g1)) / 5
+    if a.breakdown:
+        from torch.profiler import ProfilerActivity, profile
+
+        torch.cuda.synchronize()
+        rt.control.barrier()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+        rt.control.barrier()
+        if rt.rank == 0:
+            evs = [e for e in prof.key_averages() if getattr(e, "self_device_time_total", 0) > 0]
+            tot = sum(e.self_device_time_total for e in evs)
+            evs.sort(key=lambda e: -e.self_device_time_total)
+            lines = [f"# BERT-{a.model} step (batch {a.batch} x seq {a.seq}, impl {a.impl}, {N} GPUs): kernel device time from CUPTI, 3 graph replays\n",
+                     f"sum of kernel time per step: {tot / 3 / 1e3:.2f} ms (streams overlap: the step itself is {ms:.2f} ms)\n",
+                     "| ms/step | share | calls/step | kernel |", "|---:|---:|---:|---|"]
+            for e in evs[:28]:
+                lines.append(f"| {e.self_device_time_total / 3 / 1e3:.3f} | {100 * e.self_device_time_total / tot:.1f}% | {e.count / 3:.0f} | `{e.key[:100]}` |")
+            ours = sum(e.self_device_time_total for e in evs if "kf::" in e.key)
+            lines.append(f"\nkungfu_b200 kernels (`kf::`): {100 * ours / tot:.1f}% of kernel time")
+            os.makedirs(os.path.dirname(os.path.abspath(a.breakdown)), exist_ok=True)
+            open(a.breakdown, "w").write("\n".join(lines) + "\n")
     if rt.rank == 0:
         out = {"metric": "BERT PairAveraging sequences/sec", "value": round(N * a.batch / (ms / 1e3), 1), "unit": "sequences/sec", "impl": a.impl,
                "n_gpus": N, "model": a.model, "params": sum(p.numel() for p in model.parameters()), "dtype": "bf16 (fp32 master + AdamW state)",

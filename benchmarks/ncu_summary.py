@@ -57,7 +57,12 @@ def main():
                 tot = sum(v for v, _ in rows) or 1.0
                 rows.sort(key=lambda x: -x[0])
                 print(f"\nTop stall sites ({int(tot)} samples):\n\n| % of samples | SASS | dominant stall |\n|---:|---|---|")
-                for v, s in rows[:a.top]:
+                uniq, last = [], None
+                for v, s in rows:  # inlined code shows up as repeated (address, SASS) rows: keep one
+                    if (s[0], s[1]) != last:
+                        uniq.append((v, s))
+                    last = (s[0], s[1])
+                for v, s in uniq[:a.top]:
                     reasons = sorted(((float(s[sx[c]]), c) for c in sh if c.startswith("stall_") and "Not Issued" not in c and s[sx[c]] not in ("", "0")), reverse=True)
                     print(f"| {100 * v / tot:.1f} | `{s[1].strip()[:70]}` | {reasons[0][1] if reasons else '-'} |")
         print()

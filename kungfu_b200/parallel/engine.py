@@ -125,7 +125,8 @@ class FlatEngine:
         whole = mode in ("pair", "sma")  # model averaging works on the whole model at once
         for s in group_params(param_groups, named):
             bb = (1 << 62) if whole else self.bucket_bytes
-            self.sets.append(_Set(s["group"], FlatLayout(s["items"], s["dtype"], bb)))
+            tail = 0 if (whole or not self.overlap) else int(float(os.environ.get("KUNGFU_TAIL_BUCKET_MB", "1")) * (1 << 20))
+            self.sets.append(_Set(s["group"], FlatLayout(s["items"], s["dtype"], bb, tail_bytes=tail)))
         if not self.sets:
             raise ValueError("kungfu_b200: optimizer has no trainable parameters")
         self._consensus_key = None  # checked lazily, once per membership (constructors never communicate)

@@ -38,7 +38,7 @@ class Bucket:
 class FlatLayout:
     """Layout of one homogeneous (dtype, hyper-parameter group) set of tensors."""
 
-    def __init__(self, named_params: Sequence, dtype: torch.dtype, bucket_bytes: int, reverse: bool = True) -> None:
+    def __init__(self, named_params: Sequence, dtype: torch.dtype, bucket_bytes: int, reverse: bool = True, tail_bytes: int = 0) -> None:
         self.dtype = dtype
         self.esize = torch.empty((), dtype=dtype).element_size()
         align = ALIGN_BYTES // self.esize
@@ -69,6 +69,26 @@ class FlatLayout:
             self.buckets.append(cur_bucket)
             cur = end
         self.total = cur  # elements
+        # The LAST bucket is the one backward produces last (the first layers of the model): nothing is left to hide its
+        # collective under, so its size is exposed step time. Cut a small tail off it: the bulk of the remainder still overlaps
+        # with the end of backward, only `tail_bytes` worth of gradients is reduced after the last backward kernel.
+        if tail_bytes > 0 and len(self.buckets) >= 1:
+            last = self.buckets[-1]
+            tail_elems = max(align, tail_bytes // self.esize)
+            if last.numel > 2 * tail_elems and len(last.entries) > 1:
+                keep = list(last.entries)
+                moved = []
+                size = 0
+                while len(keep) > 1 and size + self.entries[keep[-1]].numel <= tail_elems:
+                    size += self.entries[keep[-1]].numel
+                    moved.insert(0, keep.pop())
+                if moved:
+                    split = self.entries[moved[0]].offset  # aligned: every entry starts on an `align` boundary
+                    nb = Bucket(len(self.buckets), split, last.start + last.numel - split, moved)
+                    last.entries, last.numel = keep, split - last.start
+                    for ei in moved:
+                        self.entries[ei].bucket = nb.index
+                    self.buckets.append(nb)
 
     @property
     def nbytes(self) -> int:

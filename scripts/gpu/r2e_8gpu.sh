@@ -25,7 +25,7 @@ echo "fused paths rc=$?" | tee -a $S
 ( timeout 400 $TR --nproc-per-node $N --master-port 29703 benchmarks/allreduce_bw.py --nccl --max-mb 256 --blocks 32,64 --out gpurun_out/allreduce_bw_8gpu.json ) > gpurun_out/r2e_arbw.log 2>&1
 echo "allreduce bw rc=$?" | tee -a $S
 for impl in ours local; do
-  ( timeout 300 $TR --nproc-per-node $N --master-port $((29710 + RANDOM % 200)) benchmarks/bert_pairavg.py --impl $impl --steps 30 --out gpurun_out/bert_${impl}_8gpu.json ) > gpurun_out/r2e_bert_$impl.log 2>&1
+  ( timeout 300 $TR --nproc-per-node $N --master-port $((29710 + RANDOM % 200)) benchmarks/bert_pairavg.py --impl $impl --steps 30 --out gpurun_out/bert_${impl}_8gpu.json --breakdown gpurun_out/bert_${impl}_8gpu_kernels.md ) > gpurun_out/r2e_bert_$impl.log 2>&1
   echo "bert $impl rc=$? $(grep -o '"ms_per_step": [0-9.]*' gpurun_out/r2e_bert_$impl.log | head -1) $(grep -o '"value": [0-9.]*' gpurun_out/r2e_bert_$impl.log | head -1) $(grep -o '"torn_reads_max_over_ranks": [0-9]*' gpurun_out/r2e_bert_$impl.log | head -1)" | tee -a $S
 done
 # BASELINE.json config #5: elastic 4 -> 8 -> 4 with the gradient-noise-scale monitor, warm standby workers

@@ -12,6 +12,8 @@ echo "kernel tests rc=$? $(tail -1 gpurun_out/r2f_kernels.log)" | tee -a $S
 echo "gemm bench rc=$?" | tee -a $S; grep '^{' gpurun_out/r2f_gemm_bench.log | cut -c1-330 | tee -a $S
 ( timeout 400 $TR --nproc-per-node 2 --master-port 29611 tests/mp_gpu_worker.py ssgd ) > gpurun_out/r2f_mp2.log 2>&1
 echo "mp2 ssgd rc=$? $(grep -o '"fails": [0-9]*' gpurun_out/r2f_mp2.log | tail -1)" | tee -a $S
+( timeout 300 $TR --nproc-per-node 2 --master-port 29641 bench.py --gpus 2 --steps 30 --warmup 5 --no-e2e ) > gpurun_out/r2f_ours2.log 2>&1
+echo "ours2 rc=$? $(grep -o '"ms_per_step": [0-9.]*' gpurun_out/r2f_ours2.log | head -1) $(grep -o '"buckets": [0-9]*' gpurun_out/r2f_ours2.log)" | tee -a $S
 ( timeout 300 $TR --nproc-per-node 2 --master-port 29702 benchmarks/fused_paths.py --models resnet50 --out gpurun_out/fused_paths_2gpu.json ) > gpurun_out/r2f_fused.log 2>&1
 echo "fused paths rc=$?" | tee -a $S; grep -o '"path": "[^"]*", "us": [0-9.]*\|counted": [0-9]*' gpurun_out/r2f_fused.log | head -30 | tr '\n' ' ' | tee -a $S
 nvidia-smi nvlink -gt d -i 0 2>&1 | head -8 | tee -a $S
