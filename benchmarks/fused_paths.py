@@ -8,7 +8,8 @@ Paths (bf16 parameters / gradients, fp32 master + state where the optimizer keep
   sma_blend local blend + momentum-SGD step over the arena                                       [HBM-bound]
   pull      TMA pull of a peer's published model into a private buffer                           [runs under forward+backward]
   pair_step local average + AdamW + publish                                                      [HBM-bound]
-NVLink bytes per GPU and direction: NVLS all-reduce = S (switch reduces and multicasts), two-shot = 2 (N-1)/N S, pull = S.
+NVLink bytes per GPU and direction: NVLS all-reduce = S (1 + 1/N) (switch reduces and multicasts; checked against the link counters),
+two-shot = 2 (N-1)/N S, pull = S. Every row also carries the bytes the hardware link counters saw per launch (`nvidia-smi nvlink -gt d`).
 Rooflines: NVLink 770 GB/s measured peer copy (900 nominal); HBM copy from MEASURED_PEAKS.json (fallback 6650 GB/s).
 
   torchrun --nproc-per-node N benchmarks/fused_paths.py [--models resnet50,bert-large] [--out profiles/fused_paths_N.json]
@@ -65,6 +66,7 @@ def main():
         torch.cuda.synchronize()
         rt.control.barrier()
         c0 = nvlink_counters(rt.cuda_index()) if me == 0 else None
+        rt.control.barrier()  # rank 0 has read its counters (a subprocess: ~0.1 s) — nobody starts the timed loop before that
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(iters):
@@ -95,7 +97,9 @@ def main():
         hyper = hp.to(dev)
         ext.hyper_tick(hyper.data_ptr(), st.cuda_stream)
         algo = ext.ALGO_NVLS if (arena.has_multicast and N > 1) else ext.ALGO_TWOSHOT
-        nv_factor = 1.0 if algo == ext.ALGO_NVLS else 2.0 * (N - 1) / max(N, 1)
+        # bytes per GPU and direction: NVLS = S (1 + 1/N) (reduce-scatter: the switch reads every rank's whole message once, S out /
+        # S/N in; all-gather: S/N out / S in — confirmed by the link counters), two-shot P2P = 2 (N-1)/N S
+        nv_factor = (1.0 + 1.0 / N) if algo == ext.ALGO_NVLS else 2.0 * (N - 1) / max(N, 1)
         lanes = 8
         per_rank = ((n // lanes + N - 1) // N) * lanes
         master = torch.zeros(per_rank + 4096, device=dev)
