@@ -68,17 +68,16 @@ def analyze_rank(path):
     for st in steps[1:]:  # skip the first replay (profiler warm-up)
         t0 = st[0]["ts"]
         t1 = max(e["ts"] + e["dur"] for e in st)
-        streams = {}
-        for e in st:
-            streams.setdefault(e["args"].get("stream"), []).append(e)
-        main_id = max(streams, key=lambda k: sum(x["dur"] for x in streams[k]))
-        main = streams[main_id]
+        # "compute" = every kernel that is not one of the collective / gate / wait kernels (graph replays spread the compute
+        # kernels over several internal streams, so the stream id is not a usable discriminator)
+        main_id = None
+        main = [e for e in st if not COMM_PAT.search(e["name"])]
         busy = merged_busy([(e["ts"], e["ts"] + e["dur"]) for e in main])
         main_busy = sum(b - a for a, b in busy)
         main_end = busy[-1][1]
         comm = []
         for e in st:
-            if e["args"].get("stream") != main_id and COMM_PAT.search(e["name"]):
+            if COMM_PAT.search(e["name"]):
                 s, d = e["ts"], e["dur"]
                 comm.append({"name": e["name"][:60], "at_ms": (s - t0) / 1e3, "dur_us": d, "hidden_us": overlap_with(busy, s, s + d),
                              "grid": e["args"].get("grid"), "stream": e["args"].get("stream")})
