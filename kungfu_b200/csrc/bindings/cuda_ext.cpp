@@ -70,6 +70,7 @@ PYBIND11_MODULE(_kfcuda, m) {
         .def("peer_ptr", &PeerMesh::peer_ptr)
         .def("status", &PeerMesh::status)
         .def("clear_status", &PeerMesh::clear_status)
+        .def("abort", &PeerMesh::abort)
         .def("set_timeout_ms", &PeerMesh::set_timeout_ms)
         .def("reset_signals", [](PeerMesh& self, uintptr_t st) { self.reset_signals(S(st)); })
         .def("topology", [](const PeerMesh& self) {

@@ -41,6 +41,6 @@ struct MeshArgs {
     int nranks;
 };
 
-enum SignalError : uint32_t { kOk = 0, kErrBarrierTimeout = 1, kErrSeqlockTorn = 2 };
+enum SignalError : uint32_t { kOk = 0, kErrBarrierTimeout = 1, kErrSeqlockTorn = 2, kErrAbortedByHost = 3 };
 
 } // namespace kf

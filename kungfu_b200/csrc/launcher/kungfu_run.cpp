@@ -71,6 +71,7 @@ struct Flags {
     int standby = 0; // -standby N (watch mode): warmed-up processes kept ready to become workers at the next grow
     bool watch = false;
     bool keep = false;
+    bool shrink_on_failure = false; // -shrink-on-failure (watch mode): a crashed worker is removed from the cluster, the rest go on
     int init_version = 0;
     std::string config_server;
     long t0 = (long)time(nullptr);
@@ -88,7 +89,8 @@ struct Flags {
             "usage: kungfu-run [-np N] [-H ip:slots,...] [-hostfile f] [-self ip] [-nic name] [-strategy S]\n"
             "                  [-port-range a-b] [-port p] [-w] [-k] [-config-server URL] [-builtin-config-port p]\n"
             "                  [-init-version v] [-timeout d] [-logdir d] [-logfile f] [-q] [-v] [-allow-nvlink]\n"
-            "                  [-auto-recover d] [-delay d] [-debug-port p] [-standby n] prog args...\n"
+            "                  [-auto-recover d] [-delay d] [-debug-port p] [-standby n] [-shrink-on-failure]\n"
+            "                  prog args...\n"
             "strategies: ");
     for (auto& s : strategy_names()) fprintf(stderr, "%s ", s.c_str());
     fprintf(stderr, "\n");
@@ -101,7 +103,7 @@ Flags parse_flags(int argc, char** argv) {
     Flags f;
     int i = 1;
     auto is_bool_flag = [](const std::string& k) {
-        return k == "w" || k == "k" || k == "q" || k == "v" || k == "allow-nvlink" || k == "h" || k == "help";
+        return k == "w" || k == "k" || k == "q" || k == "v" || k == "allow-nvlink" || k == "h" || k == "help" || k == "shrink-on-failure";
     };
     for (; i < argc; ++i) {
         std::string a = argv[i];
@@ -140,6 +142,7 @@ Flags parse_flags(int argc, char** argv) {
         else if (k == "standby") f.standby = atoi(v.c_str());
         else if (k == "w") f.watch = parse_bool(v);
         else if (k == "k") f.keep = parse_bool(v);
+        else if (k == "shrink-on-failure") f.shrink_on_failure = parse_bool(v);
         else if (k == "init-version") f.init_version = atoi(v.c_str());
         else if (k == "config-server") f.config_server = v;
         else if (k == "t0") f.t0 = atol(v.c_str());
@@ -485,6 +488,8 @@ struct Watcher {
     int n_running = 0;
     bool failed = false;
     int fail_code = 0;
+    int n_shrinks = 0;
+    std::vector<std::thread> helpers; // loss announcements in flight
     Cluster current;
     // -standby N: warmed-up processes (interpreter, torch, CUDA context on a reserved GPU slot) waiting on a pipe for an identity
     struct Standby {
@@ -600,13 +605,63 @@ struct Watcher {
             finished[id.key()] = true;
             if (rc != 0 && !cancel.flag) {
                 KF_LOGE("%s finished with error %d", p.name.c_str(), rc);
-                failed = true;
-                fail_code = rc;
+                if (!shrink_without_locked(id)) {
+                    failed = true;
+                    fail_code = rc;
+                }
             }
             cv.notify_all();
         });
         std::lock_guard<std::mutex> g(mu);
         running[id.key()] = std::move(t);
+    }
+
+    // -shrink-on-failure: worker `id` of this host died. Instead of taking the job down, announce the cluster without it as
+    // the next stage: survivors get a "lost" control message (their collectives in flight abort, `recover()` adopts the stage),
+    // the other runners get the usual "update", the config server is told so that later resizes start from the truth.
+    // Called with `mu` held by the waiter thread of the dead process; the sends happen on a helper thread.
+    bool shrink_without_locked(const PeerID& id) {
+        if (!f.shrink_on_failure || history.empty()) return false;
+        const Stage& last = history.back();
+        if (!last.cluster.workers.contains(id)) return true; // already on its way out (a detached worker that crashed at exit)
+        if (last.cluster.workers.size() <= 1) return false;  // nobody left to continue
+        Stage st;
+        st.version = last.version + 1;
+        st.cluster = last.cluster;
+        st.cluster.workers = last.cluster.workers.minus(PeerList{id});
+        KF_LOGW("%s is gone: shrinking to %d workers (v%d)", id.str().c_str(), (int)st.cluster.workers.size(), st.version);
+        fprintf(stderr, "[kungfu-run] worker %s lost, continuing with %d workers\n", id.str().c_str(), (int)st.cluster.workers.size());
+        history.push_back(st);
+        stages.push_back(st);
+        ++n_shrinks;
+        helpers.emplace_back([this, st] { announce_loss(st); });
+        return true;
+    }
+
+    void announce_loss(const Stage& st) {
+        const std::string payload = st.to_json();
+        if (!job.config_server.empty()) {
+            std::string resp;
+            const int code = http_request("PUT", job.config_server, st.cluster.to_json(), &resp);
+            if (code != 200) KF_LOGW("config server did not take the shrunk cluster: %d %s", code, resp.c_str());
+        }
+        Client client(self);
+        for (auto& w : st.cluster.workers) {
+            try {
+                client.send(w, "lost", payload.data(), payload.size(), kConnControl, kNoFlag);
+            } catch (const std::exception& e) {
+                KF_LOGW("could not tell %s about the lost peer: %s", w.str().c_str(), e.what());
+            }
+        }
+        for (auto& r : st.cluster.runners) {
+            if (r == self) continue;
+            try {
+                client.send(r, "update", payload.data(), payload.size(), kConnControl, kNoFlag);
+            } catch (const std::exception& e) {
+                KF_LOGW("could not tell runner %s about the lost peer: %s", r.str().c_str(), e.what());
+            }
+        }
+        client.close_all();
     }
 
     void remove(const PeerID& id) {
@@ -672,6 +727,13 @@ struct Watcher {
 
     void join_all() {
         stop_standbys();
+        std::vector<std::thread> hs;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            hs.swap(helpers);
+        }
+        for (auto& h : hs)
+            if (h.joinable()) h.join();
         std::map<uint64_t, std::thread> ts;
         {
             std::lock_guard<std::mutex> g(mu);

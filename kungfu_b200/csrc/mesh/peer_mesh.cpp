@@ -563,6 +563,15 @@ std::vector<uint32_t> PeerMesh::status() const {
     return v;
 }
 void PeerMesh::clear_status() { memset(status_host_, 0, 64 * sizeof(uint32_t)); }
+void PeerMesh::abort() {
+    if (!status_host_) return;
+    volatile uint32_t* st = (volatile uint32_t*)status_host_;
+    if (st[0] == 0) {
+        st[1] = ((uint32_t)rank_ << 16) | 0xffffu;
+        __sync_synchronize();
+        st[0] = kErrAbortedByHost;
+    }
+}
 
 MeshTopology PeerMesh::topology() const {
     MeshTopology t;

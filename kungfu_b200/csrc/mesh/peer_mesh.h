@@ -68,6 +68,9 @@ public:
 
     std::vector<uint32_t> status() const;
     void clear_status();
+    // host -> device: make every device-side wait of this mesh give up at its next look at the status word (a peer is known to
+    // be dead: do not sit out the time-out). Kernels in flight finish with whatever they have; the caller discards the step.
+    void abort();
     void set_timeout_ms(double ms) { timeout_ns_ = (unsigned long long)(ms * 1e6); }
     void reset_signals(cudaStream_t st);
 

@@ -395,6 +395,25 @@ PYBIND11_MODULE(_kfrt, m) {
         .def("last_throughput", [](Peer& p) { return p.session()->last_throughput(); })
         .def("resize_cluster", &Peer::resize_cluster, py::call_guard<py::gil_scoped_release>())
         .def("resize_cluster_from_url", &Peer::resize_cluster_from_url, py::call_guard<py::gil_scoped_release>())
+        .def("recover", &Peer::recover, py::arg("timeout_s") = 30.0, py::call_guard<py::gil_scoped_release>())
+        .def("failure_pending", &Peer::failure_pending)
+        .def("set_lost_callback", [](Peer& p, py::object fn) {
+            if (fn.is_none()) {
+                p.set_lost_callback(nullptr);
+                return;
+            }
+            // the callable is invoked from a transport thread: take the GIL there, and never destroy it without the GIL
+            auto holder = std::shared_ptr<py::object>(new py::object(fn), [](py::object* o) {
+                if (!Py_IsInitialized()) return; // interpreter is gone: leak the reference rather than touch it
+                py::gil_scoped_acquire g;
+                delete o;
+            });
+            p.set_lost_callback([holder] {
+                if (!Py_IsInitialized()) return;
+                py::gil_scoped_acquire g;
+                (*holder)();
+            });
+        })
         .def("propose_new_size", &Peer::propose_new_size, py::call_guard<py::gil_scoped_release>())
         .def("propose", [](Peer& p, const std::string& cluster_json) { return p.propose(Cluster::from_json(cluster_json)); },
              py::call_guard<py::gil_scoped_release>())

@@ -111,22 +111,98 @@ void Peer::close() {
     client_->close_all();
 }
 
-void Peer::on_control(const PeerID& src, const std::string& name, const Bytes&) {
+void Peer::on_control(const PeerID& src, const std::string& name, const Bytes& payload) {
     if (name == "exit") { // fault injection / orderly removal (reference: rchannel/handler/control.go:17-21)
-        // only hosts that take part in the job (workers, runners) or this machine may ask a worker to leave
-        bool known = (src.ipv4 >> 24) == 127 || src.ipv4 == cfg_.self.ipv4;
-        {
-            std::lock_guard<std::mutex> g(mu_);
-            for (auto& p : cluster_.workers) known = known || p.ipv4 == src.ipv4;
-            for (auto& p : cluster_.runners) known = known || p.ipv4 == src.ipv4;
-        }
-        if (!known && !getenv_bool("KUNGFU_ALLOW_REMOTE_EXIT", false)) {
+        if (!trusted_source(src) && !getenv_bool("KUNGFU_ALLOW_REMOTE_EXIT", false)) {
             KF_LOGW("ignoring exit request from %s: not a host of this job", src.str().c_str());
             return;
         }
         KF_LOGW("exit requested by %s", src.str().c_str());
         _exit(0);
     }
+    if (name == "lost") { // a runner saw one of the workers die: abort what is in flight, keep the stage for recover()
+        if (!trusted_source(src)) {
+            KF_LOGW("ignoring membership notice from %s: not a host of this job", src.str().c_str());
+            return;
+        }
+        Stage st;
+        try {
+            st = Stage::from_json(std::string(payload.begin(), payload.end()));
+        } catch (const std::exception& e) {
+            KF_LOGE("bad stage in a lost-peer notice from %s: %s", src.str().c_str(), e.what());
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            if (st.version <= cluster_version_) return; // old news
+            for (auto& q : lost_stages_)
+                if (q.version == st.version) return; // every runner announces it
+            lost_stages_.push_back(st);
+            KF_LOGW("peer lost (announced by %s): v%d has %d workers: %s", src.str().c_str(), st.version, (int)st.cluster.workers.size(),
+                    st.cluster.workers.str().c_str());
+        }
+        coll_.shutdown("a peer of this cluster was lost");
+        client_->interrupt();
+        NetMonitor::get().add_counter("kungfu_peer_failures_total", 1);
+        lost_cv_.notify_all();
+        std::function<void()> cb;
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            cb = on_lost_;
+        }
+        if (cb) {
+            try {
+                cb();
+            } catch (const std::exception& e) {
+                KF_LOGW("lost-peer callback: %s", e.what());
+            }
+        }
+    }
+}
+
+void Peer::set_lost_callback(std::function<void()> f) {
+    std::lock_guard<std::mutex> g(mu_);
+    on_lost_ = std::move(f);
+}
+
+bool Peer::trusted_source(const PeerID& src) {
+    // only hosts that take part in the job (workers, runners) or this machine may change a worker's fate
+    bool known = (src.ipv4 >> 24) == 127 || src.ipv4 == cfg_.self.ipv4;
+    std::lock_guard<std::mutex> g(mu_);
+    for (auto& p : cluster_.workers) known = known || p.ipv4 == src.ipv4;
+    for (auto& p : cluster_.runners) known = known || p.ipv4 == src.ipv4;
+    return known;
+}
+
+bool Peer::failure_pending() {
+    std::lock_guard<std::mutex> g(mu_);
+    return !lost_stages_.empty();
+}
+
+std::pair<bool, bool> Peer::recover(double timeout_s) {
+    StallGuard sg("recover");
+    Stage st;
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        if (!lost_cv_.wait_for(lk, std::chrono::milliseconds((long)(timeout_s * 1000)), [&] { return !lost_stages_.empty(); }))
+            fail("recover: no runner announced a membership change within " + std::to_string(timeout_s) + " s");
+        // several workers may have died: jump to the newest announced stage (versions are strictly increasing)
+        st = lost_stages_.back();
+        lost_stages_.clear();
+        if (st.version <= cluster_version_) return {false, false};
+        KF_LOGW("recovering: v%d -> v%d, %d -> %d workers", cluster_version_, st.version, (int)cluster_.workers.size(), (int)st.cluster.workers.size());
+        cluster_ = st.cluster;
+        cluster_version_ = st.version;
+        updated_ = false;
+        session_.reset();
+    }
+    const bool keep = st.cluster.workers.contains(cfg_.self);
+    if (!keep) {
+        detached_ = true;
+        return {true, true};
+    }
+    update();
+    return {true, false};
 }
 
 uint64_t Peer::uid() const {
@@ -154,12 +230,16 @@ bool Peer::update() {
 
 bool Peer::update_to(const PeerList& pl) {
     StallGuard sg("updateTo(" + pl.str() + ")");
+    if (updated_) {
+        server_->set_token((uint32_t)cluster_version_);
+        return true;
+    }
+    // open the mailboxes for the new epoch BEFORE peers of that epoch can connect (they are refused until the token moves)
+    coll_.reopen(cluster_version_);
     server_->set_token((uint32_t)cluster_version_);
-    if (updated_) return true;
     KF_LOGD("updateTo v%d of %d peers: %s", cluster_version_, (int)pl.size(), pl.str().c_str());
     client_->reset_connections(pl, (uint32_t)cluster_version_);
     if (!pl.contains(cfg_.self)) return false;
-    coll_.reopen();
     auto sess = std::make_shared<Session>(cfg_.strategy, cfg_.self, pl, client_.get(), &coll_);
     sess->barrier(); // meets the barrier of every other member of the new cluster version
     session_ = sess;

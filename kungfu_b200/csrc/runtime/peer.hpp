@@ -7,6 +7,9 @@
 // the version; survivors rebuild their session (new token = new version, fresh connections, barrier with the NEW
 // membership), detached peers stop themselves.
 #pragma once
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -55,6 +58,15 @@ public:
     std::pair<bool, bool> resize_cluster_from_url();
     void propose_new_size(int new_size);      // rank 0 PUTs the resized cluster to the config server
     std::pair<bool, bool> propose(const Cluster& c);
+    // Shrink-and-continue after a worker died: the runner that saw the process go sends every survivor a "lost" control
+    // message carrying Stage{version + 1, cluster without the dead worker}; it aborts the collectives in flight (they throw)
+    // and is kept here. `recover()` waits for that stage (at most timeout_s), adopts it WITHOUT a consensus round on the old
+    // session (which the dead peer can no longer answer) and meets the other survivors at the barrier of the new session.
+    // Returns (changed, detached). The reference only restarts the whole job from a checkpoint (runner/monitored.go:48-73).
+    std::pair<bool, bool> recover(double timeout_s);
+    bool failure_pending();
+    // called (on the server's reader thread) the moment a loss is announced: the GPU plane uses it to abort device-side waits
+    void set_lost_callback(std::function<void()> f);
 
     // p2p blob store
     void save(const std::string& name, const void* data, size_t len);
@@ -67,6 +79,7 @@ public:
 private:
     bool update_to(const PeerList& pl);
     bool fetch_cluster(Cluster& out);
+    bool trusted_source(const PeerID& src);
     void on_control(const PeerID& src, const std::string& name, const Bytes& payload);
 
     PeerConfig cfg_;
@@ -78,6 +91,9 @@ private:
     std::unique_ptr<class HttpServer> metrics_;
     std::shared_ptr<Session> session_;
     Cluster cluster_;
+    std::condition_variable lost_cv_;
+    std::deque<Stage> lost_stages_; // announced by the runners, not yet adopted
+    std::function<void()> on_lost_;
     int cluster_version_ = 0;
     bool updated_ = false;
     bool detached_ = false;

@@ -299,7 +299,9 @@ void NetMonitor::reset() {
 Socket Client::dial(const PeerID& to, ConnType type, bool retry) {
     const Config& cfg = Config::get();
     const int tries = retry ? cfg.conn_retry_count : 1;
+    const uint64_t gen = abort_gen_.load();
     for (int attempt = 0; attempt < tries; ++attempt) {
+        if (abort_gen_.load() != gen) break; // interrupt(): the peer is known to be lost
         Socket s;
         if (cfg.use_unix_sock && to.colocated_with(self_)) s = Socket::connect_unix(to.sock_file());
         if (!s.valid()) s = Socket::connect_tcp(to.ipv4, to.port, 2000);
@@ -505,11 +507,15 @@ Bytes CollectiveEndpoint::recv(const PeerID& src, const std::string& name) {
     return std::move(w.data);
 }
 
-bool CollectiveEndpoint::on_message(const PeerID& src, const std::string& name, uint32_t, uint64_t len, Socket& s) {
+bool CollectiveEndpoint::on_message(const PeerID& src, const std::string& name, uint32_t, uint64_t len, Socket& s, uint32_t conn_epoch) {
     const std::string k = key(src, name);
     Waiter* w = nullptr;
     {
         std::lock_guard<std::mutex> g(mu_);
+        if (closed_ || (epoch_ >= 0 && (int64_t)conn_epoch != epoch_)) {
+            KF_LOGD("dropping %s from %s: %s", name.c_str(), src.str().c_str(), closed_ ? "endpoint closed" : "stale epoch");
+            return s.discard(len);
+        }
         auto it = slots_.find(k);
         if (it != slots_.end() && it->second.waiter) {
             w = it->second.waiter;
@@ -543,6 +549,7 @@ bool CollectiveEndpoint::on_message(const PeerID& src, const std::string& name, 
     Bytes b(len);
     if (len && !s.recv_all(b.data(), len)) return false;
     std::lock_guard<std::mutex> g(mu_);
+    if (closed_ || (epoch_ >= 0 && (int64_t)conn_epoch != epoch_)) return true; // membership changed while we were reading
     Slot& slot = slots_[k];
     if (slot.waiter) { // a receiver registered while we were reading
         Waiter* w2 = slot.waiter;
@@ -580,9 +587,11 @@ void CollectiveEndpoint::shutdown(const std::string& why) {
         }
     slots_.clear();
 }
-void CollectiveEndpoint::reopen() {
+void CollectiveEndpoint::reopen(int64_t epoch) {
     std::lock_guard<std::mutex> g(mu_);
+    if (closed_) slots_.clear(); // nothing parked before a shutdown belongs to the session that comes next
     closed_ = false;
+    if (epoch >= 0) epoch_ = epoch;
     close_reason_.clear();
 }
 size_t CollectiveEndpoint::parked() const {
@@ -826,7 +835,7 @@ void Server::serve(Socket s) {
         NetMonitor::get().ingress(src, mh.data_len);
         switch (type) {
         case kConnCollective:
-            if (!coll_ || !coll_->on_message(src, name, mh.flags, mh.data_len, s)) return;
+            if (!coll_ || !coll_->on_message(src, name, mh.flags, mh.data_len, s, ack.token)) return;
             break;
         case kConnPeerToPeer:
             if (!p2p_ || !p2p_->on_message(src, name, mh.flags, mh.data_len, s)) return;

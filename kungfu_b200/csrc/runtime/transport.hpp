@@ -108,6 +108,8 @@ public:
     bool wait_peer(const PeerID& to, double timeout_s);   // polls ping until reachable
     void reset_connections(const PeerList& keeps, uint32_t token);
     void close_all();
+    // abandon every dial that is being retried right now (a peer is known to be gone: do not sit out the retry budget)
+    void interrupt() { ++abort_gen_; }
 
 private:
     struct Conn {
@@ -118,6 +120,7 @@ private:
     Socket dial(const PeerID& to, ConnType type, bool retry);
     PeerID self_;
     std::atomic<uint32_t> token_{0};
+    std::atomic<uint64_t> abort_gen_{0};
     std::mutex mu_;
     std::map<std::pair<uint64_t, int>, std::shared_ptr<Conn>> pool_;
 };
@@ -164,10 +167,12 @@ public:
     // blocking receive of the message (src, name) into `buf` (exactly len bytes). Throws on shutdown / size mismatch.
     void recv_into(const PeerID& src, const std::string& name, void* buf, size_t len);
     Bytes recv(const PeerID& src, const std::string& name);
-    // called by the server's reader thread; must consume exactly `len` payload bytes from `s`
-    bool on_message(const PeerID& src, const std::string& name, uint32_t flags, uint64_t len, Socket& s);
-    void shutdown(const std::string& why); // wakes every waiter with an error
-    void reopen();
+    // called by the server's reader thread; must consume exactly `len` payload bytes from `s`. `conn_epoch` is the cluster
+    // version the connection was accepted under: traffic of another epoch (a peer that has not noticed a membership change
+    // yet) is consumed and dropped instead of being parked under a name the new session may reuse.
+    bool on_message(const PeerID& src, const std::string& name, uint32_t flags, uint64_t len, Socket& s, uint32_t conn_epoch = 0);
+    void shutdown(const std::string& why); // wakes every waiter with an error; later receives fail until reopen()
+    void reopen(int64_t epoch = -1);       // forgets parked messages; epoch >= 0 turns the fence on
     size_t parked() const;
 
 private:
@@ -190,6 +195,7 @@ private:
     mutable std::mutex mu_;
     std::unordered_map<std::string, Slot> slots_;
     bool closed_ = false;
+    int64_t epoch_ = -1;
     std::string close_reason_;
 };
 

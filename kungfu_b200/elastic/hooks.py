@@ -18,7 +18,8 @@ import torch
 
 from ..initializer import BroadcastGlobalVariablesOp
 from ..ops.adapt import StepBasedSchedule
-from ..python import all_reduce_int_max, current_cluster_size, current_rank, detached, propose_new_size, resize
+from ..python import (all_reduce_int_max, current_cluster_size, current_rank, detached, failure_pending, propose_new_size,
+                      recover, resize)
 
 
 @dataclass
@@ -26,6 +27,7 @@ class ElasticState:
     step: int = 0
     trained_samples: int = 0
     epoch: int = 0
+    recovering: bool = False  # set between a lost peer and the re-sync of the survivors
 
 
 class ResizeProfiler:
@@ -60,8 +62,67 @@ def sync_after_resize(state: ElasticState, model: torch.nn.Module, optimizer: Op
     eng = getattr(optimizer, "engine", None) if optimizer is not None else None
     BroadcastGlobalVariablesOp(model, optimizer if eng is None else None, 0)
     if eng is not None:
+        if getattr(eng, "_lost", None) is not None or getattr(state, "recovering", False):
+            eng.rebuild_state_after_loss()  # survivors of a crash: put the old shards back together first
         eng.sync_state_from_root(0)  # re-shard fp32 master weights / optimizer state for the new world size
+    state.recovering = False
     return state
+
+
+def is_peer_failure(exc: BaseException) -> bool:
+    """Does this exception look like "a collective broke because a peer went away"? (host plane: closed endpoint / refused
+    connection / lost connection; GPU plane: a device-side wait ran into its time-out)."""
+    if failure_pending():
+        return True
+    msg = str(exc)
+    return isinstance(exc, RuntimeError) and any(k in msg for k in (
+        "collective endpoint closed", "cannot connect to", "send to", "connection lost", "device-side barrier timed out", "a peer lost", "peer lost"))
+
+
+class ShrinkOnFailure:
+    """Shrink-and-continue for a training loop under `kungfu-run -w -shrink-on-failure`.
+
+        guard = ShrinkOnFailure(state, model, optimizer)
+        while state.step < max_step:
+            if guard.run(train_one_step):      # False: a peer died during this step, the survivors are re-synced — redo it
+                state.step += 1
+            if guard.detached: break
+
+    `run` executes the step; if it raises because a peer died, the survivors adopt the cluster the runner announced
+    (`kungfu_b200.python.recover`), reconnect the GPU arenas among themselves, agree on progress and take rank 0's model /
+    optimizer state (`sync_after_resize`), and `run` returns False so the caller repeats the step with the smaller cluster.
+    Anything that does not look like a lost peer is re-raised. SURVEY.md §5.3; the reference restarts the job instead
+    (srcs/go/kungfu/runner/monitored.go:48-73)."""
+
+    def __init__(self, state: ElasticState, model: torch.nn.Module, optimizer: Optional[torch.optim.Optimizer] = None,
+                 timeout_s: float = 30.0, max_failures: int = 16) -> None:
+        self.state, self.model, self.optimizer = state, model, optimizer
+        self.timeout_s = float(timeout_s)
+        self.max_failures = int(max_failures)
+        self.failures: List[Tuple[int, int, float]] = []  # (old size, new size, seconds to be training again)
+        self.detached = False
+
+    def run(self, step_fn, *args, **kwargs) -> bool:
+        try:
+            step_fn(*args, **kwargs)
+            return True
+        except Exception as e:  # noqa: BLE001 - classified below
+            if not is_peer_failure(e) or len(self.failures) >= self.max_failures:
+                raise
+            t0 = time.time()
+            old = current_cluster_size()
+            try:
+                changed, det = recover(self.timeout_s)
+            except Exception:
+                raise e  # nobody announced a membership change: it was not a lost peer after all
+            if det:
+                self.detached = True
+                return False
+            if changed:
+                self.state.recovering = True  # type: ignore[attr-defined]
+                sync_after_resize(self.state, self.model, self.optimizer)
+            self.failures.append((old, current_cluster_size(), time.time() - t0))
+            return False
 
 
 class KungFuElasticTrainHook:

@@ -734,6 +734,67 @@ class FlatEngine:
         self._pair_ready = False
         self._launched = [0 for _ in self.sets]
 
+    def prepare_recover(self) -> None:
+        """Called on every SURVIVOR after a peer died (`kungfu_b200.python.recover`), before the membership changes. Unlike
+        `prepare_resize` nothing collective can run (the dead rank would never answer): the fp32 shards stay where they are,
+        tagged with the world they were cut for, and `rebuild_state_after_loss` reassembles them once the survivors are
+        reconnected. Device-side waits that ran into their time-out have poisoned the status word: clear it."""
+        try:
+            torch.cuda.synchronize(self.plane.device_index)
+        except Exception:
+            pass
+        for a in list(self.plane._arenas):
+            try:
+                a.mesh.clear_status()
+            except Exception:
+                pass
+        self._full_state = None
+        self._held = []
+        ready = all(s.state_ready for s in self.sets) and self.mode in ("ssgd", "sma", "pair") and self.opt_kind is not None
+        self._lost = (self.rank, self.nranks, self._sharded) if ready else None
+
+    def rebuild_state_after_loss(self) -> None:
+        """COLLECTIVE over the survivors, after the arenas were reconnected: every survivor contributes the shards it owned in
+        the OLD world; the ranges the dead ranks owned are refilled from the (replicated) low-precision parameters for the fp32
+        master weights and with zeros for momentum / Adam moments — that slice of the optimizer history is gone, the model is
+        not. The result is the un-sharded state `sync_state_from_root` distributes."""
+        lost = getattr(self, "_lost", None)
+        self._lost = None
+        # who has what: agreed on the host plane (one small message; the survivors' new session is already up)
+        mine = b"-" if lost is None else f"{lost[0]}/{lost[1]}/{int(lost[2])}".encode()
+        views = self.rt.control.all_gather_bytes(mine) if self.nranks > 1 else [mine]
+        if lost is None or any(v == b"-" for v in views) or len({v.split(b"/", 1)[1] for v in views}) != 1:
+            return  # somebody never stepped (or the survivors disagree about the old world): lazily initialised state is right
+        old_rank, old_n, was_sharded = lost
+        dev = self.plane.device
+        full: Dict[str, torch.Tensor] = {}
+        owners = [int(v.split(b"/")[0]) for v in views]
+        for si, s in enumerate(self.sets):
+            lay = s.layout
+            for key, shards in (("master", s.master), ("s1", s.s1), ("s2", s.s2)):
+                if not any(t is not None for t in shards):
+                    continue
+                parts = []
+                for b in lay.buckets:
+                    t = shards[b.index]
+                    if t is None:
+                        continue
+                    if not was_sharded:
+                        parts.append(t[:b.numel].clone())
+                        continue
+                    per = lay.shard_elems(b, old_n)
+                    if key == "master":
+                        whole = torch.zeros(per * old_n, dtype=torch.float32, device=dev)
+                        whole[:b.numel].copy_(s.params[b.start:b.start + b.numel])
+                    else:
+                        whole = torch.zeros(per * old_n, dtype=torch.float32, device=dev)
+                    got = coll.all_gather(t.contiguous()).view(len(owners), -1) if self.nranks > 1 else t.view(1, -1)
+                    for i, r in enumerate(owners):
+                        whole[r * per:(r + 1) * per].copy_(got[i][:per])
+                    parts.append(whole[:b.numel])
+                full[f"set{si}.{key}"] = torch.cat(parts)
+        self._full_state = full
+
     def sync_state_from_root(self, root: int = 0) -> None:
         """Collective over the NEW membership (survivors and newcomers): rank `root` broadcasts the full fp32 state,
         every rank keeps the shard it now owns. Newcomers call it with no local state."""

@@ -128,6 +128,8 @@ class SymmetricArena:
             info = (f"code={st[0]} rank={st[1] >> 16} waiting_for_peer={st[1] & 0xffff} timeouts={st[2]} "
                     f"want_seq={st[3]} seen_seq={st[4]}")
             self.mesh.clear_status()
+            if st[0] == 3:
+                raise RuntimeError("kungfu_b200: device-side waits aborted by the host, a peer lost: " + info)
             raise RuntimeError("kungfu_b200: device-side barrier timed out: " + info)
 
     def close(self) -> None:
@@ -160,6 +162,18 @@ class GpuPlane:
         self._staging_off = 0
         self._staging_bytes = 0
         self.sm_count = torch.cuda.get_device_properties(self.device_index).multi_processor_count
+        # shrink-and-continue: the moment a runner announces a dead worker, every device-side wait is told to give up (the
+        # host-mapped status word) instead of sitting out KUNGFU_DEVICE_TIMEOUT_MS; `python.recover()` clears it again
+        peer = getattr(runtime.control, "peer", None)
+        if peer is not None and hasattr(peer, "set_lost_callback"):
+            peer.set_lost_callback(self.abort_device_waits)
+
+    def abort_device_waits(self) -> None:
+        for a in list(self._arenas):
+            try:
+                a.mesh.abort()
+            except Exception:
+                pass
 
     def membership_key(self):
         rt = self.runtime

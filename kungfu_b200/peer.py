@@ -203,6 +203,16 @@ class NativeControl(Control):
     def propose_new_size(self, n: int) -> None:
         self.peer.propose_new_size(int(n))
 
+    def recover(self, timeout_s: float = 30.0) -> Tuple[bool, bool]:
+        """Adopt the cluster the runners announced after a worker died (see `Peer::recover`). Returns (changed, detached)."""
+        changed, detached = self.peer.recover(float(timeout_s))
+        if changed and not detached:
+            self._refresh()
+        return bool(changed), bool(detached)
+
+    def failure_pending(self) -> bool:
+        return bool(self.peer.failure_pending())
+
     # ---- p2p store ------------------------------------------------------------------------------------
     def save(self, name: str, t: torch.Tensor, version: Optional[str] = None) -> None:
         t = t.contiguous()
@@ -219,6 +229,8 @@ class NativeControl(Control):
 
     def close(self) -> None:
         try:
+            if hasattr(self.peer, "set_lost_callback"):
+                self.peer.set_lost_callback(None)
             self.peer.close()
         except Exception:
             pass

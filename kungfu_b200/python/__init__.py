@@ -99,6 +99,44 @@ def resize(n: Optional[int] = None) -> Tuple[bool, bool]:
     return changed, det
 
 
+def recover(timeout_s: float = 30.0) -> Tuple[bool, bool]:
+    """Shrink-and-continue: call after a collective raised because a worker died under `kungfu-run -w -shrink-on-failure`.
+
+    The runner that saw the process die announces the cluster without it; this call adopts that cluster (no consensus with
+    the dead peer), rebuilds the session among the survivors and returns (changed, detached) like `resize()`. The caller then
+    re-syncs step and state exactly as after a resize (`elastic.sync_after_resize`): the interrupted step may have been applied
+    on some survivors and not on others, rank 0's copy becomes everybody's. The reference has no counterpart: its failure
+    detector restarts every worker from the last checkpoint (srcs/go/kungfu/runner/monitored.go:48-73).
+    """
+    rt = get_runtime()
+    f = getattr(rt.control, "recover", None)
+    if f is None:
+        raise RuntimeError("kungfu_b200: recover() needs the native runtime (kungfu-run -w -shrink-on-failure)")
+    if rt._gpu is not None:
+        import torch
+
+        try:
+            torch.cuda.synchronize()  # kernels spinning on the dead rank's flags run into their device time-out
+        except Exception:
+            pass
+        for e in rt._gpu.engines:
+            e.prepare_recover()
+    from ..utils.trace import trace_scope
+
+    with trace_scope("recover"):
+        changed, det = f(timeout_s)
+    if changed and not det and rt._gpu is not None:
+        for e in rt._gpu.engines:
+            e.finish_resize()
+    return changed, det
+
+
+def failure_pending() -> bool:
+    """True once a runner announced a lost worker that `recover()` has not adopted yet (collectives fail until then)."""
+    f = getattr(_ctl(), "failure_pending", None)
+    return bool(f()) if f else False
+
+
 def all_reduce_int_max(x: int) -> int:
     """Max of a Python int over all workers — how newcomers adopt the survivors' step counter (python/__init__.py:152-155)."""
     f = getattr(_ctl(), "all_reduce_int_max", None)

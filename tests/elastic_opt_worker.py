@@ -35,6 +35,51 @@ if which == "elastichook":
     elif kfp.current_rank() == 0:
         print(json.dumps({"done": which, "trained": hook.state.trained_samples, "steps": hook.state.step, "sizes": sorted(sizes)}), flush=True)
     sys.exit(0)
+if which == "shrink":
+    # shrink-and-continue: `schedule` = "<rank that dies>@<step>[,<rank>@<step>...]"; the survivors must finish `max_step` steps with identical
+    # models. Ranks are those of the cluster at the time of the crash.
+    from kungfu_b200.elastic import ElasticState, ShrinkOnFailure, sync_after_resize
+
+    torch.manual_seed(1234 + kfp.current_rank())
+    dev = torch.device("cpu")
+    if os.environ.get("KUNGFU_TEST_CUDA") == "1":  # the fused GPU engine: bf16 model, sharded fp32 master weights + momentum
+        from kungfu_b200.runtime import get_runtime as _grt
+
+        dev = torch.device("cuda", _grt().cuda_index())
+        torch.cuda.set_device(dev)
+        m = torch.nn.Sequential(torch.nn.Linear(4, 512), torch.nn.ReLU(), torch.nn.Linear(512, 2)).to(dev).bfloat16()
+    crashes = [tuple(int(x) for x in c.split("@")) for c in schedule.split(",")]
+    opt = kf.optimizers.SynchronousSGDOptimizer(torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9), named_parameters=m.named_parameters())
+    state = ElasticState()
+    sync_after_resize(state, m, opt)
+    guard = ShrinkOnFailure(state, m, opt, timeout_s=20)
+    sizes = []
+
+    def one_step():
+        if (kfp.current_rank(), state.step) in crashes and len(guard.failures) == sum(1 for r, t in crashes if t < state.step):
+            os._exit(17)  # dies mid-training without saying goodbye
+        opt.zero_grad()
+        m(torch.randn(3, 4, device=dev, dtype=next(m.parameters()).dtype)).float().pow(2).mean().backward()
+        opt.step()
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
+
+    while state.step < max_step and not guard.detached:
+        if guard.run(one_step):
+            state.step += 1
+            sizes.append(kfp.current_cluster_size())
+    # every survivor holds the same model: compare a checksum through the (new) session
+    flat = torch.cat([p.detach().reshape(-1) for p in m.parameters()]).double().cpu()
+    from kungfu_b200.runtime import get_runtime
+
+    ctl = get_runtime().control
+    lo = ctl.all_reduce_cpu_(flat.clone(), "min", "shrink::lo")
+    hi = ctl.all_reduce_cpu_(flat.clone(), "max", "shrink::hi")
+    print(json.dumps({"done": which, "rank": kfp.current_rank(), "step": state.step, "final_size": kfp.current_cluster_size(),
+                      "sizes": sorted(set(sizes)), "failures": [(a, b) for a, b, _ in guard.failures],
+                      "recover_s": [round(t, 3) for _, _, t in guard.failures], "identical": bool(torch.equal(lo, hi)),
+                      "finite": bool(torch.isfinite(flat).all())}), flush=True)
+    sys.exit(0)
 mk = {
     "sma": lambda o, n: kf.optimizers.SynchronousAveragingOptimizer(o, named_parameters=n),
     "pair": lambda o, n: kf.optimizers.PairAveragingOptimizer(o, named_parameters=n),

@@ -206,6 +206,38 @@ def test_every_optimizer_survives_resizes(which):
     assert done == [{"done": which, "step": 8, "sizes": [1, 2, 3], "finite": True}], r.stdout[-3000:]
 
 
+def test_shrink_and_continue_after_a_worker_crash():
+    """`kungfu-run -w -shrink-on-failure`: rank 2 of 3 dies (os._exit) inside step 4, later rank 0 of the remaining 2 dies inside step 8.
+    Each time the runner announces the cluster without the dead worker, the survivors' collectives abort, `ShrinkOnFailure` adopts
+    the new cluster, re-syncs from rank 0 and training goes on: the job ends with exit code 0, 12 steps done, one worker left."""
+    rport, prange = ports()
+    cfg_port = 9300 + os.getpid() % 100
+    cmd = [kungfu_run(), "-q", "-w", "-shrink-on-failure", "-np", "3", "-H", "127.0.0.1:4", "-port", str(rport), "-port-range", prange,
+           "-builtin-config-port", str(cfg_port), sys.executable, os.path.join(ROOT, "tests", "elastic_opt_worker.py"), "shrink", "2@4,0@8", "12"]
+    e = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN")
+    r = subprocess.run(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=200)
+    assert r.returncode == 0, r.stdout[-5000:]
+    done = [j for j in json_lines(r.stdout) if j.get("done") == "shrink"]
+    assert len(done) == 1, r.stdout[-5000:]
+    d = done[0]
+    assert d["step"] == 12 and d["final_size"] == 1 and d["sizes"] == [1, 2, 3] and d["failures"] == [[3, 2], [2, 1]], d
+    assert d["identical"] and d["finite"] and max(d["recover_s"]) < 20, d
+    assert r.stdout.count("lost, continuing with") == 2, r.stdout[-3000:]
+
+
+def test_shrink_keeps_survivors_identical():
+    """One crash in a 4-worker job: the 3 survivors finish with bit-identical models (rank 0's state is broadcast after the loss)."""
+    rport, prange = ports()
+    cfg_port = 9300 + (os.getpid() + 50) % 100
+    cmd = [kungfu_run(), "-q", "-w", "-shrink-on-failure", "-np", "4", "-H", "127.0.0.1:4", "-port", str(rport), "-port-range", prange,
+           "-builtin-config-port", str(cfg_port), sys.executable, os.path.join(ROOT, "tests", "elastic_opt_worker.py"), "shrink", "1@3", "8"]
+    e = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN")
+    r = subprocess.run(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=200)
+    assert r.returncode == 0, r.stdout[-5000:]
+    done = [j for j in json_lines(r.stdout) if j.get("done") == "shrink"]
+    assert len(done) == 3 and all(d["identical"] and d["step"] == 8 and d["final_size"] == 3 for d in done), r.stdout[-5000:]
+
+
 def test_sample_count_driven_elastic_hook():
     """`ElasticHook`: the loop ends after epochs x epoch_size samples whatever sizes the cluster went through (1 -> 2 -> 3 -> 1)."""
     rport, prange = ports()
