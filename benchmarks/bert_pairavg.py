@@ -112,9 +112,12 @@ def main():
         dist.all_reduce(torch.ones(1 << 16, device=dev))
         opt = NcclGossip(model, lr)
     elif a.impl == "local" or N == 1:
-        opt = kf.optimizers.SynchronousSGDOptimizer(torch.optim.AdamW(model.parameters(), lr=lr), named_parameters=model.named_parameters(),
-                                                    overlap=False)
-        if N > 1:  # same fused local AdamW kernel, nobody to talk to
+        if N > 1:
+            # nobody to talk to: the Python bucket path honours the nranks override below (the native engine asks the mesh); it hands the
+            # gradients over with one batched copy per bucket like the native one, and runs the same fused AdamW kernel
+            os.environ["KUNGFU_NATIVE_ENGINE"] = "0"
+        opt = kf.optimizers.SynchronousSGDOptimizer(torch.optim.AdamW(model.parameters(), lr=lr), named_parameters=model.named_parameters())
+        if N > 1:
             opt.engine.nranks = 1
     else:
         opt = kf.optimizers.PairAveragingOptimizer(torch.optim.AdamW(model.parameters(), lr=lr), named_parameters=model.named_parameters())

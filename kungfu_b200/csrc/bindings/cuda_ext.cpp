@@ -106,6 +106,7 @@ PYBIND11_MODULE(_kfcuda, m) {
         .def_property_readonly("nranks", &GradEngine::nranks);
     m.attr("MODE_SSGD") = (int)kModeSsgd;
     m.attr("MODE_GRADS") = (int)kModeGrads;
+    m.attr("MODE_COPY") = (int)kModeCopy;
     m.def("multi_copy", [](const std::vector<uintptr_t>& src, const std::vector<uintptr_t>& dst, const std::vector<size_t>& nbytes, uintptr_t st) {
         if (src.size() != dst.size() || src.size() != nbytes.size()) throw std::runtime_error("kungfu_b200: multi_copy lists differ in length");
         std::vector<const void*> s(src.size());
@@ -247,15 +248,22 @@ PYBIND11_MODULE(_kfcuda, m) {
     });
     m.def("add_ln_num_blocks", &add_ln_num_blocks);
     m.def("bias_gelu_num_blocks", &bias_gelu_num_blocks);
-    m.def("add_ln_fwd", [](uintptr_t x, uintptr_t res, uintptr_t gamma, uintptr_t beta, uintptr_t z, uintptr_t y, uintptr_t mean, uintptr_t rstd,
-                           int dtype, int rows, int H, float eps, uintptr_t st) {
-        launch_add_ln_fwd(P<const void>(x), P<const void>(res), P<const void>(gamma), P<const void>(beta), P<void>(z), P<void>(y), P<float>(mean),
-                          P<float>(rstd), dtype, rows, H, eps, S(st));
+    m.def("add_ln_fwd", [](uintptr_t x, uintptr_t res, uintptr_t lin_bias, uintptr_t gamma, uintptr_t beta, uintptr_t z, uintptr_t y, uintptr_t mean,
+                           uintptr_t rstd, int dtype, int rows, int H, float eps, uintptr_t st) {
+        launch_add_ln_fwd(P<const void>(x), P<const void>(res), P<const void>(lin_bias), P<const void>(gamma), P<const void>(beta), P<void>(z),
+                          P<void>(y), P<float>(mean), P<float>(rstd), dtype, rows, H, eps, S(st));
     });
     m.def("add_ln_bwd", [](uintptr_t dy, uintptr_t z, uintptr_t mean, uintptr_t rstd, uintptr_t gamma, uintptr_t dz, uintptr_t dgamma, uintptr_t dbeta,
-                           uintptr_t partial, int dtype, int rows, int H, uintptr_t st) {
+                           uintptr_t dlin_bias, uintptr_t partial, int dtype, int rows, int H, uintptr_t st) {
         launch_add_ln_bwd(P<const void>(dy), P<const void>(z), P<const float>(mean), P<const float>(rstd), P<const void>(gamma), P<void>(dz),
-                          P<void>(dgamma), P<void>(dbeta), P<float>(partial), dtype, rows, H, S(st));
+                          P<void>(dgamma), P<void>(dbeta), P<void>(dlin_bias), P<float>(partial), dtype, rows, H, S(st));
+    });
+    m.def("qkv_pack_num_blocks", &qkv_pack_num_blocks);
+    m.def("qkv_pack_bwd", [](uintptr_t dq, uintptr_t dk, uintptr_t dv, std::vector<long long> strides, uintptr_t out, uintptr_t dbias,
+                             uintptr_t partial, int dtype, int B, int S_, int heads, int d, uintptr_t st) {
+        if (strides.size() != 9) throw std::runtime_error("qkv_pack_bwd: 9 strides expected ({batch, head, seq} of dq, dk, dv)");
+        launch_qkv_pack_bwd(P<const void>(dq), P<const void>(dk), P<const void>(dv), strides.data(), P<void>(out), P<void>(dbias), P<float>(partial),
+                            dtype, B, S_, heads, d, S(st));
     });
     m.def("bias_gelu_fwd", [](uintptr_t x, uintptr_t bias, uintptr_t y, int dtype, size_t rows, int I, uintptr_t st) {
         launch_bias_gelu_fwd(P<const void>(x), P<const void>(bias), P<void>(y), dtype, rows, I, S(st));

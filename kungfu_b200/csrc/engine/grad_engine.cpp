@@ -14,7 +14,7 @@ namespace kf {
 GradEngine::GradEngine(PeerMesh* mesh, int mode, bool average, bool gated, int max_blocks, int threads, int algo)
     : mesh_(mesh), mode_(mode), average_(average), gated_(gated), max_blocks_(max_blocks), threads_(threads), algo_(algo) {
     if (!mesh) throw std::runtime_error("kungfu_b200 GradEngine: no mesh");
-    if (mode != kModeSsgd && mode != kModeGrads) throw std::runtime_error("kungfu_b200 GradEngine: bad mode");
+    if (mode != kModeSsgd && mode != kModeGrads && mode != kModeCopy) throw std::runtime_error("kungfu_b200 GradEngine: bad mode");
 }
 
 GradEngine::~GradEngine() {
@@ -101,7 +101,7 @@ void GradEngine::open_step(cudaStream_t stream) {
     KF_ENG_CHECK(cudaEventRecord(e, stream));
     KF_ENG_CHECK(cudaStreamWaitEvent(comm_, e, 0));
     for (auto& s : sets_) {
-        if (s.hyper && mode_ == kModeSsgd) {
+        if (s.hyper && mode_ != kModeGrads) {
             launch_hyper_tick(s.hyper, comm_);
             launches_ += 1;
         }
@@ -150,6 +150,7 @@ void GradEngine::launch_bucket(EngineSet& s, int bi, cudaStream_t stream, bool a
         b.bytes.clear();
         after_stream = true;
     }
+    if (mode_ == kModeCopy) return; // the optimizer's own kernel reads the arena on `stream` after the last hand-over
     if (after_stream) {
         cudaEvent_t e = next_event();
         KF_ENG_CHECK(cudaEventRecord(e, stream));

@@ -25,7 +25,9 @@
 
 namespace kf {
 
-enum EngineMode : int { kModeSsgd = 0, kModeGrads = 1 };
+// kModeCopy: hand-over only — gradients stolen from autograd are moved into the arena bucket by bucket, nothing is reduced (the model-
+// averaging optimizers consume the arena in their own kernel at the end of the step)
+enum EngineMode : int { kModeSsgd = 0, kModeGrads = 1, kModeCopy = 2 };
 
 struct EngineBucket {
     size_t start_bytes = 0; // offset of the bucket inside the set's flat region

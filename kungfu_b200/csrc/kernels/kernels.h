@@ -133,17 +133,21 @@ void launch_maxpool3x3s2_fwd(const void* x, void* y, uint8_t* idx, int dtype, in
 void launch_maxpool3x3s2_bwd(const void* dy, const uint8_t* idx, void* dx, int dtype, int N, int H, int W, int C, cudaStream_t st);
 
 // ---- transformer.cu: fused residual + LayerNorm and bias + GELU (forward / backward), bf16 / f16 activations
-int add_ln_num_blocks(int rows);    // rows of the [blocks][2][H] fp32 scratch the backward needs
+int add_ln_num_blocks(int rows);    // rows of the [blocks][2 or 3][H] fp32 scratch the backward needs
 int bias_gelu_num_blocks(int rows); // rows of the [blocks][I] fp32 scratch the backward needs
-// z = x + res (res may be null), y = LN(z) * gamma + beta; saves z (may be null: inference), mean, rstd
-void launch_add_ln_fwd(const void* x, const void* res, const void* gamma, const void* beta, void* z, void* y, float* mean, float* rstd, int dtype,
-                       int rows, int H, float eps, cudaStream_t st);
-// dz (= dx = dres), dgamma, dbeta from (dy, z, mean, rstd, gamma)
+int qkv_pack_num_blocks(int rows);  // rows of the [blocks][3H] fp32 scratch of qkv_pack_bwd
+// z = x (+ lin_bias) + res (res / lin_bias may be null), y = LN(z) * gamma + beta; saves z (may be null: inference), mean, rstd
+void launch_add_ln_fwd(const void* x, const void* res, const void* lin_bias, const void* gamma, const void* beta, void* z, void* y, float* mean,
+                       float* rstd, int dtype, int rows, int H, float eps, cudaStream_t st);
+// dz (= dx = dres), dgamma, dbeta and (dlin_bias != null) the gradient of the folded linear bias from (dy, z, mean, rstd, gamma)
 void launch_add_ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const void* gamma, void* dz, void* dgamma, void* dbeta,
-                       float* partial, int dtype, int rows, int H, cudaStream_t st);
+                       void* dlin_bias, float* partial, int dtype, int rows, int H, cudaStream_t st);
 void launch_bias_gelu_fwd(const void* x, const void* bias, void* y, int dtype, size_t rows, int I, cudaStream_t st);
 void launch_bias_gelu_bwd(const void* dy, const void* x, const void* bias, void* dx, void* dbias, float* partial, int dtype, int rows, int I,
                           cudaStream_t st);
+// (dq, dk, dv) [B, heads, S, d] with element strides {batch, head, seq} x 3 in `strides` -> out [B * S, 3 * heads * d] contiguous + dbias [3 * heads * d]
+void launch_qkv_pack_bwd(const void* dq, const void* dk, const void* dv, const long long* strides, void* out, void* dbias, float* partial, int dtype,
+                         int B, int S, int heads, int d, cudaStream_t st);
 
 // ---- gemm_sm100.cu: tcgen05 GEMM + bias (+GELU) epilogue (CUTLASS/CuTe sm100 collectives); act: 0 = identity, 1 = GELU
 bool gemm_sm100_available();

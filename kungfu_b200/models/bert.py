@@ -65,17 +65,21 @@ class BertLayer(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         B, S, H = x.shape
-        q, k, v = self.qkv(x).view(B, S, 3, self.heads, H // self.heads).permute(2, 0, 3, 1, 4)
-        a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H)
         if not self.fused_ops:
+            q, k, v = self.qkv(x).view(B, S, 3, self.heads, H // self.heads).permute(2, 0, 3, 1, 4)
+            a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H)
             x = self.ln1(x + self.out(a))
             h = self.ff1(x) if self.fused_mlp else F.gelu(self.ff1(x))
             return self.ln2(x + self.ff2(h))
-        from ..ops.transformer import add_layernorm, bias_gelu
+        from ..ops.transformer import add_layernorm, bias_gelu, qkv_projection
 
-        x = add_layernorm(self.out(a), x, self.ln1.weight, self.ln1.bias, self.ln1.eps)
+        # the biases of the two output GEMMs ride in the residual+LayerNorm kernels, the gradient of the fused QKV projection is packed
+        # by one kernel (no cat / layout copy / column-sum kernels in backward)
+        q, k, v = qkv_projection(x, self.qkv.weight, self.qkv.bias, self.heads)
+        a = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H)
+        x = add_layernorm(F.linear(a, self.out.weight), x, self.ln1.weight, self.ln1.bias, self.ln1.eps, lin_bias=self.out.bias)
         h = self.ff1(x) if self.fused_mlp else bias_gelu(F.linear(x, self.ff1.weight), self.ff1.bias)
-        return add_layernorm(self.ff2(h), x, self.ln2.weight, self.ln2.bias, self.ln2.eps)
+        return add_layernorm(F.linear(h, self.ff2.weight), x, self.ln2.weight, self.ln2.bias, self.ln2.eps, lin_bias=self.ff2.bias)
 
 
 class Bert(nn.Module):

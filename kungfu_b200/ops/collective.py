@@ -127,7 +127,11 @@ def _gpu_all_reduce_(x: torch.Tensor, op_code: int, average: bool, stream: Optio
         _gpu_all_reduce_hier_(plane, flat, op_code, average, st, algo)
         return
     nbytes = n * esize
-    if (nbytes <= plane.ll_max and nbytes % 8 == 0 and (algo or CONFIG.algo).lower() in ("auto", "ll")
+    # every rank pushes its whole (flag-doubled) message to N-1 peers: beyond ~128 KiB of pushes per rank the copy + barrier one-shot
+    # is faster (measured, profiles/allreduce_bw_8gpu.json: 64 KiB at N=8 LL 12.8 us vs one-shot 9.7 us; at N=2 LL wins up to 64 KiB)
+    forced_ll = (algo or CONFIG.algo).lower() == "ll"
+    ll_cap = plane.ll_max if forced_ll else min(plane.ll_max, (128 << 10) // max(1, plane.group_size - 1))
+    if (nbytes <= ll_cap and nbytes % 8 == 0 and (algo or CONFIG.algo).lower() in ("auto", "ll")
             and os.environ.get("KUNGFU_DISABLE_LL", "0") != "1"):
         # latency path: flag-carrying pushes straight from / into the user tensor — no staging copy, no barrier. The choice
         # depends on the message size only (identical on every rank); a misaligned view goes through an aligned temporary.

@@ -109,7 +109,16 @@ class TorchDistControl(Control):
                 pass
 
 
+# Set by `kungfu_b200.cmd.standby`: a warm standby worker runs the training script ahead of time (imports, model construction, moving it
+# to the GPU) and is held HERE, at the first thing that needs an identity, until the launcher hands it one.
+_activation_gate: Optional[Callable[[], None]] = None
+
+
 def _make_control() -> Control:
+    global _activation_gate
+    gate, _activation_gate = _activation_gate, None
+    if gate is not None:
+        gate()
     env = os.environ
     want = env.get("KUNGFU_CONTROL", "auto").lower()
     launched_by_kungfu = "KUNGFU_SELF_SPEC" in env
@@ -130,9 +139,24 @@ def _make_control() -> Control:
 
 class Runtime:
     def __init__(self) -> None:
-        self.control: Control = _make_control()
+        self._control: Optional[Control] = None
+        self._control_lock = threading.Lock()
         self._gpu = None
         self._finalizers: List[Callable[[], None]] = []
+
+    @property
+    def control(self) -> Control:
+        """The control plane, created at first use (so that what does not need an identity — `cuda_index()`, building a model — can
+        run in a standby worker before the launcher has assigned one)."""
+        if self._control is None:
+            with self._control_lock:
+                if self._control is None:
+                    self._control = _make_control()
+        return self._control
+
+    @control.setter
+    def control(self, c: Control) -> None:
+        self._control = c
 
     # ---- identity --------------------------------------------------------------------------------
     @property
@@ -197,7 +221,8 @@ class Runtime:
             except Exception:
                 pass
             self._gpu = None
-        self.control.close()
+        if self._control is not None:
+            self._control.close()
 
 
 def get_runtime() -> Runtime:

@@ -433,6 +433,78 @@ def test_add_layernorm_matches_fp32(H, with_res):
         assert (got.float() - ref).abs().max() <= 2e-2 * ref.abs().max() + 1e-2
 
 
+@pytest.mark.parametrize("H", [256, 1024])
+def test_add_layernorm_folds_the_linear_bias(H):
+    """`lin_bias` (the bias of the GEMM that produced x) is added inside the kernel; its gradient is the column sum of dz."""
+    from kungfu_b200.ops.transformer import add_layernorm
+
+    torch.manual_seed(5)
+    rows = 777
+    x = torch.randn(rows, H, device="cuda").bfloat16().requires_grad_()
+    r = torch.randn(rows, H, device="cuda").bfloat16().requires_grad_()
+    lb = (0.3 * torch.randn(H, device="cuda")).bfloat16().requires_grad_()
+    w = (1 + 0.1 * torch.randn(H, device="cuda")).bfloat16().requires_grad_()
+    b = (0.1 * torch.randn(H, device="cuda")).bfloat16().requires_grad_()
+    dy = torch.randn(rows, H, device="cuda").bfloat16()
+    y = add_layernorm(x, r, w, b, 1e-5, lin_bias=lb)
+    y.backward(dy)
+    xf, rf, lf, wf, bf = (t.detach().float().requires_grad_() for t in (x, r, lb, w, b))
+    zf = (xf + lf + rf).bfloat16().float()
+    yf = torch.nn.functional.layer_norm(zf, (H,), wf, bf, 1e-5)
+    yf.backward(dy.float())
+    assert torch.allclose(y.float(), yf, atol=3e-2, rtol=3e-2)
+    assert torch.allclose(x.grad.float(), xf.grad, atol=3e-2, rtol=3e-2) and torch.equal(x.grad, r.grad)
+    for got, ref in ((w.grad, wf.grad), (b.grad, bf.grad), (lb.grad, lf.grad)):
+        assert (got.float() - ref).abs().max() <= 2e-2 * ref.abs().max() + 1e-2
+    # the bias gradient is exactly the column sum of the dz the kernel stored (fp32 accumulation, one rounding)
+    assert torch.allclose(lb.grad.float(), x.grad.float().sum(0), atol=2e-2 * float(x.grad.float().sum(0).abs().max()) + 1e-3, rtol=0)
+
+
+@pytest.mark.parametrize("heads,d", [(4, 64), (16, 64)])
+def test_qkv_projection_matches_autograd(heads, d):
+    """Fused QKV projection: forward views equal the plain expression; backward (one pack kernel for cat + layout copy + bias column sum, then
+    the two GEMMs) equals autograd's through the same attention."""
+    from kungfu_b200.ops.transformer import qkv_projection
+
+    torch.manual_seed(6)
+    B, S, H = 3, 40, heads * d
+    x = torch.randn(B, S, H, device="cuda").bfloat16().requires_grad_()
+    w = (torch.randn(3 * H, H, device="cuda") / H ** 0.5).bfloat16().requires_grad_()
+    b = (0.1 * torch.randn(3 * H, device="cuda")).bfloat16().requires_grad_()
+    q, k, v = qkv_projection(x, w, b, heads)
+    a = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, S, H)
+    da = torch.randn_like(a)
+    a.backward(da)
+    x2, w2, b2 = (t.detach().clone().requires_grad_() for t in (x, w, b))
+    q2, k2, v2 = torch.nn.functional.linear(x2, w2, b2).view(B, S, 3, heads, d).permute(2, 0, 3, 1, 4)
+    a2 = torch.nn.functional.scaled_dot_product_attention(q2, k2, v2).transpose(1, 2).reshape(B, S, H)
+    a2.backward(da)
+    assert torch.equal(q, q2) and torch.equal(k, k2) and torch.equal(v, v2) and torch.equal(a, a2)
+    for got, ref in ((x.grad, x2.grad), (w.grad, w2.grad), (b.grad, b2.grad)):
+        assert (got.float() - ref.float()).abs().max() <= 2e-2 * ref.float().abs().max() + 1e-3
+    # non-contiguous / odd gradients take the repack fallback and must give the same answer
+    from kungfu_b200.ops.transformer import _QKVProjection
+
+    q, k, v = _QKVProjection.apply(x.detach().requires_grad_(), w.detach(), b.detach(), heads)
+    g = torch.randn(B, heads, S, d + 8, device="cuda").bfloat16()[..., 4:d + 4]  # misaligned base pointer
+    (q * g).sum().backward()
+
+
+def test_gelu_rational_erf_accuracy():
+    """The A&S 7.1.26 form used by bias_gelu stays within bf16 resolution of the exact erf GELU over the whole useful range."""
+    from kungfu_b200.ops.transformer import bias_gelu
+
+    x = torch.linspace(-9, 9, 1 << 16, device="cuda").half().view(-1, 1 << 10).requires_grad_()
+    zero = torch.zeros(1 << 10, device="cuda").half()
+    y = bias_gelu(x, zero)
+    y.backward(torch.ones_like(y))
+    xf = x.detach().double().requires_grad_()
+    yf = torch.nn.functional.gelu(xf)
+    yf.backward(torch.ones_like(yf))
+    assert (y.double() - yf).abs().max() < 2e-3 and (x.grad.double() - xf.grad).abs().max() < 2e-3
+    assert torch.isfinite(y).all() and torch.isfinite(x.grad).all()
+
+
 @pytest.mark.parametrize("I", [128, 3072, 4096])
 def test_bias_gelu_matches_fp32(I):
     from kungfu_b200.ops.transformer import bias_gelu
