@@ -79,6 +79,13 @@ def is_peer_failure(exc: BaseException) -> bool:
         "collective endpoint closed", "cannot connect to", "send to", "connection lost", "device-side barrier timed out", "a peer lost", "peer lost"))
 
 
+def cuda_context_lost(exc: BaseException) -> bool:
+    """A peer died while this worker's kernels had its memory mapped: the GPU contains the fault (`cudaErrorContained`, "Invalid access of
+    peer GPU memory over nvlink") and CUDA refuses all further work in this process — nothing on the device can be saved."""
+    msg = str(exc)
+    return "Invalid access of peer GPU memory" in msg or "cudaErrorContained" in msg
+
+
 class ShrinkOnFailure:
     """Shrink-and-continue for a training loop under `kungfu-run -w -shrink-on-failure`.
 
@@ -92,7 +99,13 @@ class ShrinkOnFailure:
     (`kungfu_b200.python.recover`), reconnect the GPU arenas among themselves, agree on progress and take rank 0's model /
     optimizer state (`sync_after_resize`), and `run` returns False so the caller repeats the step with the smaller cluster.
     Anything that does not look like a lost peer is re-raised. SURVEY.md §5.3; the reference restarts the job instead
-    (srcs/go/kungfu/runner/monitored.go:48-73)."""
+    (srcs/go/kungfu/runner/monitored.go:48-73).
+
+    GPU plane: measured on 2 x B200 — when a worker dies while a survivor's collective kernels have its HBM mapped (always the case
+    inside a fused S-SGD step), the survivor's next access faults, the GPU contains the error (`cudaErrorContained`) and CUDA refuses
+    all further work in that process. That cannot be continued in-process by anybody (NCCL has the same limit); `run` reports it as
+    such. Shrink-and-continue therefore serves the host plane (CPU tensors, control-plane collectives, elastic data loading) and
+    GPU jobs between steps; a GPU worker killed mid-step needs `-auto-recover`."""
 
     def __init__(self, state: ElasticState, model: torch.nn.Module, optimizer: Optional[torch.optim.Optimizer] = None,
                  timeout_s: float = 30.0, max_failures: int = 16) -> None:
@@ -107,6 +120,12 @@ class ShrinkOnFailure:
             step_fn(*args, **kwargs)
             return True
         except Exception as e:  # noqa: BLE001 - classified below
+            if cuda_context_lost(e):
+                raise RuntimeError(
+                    "kungfu_b200: a peer was lost while its HBM was mapped into this worker's kernels; the GPU contained the NVLink fault and "
+                    "this process' CUDA context is gone (CUDA requires a relaunch). Shrink-and-continue covers the host plane and GPU "
+                    "workers whose kernels were not touching the dead peer; for this case run under `kungfu-run -auto-recover` and "
+                    "resume from the last checkpoint.") from e
             if not is_peer_failure(e) or len(self.failures) >= self.max_failures:
                 raise
             t0 = time.time()

@@ -28,7 +28,9 @@ WANT = {
     "barrier_kernel": ("misc.o", r"barrier_kernel"),
     "multi_copy_kernel": ("optim.o", r"multi_copy_kernel"),
     "add_ln_fwd_bf16_h1024": ("transformer.o", r"add_ln_fwd_kernel<__nv_bfloat16, *4>"),
-    "add_ln_bwd_bf16_h1024": ("transformer.o", r"add_ln_bwd_kernel<__nv_bfloat16, *4>"),
+    "add_ln_bwd_bf16_h1024": ("transformer.o", r"add_ln_bwd_kernel<__nv_bfloat16, *4, *true>"),
+    "qkv_pack_bwd_bf16": ("transformer.o", r"qkv_pack_bwd_kernel<__nv_bfloat16, *2>"),
+    "colsum_finalize_bf16": ("transformer.o", r"colsum_finalize_kernel<__nv_bfloat16>"),
     "bias_gelu_bwd_bf16": ("transformer.o", r"bias_gelu_bwd_kernel<__nv_bfloat16, *2>"),
     "bn_apply_res_relu_bf16": ("bn_act.o", r"bn_apply_kernel<__nv_bfloat16, *true, *true"),
     "bn_stats_bf16": ("bn_act.o", r"bn_stats_kernel<__nv_bfloat16"),

@@ -70,6 +70,12 @@ def check_pair(rt, log):
     eng = opt.engine
     assert eng is not None and eng.mode == "pair"
     rr = [0] * N
+    # Only one rank trains at a time below, so the things every member does TOGETHER at the first step of a membership (agree on the step
+    # counter, bucket-plan consensus, connect the arena, publish + barrier) happen here, in the same order on every rank; inside the loop
+    # the first backward of a rank would otherwise run the plan consensus from its gradient hook while the others sit in the step-counter
+    # all-reduce of `_kf_membership_changed`.
+    opt._kf_membership_changed()
+    opt._kf_first_publish()
     # deterministic schedule: one rank steps at a time (what it pulls is then well defined)
     for step in range(3):
         for r in range(N):
@@ -87,10 +93,6 @@ def check_pair(rt, log):
                 loss_of(m, me, step).backward()
                 opt.step()
                 torch.cuda.synchronize()
-            elif step == 0 and not opt._kf_published:
-                # every rank must take part in the first publish + barrier
-                opt._kf_membership_changed()
-                opt._kf_first_publish()
             coll.barrier()
     for a, b in zip(sims[me].parameters(), m.parameters()):
         if not torch.allclose(a, b, atol=2e-5, rtol=2e-5):
