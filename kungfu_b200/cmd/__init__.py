@@ -43,7 +43,8 @@ def config_server_path() -> str:
 def _monitor_addr() -> str:
     peers = os.environ.get("KUNGFU_INIT_PEERS", "")
     host = peers.split(",")[0].rsplit(":", 1)[0] if peers else "127.0.0.1"
-    return os.environ.get("KUNGFU_MONITOR_ADDR", f"http://{host}:{MONITOR_PORT}/")
+    # under `kungfu-run -w -shrink-on-failure -auto-recover d` every runner watches its own workers: report to it
+    return os.environ.get("KUNGFU_MONITOR_ADDR", os.environ.get("KUNGFU_HANG_WATCH", f"http://{host}:{MONITOR_PORT}/"))
 
 
 def _send_signal(kind: str) -> bool:

@@ -91,6 +91,8 @@ struct Flags {
             "                  [-init-version v] [-timeout d] [-logdir d] [-logfile f] [-q] [-v] [-allow-nvlink]\n"
             "                  [-auto-recover d] [-delay d] [-debug-port p] [-standby n] [-shrink-on-failure]\n"
             "                  prog args...\n"
+            "  -w -shrink-on-failure: a worker that exits with an error is removed, the others continue; with -auto-recover d also a\n"
+            "  worker whose batch stays open for d while it is not waiting in a collective (it hangs) is killed and removed.\n"
             "strategies: ");
     for (auto& s : strategy_names()) fprintf(stderr, "%s ", s.c_str());
     fprintf(stderr, "\n");
@@ -214,6 +216,7 @@ private:
 };
 
 struct Job {
+    std::string hang_watch; // URL the workers report "waiting in a collective" to (watch mode with -shrink-on-failure -auto-recover)
     long start_time = 0;
     std::string strategy;
     PeerID parent;
@@ -253,6 +256,7 @@ struct Job {
         e[envkeys::kJobStart] = std::to_string(start_time);
         e[envkeys::kProcStart] = std::to_string((long)time(nullptr));
         if (!config_server.empty()) e[envkeys::kConfigServer] = config_server;
+        if (!hang_watch.empty()) e["KUNGFU_HANG_WATCH"] = hang_watch;
         const std::string idx = cuda_index(gpu_slot);
         e[envkeys::kCudaVisibleDevices] = idx;
         if (allow_nvlink) e[envkeys::kAllowNvlink] = "1";
@@ -473,6 +477,87 @@ int simple_run(const Flags& f, const Job& job, const Cluster& cluster, uint32_t 
 // ---------------------------------------------------------------------------------------------------
 // watch (elastic) mode
 // ---------------------------------------------------------------------------------------------------
+// Watch mode + -shrink-on-failure + -auto-recover d: workers send the same heartbeats as under the restart detector
+// (`monitor_batch_begin/end`, key "begin:<rank>"); a rank whose batch has been open for longer than d is not dead, so nobody would ever
+// see an exit status — the watch kills it, which turns "hung" into "crashed" and hands it to the shrink path.
+class HangWatch {
+public:
+    using OnHang = std::function<void(int rank, double stalled_s)>;
+    explicit HangWatch(double threshold_s) : threshold_s_(threshold_s) {}
+    ~HangWatch() { stop(); }
+    void start(const std::string& self_ip, int port, OnHang cb) {
+        cb_ = std::move(cb);
+        try {
+            http_.start(self_ip.rfind("127.", 0) == 0 ? self_ip : std::string("0.0.0.0"), port, [this](const HttpRequest& r) { return handle(r); });
+        } catch (const std::exception& e) {
+            KF_LOGE("hang watch: %s", e.what());
+            return;
+        }
+        running_ = true;
+        th_ = std::thread([this] {
+            while (running_) {
+                sleep_ms(100);
+                std::vector<std::pair<int, double>> late;
+                {
+                    std::lock_guard<std::mutex> g(mu_);
+                    const double t = now_s();
+                    for (size_t i = 0; i < begin_.size(); ++i)
+                        if (begin_[i] != 0 && t - begin_[i] > threshold_s_ && (i >= waiting_.size() || t - waiting_[i] > 2.0)) {
+                            late.emplace_back((int)i, t - begin_[i]);
+                            begin_[i] = 0;
+                        }
+                }
+                for (auto& l : late) cb_(l.first, l.second);
+            }
+        });
+    }
+    // the membership changed: ranks are renumbered, batches that were open belong to the old numbering
+    void reset() {
+        std::lock_guard<std::mutex> g(mu_);
+        begin_.clear();
+        waiting_.clear();
+    }
+    void stop() {
+        if (!running_.exchange(false)) return;
+        if (th_.joinable()) th_.join();
+        http_.stop();
+    }
+
+private:
+    HttpResponse handle(const HttpRequest& r) {
+        HttpResponse resp;
+        std::string key;
+        try {
+            JsonValue v = JsonValue::parse(r.body);
+            const JsonValue* k = v.find("key");
+            if (k) key = k->str;
+        } catch (...) {
+        }
+        const auto colon = key.find(':');
+        if (colon == std::string::npos) {
+            resp.status = 400;
+            return resp;
+        }
+        const std::string kind = key.substr(0, colon);
+        const int v = atoi(key.c_str() + colon + 1);
+        if (v < 0 || v > 65535) return resp;
+        std::lock_guard<std::mutex> g(mu_);
+        if ((size_t)v >= begin_.size()) begin_.resize(v + 1, 0.0);
+        if ((size_t)v >= waiting_.size()) waiting_.resize(v + 1, 0.0);
+        if (kind == "begin") begin_[v] = now_s();
+        else if (kind == "end" || kind == "trainend") begin_[v] = 0;
+        else if (kind == "waiting") waiting_[v] = now_s(); // inside a collective, waiting for somebody else: a victim
+        return resp;
+    }
+    double threshold_s_;
+    OnHang cb_;
+    HttpServer http_;
+    std::thread th_;
+    std::mutex mu_;
+    std::vector<double> begin_, waiting_;
+    std::atomic<bool> running_{false};
+};
+
 struct Watcher {
     const Flags& f;
     Job job;
@@ -490,6 +575,8 @@ struct Watcher {
     int fail_code = 0;
     int n_shrinks = 0;
     std::vector<std::thread> helpers; // loss announcements in flight
+    std::map<uint64_t, pid_t> pids;   // peer key -> process of the worker that currently has this identity
+    std::unique_ptr<HangWatch> hang;
     Cluster current;
     // -standby N: warmed-up processes (interpreter, torch, CUDA context on a reserved GPU slot) waiting on a pipe for an identity
     struct Standby {
@@ -598,9 +685,17 @@ struct Watcher {
         }
         const int color = (int)(id.port % 6);
         std::thread t([this, p, gpu, id, color, sb] {
-            const int rc = sb ? wait_proc(sb->child, &cancel) : run_proc(p, true, job.logdir, &cancel, color);
+            Child own;
+            if (!sb) own = spawn_proc(p, true, job.logdir, &cancel, color, false);
+            Child& c = sb ? sb->child : own;
+            {
+                std::lock_guard<std::mutex> g(mu);
+                pids[id.key()] = c.pid;
+            }
+            const int rc = wait_proc(c, &cancel);
             gpus.put(gpu);
             std::lock_guard<std::mutex> g(mu);
+            pids.erase(id.key());
             --n_running;
             finished[id.key()] = true;
             if (rc != 0 && !cancel.flag) {
@@ -636,6 +731,23 @@ struct Watcher {
         ++n_shrinks;
         helpers.emplace_back([this, st] { announce_loss(st); });
         return true;
+    }
+
+    // HangWatch callback: `rank` of the current cluster has had a batch open for `stalled_s`
+    void kill_hung(int rank, double stalled_s) {
+        pid_t pid = -1;
+        PeerID id{};
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (rank < 0 || rank >= (int)current.workers.size()) return;
+            id = current.workers[rank];
+            auto it = pids.find(id.key());
+            if (it == pids.end()) return; // not one of ours (another host's runner watches it)
+            pid = it->second;
+        }
+        KF_LOGW("rank %d (%s) made no progress for %.1f s: killing it", rank, id.str().c_str(), stalled_s);
+        fprintf(stderr, "[kungfu-run] worker %s hung for %.1f s, killing it\n", id.str().c_str(), stalled_s);
+        kill(pid, SIGKILL);
     }
 
     void announce_loss(const Stage& st) {
@@ -684,7 +796,11 @@ struct Watcher {
         KF_LOGI("arrived at v%d, new np=%d, local: +%d/-%d", st.version, (int)st.cluster.workers.size(), (int)add.size(), (int)del.size());
         for (auto& id : del) remove(id);
         for (auto& id : add) create(id, st);
-        current = st.cluster;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            current = st.cluster;
+        }
+        if (hang) hang->reset();
         replenish_standbys();
     }
 
@@ -726,6 +842,7 @@ struct Watcher {
     }
 
     void join_all() {
+        if (hang) hang->stop();
         stop_standbys();
         std::vector<std::thread> hs;
         {
@@ -776,6 +893,14 @@ int watch_run(const Flags& f, const Job& job, const Cluster& init, const PeerID&
             return r;
         });
         KF_LOGI("debug server: http://127.0.0.1:%d/", f.debug_port);
+    }
+    if (f.shrink_on_failure && f.auto_recover_s > 0) {
+        const int mport = atoi(getenv_str("KUNGFU_MONITOR_PORT", "7756").c_str());
+        w.job.hang_watch = "http://" + format_ipv4(self.ipv4) + ":" + std::to_string(mport) + "/";
+        w.hang.reset(new HangWatch(f.auto_recover_s));
+        w.hang->start(format_ipv4(self.ipv4), mport,
+                      [&w](int rank, double stalled_s) { w.kill_hung(rank, stalled_s); });
+        KF_LOGI("hang watch: a worker whose batch stays open for %.1f s is killed and the cluster shrinks", f.auto_recover_s);
     }
     if (f.init_version < 0) {
         KF_LOGI("waiting to be initialized");

@@ -131,6 +131,7 @@ struct Watchdog {
     std::map<uint64_t, std::pair<std::string, double>> ops;
     uint64_t next = 1;
     bool started = false;
+    std::function<void(double)> reporter; // guarded by mu
     void ensure() {
         if (started) return;
         started = true;
@@ -140,8 +141,18 @@ struct Watchdog {
             std::map<uint64_t, double> last_report;
             std::unique_lock<std::mutex> lk(mu);
             while (true) {
-                cv.wait_for(lk, std::chrono::seconds(3));
+                cv.wait_for(lk, reporter ? std::chrono::milliseconds(500) : std::chrono::milliseconds(3000));
                 const double t = now_s();
+                if (reporter && !ops.empty()) {
+                    double oldest = 0;
+                    for (auto& kv : ops) oldest = std::max(oldest, t - kv.second.second);
+                    if (oldest >= 0.5) {
+                        auto f = reporter;
+                        lk.unlock();
+                        f(oldest);
+                        lk.lock();
+                    }
+                }
                 std::vector<std::string> msgs; // formatted under the lock, logged after it is released (ops may change meanwhile)
                 for (auto& kv : ops) {
                     const double d = t - kv.second.second;
@@ -165,6 +176,14 @@ Watchdog& wd() {
     return *w;
 }
 } // namespace
+
+void set_stall_reporter(std::function<void(double)> f) {
+    Watchdog& w = wd();
+    std::lock_guard<std::mutex> g(w.mu);
+    w.reporter = std::move(f);
+    if (w.reporter) w.ensure();
+    w.cv.notify_all();
+}
 
 StallGuard::StallGuard(const std::string& what, bool fine) {
     const Config& cfg = Config::get();

@@ -106,6 +106,9 @@ public:
 private:
     uint64_t id_ = 0;
 };
+// Called by the watchdog about twice per second with the age (seconds) of the oldest watched operation that is still pending, while
+// there is one older than 0.5 s. The peer uses it to tell a hang watch "I am waiting inside a collective" (a victim, not the culprit).
+void set_stall_reporter(std::function<void(double)> f);
 
 // ---------------------------------------------------------------------------------------------------
 // scope tracer (reference: TRACE_SCOPE / stdtracer, srcs/cpp/include/kungfu/utils/trace.hpp:2-16): per-scope call count

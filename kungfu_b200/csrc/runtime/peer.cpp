@@ -98,12 +98,26 @@ void Peer::start() {
             }
         }
     }
+    // under a launcher that watches for hung workers: tell it whenever this worker is WAITING inside a collective, so that the one that
+    // keeps everybody waiting can be told apart from its victims
+    const std::string hw = getenv_str("KUNGFU_HANG_WATCH", "");
+    if (!hw.empty() && !cfg_.single) {
+        reports_waiting_ = true;
+        set_stall_reporter([this, hw](double) {
+            const int r = rank_hint_.load();
+            if (r >= 0) http_request("POST", hw, "{\"key\":\"waiting:" + std::to_string(r) + "\"}", nullptr);
+        });
+    }
     update();
 }
 
 void Peer::close() {
     if (!started_) return;
     started_ = false;
+    if (reports_waiting_) {
+        set_stall_reporter(nullptr);
+        reports_waiting_ = false;
+    }
     coll_.shutdown("peer closed");
     p2p_->shutdown();
     if (metrics_) metrics_->stop();
@@ -243,6 +257,7 @@ bool Peer::update_to(const PeerList& pl) {
     auto sess = std::make_shared<Session>(cfg_.strategy, cfg_.self, pl, client_.get(), &coll_);
     sess->barrier(); // meets the barrier of every other member of the new cluster version
     session_ = sess;
+    rank_hint_ = sess->rank();
     updated_ = true;
     NetMonitor::get().set_gauge("kungfu_cluster_version", cluster_version_);
     NetMonitor::get().set_gauge("kungfu_cluster_size", (double)pl.size());

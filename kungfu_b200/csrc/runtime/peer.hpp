@@ -7,6 +7,7 @@
 // the version; survivors rebuild their session (new token = new version, fresh connections, barrier with the NEW
 // membership), detached peers stop themselves.
 #pragma once
+#include <atomic>
 #include <condition_variable>
 #include <deque>
 #include <functional>
@@ -94,6 +95,8 @@ private:
     std::condition_variable lost_cv_;
     std::deque<Stage> lost_stages_; // announced by the runners, not yet adopted
     std::function<void()> on_lost_;
+    std::atomic<int> rank_hint_{-1}; // rank in the current session, readable without the lock (watchdog thread)
+    bool reports_waiting_ = false;
     int cluster_version_ = 0;
     bool updated_ = false;
     bool detached_ = false;

@@ -13,8 +13,12 @@
 #include <numeric>
 #include <random>
 #include <set>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <unistd.h>
 
 #include "base.hpp"
 #include "graph.hpp"
@@ -23,6 +27,7 @@
 #include "plan.hpp"
 #include "reduce.hpp"
 #include "store.hpp"
+#include "transport.hpp"
 
 using namespace kfrt;
 
@@ -297,12 +302,147 @@ static void test_single_process_peer() {
     }
 }
 
+// ---- transport: stale-epoch fencing of collective connections, shutdown / reopen of the mailboxes ----------------------------------
+static void test_epoch_fence() {
+    setenv("KUNGFU_CONFIG_CONN_RETRY_COUNT", "2", 1); // a refused dial fails fast in this test
+    setenv("KUNGFU_CONFIG_CONN_RETRY_PERIOD", "20ms", 1);
+    Config::reload();
+    const uint16_t port = (uint16_t)(41000 + getpid() % 2000);
+    const PeerID srv{parse_ipv4("127.0.0.1"), port}, cli{parse_ipv4("127.0.0.1"), (uint16_t)(port + 1)};
+    CollectiveEndpoint coll;
+    Server server(srv, &coll, nullptr, false);
+    coll.reopen(5);
+    server.set_token(5);
+    server.start();
+    Client a(cli);
+    a.set_token(5);
+    const char m1[] = "epoch5";
+    a.send(srv, "m", m1, sizeof(m1), kConnCollective, kNoFlag);
+    Bytes got = coll.recv(cli, "m");
+    CHECK(got.size() == sizeof(m1) && std::memcmp(got.data(), m1, sizeof(m1)) == 0);
+    // a receiver that waits while the endpoint is shut down is woken with an error; later receives fail at once
+    std::string err;
+    std::thread waiter([&] {
+        try {
+            coll.recv(cli, "never");
+        } catch (const std::exception& e) {
+            err = e.what();
+        }
+    });
+    sleep_ms(50);
+    coll.shutdown("a peer of this cluster was lost");
+    waiter.join();
+    CHECK(err.find("lost") != std::string::npos);
+    CHECK_THROWS(coll.recv(cli, "m"));
+    // while closed, traffic is consumed and dropped, not parked
+    a.send(srv, "m", m1, sizeof(m1), kConnCollective, kNoFlag);
+    sleep_ms(50);
+    CHECK(coll.parked() == 0);
+    // the membership moves to epoch 6: the connection that was accepted under epoch 5 may still deliver — it must not reach a mailbox
+    coll.reopen(6);
+    server.set_token(6);
+    a.send(srv, "m", m1, sizeof(m1), kConnCollective, kNoFlag);
+    sleep_ms(50);
+    CHECK(coll.parked() == 0);
+    // a client that still believes in epoch 5 cannot open a new collective connection
+    Client stale(PeerID{parse_ipv4("127.0.0.1"), (uint16_t)(port + 2)});
+    stale.set_token(5);
+    CHECK_THROWS(stale.send(srv, "m", m1, sizeof(m1), kConnCollective, kNoFlag));
+    // one that moved on can
+    Client b(cli);
+    b.set_token(6);
+    const char m2[] = "epoch6";
+    b.send(srv, "m", m2, sizeof(m2), kConnCollective, kNoFlag);
+    got = coll.recv(cli, "m");
+    CHECK(got.size() == sizeof(m2) && std::memcmp(got.data(), m2, sizeof(m2)) == 0);
+    a.close_all();
+    b.close_all();
+    stale.close_all();
+    server.stop();
+    unsetenv("KUNGFU_CONFIG_CONN_RETRY_COUNT");
+    unsetenv("KUNGFU_CONFIG_CONN_RETRY_PERIOD");
+    Config::reload();
+}
+
+// ---- three peers in one process; one goes away; a "runner" announces it; the other two recover and keep reducing (test_kungfu_world.cpp +
+// the shrink-and-continue protocol, which the reference does not have) ----------------------------------------------------------------
+static void test_world_loses_a_peer() {
+    const uint16_t base = (uint16_t)(43000 + getpid() % 2000);
+    const int n = 3;
+    std::vector<std::unique_ptr<Peer>> peers;
+    for (int r = 0; r < n; ++r) peers.emplace_back(new Peer(PeerConfig::single_machine(r, n, base)));
+    std::vector<std::string> errs(n);
+    auto on_all = [&](std::vector<int> ranks, std::function<void(int)> f) {
+        std::vector<std::thread> ts;
+        for (int r : ranks)
+            ts.emplace_back([&, r] {
+                try {
+                    f(r);
+                } catch (const std::exception& e) {
+                    errs[r] = e.what();
+                }
+            });
+        for (auto& t : ts) t.join();
+    };
+    on_all({0, 1, 2}, [&](int r) { peers[r]->start(); });
+    std::vector<float> sums(n, 0.f);
+    on_all({0, 1, 2}, [&](int r) {
+        float x = (float)(r + 1), y = 0;
+        Workspace w{&x, &y, 1, kF32, kSum, "before"};
+        peers[r]->session()->all_reduce(w);
+        sums[r] = y;
+    });
+    CHECK(sums[0] == 6.f && sums[1] == 6.f && sums[2] == 6.f && errs[0].empty() && errs[1].empty() && errs[2].empty());
+    // peer 2 disappears while 0 and 1 are inside an all-reduce that needs it
+    Cluster before = peers[0]->current_cluster();
+    std::thread announcer([&] {
+        sleep_ms(150);
+        peers[2]->close();
+        Stage st;
+        st.version = peers[0]->cluster_version() + 1;
+        st.cluster = before;
+        st.cluster.workers = before.workers.minus(PeerList{before.workers[2]});
+        const std::string payload = st.to_json();
+        Client runner(PeerID{parse_ipv4("127.0.0.1"), (uint16_t)(base + 100)});
+        for (int r : {0, 1}) runner.send(before.workers[r], "lost", payload.data(), payload.size(), kConnControl, kNoFlag);
+        runner.close_all();
+    });
+    on_all({0, 1}, [&](int r) {
+        float x = 1.f, y = 0;
+        Workspace w{&x, &y, 1, kF32, kSum, "during"};
+        peers[r]->session()->all_reduce(w); // must throw, not hang
+    });
+    announcer.join();
+    CHECK(!errs[0].empty() && !errs[1].empty());
+    CHECK(peers[0]->failure_pending() && peers[1]->failure_pending());
+    errs.assign(n, "");
+    std::vector<int> changed(n, 0), detached(n, 0);
+    on_all({0, 1}, [&](int r) {
+        auto res = peers[r]->recover(10.0);
+        changed[r] = res.first;
+        detached[r] = res.second;
+    });
+    CHECK(errs[0].empty() && errs[1].empty() && changed[0] && changed[1] && !detached[0] && !detached[1]);
+    CHECK(peers[0]->cluster_version() == peers[1]->cluster_version() && !peers[0]->failure_pending());
+    on_all({0, 1}, [&](int r) {
+        float x = (float)(r + 1), y = 0;
+        Workspace w{&x, &y, 1, kF32, kSum, "after"};
+        auto sess = peers[r]->session();
+        sess->all_reduce(w);
+        sums[r] = y + 100.f * (float)sess->size();
+    });
+    CHECK(errs[0].empty() && errs[1].empty() && sums[0] == 203.f && sums[1] == 203.f);
+    CHECK_THROWS(peers[0]->recover(0.05)); // nothing announced: times out instead of inventing a membership
+    on_all({0, 1}, [&](int r) { peers[r]->close(); });
+}
+
 int main() {
     struct {
         const char* name;
         void (*fn)();
     } tests[] = {{"dtypes_and_transform2", test_dtypes_and_transform2}, {"plan", test_plan}, {"topologies", test_topologies}, {"mst", test_mst},
-                 {"placement", test_placement}, {"stores", test_stores}, {"single_process_peer", test_single_process_peer}};
+                 {"placement", test_placement}, {"stores", test_stores}, {"single_process_peer", test_single_process_peer},
+                 {"epoch_fence", test_epoch_fence}, {"world_loses_a_peer", test_world_loses_a_peer}};
     for (auto& t : tests) {
         const int before = g_fail;
         try {

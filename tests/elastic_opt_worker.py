@@ -55,14 +55,26 @@ if which == "shrink":
     guard = ShrinkOnFailure(state, m, opt, timeout_s=20)
     sizes = []
 
+    hang = os.environ.get("KUNGFU_TEST_HANG") == "1"  # the faulty worker hangs inside a batch instead of dying
+    if hang:
+        from kungfu_b200.cmd import monitor_batch_begin, monitor_batch_end
+
     def one_step():
+        if hang:
+            monitor_batch_begin()
         if (kfp.current_rank(), state.step) in crashes and len(guard.failures) == sum(1 for r, t in crashes if t < state.step):
+            if hang:
+                import time
+
+                time.sleep(3600)  # never comes back: only the launcher's hang watch can end this
             os._exit(17)  # dies mid-training without saying goodbye
         opt.zero_grad()
         m(torch.randn(3, 4, device=dev, dtype=next(m.parameters()).dtype)).float().pow(2).mean().backward()
         opt.step()
         if dev.type == "cuda":
             torch.cuda.synchronize()
+        if hang:
+            monitor_batch_end()
 
     while state.step < max_step and not guard.detached:
         if guard.run(one_step):

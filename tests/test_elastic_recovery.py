@@ -225,6 +225,26 @@ def test_shrink_and_continue_after_a_worker_crash():
     assert r.stdout.count("lost, continuing with") == 2, r.stdout[-3000:]
 
 
+def test_hung_worker_is_killed_and_the_cluster_shrinks():
+    """`-shrink-on-failure -auto-recover 3s` in watch mode: rank 1 of 3 goes to sleep inside step 3 (it is not dead: no exit status to see).
+    Its peers block in the all-reduce and report "waiting" to the launcher's hang watch, the sleeper's batch stays open without such a
+    report, so the launcher kills exactly that one; from there it is the crash path: the survivors recover and finish."""
+    rport, prange = ports()
+    cfg_port = 9300 + (os.getpid() + 25) % 100
+    mon_port = 17000 + (os.getpid() + 7) % 2000
+    cmd = [kungfu_run(), "-q", "-w", "-shrink-on-failure", "-auto-recover", "3s", "-np", "3", "-H", "127.0.0.1:4", "-port", str(rport),
+           "-port-range", prange, "-builtin-config-port", str(cfg_port), sys.executable, os.path.join(ROOT, "tests", "elastic_opt_worker.py"),
+           "shrink", "1@3", "8"]
+    e = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN", KUNGFU_MONITOR_PORT=str(mon_port), KUNGFU_TEST_HANG="1")
+    t0 = time.time()
+    r = subprocess.run(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=200)
+    assert r.returncode == 0, r.stdout[-5000:]
+    done = [j for j in json_lines(r.stdout) if j.get("done") == "shrink"]
+    assert len(done) == 2 and all(d["identical"] and d["step"] == 8 and d["final_size"] == 2 and d["failures"] == [[3, 2]] for d in done), r.stdout[-5000:]
+    assert r.stdout.count("hung for") == 1 and r.stdout.count("lost, continuing with 2 workers") == 1, r.stdout[-3000:]
+    assert time.time() - t0 < 120
+
+
 def test_shrink_keeps_survivors_identical():
     """One crash in a 4-worker job: the 3 survivors finish with bit-identical models (rank 0's state is broadcast after the loss)."""
     rport, prange = ports()
