@@ -53,28 +53,37 @@ template <> __device__ __forceinline__ Vec16 pack8<__half>(const float* f) {
     return v;
 }
 
+// Hands back `v` through an empty asm statement: the compiler cannot prove the value loop-invariant any more, so the fp32 expansion of a
+// packed parameter vector is recomputed where it is used (two ALU ops per element pair) instead of living in 8 registers for the whole
+// kernel.
+__device__ __forceinline__ Vec16 opaque(Vec16 v) {
+    asm volatile("" : "+r"(v.w[0]), "+r"(v.w[1]), "+r"(v.w[2]), "+r"(v.w[3]));
+    return v;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, VPL 16-byte vectors (8 elements) per lane -> H <= 256 * VPL
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kLnWarps = 4;
 
 template <typename T, int VPL>
-__global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const T* __restrict__ lin_bias,
+__global__ void __launch_bounds__(kLnWarps * 32, (VPL <= 4 ? 4 : 1)) add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const T* __restrict__ lin_bias,
                                                                     const T* __restrict__ gamma, const T* __restrict__ beta, T* __restrict__ z,
                                                                     T* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int rows,
                                                                     int H, float eps) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nvec = H / 8;
-    float g[VPL][8], b[VPL][8], lb[VPL][8];
+    // parameters stay PACKED in registers (4 per 8 elements, unpacked where they are used): with fp32 copies of gamma / beta / bias the
+    // kernel needed 157 registers -> 3 CTAs per SM -> 15 % occupancy, and it is a latency-bound streaming kernel (ncu: long-scoreboard)
+    Vec16 gp[VPL], bp[VPL], lp[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
         const int v = lane + 32 * i;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) lb[i][j] = 0.f;
+        gp[i] = bp[i] = lp[i] = Vec16{{0u, 0u, 0u, 0u}};
         if (v < nvec) {
-            unpack8<T>(ld_plain(gamma + (size_t)v * 8), g[i]);
-            unpack8<T>(ld_plain(beta + (size_t)v * 8), b[i]);
-            if (lin_bias) unpack8<T>(ld_plain(lin_bias + (size_t)v * 8), lb[i]);
+            gp[i] = ld_plain(gamma + (size_t)v * 8);
+            bp[i] = ld_plain(beta + (size_t)v * 8);
+            if (lin_bias) lp[i] = ld_plain(lin_bias + (size_t)v * 8);
         }
     }
     for (int row = blockIdx.x * kLnWarps + warp; row < rows; row += gridDim.x * kLnWarps) {
@@ -86,8 +95,12 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(const T* __re
             const int v = lane + 32 * i;
             if (v < nvec) {
                 unpack8<T>(ld_ro_stream(x + base + (size_t)v * 8), f[i]);
+                if (lin_bias) {
+                    float lb[8];
+                    unpack8<T>(opaque(lp[i]), lb);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[i][j] += lb[i][j];
+                    for (int j = 0; j < 8; ++j) f[i][j] += lb[j];
+                }
                 if (res) {
                     float r[8];
                     unpack8<T>(ld_ro_stream(res + base + (size_t)v * 8), r);
@@ -124,9 +137,11 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_fwd_kernel(const T* __re
         for (int i = 0; i < VPL; ++i) {
             const int v = lane + 32 * i;
             if (v < nvec) {
-                float o[8];
+                float o[8], g[8], b[8];
+                unpack8<T>(opaque(gp[i]), g);
+                unpack8<T>(opaque(bp[i]), b);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = fmaf((f[i][j] - mu) * rs, g[i][j], b[i][j]);
+                for (int j = 0; j < 8; ++j) o[j] = fmaf((f[i][j] - mu) * rs, g[j], b[j]);
                 st_plain(y + base + (size_t)v * 8, pack8<T>(o));
             }
         }
@@ -143,6 +158,9 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const T* __re
     constexpr int NP = LB ? 3 : 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nvec = H / 8;
+    // Unlike the forward kernel this one keeps gamma expanded: three fp32 accumulator sets (96 registers) cannot be avoided, and the
+    // variant with packed gamma + __launch_bounds__(128, 3) (168 registers, 128 bytes of spills, 3 CTAs per SM) measured SLOWER:
+    // 23.5 us vs 18.2 us per call at 4096 x 1024.
     float g[VPL][8], dg[VPL][8], db[VPL][8], dl[LB ? VPL : 1][8];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
@@ -220,25 +238,25 @@ __global__ void __launch_bounds__(kLnWarps * 32) add_ln_bwd_kernel(const T* __re
 }
 
 // out_k[c] = sum_b partial[b][k * H + c] for the W = NP * H columns of `partial` ([nblocks][W]), written in the parameter dtype.
-// 32 columns per block, 8 warps stride over the partial rows (the first version walked the rows serially per column: 11-13 us for
-// 296 x 4096 floats, pure latency), folded through shared memory in a fixed order -> deterministic.
+// 32 columns per block, 32 warps stride over the partial rows (the first version walked the rows serially per column: 11-13 us for
+// 296 x 4096 floats, pure latency; 8 warps: 5.6 us), folded through shared memory in a fixed order -> deterministic.
 template <typename T>
-__global__ void __launch_bounds__(256) colsum_finalize_kernel(const float* __restrict__ partial, int nblocks, int W, int H, T* __restrict__ o0,
-                                                              T* __restrict__ o1, T* __restrict__ o2) {
-    __shared__ float sm[8][33];
+__global__ void __launch_bounds__(1024) colsum_finalize_kernel(const float* __restrict__ partial, int nblocks, int W, int H, T* __restrict__ o0,
+                                                               T* __restrict__ o1, T* __restrict__ o2) {
+    __shared__ float sm[32][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cx;
     float a = 0.f;
     if (c < W) {
 #pragma unroll 4
-        for (int b = ry; b < nblocks; b += 8) a += partial[(size_t)b * W + c];
+        for (int b = ry; b < nblocks; b += 32) a += partial[(size_t)b * W + c];
     }
     sm[ry][cx] = a;
     __syncthreads();
     if (ry == 0 && c < W) {
         float t = 0.f;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) t += sm[r][cx];
+        for (int r = 0; r < 32; ++r) t += sm[r][cx];
         const int which = c / H, col = c - which * H;
         T* out = which == 0 ? o0 : which == 1 ? o1 : o2;
         out[col] = Elem<T>::down(t);
@@ -402,8 +420,10 @@ __global__ void __launch_bounds__(256) qkv_pack_bwd_kernel(QkvSrc src, T* __rest
 
 } // namespace
 
+// backward: 2 CTAs of 4 warps are resident per SM (225 registers)
 int add_ln_num_blocks(int rows) { return ln_blocks(rows) < 148 * 2 ? ln_blocks(rows) : 148 * 2; }
-int bias_gelu_num_blocks(int rows) { return rows < 148 * 2 ? (rows < 1 ? 1 : rows) : 148 * 2; }
+// 4 CTAs of 256 threads per SM: the kernel is latency-bound (ncu: 2 CTAs/SM = 24 % occupancy, long-scoreboard stalls, 2.2 TB/s)
+int bias_gelu_num_blocks(int rows) { return rows < 148 * 4 ? (rows < 1 ? 1 : rows) : 148 * 4; }
 int qkv_pack_num_blocks(int rows) { return rows < 148 * 4 ? (rows < 1 ? 1 : rows) : 148 * 4; }
 
 template <typename T>
@@ -463,7 +483,7 @@ static void add_ln_bwd_t(const void* dy, const void* z, const float* mean, const
     else KF_LN_BWD(8);
 #undef KF_LN_BWD
     const int W = (lb ? 3 : 2) * H;
-    colsum_finalize_kernel<T><<<(W + 31) / 32, 256, 0, st>>>(partial, blocks, W, H, (T*)dgamma, (T*)dbeta, (T*)dlin_bias);
+    colsum_finalize_kernel<T><<<(W + 31) / 32, 1024, 0, st>>>(partial, blocks, W, H, (T*)dgamma, (T*)dbeta, (T*)dlin_bias);
 }
 
 void launch_add_ln_bwd(const void* dy, const void* z, const float* mean, const float* rstd, const void* gamma, void* dz, void* dgamma, void* dbeta,
@@ -503,7 +523,7 @@ void launch_bias_gelu_bwd(const void* dy, const void* x, const void* bias, void*
         else if (vpt == 2) KF_BG(T, 2);                                                                                                   \
         else if (vpt <= 4) KF_BG(T, 4);                                                                                                   \
         else KF_BG(T, 8);                                                                                                                 \
-        colsum_finalize_kernel<T><<<(I + 31) / 32, 256, 0, st>>>(partial, blocks, I, I, (T*)dbias, (T*)nullptr, (T*)nullptr);             \
+        colsum_finalize_kernel<T><<<(I + 31) / 32, 1024, 0, st>>>(partial, blocks, I, I, (T*)dbias, (T*)nullptr, (T*)nullptr);             \
     } while (0)
     if (dtype == kBF16) KF_BG_V(__nv_bfloat16);
     else if (dtype == kF16) KF_BG_V(__half);
@@ -539,7 +559,7 @@ void launch_qkv_pack_bwd(const void* dq, const void* dk, const void* dv, const l
         else if (vpt == 2) KF_QP(T, 2);                                                                                                   \
         else if (vpt == 3) KF_QP(T, 3);                                                                                                   \
         else KF_QP(T, 4);                                                                                                                 \
-        colsum_finalize_kernel<T><<<(W + 31) / 32, 256, 0, st>>>(partial, blocks, W, W, (T*)dbias, (T*)nullptr, (T*)nullptr);             \
+        colsum_finalize_kernel<T><<<(W + 31) / 32, 1024, 0, st>>>(partial, blocks, W, W, (T*)dbias, (T*)nullptr, (T*)nullptr);             \
     } while (0)
     if (dtype == kBF16) KF_QP_V(__nv_bfloat16);
     else if (dtype == kF16) KF_QP_V(__half);
