@@ -72,6 +72,7 @@ struct Flags {
     bool watch = false;
     bool keep = false;
     bool shrink_on_failure = false; // -shrink-on-failure (watch mode): a crashed worker is removed from the cluster, the rest go on
+    bool refill = false;            // -refill: after a shrink, propose a cluster with a replacement worker to the config server
     int init_version = 0;
     std::string config_server;
     long t0 = (long)time(nullptr);
@@ -89,10 +90,12 @@ struct Flags {
             "usage: kungfu-run [-np N] [-H ip:slots,...] [-hostfile f] [-self ip] [-nic name] [-strategy S]\n"
             "                  [-port-range a-b] [-port p] [-w] [-k] [-config-server URL] [-builtin-config-port p]\n"
             "                  [-init-version v] [-timeout d] [-logdir d] [-logfile f] [-q] [-v] [-allow-nvlink]\n"
-            "                  [-auto-recover d] [-delay d] [-debug-port p] [-standby n] [-shrink-on-failure]\n"
+            "                  [-auto-recover d] [-delay d] [-debug-port p] [-standby n] [-shrink-on-failure] [-refill]\n"
             "                  prog args...\n"
             "  -w -shrink-on-failure: a worker that exits with an error is removed, the others continue; with -auto-recover d also a\n"
             "  worker whose batch stays open for d while it is not waiting in a collective (it hangs) is killed and removed.\n"
+            "  -refill: after such a loss the runner proposes a cluster with a replacement worker (a warm standby if there is one) to\n"
+            "  the config server; workers that follow it (elastic.ShrinkOnFailure(follow_config_server=True)) grow back.\n"
             "strategies: ");
     for (auto& s : strategy_names()) fprintf(stderr, "%s ", s.c_str());
     fprintf(stderr, "\n");
@@ -105,7 +108,7 @@ Flags parse_flags(int argc, char** argv) {
     Flags f;
     int i = 1;
     auto is_bool_flag = [](const std::string& k) {
-        return k == "w" || k == "k" || k == "q" || k == "v" || k == "allow-nvlink" || k == "h" || k == "help" || k == "shrink-on-failure";
+        return k == "w" || k == "k" || k == "q" || k == "v" || k == "allow-nvlink" || k == "h" || k == "help" || k == "shrink-on-failure" || k == "refill";
     };
     for (; i < argc; ++i) {
         std::string a = argv[i];
@@ -145,6 +148,7 @@ Flags parse_flags(int argc, char** argv) {
         else if (k == "w") f.watch = parse_bool(v);
         else if (k == "k") f.keep = parse_bool(v);
         else if (k == "shrink-on-failure") f.shrink_on_failure = parse_bool(v);
+        else if (k == "refill") f.refill = parse_bool(v);
         else if (k == "init-version") f.init_version = atoi(v.c_str());
         else if (k == "config-server") f.config_server = v;
         else if (k == "t0") f.t0 = atol(v.c_str());
@@ -774,6 +778,22 @@ struct Watcher {
             }
         }
         client.close_all();
+        if (f.refill && !job.config_server.empty()) {
+            // self-healing: once the survivors have had time to regroup, ask for the old size again. Nothing is forced: the bigger
+            // cluster takes effect when the workers next consult the config server (their resize protocol), and the new worker is
+            // created by whichever runner owns the address — from its standby pool when it has one.
+            sleep_ms(1000);
+            if (cancel.flag || g_stop) return;
+            const Cluster grown = st.cluster.resized((int)st.cluster.workers.size() + 1);
+            std::string resp;
+            const int code = http_request("PUT", job.config_server, grown.to_json(), &resp);
+            if (code == 200) {
+                KF_LOGI("refill: proposed %d workers again (%s)", (int)grown.workers.size(), grown.workers.str().c_str());
+                fprintf(stderr, "[kungfu-run] refill: proposed %d workers again\n", (int)grown.workers.size());
+            } else {
+                KF_LOGW("refill: config server answered %d %s", code, resp.c_str());
+            }
+        }
     }
 
     void remove(const PeerID& id) {

@@ -108,16 +108,37 @@ class ShrinkOnFailure:
     GPU jobs between steps; a GPU worker killed mid-step needs `-auto-recover`."""
 
     def __init__(self, state: ElasticState, model: torch.nn.Module, optimizer: Optional[torch.optim.Optimizer] = None,
-                 timeout_s: float = 30.0, max_failures: int = 16) -> None:
+                 timeout_s: float = 30.0, max_failures: int = 16, follow_config_server: bool = False, poll_every: int = 10) -> None:
         self.state, self.model, self.optimizer = state, model, optimizer
         self.timeout_s = float(timeout_s)
         self.max_failures = int(max_failures)
         self.failures: List[Tuple[int, int, float]] = []  # (old size, new size, seconds to be training again)
+        self.regrown: List[Tuple[int, int, float]] = []  # (old size, new size, seconds) of resizes adopted from the config server
         self.detached = False
+        # `kungfu-run -w -shrink-on-failure -refill`: after a loss the runner proposes a cluster with a replacement worker (taken from its
+        # standby pool when it has one) to the config server; the survivors pick it up here, every `poll_every` steps, through the
+        # ordinary resize protocol — all of them at the same step, because `state.step` is agreed.
+        self.follow_config_server = bool(follow_config_server)
+        self.poll_every = max(1, int(poll_every))
+
+    def _follow(self) -> None:
+        if not self.follow_config_server or (self.state.step + 1) % self.poll_every != 0:
+            return
+        t0 = time.time()
+        old = current_cluster_size()
+        changed, det = resize(None)
+        if det:
+            self.detached = True
+        elif changed:
+            self.state.step += 1  # the step that just ran counts; newcomers adopt max(step)
+            sync_after_resize(self.state, self.model, self.optimizer)
+            self.state.step -= 1
+            self.regrown.append((old, current_cluster_size(), time.time() - t0))
 
     def run(self, step_fn, *args, **kwargs) -> bool:
         try:
             step_fn(*args, **kwargs)
+            self._follow()
             return True
         except Exception as e:  # noqa: BLE001 - classified below
             if cuda_context_lost(e):

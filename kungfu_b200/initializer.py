@@ -45,14 +45,44 @@ def broadcast_optimizer_state(optimizer: torch.optim.Optimizer, root: int = 0) -
     """Broadcast every tensor in the optimizer state (momentum buffers, Adam moments, step counters) and the numeric
     hyper-parameters of the param groups (lr, momentum, betas, weight decay, ...): in the reference these are graph variables
     and `BroadcastGlobalVariablesOp` covers them; a learning rate that a scheduler already moved on the root must reach
-    workers that join or restart."""
-    for group in optimizer.param_groups:
-        for p in group["params"]:
+    workers that join or restart.
+
+    torch creates optimizer state lazily, at the first `step()`: a worker that joins a running job has none while the root has
+    momentum for every parameter. The root therefore announces the LAYOUT of its state first (which parameter has which slot, shape,
+    dtype, device kind); everybody else creates what it lacks, and only then are the tensors broadcast — all members issue the same
+    collectives in the same order whatever they held before."""
+    import json
+
+    from .runtime import get_runtime
+
+    rt = get_runtime()
+    layout = []
+    for gi, group in enumerate(optimizer.param_groups):
+        for pi, p in enumerate(group["params"]):
             st = optimizer.state.get(p, {})
             for k in sorted(st.keys()):
                 v = st[k]
                 if isinstance(v, torch.Tensor):
-                    coll.broadcast_(v, root)
+                    layout.append([gi, pi, k, "t", list(v.shape), str(v.dtype).replace("torch.", ""), v.device.type])
+                elif isinstance(v, (int, float)) and not isinstance(v, bool):
+                    layout.append([gi, pi, k, "s", type(v).__name__, v])
+    if rt.size > 1:
+        layout = json.loads(rt.control.broadcast_bytes(json.dumps(layout).encode(), root).decode())
+    for e in layout:
+        gi, pi, k, kind = e[:4]
+        p = optimizer.param_groups[gi]["params"][pi]
+        st = optimizer.state[p]
+        if kind == "s":
+            st[k] = int(e[5]) if e[4] == "int" else float(e[5])
+            continue
+        shape, dtype, devkind = e[4], getattr(torch, e[5]), e[6]
+        v = st.get(k)
+        dev = p.device if devkind == p.device.type else torch.device(devkind)
+        if not isinstance(v, torch.Tensor) or list(v.shape) != shape or v.dtype != dtype or v.device.type != dev.type:
+            v = torch.zeros(shape, dtype=dtype, device=dev)
+            st[k] = v
+        coll.broadcast_(v, root)
+    for group in optimizer.param_groups:
         slots = _numeric_hyper(group)
         if not slots:
             continue

@@ -645,6 +645,27 @@ def cmd_initializer(args):
     bufs = torch.cat([opt.state[p]["momentum_buffer"].reshape(-1) for p in m.parameters()])
     check(ops.consensus(bufs), "optimizer state identical after the broadcast")
     check(opt.param_groups[0]["lr"] == 0.1, f"hyper-parameters follow the root: lr={opt.param_groups[0]['lr']}")
+    # a worker that joins a running job has NO optimizer state yet (torch creates it at the first step); the root does. The broadcast
+    # must still line up: the root announces its layout, the newcomer creates the slots, then the tensors travel
+    for make in (lambda ps: torch.optim.SGD(ps, lr=0.1, momentum=0.9), lambda ps: torch.optim.Adam(ps, lr=1e-3)):
+        m2 = torch.nn.Linear(5, 3)
+        o2 = make(m2.parameters())
+        if r == 0:
+            for _ in range(2):
+                o2.zero_grad()
+                m2(torch.randn(4, 5)).sum().backward()
+                o2.step()
+        initializer.BroadcastGlobalVariablesOp(m2, o2)
+        keys = sorted(k for p in m2.parameters() for k in o2.state[p].keys())
+        check(len(keys) > 0 and ops.consensus(torch.tensor([float(len(keys))])), f"newcomer created the root's optimizer slots: {keys}")
+        st = torch.cat([o2.state[p][k].detach().reshape(-1).float() for p in m2.parameters() for k in sorted(o2.state[p].keys())
+                        if isinstance(o2.state[p][k], torch.Tensor)])
+        check(ops.consensus(st) and float(st.abs().sum()) > 0, "lazily created optimizer state equals the root's after the broadcast")
+        o2.zero_grad()
+        torch.manual_seed(7)
+        m2(torch.randn(4, 5)).sum().backward()
+        o2.step()  # same data everywhere: identical state => identical parameters after the step
+        check(ops.consensus(torch.cat([p.detach().reshape(-1) for p in m2.parameters()])), "a step from the broadcast state agrees on every worker")
     with torch.no_grad():
         for p in m.parameters():
             p.add_(float(r))

@@ -52,7 +52,8 @@ if which == "shrink":
     opt = kf.optimizers.SynchronousSGDOptimizer(torch.optim.SGD(m.parameters(), lr=0.05, momentum=0.9), named_parameters=m.named_parameters())
     state = ElasticState()
     sync_after_resize(state, m, opt)
-    guard = ShrinkOnFailure(state, m, opt, timeout_s=20)
+    refill = os.environ.get("KUNGFU_TEST_REFILL") == "1"  # follow the config server: the launcher proposes a replacement after a loss
+    guard = ShrinkOnFailure(state, m, opt, timeout_s=20, follow_config_server=refill, poll_every=2)
     sizes = []
 
     hang = os.environ.get("KUNGFU_TEST_HANG") == "1"  # the faulty worker hangs inside a batch instead of dying
@@ -73,6 +74,10 @@ if which == "shrink":
         opt.step()
         if dev.type == "cuda":
             torch.cuda.synchronize()
+        if refill:
+            import time
+
+            time.sleep(0.1)  # a step of a real model takes time; the launcher proposes the replacement about a second after the loss
         if hang:
             monitor_batch_end()
 
@@ -88,7 +93,7 @@ if which == "shrink":
     lo = ctl.all_reduce_cpu_(flat.clone(), "min", "shrink::lo")
     hi = ctl.all_reduce_cpu_(flat.clone(), "max", "shrink::hi")
     print(json.dumps({"done": which, "rank": kfp.current_rank(), "step": state.step, "final_size": kfp.current_cluster_size(),
-                      "sizes": sorted(set(sizes)), "failures": [(a, b) for a, b, _ in guard.failures],
+                      "sizes": sorted(set(sizes)), "failures": [(a, b) for a, b, _ in guard.failures], "regrown": [(a, b) for a, b, _ in guard.regrown],
                       "recover_s": [round(t, 3) for _, _, t in guard.failures], "identical": bool(torch.equal(lo, hi)),
                       "finite": bool(torch.isfinite(flat).all())}), flush=True)
     sys.exit(0)

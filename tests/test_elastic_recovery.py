@@ -245,6 +245,25 @@ def test_hung_worker_is_killed_and_the_cluster_shrinks():
     assert time.time() - t0 < 120
 
 
+def test_lost_worker_is_replaced_from_the_standby_pool():
+    """`-shrink-on-failure -refill -standby 1`: rank 2 of 3 dies inside step 4; the survivors go on as 2; the runner proposes 3 workers again
+    to the config server; the survivors pick that up at their next poll (ordinary resize protocol), the runner turns its warm standby into
+    the third worker, which inherits step and model; everybody finishes together with identical models."""
+    rport, prange = ports()
+    cfg_port = 9300 + (os.getpid() + 75) % 100
+    cmd = [kungfu_run(), "-q", "-w", "-shrink-on-failure", "-refill", "-standby", "1", "-np", "3", "-H", "127.0.0.1:4", "-port", str(rport),
+           "-port-range", prange, "-builtin-config-port", str(cfg_port), sys.executable, os.path.join(ROOT, "tests", "elastic_opt_worker.py"),
+           "shrink", "2@4", "40"]
+    e = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN", KUNGFU_TEST_REFILL="1")
+    r = subprocess.run(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-5000:]
+    done = [j for j in json_lines(r.stdout) if j.get("done") == "shrink"]
+    assert len(done) == 3 and all(d["identical"] and d["finite"] and d["step"] == 40 and d["final_size"] == 3 for d in done), r.stdout[-5000:]
+    survivors = [d for d in done if d["failures"]]
+    assert len(survivors) == 2 and all(d["failures"] == [[3, 2]] and d["regrown"] == [[2, 3]] and d["sizes"] == [2, 3] for d in survivors), done
+    assert "refill: proposed 3 workers again" in r.stdout and "becomes 127.0.0.1" in r.stdout, r.stdout[-3000:]
+
+
 def test_shrink_keeps_survivors_identical():
     """One crash in a 4-worker job: the 3 survivors finish with bit-identical models (rank 0's state is broadcast after the loss)."""
     rport, prange = ports()
