@@ -5,6 +5,7 @@
 // plan/{cluster,hostspec}_test.go, plan/hostfile/hostfile_test.go, plan/graph/graph_test.go, store/versionedstore_test.go).
 // No framework dependency: CHECK records a failure with file:line, main() prints a summary and returns the failure count.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -364,6 +365,66 @@ static void test_epoch_fence() {
     Config::reload();
 }
 
+// ---- transport: a listener that anybody can reach must shrug off garbage (lengths come from the wire) -----------------
+static void test_server_survives_garbage() {
+    const uint16_t port = (uint16_t)(45000 + getpid() % 2000);
+    const PeerID srv{parse_ipv4("127.0.0.1"), port}, cli{parse_ipv4("127.0.0.1"), (uint16_t)(port + 1)};
+    CollectiveEndpoint coll;
+    std::atomic<int> controls{0};
+    Server server(srv, &coll, nullptr, false);
+    server.set_control_handler([&](const PeerID&, const std::string&, const Bytes&) { ++controls; });
+    coll.reopen(1);
+    server.set_token(1);
+    server.start();
+    std::mt19937 rng(7);
+    auto raw = [&] { return Socket::connect_tcp(srv.ipv4, srv.port, 1000); };
+    // 1. random bytes instead of a connection header, then silence
+    for (int i = 0; i < 8; ++i) {
+        Socket s = raw();
+        CHECK(s.valid());
+        std::vector<uint8_t> junk(1 + rng() % 64);
+        for (auto& b : junk) b = (uint8_t)rng();
+        s.send_all(junk.data(), junk.size());
+    }
+    // 2. a valid collective handshake followed by headers that announce absurd sizes: the connection is dropped, nothing is allocated
+    struct __attribute__((packed)) Hdr {
+        uint16_t type, src_port;
+        uint32_t src_ipv4;
+    };
+    struct __attribute__((packed)) Msg {
+        uint32_t name_len, flags;
+        uint64_t data_len;
+    };
+    for (uint16_t type : {(uint16_t)kConnCollective, (uint16_t)kConnControl, (uint16_t)kConnPing, (uint16_t)77}) {
+        Socket s = raw();
+        Hdr h{type, cli.port, cli.ipv4};
+        uint32_t ack = 0;
+        CHECK(s.send_all(&h, sizeof(h)) && s.recv_all(&ack, sizeof(ack)) && ack == 1);
+        Msg big{8, 0, ~0ull}; // 16 EiB of payload
+        s.send_all(&big, sizeof(big));
+        s.send_all("deadbeef", 8);
+        Socket s2 = raw();
+        CHECK(s2.send_all(&h, sizeof(h)) && s2.recv_all(&ack, sizeof(ack)));
+        Msg longname{1u << 30, 0, 4}; // 1 GiB name
+        s2.send_all(&longname, sizeof(longname));
+    }
+    sleep_ms(100);
+    CHECK(coll.parked() == 0);
+    // 3. the server still serves well-formed peers
+    Client a(cli);
+    a.set_token(1);
+    const char m[] = "still here";
+    a.send(srv, "m", m, sizeof(m), kConnCollective, kNoFlag);
+    Bytes got = coll.recv(cli, "m");
+    CHECK(got.size() == sizeof(m) && std::memcmp(got.data(), m, sizeof(m)) == 0);
+    a.send(srv, "note", m, sizeof(m), kConnControl, kNoFlag);
+    for (int i = 0; i < 50 && controls.load() == 0; ++i) sleep_ms(10);
+    CHECK(controls.load() == 1);
+    CHECK(a.ping(srv, 1000) >= 0);
+    a.close_all();
+    server.stop();
+}
+
 // ---- three peers in one process; one goes away; a "runner" announces it; the other two recover and keep reducing (test_kungfu_world.cpp +
 // the shrink-and-continue protocol, which the reference does not have) ----------------------------------------------------------------
 static void test_world_loses_a_peer() {
@@ -442,7 +503,8 @@ int main() {
         void (*fn)();
     } tests[] = {{"dtypes_and_transform2", test_dtypes_and_transform2}, {"plan", test_plan}, {"topologies", test_topologies}, {"mst", test_mst},
                  {"placement", test_placement}, {"stores", test_stores}, {"single_process_peer", test_single_process_peer},
-                 {"epoch_fence", test_epoch_fence}, {"world_loses_a_peer", test_world_loses_a_peer}};
+                 {"epoch_fence", test_epoch_fence}, {"server_survives_garbage", test_server_survives_garbage},
+                 {"world_loses_a_peer", test_world_loses_a_peer}};
     for (auto& t : tests) {
         const int before = g_fail;
         try {
