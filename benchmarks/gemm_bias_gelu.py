@@ -49,6 +49,9 @@ def main():
     except (OSError, ValueError):
         pass
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    from kungfu_b200.utils.timing import ClockSampler
+
+    sampler = ClockSampler(torch.cuda.current_device()).start()  # nvidia-smi clocks / throttle reasons during the timed region
     rows = []
     for name, tokens, in_f, out_f in [("bert-base ffn-up b32xs128", 4096, 768, 3072), ("bert-large ffn-up b32xs128", 4096, 1024, 4096),
                                       ("bert-large ffn-up b128xs128", 16384, 1024, 4096), ("square 8192", 8192, 8192, 8192)]:
@@ -70,9 +73,11 @@ def main():
                "speedup": round(t_lib / t_ours, 2), "frac_of_measured_peak": round(flops / t_ours / 1e9 / peak, 3)}
         rows.append(row)
         print(json.dumps(row), flush=True)
+    clocks = sampler.stop()
+    print(json.dumps({"clocks": clocks}), flush=True)
     if a.out:
         with open(a.out, "w") as f:
-            json.dump({"peak_tflops": peak, "rows": rows}, f, indent=1)
+            json.dump({"peak_tflops": peak, "clocks": clocks, "rows": rows}, f, indent=1)
 
 
 if __name__ == "__main__":
