@@ -132,6 +132,8 @@ struct Watchdog {
     uint64_t next = 1;
     bool started = false;
     std::function<void(double)> reporter; // guarded by mu
+    bool reporting = false;               // a reporter call is in flight (made without the lock)
+    std::condition_variable idle;
     void ensure() {
         if (started) return;
         started = true;
@@ -148,9 +150,12 @@ struct Watchdog {
                     for (auto& kv : ops) oldest = std::max(oldest, t - kv.second.second);
                     if (oldest >= 0.5) {
                         auto f = reporter;
+                        reporting = true;
                         lk.unlock();
                         f(oldest);
                         lk.lock();
+                        reporting = false;
+                        idle.notify_all();
                     }
                 }
                 std::vector<std::string> msgs; // formatted under the lock, logged after it is released (ops may change meanwhile)
@@ -179,9 +184,10 @@ Watchdog& wd() {
 
 void set_stall_reporter(std::function<void(double)> f) {
     Watchdog& w = wd();
-    std::lock_guard<std::mutex> g(w.mu);
+    std::unique_lock<std::mutex> g(w.mu);
     w.reporter = std::move(f);
     if (w.reporter) w.ensure();
+    else w.idle.wait(g, [&] { return !w.reporting; }); // whoever clears the reporter may destroy what it captured right after
     w.cv.notify_all();
 }
 

@@ -139,7 +139,18 @@ class _PairAveraging(KungFuMixin):
                 target = self._kf_pick_peer()
                 mine = self._kf_flat_cpu()
                 other = torch.empty_like(mine)
-                ok = ctl.request(target, self._kf_model_name, other)
+                try:
+                    ok = ctl.request(target, self._kf_model_name, other)
+                except RuntimeError as e:
+                    # Asynchronous gossip has no rendezvous: the target may already have finished its last step and gone away (or be
+                    # restarting). A missed pull is a local step, not an error (found by a test that failed once in ~10 suite runs:
+                    # the first worker to finish exited while a slower one was still pulling from it).
+                    ok = False
+                    self._kf_missed_pulls = getattr(self, "_kf_missed_pulls", 0) + 1
+                    if self._kf_missed_pulls == 1:
+                        import warnings
+
+                        warnings.warn(f"kungfu_b200: PairAveraging could not pull from rank {target} ({e}); continuing with a local step")
                 if ok:
                     self._kf_unflat_cpu(other, 0.5)
                 self._kf_inner_step()
