@@ -384,8 +384,13 @@ void Client::reset_connections(const PeerList& keeps, uint32_t token) {
         PeerID p{(uint32_t)(it->first.first >> 16), (uint16_t)(it->first.first & 0xffff)};
         const bool keep = keeps.contains(p) && it->first.second != (int)kConnCollective;
         if (!keep) {
-            std::lock_guard<std::mutex> g2(it->second->mu);
-            it->second->sock.close();
+            // keep the connection object alive past the erase: the guard below unlocks a mutex that lives INSIDE it (TSan: heap-use-after-
+            // free when the pool held the last reference)
+            std::shared_ptr<Conn> conn = it->second;
+            {
+                std::lock_guard<std::mutex> g2(conn->mu);
+                conn->sock.close();
+            }
             it = pool_.erase(it);
         } else {
             ++it;

@@ -305,9 +305,6 @@ static void test_single_process_peer() {
 
 // ---- transport: stale-epoch fencing of collective connections, shutdown / reopen of the mailboxes ----------------------------------
 static void test_epoch_fence() {
-    setenv("KUNGFU_CONFIG_CONN_RETRY_COUNT", "2", 1); // a refused dial fails fast in this test
-    setenv("KUNGFU_CONFIG_CONN_RETRY_PERIOD", "20ms", 1);
-    Config::reload();
     const uint16_t port = (uint16_t)(41000 + getpid() % 2000);
     const PeerID srv{parse_ipv4("127.0.0.1"), port}, cli{parse_ipv4("127.0.0.1"), (uint16_t)(port + 1)};
     CollectiveEndpoint coll;
@@ -360,9 +357,6 @@ static void test_epoch_fence() {
     b.close_all();
     stale.close_all();
     server.stop();
-    unsetenv("KUNGFU_CONFIG_CONN_RETRY_COUNT");
-    unsetenv("KUNGFU_CONFIG_CONN_RETRY_PERIOD");
-    Config::reload();
 }
 
 // ---- transport: a listener that anybody can reach must shrug off garbage (lengths come from the wire) -----------------
@@ -498,6 +492,9 @@ static void test_world_loses_a_peer() {
 }
 
 int main() {
+    // read once, before any thread exists: a refused dial fails fast in these tests (50 x 20 ms instead of 500 x 200 ms)
+    setenv("KUNGFU_CONFIG_CONN_RETRY_COUNT", "50", 1);
+    setenv("KUNGFU_CONFIG_CONN_RETRY_PERIOD", "20ms", 1);
     struct {
         const char* name;
         void (*fn)();

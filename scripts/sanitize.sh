@@ -25,4 +25,6 @@ bin="kungfu_b200/bin-$mode"
 R=$((32000 + RANDOM % 4000))
 "$bin/kungfu-run" -q -np 4 -H 127.0.0.1:4 -port "$R" -port-range "$((R + 1))-$((R + 50))" -strategy RING "$bin/kungfu-fake-agent" test
 "$bin/kungfu-run" -q -np 3 -H 127.0.0.1:3 -port "$R" -port-range "$((R + 1))-$((R + 50))" -strategy BINARY_TREE "$bin/kungfu-fake-agent" bench slp
+# the C++ unit tests under the same instrumentation: in-process multi-peer worlds (threads), the epoch fence, a world that loses a peer
+"$bin/kungfu-unit-tests"
 echo "sanitizer run ($mode) passed"
