@@ -25,6 +25,13 @@ bin="kungfu_b200/bin-$mode"
 R=$((32000 + RANDOM % 4000))
 "$bin/kungfu-run" -q -np 4 -H 127.0.0.1:4 -port "$R" -port-range "$((R + 1))-$((R + 50))" -strategy RING "$bin/kungfu-fake-agent" test
 "$bin/kungfu-run" -q -np 3 -H 127.0.0.1:3 -port "$R" -port-range "$((R + 1))-$((R + 50))" -strategy BINARY_TREE "$bin/kungfu-fake-agent" bench slp
+# the watch-mode launcher paths of round 2 (loss announcements, hang watch, refill from the standby pool) with plain Python workers: the
+# instrumented process is the launcher
+export PYTHONPATH="$PWD" KUNGFU_CONFIG_LOG_LEVEL=WARN
+KUNGFU_TEST_HANG=1 KUNGFU_MONITOR_PORT=$((17000 + RANDOM % 2000)) "$bin/kungfu-run" -q -w -shrink-on-failure -auto-recover 3s -np 3 -H 127.0.0.1:4 \
+    -port "$R" -port-range "$((R + 1))-$((R + 50))" -builtin-config-port $((9200 + RANDOM % 90)) python tests/elastic_opt_worker.py shrink 1@3 8
+KUNGFU_TEST_REFILL=1 "$bin/kungfu-run" -q -w -shrink-on-failure -refill -standby 1 -np 3 -H 127.0.0.1:4 \
+    -port "$R" -port-range "$((R + 1))-$((R + 50))" -builtin-config-port $((9200 + RANDOM % 90)) python tests/elastic_opt_worker.py shrink 2@4 40
 # the C++ unit tests under the same instrumentation: in-process multi-peer worlds (threads), the epoch fence, a world that loses a peer
 "$bin/kungfu-unit-tests"
 echo "sanitizer run ($mode) passed"
