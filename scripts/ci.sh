@@ -6,6 +6,7 @@
 set -euo pipefail
 cd "$(dirname "$0")/.."
 python -c "import __graft_entry__ as g; g.build()"
+python scripts/check_names.py   # undefined names in code paths the CPU suite cannot execute (GPU-only branches)
 kungfu_b200/bin/kungfu-unit-tests
 python -m pytest tests -x -q -m "not gpu"
 scripts/sanitize.sh thread
