@@ -49,25 +49,6 @@ if _san in ("thread", "address"):
     BIN = PKG / ("bin-" + _san)
 
 
-def _cutlass_root():
-    """CUTLASS / CuTe header tree vendored in the image (used by gemm_sm100.cu only). None -> that kernel is stubbed."""
-    cands = [os.environ.get("CUTLASS_HOME", "")]
-    try:  # locate the package directory without importing it (importing flashinfer drags in half the image)
-        import importlib.util
-
-        spec = importlib.util.find_spec("flashinfer")
-        if spec is not None and spec.origin:
-            cands.append(str(Path(spec.origin).resolve().parent / "data" / "cutlass"))
-    except Exception:
-        pass
-    sp = sysconfig.get_paths()["purelib"]
-    cands += [sp + "/flashinfer/data/cutlass", sp + "/tilelang/3rdparty/cutlass"]
-    for c in cands:
-        if c and (Path(c) / "include" / "cutlass" / "gemm" / "collective" / "collective_builder.hpp").exists():
-            return c
-    return None
-
-
 def _pybind_includes() -> list[str]:
     import pybind11
 

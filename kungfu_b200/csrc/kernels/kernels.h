@@ -149,7 +149,8 @@ void launch_bias_gelu_bwd(const void* dy, const void* x, const void* bias, void*
 void launch_qkv_pack_bwd(const void* dq, const void* dk, const void* dv, const long long* strides, void* out, void* dbias, float* partial, int dtype,
                          int B, int S, int heads, int d, cudaStream_t st);
 
-// ---- gemm_sm100.cu: tcgen05 GEMM + bias (+GELU) epilogue (CUTLASS/CuTe sm100 collectives); act: 0 = identity, 1 = GELU
+// ---- gemm_tc5.cu: hand-written tcgen05 GEMM + bias (+GELU) epilogue (TMA ring, TMEM accumulators; no CUTLASS); act: 0 = identity, 1 = GELU.
+// `gemm_sm100_available` keeps its round-1 name: true when the driver exports cuTensorMapEncodeTiled
 bool gemm_sm100_available();
 size_t gemm_bias_act_workspace(int tokens, int in_f, int out_f, int act);
 void launch_gemm_bias_act(const void* x, const void* w, const void* bias, void* y, int tokens, int in_f, int out_f, int act, void* workspace,
