@@ -137,3 +137,23 @@ def test_elastic_data_adaptor():
     ad.set_offset(96)
     _, y = ad.next_batch()
     assert y.tolist() == [96, 97, 98, 99, 0, 1, 2, 3]
+
+
+def test_monitoring_benchmark_reports_overhead_and_values():
+    """benchmarks/monitoring/benchmark.py: plain S-SGD and both monitors in one job, one RESULT line per arm and interval, live monitor values
+    (workers see different data, so variance and noise scale are not zero), JSON summary."""
+    import json
+
+    rport, prange = ports()
+    cmd = [kungfu_run(), "-q", "-np", "2", "-H", "127.0.0.1:2", "-port", str(rport), "-port-range", prange, sys.executable,
+           os.path.join(ROOT, "benchmarks", "monitoring", "benchmark.py"), "--no-cuda", "--model", "slp", "--num-iters", "2",
+           "--num-batches-per-iter", "4", "--num-warmup-batches", "2", "--intervals", "1,3"]
+    e = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN")
+    r = subprocess.run(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert r.stdout.count("RESULT:") == 5, r.stdout[-3000:]  # sync-sgd + 2 monitors x 2 intervals
+    line = [l for l in r.stdout.splitlines() if '"bench": "monitoring"' in l][-1]
+    summary = json.loads(line[line.index("{"):])
+    rows = summary["rows"]
+    assert [r_["arm"] for r_ in rows] == ["sync-sgd", "variance", "variance", "noise-scale", "noise-scale"] and summary["np"] == 2
+    assert all(r_["img_per_sec"] > 0 for r_ in rows) and rows[1]["value"] > 0 and rows[3]["value"] != 0
