@@ -51,9 +51,37 @@ def group_nccl_all_reduce(ts: Sequence[torch.Tensor], op="sum") -> List[torch.Te
 
 
 def group_hierarchical_nccl_all_reduce(ts: Sequence[torch.Tensor], op="sum") -> List[torch.Tensor]:
-    """Reference: local reduce -> cross-host all-reduce -> local broadcast per tensor (ops/collective.py:109-135). The
-    dispatcher of `all_reduce` already chooses flat (one NVLink domain) or hierarchical (job spans hosts)."""
-    return group_nccl_all_reduce(ts, op)
+    """Reference: local reduce -> cross-host all-reduce -> local broadcast, per tensor (ops/collective.py:109-135).
+
+    Host tensors run exactly those three steps on the native runtime (`Session::local_reduce` to the first rank of every host,
+    `cross_all_reduce` among the hosts' first ranks, `local_broadcast` back) — on one host that degenerates to reduce + broadcast inside
+    the host. Device tensors go through `all_reduce`'s dispatcher, which IS hierarchical when the job spans hosts (kernel all-reduce
+    inside the NVLink group, control plane between the groups' first ranks, broadcast kernel) and a single flat kernel inside one NVLink
+    domain, where a three-step schedule would only add two passes over the data."""
+    from ..runtime import get_runtime
+
+    ctl = get_runtime().control
+    three_step = all(hasattr(ctl, n) for n in ("local_reduce_cpu", "cross_all_reduce_cpu_", "local_broadcast_cpu_"))
+    outs: List = []
+    device: List[torch.Tensor] = []
+    for t in ts:
+        if t is None:
+            outs.append(None)
+        elif t.is_cuda or not three_step or get_runtime().size == 1:
+            c = t.detach().clone().contiguous()
+            outs.append(c)
+            if t.is_cuda or get_runtime().size > 1:
+                device.append(c)
+        else:
+            part = ctl.local_reduce_cpu(t.detach().contiguous(), op)  # the host's first rank holds the host's partial result
+            ctl.cross_all_reduce_cpu_(part, op)  # ... combines it with the other hosts' (a no-op exchange for everybody else)
+            ctl.local_broadcast_cpu_(part)  # ... and hands the total back to its host
+            outs.append(part)
+    if device:
+        from .collective import all_reduce_group_async_
+
+        all_reduce_group_async_(device, op).wait()
+    return outs
 
 
 def calc_stats():

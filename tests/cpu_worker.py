@@ -408,6 +408,10 @@ def cmd_multihost(args):
     c.cross_all_reduce_cpu_(y)
     c.local_broadcast_cpu_(y)
     check(torch.equal(y, ops.all_reduce(torch.full((9,), float(r + 1)))), "local reduce -> cross all-reduce -> local broadcast == all-reduce")
+    hs = ops.group_hierarchical_nccl_all_reduce([torch.full((9,), float(r + 1)), None, torch.arange(6, dtype=torch.float32) * (r + 1)], "sum")
+    tot = float(n * (n + 1) // 2)
+    check(hs[1] is None and torch.equal(hs[0], torch.full((9,), tot)) and torch.equal(hs[2], torch.arange(6, dtype=torch.float32) * tot),
+          "group_hierarchical_nccl_all_reduce (local reduce -> cross all-reduce -> local broadcast per tensor) == flat all-reduce")
     # the shape of the GPU hierarchical all-reduce: only the hosts' first ranks take part in the cross-host step, then everybody
     # joins an automatically named op — op numbering is per kind, so the extra op on the masters must not shift the others
     for it in range(3):
