@@ -5,6 +5,7 @@
 // -> Request). Also the model-shaped all-reduce micro-benchmark of `kungfu-bench-allreduce`
 // (tests/go/cmd/kungfu-bench-allreduce/kungfu-bench-allreduce.go:73-110): prints
 // `RESULT: <rate> GiB/s` with the reference's "equivalent data rate" 4(np-1)*S/t.
+#include <algorithm>
 #include <atomic>
 #include <unistd.h>
 #include <chrono>
@@ -110,6 +111,34 @@ int main(int argc, char** argv) {
         }
         CHECK(kungfu_barrier() == 0);
         if (rank == 0) printf("fake-agent ok np=%d\n", np);
+    } else if (mode == "shrink") {
+        // shrink-and-continue through the C ABI (under `kungfu-run -w -shrink-on-failure`): `argv[2]` = "<rank>@<step>", that worker
+        // dies without a word inside that step; the others see their all-reduce fail, call kungfu_recover and finish 20 steps. The value
+        // every step reduces is 1 per worker, so the result IS the cluster size of that step.
+        int die_rank = -1, die_step = -1;
+        if (argc > 2) sscanf(argv[2], "%d@%d", &die_rank, &die_step);
+        int recovered = 0, size_seen_min = np, size_seen_max = np;
+        for (int step = 0; step < 20; ++step) {
+            if (recovered == 0 && kungfu_rank() == die_rank && step == die_step) _exit(17);
+            float one = 1.f, sum = 0.f;
+            const std::string name = "s" + std::to_string(step) + "v" + std::to_string(kungfu_cluster_version());
+            if (kungfu_all_reduce(&one, &sum, 1, KungFu_F32, KungFu_SUM, name.c_str(), nullptr, nullptr) != 0) {
+                int changed = 0, detached = 0;
+                CHECK(kungfu_recover(20.0, &changed, &detached) == 0);
+                CHECK(changed == 1 && detached == 0);
+                ++recovered;
+                --step; // repeat the interrupted step with the smaller cluster
+                continue;
+            }
+            CHECK((int)sum == kungfu_size());
+            size_seen_min = std::min(size_seen_min, (int)sum);
+            size_seen_max = std::max(size_seen_max, (int)sum);
+            usleep(20000);
+        }
+        int pending = -1;
+        CHECK(kungfu_failure_pending(&pending) == 0 && pending == 0);
+        CHECK(kungfu_barrier() == 0);
+        printf("fake-agent shrink ok rank=%d recovered=%d sizes=%d..%d final=%d\n", kungfu_rank(), recovered, size_seen_min, size_seen_max, kungfu_size());
     } else {
         // model-shaped all-reduce micro-benchmark (fused or per tensor)
         const bool fuse = mode == "bench-fused";

@@ -161,6 +161,16 @@ KF_API int kungfu_resize_from_url(int* changed, int* detached) {
         *detached = r.second;
     });
 }
+KF_API int kungfu_recover(double timeout_s, int* changed, int* detached) {
+    return guard([&] {
+        auto r = peer().recover(timeout_s);
+        *changed = r.first;
+        *detached = r.second;
+    });
+}
+KF_API int kungfu_failure_pending(int* pending) {
+    return guard([&] { *pending = peer().failure_pending() ? 1 : 0; });
+}
 KF_API int kungfu_propose_new_size(int new_size) {
     return guard([&] { peer().propose_new_size(new_size); });
 }

@@ -55,6 +55,10 @@ int kungfu_request(int rank, const char* version, const char* name, void* buf, s
 int kungfu_resize(int new_size, int* changed, int* detached);
 int kungfu_resize_from_url(int* changed, int* detached);
 int kungfu_propose_new_size(int new_size);
+/* shrink-and-continue (kungfu-run -w -shrink-on-failure): after a collective failed because a worker died, adopt the cluster the runner
+ * announced (waits at most timeout_s for the announcement); collectives fail fast while *pending is set and recover has not run */
+int kungfu_recover(double timeout_s, int* changed, int* detached);
+int kungfu_failure_pending(int* pending);
 int kungfu_set_tree(const int32_t* father, int n);
 int kungfu_get_peer_latencies(float* out, int n);
 int kungfu_get_egress_rates(float* out, int n);

@@ -32,6 +32,9 @@ KUNGFU_TEST_HANG=1 KUNGFU_MONITOR_PORT=$((17000 + RANDOM % 2000)) "$bin/kungfu-r
     -port "$R" -port-range "$((R + 1))-$((R + 50))" -builtin-config-port $((9200 + RANDOM % 90)) python tests/elastic_opt_worker.py shrink 1@3 8
 KUNGFU_TEST_REFILL=1 "$bin/kungfu-run" -q -w -shrink-on-failure -refill -standby 1 -np 3 -H 127.0.0.1:4 \
     -port "$R" -port-range "$((R + 1))-$((R + 50))" -builtin-config-port $((9200 + RANDOM % 90)) python tests/elastic_opt_worker.py shrink 2@4 40
+# ... and a fully instrumented job (launcher AND workers): the C-ABI agent loses a worker and recovers
+"$bin/kungfu-run" -q -w -shrink-on-failure -np 3 -H 127.0.0.1:4 -port "$R" -port-range "$((R + 1))-$((R + 50))" \
+    -builtin-config-port $((9200 + RANDOM % 90)) "$bin/kungfu-fake-agent" shrink 1@5
 # the C++ unit tests under the same instrumentation: in-process multi-peer worlds (threads), the epoch fence, a world that loses a peer
 "$bin/kungfu-unit-tests"
 echo "sanitizer run ($mode) passed"

@@ -77,6 +77,21 @@ def test_fake_agent_c_abi():
     assert out.returncode == 0 and "RESULT:" in out.stdout and "Img/sec" in out.stdout, out.stdout[-2000:]
 
 
+def test_fake_agent_survives_a_lost_worker_through_the_c_abi():
+    """`kungfu-fake-agent shrink 1@5` under `kungfu-run -w -shrink-on-failure`: a C program on the C ABI (kungfu_all_reduce fails ->
+    kungfu_recover -> repeat the step) loses rank 1 inside step 5 and finishes its 20 steps with two workers."""
+    from kungfu_b200.cmd import kungfu_run_path
+
+    agent = os.path.join(os.path.dirname(kungfu_run_path()), "kungfu-fake-agent")
+    rport, prange = ports()
+    cmd = [kungfu_run(), "-q", "-w", "-shrink-on-failure", "-np", "3", "-H", "127.0.0.1:4", "-port", str(rport), "-port-range", prange,
+           "-builtin-config-port", str(9200 + os.getpid() % 90), agent, "shrink", "1@5"]
+    r = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, KUNGFU_CONFIG_LOG_LEVEL="WARN"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert r.stdout.count("fake-agent shrink ok") == 2 and r.stdout.count("recovered=1 sizes=2..3 final=2") == 2, r.stdout[-3000:]
+
+
 def test_examples_and_microbench_run():
     rport, prange = ports()
     env = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN")
