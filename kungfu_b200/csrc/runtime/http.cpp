@@ -34,6 +34,11 @@ static bool read_http(Socket& s, std::string& head, std::string& body, int timeo
             break; // connection closed: body is whatever arrived
         }
         buf.append(tmp, (size_t)k);
+        // these endpoints (config server, monitors, metrics) exchange kilobytes: anything bigger is not ours, and nobody gets to make the
+        // process buffer without bound
+        constexpr size_t kMaxHead = 64u << 10, kMaxBody = 16u << 20;
+        if (hdr_end == std::string::npos && buf.size() > kMaxHead && buf.find("\r\n\r\n") == std::string::npos) return false;
+        if (hdr_end != std::string::npos && buf.size() > hdr_end + 4 + kMaxBody) return false;
         if (hdr_end == std::string::npos) {
             hdr_end = buf.find("\r\n\r\n");
             if (hdr_end != std::string::npos) {
@@ -42,7 +47,9 @@ static bool read_http(Socket& s, std::string& head, std::string& body, int timeo
                 for (char c : h) lower.push_back((char)tolower(c));
                 auto pos = lower.find("content-length:");
                 if (pos != std::string::npos) {
-                    content_len = (size_t)atol(h.c_str() + pos + 15);
+                    const long long cl = atoll(h.c_str() + pos + 15);
+                    if (cl < 0 || (unsigned long long)cl > (16ull << 20)) return false;
+                    content_len = (size_t)cl;
                     have_len = true;
                 } else if (lower.compare(0, 4, "http") != 0) {
                     have_len = true; // a request without a body

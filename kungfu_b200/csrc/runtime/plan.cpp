@@ -379,7 +379,20 @@ struct JsonParser {
         while (i < t.size() && isspace((unsigned char)t[i])) ++i;
     }
     [[noreturn]] void err(const char* what) { fail(std::string("json: ") + what + " at offset " + std::to_string(i)); }
+    // The documents this reader sees (cluster, stage, heartbeat keys) are three levels deep; the text comes from the network (config
+    // server PUT, control messages), and a recursive-descent reader without a limit turns 100 000 '[' into a stack overflow (found by
+    // tests/test_parsers_fuzz.py).
+    static constexpr int kMaxDepth = 64;
+    int depth = 0;
+    struct Nest {
+        JsonParser& p;
+        explicit Nest(JsonParser& q) : p(q) {
+            if (++p.depth > kMaxDepth) p.err("nesting too deep");
+        }
+        ~Nest() { --p.depth; }
+    };
     JsonValue value() {
+        Nest nest(*this);
         ws();
         if (i >= t.size()) err("unexpected end");
         char c = t[i];
