@@ -694,6 +694,10 @@ bool P2PEndpoint::on_message(const PeerID& src, const std::string& name, uint32_
         }
         return ok;
     }
+    if (len > kMaxNameLen) { // a request carries a version label, nothing more: never allocate what a stranger announces
+        KF_LOGW("dropping connection from %s: %llu-byte version label in a p2p request", src.str().c_str(), (unsigned long long)len);
+        return false;
+    }
     std::string version(len, '\0');
     if (len && !s.recv_all(&version[0], len)) return false;
     Pool::get().submit([this, src, name, version] { respond(src, name, version); });

@@ -365,7 +365,9 @@ static void test_server_survives_garbage() {
     const PeerID srv{parse_ipv4("127.0.0.1"), port}, cli{parse_ipv4("127.0.0.1"), (uint16_t)(port + 1)};
     CollectiveEndpoint coll;
     std::atomic<int> controls{0};
-    Server server(srv, &coll, nullptr, false);
+    Client p2p_client(srv);
+    P2PEndpoint p2p(&p2p_client, srv);
+    Server server(srv, &coll, &p2p, false);
     server.set_control_handler([&](const PeerID&, const std::string&, const Bytes&) { ++controls; });
     coll.reopen(1);
     server.set_token(1);
@@ -389,7 +391,7 @@ static void test_server_survives_garbage() {
         uint32_t name_len, flags;
         uint64_t data_len;
     };
-    for (uint16_t type : {(uint16_t)kConnCollective, (uint16_t)kConnControl, (uint16_t)kConnPing, (uint16_t)77}) {
+    for (uint16_t type : {(uint16_t)kConnCollective, (uint16_t)kConnControl, (uint16_t)kConnPing, (uint16_t)kConnPeerToPeer, (uint16_t)77}) {
         Socket s = raw();
         Hdr h{type, cli.port, cli.ipv4};
         uint32_t ack = 0;
@@ -401,6 +403,17 @@ static void test_server_survives_garbage() {
         CHECK(s2.send_all(&h, sizeof(h)) && s2.recv_all(&ack, sizeof(ack)));
         Msg longname{1u << 30, 0, 4}; // 1 GiB name
         s2.send_all(&longname, sizeof(longname));
+    }
+    { // a p2p request whose "version label" claims a gigabyte (below the generic data cap): refused, not allocated
+        Socket s = raw();
+        Hdr h{(uint16_t)kConnPeerToPeer, cli.port, cli.ipv4};
+        uint32_t ack = 0;
+        CHECK(s.send_all(&h, sizeof(h)) && s.recv_all(&ack, sizeof(ack)));
+        Msg m{4, 0, 1ull << 30};
+        s.send_all(&m, sizeof(m));
+        s.send_all("blob", 4);
+        char c;
+        CHECK(!s.recv_all(&c, 1)); // the server hung up
     }
     sleep_ms(100);
     CHECK(coll.parked() == 0);
@@ -416,6 +429,8 @@ static void test_server_survives_garbage() {
     CHECK(controls.load() == 1);
     CHECK(a.ping(srv, 1000) >= 0);
     a.close_all();
+    p2p.shutdown();
+    p2p_client.close_all();
     server.stop();
 }
 
