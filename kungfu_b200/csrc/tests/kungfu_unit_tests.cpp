@@ -303,6 +303,34 @@ static void test_single_process_peer() {
     }
 }
 
+// ---- the JSON reader behind the config server and the runners' control messages ----------------------------------------------------
+static void test_json_reader() {
+    Cluster c = Cluster::from_json("{\"Runners\":[{\"IPv4\":2130706433,\"Port\":38080}],\"Workers\":[{\"IPv4\":2130706433,\"Port\":10000}]}");
+    CHECK(c.runners.size() == 1 && c.workers.size() == 1 && c.workers[0].port == 10000);
+    CHECK(Cluster::from_json(c.to_json()) == c);
+    Stage st;
+    st.version = 7;
+    st.cluster = c;
+    CHECK(Stage::from_json(st.to_json()).version == 7 && Stage::from_json(st.to_json()).cluster == c);
+    for (const char* bad : {"", "{", "[1,2", "{\"Runners\":3}", "{\"Runners\":[{\"IPv4\":\"x\"}]}", "nul", "\"unterminated", "{\"a\" 1}", "[1 2]"}) {
+        bool threw = false;
+        try {
+            (void)JsonValue::parse(bad);
+            (void)Cluster::from_json(bad);
+        } catch (const std::exception&) {
+            threw = true;
+        }
+        CHECK(threw);
+    }
+    // depth: 64 levels are plenty for our documents; a stranger's 100 000 '[' must be an error, not a stack overflow
+    CHECK_THROWS(JsonValue::parse(std::string(100000, '[')));
+    std::string deep_obj;
+    for (int i = 0; i < 50000; ++i) deep_obj += "{\"a\":";
+    CHECK_THROWS(JsonValue::parse(deep_obj));
+    std::string ok_depth = std::string(40, '[') + "1" + std::string(40, ']');
+    CHECK(JsonValue::parse(ok_depth).kind == JsonValue::Array);
+}
+
 // ---- transport: stale-epoch fencing of collective connections, shutdown / reopen of the mailboxes ----------------------------------
 static void test_epoch_fence() {
     const uint16_t port = (uint16_t)(41000 + getpid() % 2000);
@@ -515,7 +543,7 @@ int main() {
         void (*fn)();
     } tests[] = {{"dtypes_and_transform2", test_dtypes_and_transform2}, {"plan", test_plan}, {"topologies", test_topologies}, {"mst", test_mst},
                  {"placement", test_placement}, {"stores", test_stores}, {"single_process_peer", test_single_process_peer},
-                 {"epoch_fence", test_epoch_fence}, {"server_survives_garbage", test_server_survives_garbage},
+                 {"json_reader", test_json_reader}, {"epoch_fence", test_epoch_fence}, {"server_survives_garbage", test_server_survives_garbage},
                  {"world_loses_a_peer", test_world_loses_a_peer}};
     for (auto& t : tests) {
         const int before = g_fail;
