@@ -264,6 +264,24 @@ def test_lost_worker_is_replaced_from_the_standby_pool():
     assert "refill: proposed 3 workers again" in r.stdout and "becomes 127.0.0.1" in r.stdout, r.stdout[-3000:]
 
 
+@pytest.mark.extended
+def test_three_crashes_three_refills_root_included():
+    """4 workers, 120 steps, `-shrink-on-failure -refill -standby 2`: rank 3 dies in step 5, rank 1 in step 30, rank 0 (the root every
+    broadcast starts from) in step 60; after each loss the runner proposes 4 workers again and a standby joins. All four workers of the final
+    cluster finish with bit-identical models."""
+    rport, prange = ports()
+    cfg_port = 9300 + (os.getpid() + 90) % 100
+    cmd = [kungfu_run(), "-q", "-w", "-shrink-on-failure", "-refill", "-standby", "2", "-np", "4", "-H", "127.0.0.1:6", "-port", str(rport),
+           "-port-range", prange, "-builtin-config-port", str(cfg_port), sys.executable, os.path.join(ROOT, "tests", "elastic_opt_worker.py"),
+           "shrink", "3@5,1@30,0@60", "120"]
+    e = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN", KUNGFU_TEST_REFILL="1")
+    r = subprocess.run(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-5000:]
+    done = [j for j in json_lines(r.stdout) if j.get("done") == "shrink"]
+    assert len(done) == 4 and all(d["identical"] and d["finite"] and d["step"] == 120 and d["final_size"] == 4 for d in done), r.stdout[-5000:]
+    assert r.stdout.count("lost, continuing with 3 workers") == 3 and r.stdout.count("refill: proposed 4 workers again") == 3, r.stdout[-3000:]
+
+
 def test_shrink_keeps_survivors_identical():
     """One crash in a 4-worker job: the 3 survivors finish with bit-identical models (rank 0's state is broadcast after the loss)."""
     rport, prange = ports()
