@@ -762,6 +762,7 @@ struct Watcher {
             if (code != 200) KF_LOGW("config server did not take the shrunk cluster: %d %s", code, resp.c_str());
         }
         Client client(self);
+        client.set_max_dial_tries(5); // a worker that does not answer within a second is the next casualty, not somebody to wait 100 s for
         for (auto& w : st.cluster.workers) {
             try {
                 client.send(w, "lost", payload.data(), payload.size(), kConnControl, kNoFlag);

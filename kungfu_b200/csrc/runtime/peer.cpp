@@ -147,8 +147,8 @@ void Peer::on_control(const PeerID& src, const std::string& name, const Bytes& p
             return;
         }
         {
-            std::lock_guard<std::mutex> g(mu_);
-            if (st.version <= cluster_version_) return; // old news
+            std::lock_guard<std::mutex> g(lost_mu_); // NOT mu_: a regroup in progress holds that one, and this message must abort it
+            if (st.version <= cluster_version_.load()) return; // old news
             for (auto& q : lost_stages_)
                 if (q.version == st.version) return; // every runner announces it
             lost_stages_.push_back(st);
@@ -161,7 +161,7 @@ void Peer::on_control(const PeerID& src, const std::string& name, const Bytes& p
         lost_cv_.notify_all();
         std::function<void()> cb;
         {
-            std::lock_guard<std::mutex> g(mu_);
+            std::lock_guard<std::mutex> g(lost_mu_);
             cb = on_lost_;
         }
         if (cb) {
@@ -175,47 +175,84 @@ void Peer::on_control(const PeerID& src, const std::string& name, const Bytes& p
 }
 
 void Peer::set_lost_callback(std::function<void()> f) {
-    std::lock_guard<std::mutex> g(mu_);
+    std::lock_guard<std::mutex> g(lost_mu_);
     on_lost_ = std::move(f);
 }
 
 bool Peer::trusted_source(const PeerID& src) {
     // only hosts that take part in the job (workers, runners) or this machine may change a worker's fate
-    bool known = (src.ipv4 >> 24) == 127 || src.ipv4 == cfg_.self.ipv4;
-    std::lock_guard<std::mutex> g(mu_);
-    for (auto& p : cluster_.workers) known = known || p.ipv4 == src.ipv4;
-    for (auto& p : cluster_.runners) known = known || p.ipv4 == src.ipv4;
-    return known;
+    if ((src.ipv4 >> 24) == 127 || src.ipv4 == cfg_.self.ipv4) return true;
+    for (auto& p : cfg_.init_peers)
+        if (p.ipv4 == src.ipv4) return true;
+    for (auto& p : cfg_.init_runners)
+        if (p.ipv4 == src.ipv4) return true;
+    // hosts that joined later: the current cluster — but never wait for a regroup in progress (it holds mu_ and may be what this
+    // message is about to abort)
+    std::unique_lock<std::mutex> g(mu_, std::try_to_lock);
+    if (!g.owns_lock()) return false;
+    for (auto& p : cluster_.workers)
+        if (p.ipv4 == src.ipv4) return true;
+    for (auto& p : cluster_.runners)
+        if (p.ipv4 == src.ipv4) return true;
+    return false;
 }
 
 bool Peer::failure_pending() {
-    std::lock_guard<std::mutex> g(mu_);
+    std::lock_guard<std::mutex> g(lost_mu_);
     return !lost_stages_.empty();
 }
 
 std::pair<bool, bool> Peer::recover(double timeout_s) {
     StallGuard sg("recover");
-    Stage st;
-    {
-        std::unique_lock<std::mutex> lk(mu_);
-        if (!lost_cv_.wait_for(lk, std::chrono::milliseconds((long)(timeout_s * 1000)), [&] { return !lost_stages_.empty(); }))
-            fail("recover: no runner announced a membership change within " + std::to_string(timeout_s) + " s");
-        // several workers may have died: jump to the newest announced stage (versions are strictly increasing)
-        st = lost_stages_.back();
-        lost_stages_.clear();
-        if (st.version <= cluster_version_) return {false, false};
-        KF_LOGW("recovering: v%d -> v%d, %d -> %d workers", cluster_version_, st.version, (int)cluster_.workers.size(), (int)st.cluster.workers.size());
-        cluster_ = st.cluster;
-        cluster_version_ = st.version;
-        updated_ = false;
-        session_.reset();
+    const auto wait_ms = std::chrono::milliseconds((long)(timeout_s * 1000));
+    bool changed = false;
+    for (int attempt = 0;; ++attempt) {
+        Stage st;
+        {
+            std::unique_lock<std::mutex> lk(lost_mu_);
+            if (!lost_cv_.wait_for(lk, wait_ms, [&] { return !lost_stages_.empty(); })) {
+                if (changed) break;
+                fail("recover: no runner announced a membership change within " + std::to_string(timeout_s) + " s");
+            }
+            // several workers may have died, and their announcements travel on different threads: adopt the NEWEST stage, whatever the
+            // order of arrival (versions are strictly increasing)
+            st = lost_stages_.front();
+            for (auto& q : lost_stages_)
+                if (q.version > st.version) st = q;
+            lost_stages_.clear();
+        }
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            if (st.version <= cluster_version_.load()) {
+                if (changed) break;
+                return {false, false};
+            }
+            KF_LOGW("recovering: v%d -> v%d, %d -> %d workers", cluster_version_.load(), st.version, (int)cluster_.workers.size(),
+                    (int)st.cluster.workers.size());
+            cluster_ = st.cluster;
+            cluster_version_ = st.version;
+            updated_ = false;
+            session_.reset();
+            changed = true;
+        }
+        if (!st.cluster.workers.contains(cfg_.self)) {
+            detached_ = true;
+            return {true, true};
+        }
+        try {
+            update(); // meets the other survivors at the barrier of the new session (holds mu_ meanwhile)
+            std::lock_guard<std::mutex> g(lost_mu_);
+            if (lost_stages_.empty()) return {true, false};
+            // another loss was announced while we were regrouping: go round again with it
+        } catch (const std::exception& e) {
+            // the barrier of this stage broke: one more member died meanwhile (its announcement shut the mailboxes and interrupted the
+            // dials). Take the next stage if it is there or comes within the time-out; otherwise the error goes to the caller.
+            KF_LOGW("recover: regrouping as v%d failed (%s); waiting for a newer membership", st.version, e.what());
+            if (attempt >= 8) throw;
+            std::unique_lock<std::mutex> lk(lost_mu_);
+            if (!lost_cv_.wait_for(lk, wait_ms, [&] { return !lost_stages_.empty(); })) throw;
+        }
     }
-    const bool keep = st.cluster.workers.contains(cfg_.self);
-    if (!keep) {
-        detached_ = true;
-        return {true, true};
-    }
-    update();
     return {true, false};
 }
 
@@ -249,9 +286,9 @@ bool Peer::update_to(const PeerList& pl) {
         return true;
     }
     // open the mailboxes for the new epoch BEFORE peers of that epoch can connect (they are refused until the token moves)
-    coll_.reopen(cluster_version_);
+    coll_.reopen(cluster_version_.load());
     server_->set_token((uint32_t)cluster_version_);
-    KF_LOGD("updateTo v%d of %d peers: %s", cluster_version_, (int)pl.size(), pl.str().c_str());
+    KF_LOGD("updateTo v%d of %d peers: %s", cluster_version_.load(), (int)pl.size(), pl.str().c_str());
     client_->reset_connections(pl, (uint32_t)cluster_version_);
     if (!pl.contains(cfg_.self)) return false;
     auto sess = std::make_shared<Session>(cfg_.strategy, cfg_.self, pl, client_.get(), &coll_);
@@ -259,7 +296,7 @@ bool Peer::update_to(const PeerList& pl) {
     session_ = sess;
     rank_hint_ = sess->rank();
     updated_ = true;
-    NetMonitor::get().set_gauge("kungfu_cluster_version", cluster_version_);
+    NetMonitor::get().set_gauge("kungfu_cluster_version", cluster_version_.load());
     NetMonitor::get().set_gauge("kungfu_cluster_size", (double)pl.size());
     NetMonitor::get().set_gauge("kungfu_rank", sess->rank());
     return true;
@@ -306,7 +343,7 @@ std::pair<bool, bool> Peer::propose(const Cluster& c) {
     Stage st;
     {
         std::lock_guard<std::mutex> g(mu_);
-        st.version = cluster_version_ + 1;
+        st.version = cluster_version_.load() + 1;
     }
     st.cluster = c;
     const std::string payload = st.to_json();

@@ -49,7 +49,7 @@ public:
     uint64_t uid() const;
     bool detached() const { return detached_; }
     bool single() const { return cfg_.single; }
-    int cluster_version() const { return cluster_version_; }
+    int cluster_version() const { return cluster_version_.load(); }
     const PeerConfig& config() const { return cfg_; }
     Cluster current_cluster();
     PeerID self() const { return cfg_.self; }
@@ -92,12 +92,15 @@ private:
     std::unique_ptr<class HttpServer> metrics_;
     std::shared_ptr<Session> session_;
     Cluster cluster_;
+    // Announced by the runners, not yet adopted. Own mutex: `mu_` is held for the whole of update_to() — including its barrier, which is
+    // exactly what a further loss must be able to abort — so the handler of a `lost` message may not wait for it.
+    std::mutex lost_mu_;
     std::condition_variable lost_cv_;
-    std::deque<Stage> lost_stages_; // announced by the runners, not yet adopted
+    std::deque<Stage> lost_stages_;
     std::function<void()> on_lost_;
     std::atomic<int> rank_hint_{-1}; // rank in the current session, readable without the lock (watchdog thread)
     bool reports_waiting_ = false;
-    int cluster_version_ = 0;
+    std::atomic<int> cluster_version_{0}; // written under mu_; read without it by the loss handler (which must never wait for mu_)
     bool updated_ = false;
     bool detached_ = false;
     bool started_ = false;

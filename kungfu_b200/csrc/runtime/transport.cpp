@@ -301,7 +301,8 @@ Socket Client::dial(const PeerID& to, ConnType type, bool retry) {
     // Collective / control traffic waits for its peer for as long as the configured budget says (peers of a new epoch come up at their
     // own pace). A peer-to-peer request is asynchronous by nature (model pulls of PairAveraging): its target is either there or it is
     // not worth waiting 100 s for — 15 attempts (3 s with the default period) cover a restart blip.
-    const int tries = retry ? (type == kConnPeerToPeer ? std::min(cfg.conn_retry_count, 15) : cfg.conn_retry_count) : 1;
+    int tries = retry ? (type == kConnPeerToPeer ? std::min(cfg.conn_retry_count, 15) : cfg.conn_retry_count) : 1;
+    if (retry && max_tries_.load() > 0) tries = std::min(tries, max_tries_.load());
     const uint64_t gen = abort_gen_.load();
     for (int attempt = 0; attempt < tries; ++attempt) {
         if (abort_gen_.load() != gen) break; // interrupt(): the peer is known to be lost

@@ -110,6 +110,9 @@ public:
     void close_all();
     // abandon every dial that is being retried right now (a peer is known to be gone: do not sit out the retry budget)
     void interrupt() { ++abort_gen_; }
+    // cap the number of dial attempts of this client (0 = the configured budget): notifications to peers that may be dead must not
+    // sit out 500 x 200 ms
+    void set_max_dial_tries(int n) { max_tries_ = n; }
 
 private:
     struct Conn {
@@ -121,6 +124,7 @@ private:
     PeerID self_;
     std::atomic<uint32_t> token_{0};
     std::atomic<uint64_t> abort_gen_{0};
+    std::atomic<int> max_tries_{0};
     std::mutex mu_;
     std::map<std::pair<uint64_t, int>, std::shared_ptr<Conn>> pool_;
 };

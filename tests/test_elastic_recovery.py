@@ -282,6 +282,24 @@ def test_three_crashes_three_refills_root_included():
     assert r.stdout.count("lost, continuing with 3 workers") == 3 and r.stdout.count("refill: proposed 4 workers again") == 3, r.stdout[-3000:]
 
 
+def test_two_workers_die_in_the_same_step():
+    """Ranks 2 and 3 of 4 die inside the same step. Their announcements (v1: without 2, v2: without 2 and 3) travel on different threads and
+    may arrive in either order, or the second while the survivors are already regrouping as v1 — whose barrier can never complete. The loss
+    handler therefore never waits for the peer's main mutex (held during a regroup) and `recover()` adopts the newest stage, going round
+    again when a regroup is aborted by further news. Used to hang for the 100 s dial budget in about half of the runs."""
+    rport, prange = ports()
+    cfg_port = 9300 + (os.getpid() + 60) % 100
+    cmd = [kungfu_run(), "-q", "-w", "-shrink-on-failure", "-np", "4", "-H", "127.0.0.1:4", "-port", str(rport), "-port-range", prange,
+           "-builtin-config-port", str(cfg_port), sys.executable, os.path.join(ROOT, "tests", "elastic_opt_worker.py"), "shrink", "2@4,3@4", "12"]
+    e = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN")
+    t0 = time.time()
+    r = subprocess.run(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=100)
+    assert r.returncode == 0, r.stdout[-5000:]
+    done = [j for j in json_lines(r.stdout) if j.get("done") == "shrink"]
+    assert len(done) == 2 and all(d["identical"] and d["step"] == 12 and d["final_size"] == 2 for d in done), r.stdout[-5000:]
+    assert time.time() - t0 < 60, "a loss notice sat behind a regroup (or a dead worker was waited for)"
+
+
 def test_shrink_keeps_survivors_identical():
     """One crash in a 4-worker job: the 3 survivors finish with bit-identical models (rank 0's state is broadcast after the loss)."""
     rport, prange = ports()
