@@ -107,6 +107,30 @@ def test_elastic_resize_across_hosts():
             b.kill()
 
 
+def test_shrink_and_continue_across_hosts():
+    """Two hosts with two workers each under `-w -shrink-on-failure`; a worker on the SECOND host dies inside step 4. Its runner announces
+    the loss to the survivors on both hosts and to the other runner; the three survivors regroup and finish with identical models; both
+    launchers exit 0."""
+    rport, prange = ports()
+    cfg = 9100 + (os.getpid() + 150) % 300
+    env = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN")
+    work = [sys.executable, os.path.join(ROOT, "tests", "elastic_opt_worker.py"), "shrink", "3@4", "12"]
+    base = [kungfu_run(), "-q", "-w", "-shrink-on-failure", "-np", "4", "-H", "127.0.0.1:2,127.0.0.2:2", "-port", str(rport), "-port-range", prange]
+    b = subprocess.Popen(base + ["-self", "127.0.0.2", "-config-server", f"http://127.0.0.1:{cfg}/config"] + work, cwd=ROOT, env=env,
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        a = subprocess.run(base + ["-self", "127.0.0.1", "-builtin-config-port", str(cfg)] + work, cwd=ROOT, env=env, stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True, timeout=150)
+        out_b, _ = b.communicate(timeout=60)
+        assert a.returncode == 0 and b.returncode == 0, (a.stdout[-3000:], out_b[-3000:])
+        done = [j for j in json_lines(a.stdout + out_b) if j.get("done") == "shrink"]
+        assert len(done) == 3 and all(d["identical"] and d["step"] == 12 and d["final_size"] == 3 and d["failures"] == [[4, 3]] for d in done), done
+        assert "lost, continuing with 3 workers" in out_b and "lost, continuing" not in a.stdout  # the runner that owned the worker announces
+    finally:
+        if b.poll() is None:
+            b.kill()
+
+
 def test_failure_recovery_across_hosts(tmp_path):
     """One worker per host; the worker on the second host hangs inside a batch. The main monitor server (first host) notices
     the stall, tells the other host's server (`otherdown:<epochs>`), both launchers kill and restart their workers with the
