@@ -462,6 +462,67 @@ static void test_server_survives_garbage() {
     server.stop();
 }
 
+// ---- four peers in one process, every strategy: the collectives agree with their definition (test_kungfu_world.cpp; under TSan this is
+// the session / transport / thread-pool code with real concurrency and none of Python's serialisation) ---------------------------------
+static void test_world_all_strategies() {
+    const int n = 4;
+    int round = 0;
+    for (const std::string& name : strategy_names()) {
+        const uint16_t base = (uint16_t)(47000 + (getpid() % 500) * 4 + 16 * (round++ % 60));
+        std::vector<std::unique_ptr<Peer>> peers;
+        for (int r = 0; r < n; ++r) {
+            PeerConfig cfg = PeerConfig::single_machine(r, n, base);
+            cfg.strategy = parse_strategy(name);
+            peers.emplace_back(new Peer(cfg));
+        }
+        std::vector<std::string> errs(n);
+        std::vector<int> ok(n, 0);
+        std::vector<std::thread> ts;
+        for (int r = 0; r < n; ++r)
+            ts.emplace_back([&, r] {
+                try {
+                    peers[r]->start();
+                    auto sess = peers[r]->session();
+                    bool good = sess->rank() == r && sess->size() == n;
+                    // all-reduce over several chunk sizes (1 element ... more than one 1 MiB chunk), sum and max
+                    for (size_t cnt : {(size_t)1, (size_t)1000, (size_t)300000}) {
+                        std::vector<float> x(cnt, (float)(r + 1)), y(cnt, -1.f);
+                        Workspace w{x.data(), y.data(), cnt, kF32, kSum, "sum" + std::to_string(cnt)};
+                        sess->all_reduce(w);
+                        good = good && y[0] == 10.f && y[cnt - 1] == 10.f && y[cnt / 2] == 10.f;
+                        std::vector<int32_t> a(cnt, r), b(cnt, -1);
+                        Workspace w2{a.data(), b.data(), cnt, kI32, kMax, "max" + std::to_string(cnt)};
+                        sess->all_reduce(w2);
+                        good = good && b[0] == n - 1 && b[cnt - 1] == n - 1;
+                    }
+                    std::vector<double> bc(777, r == 0 ? 3.25 : -1.0), out(777, 0.0);
+                    Workspace wb{bc.data(), out.data(), bc.size(), kF64, kSum, "bcast"};
+                    sess->broadcast(wb);
+                    good = good && out[0] == 3.25 && out[776] == 3.25;
+                    std::vector<int32_t> mine(5, r), all(5 * n, -1);
+                    Workspace wg{mine.data(), all.data(), mine.size(), kI32, kSum, "allgather"};
+                    sess->all_gather(wg);
+                    for (int q = 0; q < n; ++q) good = good && all[5 * q] == q && all[5 * q + 4] == q;
+                    const char same[] = "identical", diff_a[] = "aaaa", diff_b[] = "bbbb";
+                    good = good && sess->consensus(same, sizeof(same), "same");
+                    good = good && !sess->consensus(r == 2 ? diff_b : diff_a, 4, "differs");
+                    sess->barrier();
+                    ok[r] = good ? 1 : 0;
+                } catch (const std::exception& e) {
+                    errs[r] = e.what();
+                }
+            });
+        for (auto& t : ts) t.join();
+        for (int r = 0; r < n; ++r) {
+            if (!errs[r].empty()) std::fprintf(stderr, "strategy %s rank %d: %s\n", name.c_str(), r, errs[r].c_str());
+            CHECK(errs[r].empty() && ok[r] == 1);
+        }
+        ts.clear();
+        for (int r = 0; r < n; ++r) ts.emplace_back([&, r] { peers[r]->close(); });
+        for (auto& t : ts) t.join();
+    }
+}
+
 // ---- three peers in one process; one goes away; a "runner" announces it; the other two recover and keep reducing (test_kungfu_world.cpp +
 // the shrink-and-continue protocol, which the reference does not have) ----------------------------------------------------------------
 static void test_world_loses_a_peer() {
@@ -543,7 +604,7 @@ int main() {
         void (*fn)();
     } tests[] = {{"dtypes_and_transform2", test_dtypes_and_transform2}, {"plan", test_plan}, {"topologies", test_topologies}, {"mst", test_mst},
                  {"placement", test_placement}, {"stores", test_stores}, {"single_process_peer", test_single_process_peer},
-                 {"json_reader", test_json_reader}, {"epoch_fence", test_epoch_fence}, {"server_survives_garbage", test_server_survives_garbage},
+                 {"json_reader", test_json_reader}, {"epoch_fence", test_epoch_fence}, {"server_survives_garbage", test_server_survives_garbage}, {"world_all_strategies", test_world_all_strategies},
                  {"world_loses_a_peer", test_world_loses_a_peer}};
     for (auto& t : tests) {
         const int before = g_fail;
