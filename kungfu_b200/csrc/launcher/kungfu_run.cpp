@@ -580,6 +580,8 @@ struct Watcher {
     int n_shrinks = 0;
     std::vector<std::thread> helpers; // loss announcements in flight
     std::map<uint64_t, pid_t> pids;   // peer key -> process of the worker that currently has this identity
+    std::map<uint64_t, double> born;  // peer key -> when this runner created it (workers added after the first stage)
+    int bad_refills = 0;              // replacements that died within 20 s of their creation: three of them end -refill
     std::unique_ptr<HangWatch> hang;
     Cluster current;
     // -standby N: warmed-up processes (interpreter, torch, CUDA context on a reserved GPU slot) waiting on a pipe for an identity
@@ -686,6 +688,7 @@ struct Watcher {
             std::lock_guard<std::mutex> g(mu);
             ++n_running;
             finished[id.key()] = false;
+            if (history.size() > 1) born[id.key()] = now_s(); // not one of the workers the job started with
         }
         const int color = (int)(id.port % 6);
         std::thread t([this, p, gpu, id, color, sb] {
@@ -728,6 +731,9 @@ struct Watcher {
         st.version = last.version + 1;
         st.cluster = last.cluster;
         st.cluster.workers = last.cluster.workers.minus(PeerList{id});
+        auto bt = born.find(id.key());
+        if (bt != born.end() && now_s() - bt->second < 20.0 && ++bad_refills == 3)
+            KF_LOGW("three replacement workers in a row died right after their start: -refill is off for the rest of the job");
         KF_LOGW("%s is gone: shrinking to %d workers (v%d)", id.str().c_str(), (int)st.cluster.workers.size(), st.version);
         fprintf(stderr, "[kungfu-run] worker %s lost, continuing with %d workers\n", id.str().c_str(), (int)st.cluster.workers.size());
         history.push_back(st);
@@ -779,7 +785,12 @@ struct Watcher {
             }
         }
         client.close_all();
-        if (f.refill && !job.config_server.empty()) {
+        bool refill_on;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            refill_on = f.refill && bad_refills < 3;
+        }
+        if (refill_on && !job.config_server.empty()) {
             // self-healing: once the survivors have had time to regroup, ask for the old size again. Nothing is forced: the bigger
             // cluster takes effect when the workers next consult the config server (their resize protocol), and the new worker is
             // created by whichever runner owns the address — from its standby pool when it has one.

@@ -40,6 +40,8 @@ if which == "shrink":
     # models. Ranks are those of the cluster at the time of the crash.
     from kungfu_b200.elastic import ElasticState, ShrinkOnFailure, sync_after_resize
 
+    if os.environ.get("KUNGFU_TEST_JOINER_CRASH") == "1" and kfp.current_cluster_version() > 0:
+        os._exit(3)  # a replacement worker that never makes it into the job
     torch.manual_seed(1234 + kfp.current_rank())
     dev = torch.device("cpu")
     if os.environ.get("KUNGFU_TEST_CUDA") == "1":  # the fused GPU engine: bf16 model, sharded fp32 master weights + momentum

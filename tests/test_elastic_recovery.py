@@ -282,6 +282,22 @@ def test_three_crashes_three_refills_root_included():
     assert r.stdout.count("lost, continuing with 3 workers") == 3 and r.stdout.count("refill: proposed 4 workers again") == 3, r.stdout[-3000:]
 
 
+def test_refill_gives_up_on_replacements_that_keep_dying():
+    """`-refill` with a replacement worker that crashes at start-up every time: the survivors recover from every one of those losses too and
+    finish; after three replacements that died right after their creation the runner stops proposing new ones instead of churning for ever."""
+    rport, prange = ports()
+    cfg_port = 9300 + (os.getpid() + 35) % 100
+    cmd = [kungfu_run(), "-q", "-w", "-shrink-on-failure", "-refill", "-standby", "1", "-np", "3", "-H", "127.0.0.1:4", "-port", str(rport),
+           "-port-range", prange, "-builtin-config-port", str(cfg_port), sys.executable, os.path.join(ROOT, "tests", "elastic_opt_worker.py"),
+           "shrink", "2@4", "80"]
+    e = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN", KUNGFU_TEST_REFILL="1", KUNGFU_TEST_JOINER_CRASH="1")
+    r = subprocess.run(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=200)
+    assert r.returncode == 0, r.stdout[-5000:]
+    done = [j for j in json_lines(r.stdout) if j.get("done") == "shrink"]
+    assert len(done) == 2 and all(d["identical"] and d["step"] == 80 and d["final_size"] == 2 for d in done), r.stdout[-5000:]
+    assert r.stdout.count("refill: proposed 3 workers again") == 3 and "-refill is off for the rest of the job" in r.stdout, r.stdout[-3000:]
+
+
 def test_two_workers_die_in_the_same_step():
     """Ranks 2 and 3 of 4 die inside the same step. Their announcements (v1: without 2, v2: without 2 and 3) travel on different threads and
     may arrive in either order, or the second while the survivors are already regrouping as v1 — whose barrier can never complete. The loss
