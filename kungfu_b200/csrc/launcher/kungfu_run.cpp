@@ -666,6 +666,20 @@ struct Watcher {
                 standbys.pop_front();
             }
         }
+        if (sb) {
+            // a standby that died while waiting (a script that fails before it reaches the control plane, an OOM kill) must not be handed
+            // out as a worker: it would "crash" the moment it is activated
+            int status = 0;
+            if (waitpid(sb->child.pid, &status, WNOHANG) == sb->child.pid) {
+                KF_LOGW("standby-%d is dead (status %d): starting %s cold", sb->seq, status, id.str().c_str());
+                if (sb->child.stdin_fd >= 0) close(sb->child.stdin_fd), sb->child.stdin_fd = -1;
+                cancel.remove(sb->child.pid);
+                sb->child.out.join();
+                sb->child.err.join();
+                gpus.put(sb->gpu);
+                sb.reset();
+            }
+        }
         const int gpu = sb ? sb->gpu : gpus.get();
         if (gpu < 0) KF_LOGW("no free GPU slot for %s", id.str().c_str());
         Proc p = job.new_proc(id, gpu, st.version, st.cluster);

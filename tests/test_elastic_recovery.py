@@ -298,6 +298,28 @@ def test_refill_gives_up_on_replacements_that_keep_dying():
     assert r.stdout.count("refill: proposed 3 workers again") == 3 and "-refill is off for the rest of the job" in r.stdout, r.stdout[-3000:]
 
 
+def test_a_standby_that_died_is_not_handed_out_as_a_worker(tmp_path):
+    """The training script fails whenever it is started as a standby (exit 9 before it reaches the control plane). When the job needs a
+    replacement the runner notices that its standby is dead and starts the worker cold instead of activating a corpse."""
+    script = tmp_path / "fragile.py"
+    script.write_text(
+        "import os, sys\n"
+        "if os.environ.get('KUNGFU_STANDBY') == '1':\n"
+        "    sys.exit(9)\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        f"exec(compile(open({os.path.join(ROOT, 'tests', 'elastic_opt_worker.py')!r}).read(), 'elastic_opt_worker.py', 'exec'))\n")
+    rport, prange = ports()
+    cfg_port = 9300 + (os.getpid() + 45) % 100
+    cmd = [kungfu_run(), "-q", "-w", "-shrink-on-failure", "-refill", "-standby", "1", "-np", "3", "-H", "127.0.0.1:4", "-port", str(rport),
+           "-port-range", prange, "-builtin-config-port", str(cfg_port), sys.executable, str(script), "shrink", "2@4", "60"]
+    e = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="WARN", KUNGFU_TEST_REFILL="1")
+    r = subprocess.run(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=200)
+    assert r.returncode == 0, r.stdout[-5000:]
+    done = [j for j in json_lines(r.stdout) if j.get("done") == "shrink"]
+    assert len(done) == 3 and all(d["identical"] and d["final_size"] == 3 for d in done), r.stdout[-5000:]
+    assert "is dead" in r.stdout and "starting 127.0.0.1" in r.stdout, r.stdout[-3000:]
+
+
 def test_two_workers_die_in_the_same_step():
     """Ranks 2 and 3 of 4 die inside the same step. Their announcements (v1: without 2, v2: without 2 and 3) travel on different threads and
     may arrive in either order, or the second while the survivors are already regrouping as v1 — whose barrier can never complete. The loss
