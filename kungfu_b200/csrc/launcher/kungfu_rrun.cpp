@@ -5,8 +5,9 @@
 // cancels the rest; `RunStaticKungFuJob` / `RunElasticKungFuJob` build the per-host `kungfu-run` command lines). Here the SSH
 // client is the system `ssh` binary driven through fork/exec + pipes + poll; there is no SSH library to link.
 //
-//   kungfu-rrun -np 16 -H 10.0.0.1:8,10.0.0.2:8 [-u user] [-w [-k] -config-server URL] [-strategy S] [-port P] [-port-range a-b]
-//               [-nic N] [-logdir DIR] [-q] [-local] [-dry-run] prog args...
+//   kungfu-rrun -np 16 -H 10.0.0.1:8,10.0.0.2:8 [-u user] [-w [-k] -config-server URL | -builtin-config-port P] [-strategy S] [-port P]
+//               [-port-range a-b] [-nic N] [-logdir DIR] [-q] [-standby N] [-shrink-on-failure] [-refill] [-auto-recover D] [-timeout D]
+//               [-local] [-dry-run] prog args...
 //   kungfu-rrun -distribute -H 10.0.0.1,10.0.0.2 [-u user] cmd args...      (also: invoked as `kungfu-distribute`)
 //
 // `-local` starts the per-host launchers as local processes (hosts = loopback aliases 127.0.0.x on this machine): the multi-host
@@ -109,6 +110,8 @@ int main(int argc, char** argv) {
     int np = 1;
     std::string hosts, user, strategy, port, port_range, nic, logdir, config_server, runner = "kungfu-run";
     bool watch = false, keep = false, quiet = false, local = false, dry = false;
+    std::vector<std::string> extra;
+    std::string builtin_port;
     int i = 1;
     auto need = [&](const char* flag) -> std::string {
         if (i + 1 >= argc) {
@@ -130,6 +133,11 @@ int main(int argc, char** argv) {
         else if (a == "-logdir") logdir = need("-logdir");
         else if (a == "-config-server") config_server = need("-config-server");
         else if (a == "-kungfu-run") runner = need("-kungfu-run");
+        else if (a == "-standby" || a == "-auto-recover" || a == "-timeout" || a == "-init-version" || a == "-delay") {
+            extra.push_back(a); // kungfu-run flags with a value that every host's launcher gets unchanged
+            extra.push_back(need(a.c_str()));
+        } else if (a == "-shrink-on-failure" || a == "-refill" || a == "-allow-nvlink" || a == "-v") extra.push_back(a);
+        else if (a == "-builtin-config-port") builtin_port = need("-builtin-config-port"); // first host only: it runs the config server
         else if (a == "-w") watch = true;
         else if (a == "-k") keep = true;
         else if (a == "-q") quiet = true;
@@ -168,6 +176,13 @@ int main(int argc, char** argv) {
             inner = {runner, "-self", ip, "-np", std::to_string(np), "-H", hosts};
             if (watch) inner.push_back("-w");
             if (keep) inner.push_back("-k");
+            inner.insert(inner.end(), extra.begin(), extra.end());
+            if (!builtin_port.empty()) {
+                // the first host serves the cluster configuration, the others are pointed at it
+                const std::string first = format_ipv4(hl[0].ipv4);
+                if (&h == &hl[0]) inner.insert(inner.end(), {"-builtin-config-port", builtin_port});
+                else if (config_server.empty()) inner.insert(inner.end(), {"-config-server", "http://" + first + ":" + builtin_port + "/config"});
+            }
             if (!config_server.empty()) inner.insert(inner.end(), {"-config-server", config_server});
             if (!strategy.empty()) inner.insert(inner.end(), {"-strategy", strategy});
             if (!port.empty()) inner.insert(inner.end(), {"-port", port});

@@ -215,6 +215,13 @@ def test_native_rrun_fans_out_to_every_host_and_fails_fast():
                         "python3", "train.py"], stdout=subprocess.PIPE, text=True)
     lines = d.stdout.strip().splitlines()
     assert len(lines) == 2 and all(l.startswith("ssh ") and "kungfu-run -self 10.0.0." in l and " -w " in l for l in lines), d.stdout
+    # the self-healing flags travel to every host's launcher; the first host runs the config server, the others are pointed at it
+    d = subprocess.run([rrun, "-dry-run", "-np", "16", "-H", "10.0.0.1:8,10.0.0.2:8", "-w", "-builtin-config-port", "9100", "-standby", "2",
+                        "-shrink-on-failure", "-refill", "-auto-recover", "30s", "python3", "train.py"], stdout=subprocess.PIPE, text=True)
+    lines = d.stdout.strip().splitlines()
+    assert len(lines) == 2 and all(" -standby 2 " in l and " -shrink-on-failure " in l and " -refill " in l and " -auto-recover 30s " in l for l in lines), d.stdout
+    assert " -builtin-config-port 9100 " in lines[0] and "-config-server" not in lines[0], lines[0]
+    assert " -config-server http://10.0.0.1:9100/config " in lines[1] and "-builtin-config-port" not in lines[1], lines[1]
     # kungfu-distribute: the same binary under its second name; one failing host cancels the rest and the exit code is non-zero
     dist = str(_build.BIN / "kungfu-distribute")
     f = subprocess.run([dist, "-local", "-H", "127.0.0.1,127.0.0.2", "sh", "-c", "exit 3"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
