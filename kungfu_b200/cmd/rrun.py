@@ -81,6 +81,12 @@ def main(argv=None) -> int:
     ap.add_argument("-port", default="", help="runner port, forwarded to kungfu-run")
     ap.add_argument("-port-range", dest="port_range", default="", help="worker port range, forwarded to kungfu-run")
     ap.add_argument("-q", dest="quiet", action="store_true", help="forwarded to kungfu-run")
+    ap.add_argument("-standby", default="", help="warm standby workers per host, forwarded to kungfu-run")
+    ap.add_argument("-auto-recover", dest="auto_recover", default="", help="heartbeat threshold, forwarded to kungfu-run")
+    ap.add_argument("-timeout", default="", help="forwarded to kungfu-run")
+    ap.add_argument("-shrink-on-failure", dest="shrink", action="store_true", help="forwarded to kungfu-run")
+    ap.add_argument("-refill", action="store_true", help="forwarded to kungfu-run")
+    ap.add_argument("-config-server", dest="config_server", default="", help="forwarded to kungfu-run")
     ap.add_argument("--distribute", action="store_true", help="kungfu-distribute: run the command itself on every host")
     ap.add_argument("--local", action="store_true", help="start the per-host launchers locally (loopback-alias hosts), no ssh")
     ap.add_argument("--dry-run", action="store_true")
@@ -92,6 +98,9 @@ def main(argv=None) -> int:
 
         kr = kungfu_run_path()
     extra = (["-port", a.port] if a.port else []) + (["-port-range", a.port_range] if a.port_range else []) + (["-q"] if a.quiet else [])
+    extra += (["-standby", a.standby] if a.standby else []) + (["-auto-recover", a.auto_recover] if a.auto_recover else [])
+    extra += (["-timeout", a.timeout] if a.timeout else []) + (["-shrink-on-failure"] if a.shrink else []) + (["-refill"] if a.refill else [])
+    extra += ["-config-server", a.config_server] if a.config_server else []
     cmds = distribute_commands(a.hosts, a.prog, a.user) if a.distribute else build_commands(a.np, a.hosts, a.prog, a.user, a.watch, a.strategy,
                                                                                            extra=extra, kungfu_run=kr, local=a.local)
     if a.dry_run:
