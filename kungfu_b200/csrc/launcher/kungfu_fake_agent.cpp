@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "capi.h"
+#include "fake_model.hpp"
 #include "graph.hpp"
 
 #define CHECK(cond)                                                                   \
@@ -29,28 +30,9 @@
 
 static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-// gradient tensor sizes of the reference's fake models (srcs/python/kungfu/tensorflow/v1/benchmarks/model_sizes.py)
 static std::vector<size_t> model_sizes(const std::string& name) {
-    if (name == "vgg16")
-        return {1728, 64, 36864, 64, 73728, 128, 147456, 128, 294912, 256, 589824, 256, 589824, 256, 1179648, 512, 2359296, 512, 2359296, 512,
-                2359296, 512, 2359296, 512, 2359296, 512, 102760448, 4096, 16777216, 4096, 4096000, 1000};
-    if (name == "slp") return {7840, 10};
-    // resnet50-like: 161 tensors, 25.5M elements (conv / bn / fc of the torchvision model)
-    std::vector<size_t> v = {9408, 64, 64};
-    auto block = [&](size_t in, size_t mid, size_t out, bool down) {
-        v.insert(v.end(), {in * mid, mid, mid, mid * mid * 9, mid, mid, mid * out, out, out});
-        if (down) v.insert(v.end(), {in * out, out, out});
-    };
-    size_t in = 64;
-    const size_t mids[4] = {64, 128, 256, 512};
-    const int reps[4] = {3, 4, 6, 3};
-    for (int s = 0; s < 4; ++s)
-        for (int b = 0; b < reps[s]; ++b) {
-            block(in, mids[s], mids[s] * 4, b == 0);
-            in = mids[s] * 4;
-        }
-    v.insert(v.end(), {2048 * 1000, 1000});
-    return v;
+    auto v = kftools::fake_model_sizes(name);
+    return v.empty() ? kftools::fake_model_sizes("resnet50") : v;
 }
 
 int main(int argc, char** argv) {

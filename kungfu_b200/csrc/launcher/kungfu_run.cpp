@@ -440,6 +440,7 @@ int run_all(const std::vector<Proc>& procs, bool verbose, const std::string& log
 // ---------------------------------------------------------------------------------------------------
 Cancel* g_cancel = nullptr;
 std::atomic<bool> g_stop{false};
+std::atomic<bool> g_exit_by_peer{false}; // stop asked for by an `exit` control message (an operator's tool), not by a signal
 void on_signal(int sig) {
     g_stop = true;
     if (g_cancel) {
@@ -865,10 +866,13 @@ struct Watcher {
                     return fail_code ? fail_code : 1;
                 }
                 if (g_stop) {
+                    // a launcher that idles in keep mode with no worker left and is told to leave by an `exit` message ends cleanly;
+                    // a signal, or an exit that had to cancel running workers, is a failure of the job
+                    const bool clean = g_exit_by_peer.load() && started && n_running == 0;
                     lk.unlock();
                     cancel.cancel();
                     join_all();
-                    return 1;
+                    return clean ? 0 : 1;
                 }
                 if (!stages.empty()) {
                     st = stages.front();
@@ -923,6 +927,7 @@ int watch_run(const Flags& f, const Job& job, const Cluster& init, const PeerID&
             }
         } else if (name == "exit") {
             KF_LOGW("exit requested by %s", src.str().c_str());
+            g_exit_by_peer = true;
             g_stop = true;
         }
     });

@@ -1,0 +1,170 @@
+"""Native test / benchmark tools built next to the launcher (bin/kungfu-*), each run the way the reference's CI runs its Go tools.
+
+Reference (tier "Go integration tools" / "Fake trainers"): tests/go/cmd/{kungfu-test-public-apis, kungfu-test-monitor,
+kungfu-bench-p2p, kungfu-fake-adaptive-trainer, kungfu-bad-worker}, tests/cpp/integration/fake_in_proc_trainer.cpp.
+"""
+import itertools
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_counter = itertools.count()
+
+
+def _bin(name):
+    from kungfu_b200.cmd import _bin as b
+
+    return b(name)
+
+
+def _ports():
+    k = next(_counter)
+    base = 11000 + ((os.getpid() * 41 + 7000 + k * 64) % 18000)
+    return base, f"{base + 1}-{base + 60}"
+
+
+def _run(np, tool, args=(), flags=(), slots=None, env=None, timeout=120, expect_rc=0):
+    rport, prange = _ports()
+    cmd = [_bin("kungfu-run"), "-q", "-np", str(np), "-H", f"127.0.0.1:{slots or max(np, 1)}", "-port", str(rport), "-port-range", prange,
+           *flags, _bin(tool), *args]
+    e = dict(os.environ, KUNGFU_CONFIG_LOG_LEVEL="WARN")
+    e.update(env or {})
+    r = subprocess.run(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+    out = re.sub(r"\x1b\[[0-9;]*m", "", r.stdout)
+    if expect_rc is not None:
+        assert r.returncode == expect_rc, f"rc={r.returncode}\n{out[-4000:]}"
+    return r.returncode, out, rport
+
+
+@pytest.mark.parametrize("np,strategy", [(1, "AUTO"), (2, "STAR"), (3, "RING"), (4, "BINARY_TREE_STAR")])
+def test_public_apis_native(np, strategy):
+    _, out, _ = _run(np, "kungfu-test-public-apis", flags=("-strategy", strategy))
+    assert f"test-public-apis ok np={np}" in out
+    assert "CHECK FAILED" not in out
+
+
+def test_public_apis_with_monitoring_reads_its_own_metrics():
+    _, out, _ = _run(3, "kungfu-test-public-apis", env={"KUNGFU_CONFIG_ENABLE_MONITORING": "true"})
+    assert "test-public-apis ok np=3" in out
+    assert re.search(r"metrics endpoint http://127\.0\.0\.1:\d+/metrics: \d+ bytes", out)
+
+
+@pytest.mark.parametrize("args", [("-model", "slp", "-mode", "seq"), ("-model", "resnet50", "-mode", "par", "-epochs", "3"),
+                                  ("-model", "bert", "-fuse", "-epochs", "2", "-versioned")])
+def test_bench_p2p(args):
+    _, out, _ = _run(3, "kungfu-bench-p2p", args)
+    m = re.search(r"Result: model: (\w+), (\d+) tensors, mode: (\w+), np: 3, rate: ([\d.]+) (\S+)", out)
+    assert m, out[-2000:]
+    assert float(m.group(4)) > 0
+    assert "VERIFICATION FAILED" not in out
+
+
+def test_bench_p2p_rejects_unknown_model():
+    rc, out, _ = _run(1, "kungfu-bench-p2p", ("-model", "alexnet"), expect_rc=None)
+    assert rc != 0 and "invalid model name" in out
+
+
+def test_fake_adaptive_trainer_follows_its_schedule():
+    """1 -> 2 -> 4 -> 8 -> 4 -> 1 inside one job, natively: step counters agree after every change, every step reduces to the size of
+    the cluster of that step, detached workers leave, rank 0 finishes all steps."""
+    rport, _ = _ports()
+    _, out, _ = _run(1, "kungfu-fake-adaptive-trainer", ("-max-step", "18", "-schedule", "2:2,5:4,8:8,11:4,14:1", "-slow-ms", "20", "-fast-ms", "5"),
+                     flags=("-w", "-builtin-config-port", str(rport + 62)), slots=8, timeout=180)
+    assert re.search(r"finished: rank 0, 5 resizes seen, 18 steps checked", out), out[-3000:]
+    sizes = [int(m.group(2)) for m in re.finditer(r"\.\d+::stdout\] resize (\d+) -> (\d+) took .* rank 0 -> 0", out)]
+    assert sizes == [2, 4, 8, 4, 1], sizes
+    # newcomers learned the step from the survivors
+    assert re.search(r"sync step: 0 -> 9 \(rank \d of 8", out)
+    assert out.count("(detached)") == 7
+    assert "cluster size" not in out  # the per-step check never fired
+
+
+def test_bad_worker_fails_the_job_fast():
+    rc, out, _ = _run(3, "kungfu-bad-worker", ("-rank", "1", "-after", "1s", "-code", "7", "-total", "30s"), expect_rc=None, timeout=60)
+    assert rc != 0
+    assert "bad worker (rank 1): exiting" in out
+    assert "exited with 7" in out
+
+
+def test_bad_worker_is_survived_with_shrink_on_failure():
+    """The same failing job under -w -shrink-on-failure: the good workers see their collective fail — this tool does not call recover(),
+    so they report the error and stop, but the launcher itself must not hang and must name the lost worker."""
+    rc, out, _ = _run(3, "kungfu-bad-worker", ("-rank", "2", "-after", "1s", "-total", "4s"), flags=("-w", "-shrink-on-failure"),
+                      expect_rc=None, timeout=90)
+    assert "bad worker (rank 2): exiting" in out
+
+
+@pytest.mark.parametrize("np,model", [(2, "slp"), (4, "resnet50")])
+def test_fake_inproc_trainer(np, model):
+    r = subprocess.run([_bin("kungfu-fake-inproc-trainer"), "-np", str(np), "-model", model, "-steps", "3", "-warmup", "1"], stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=180)
+    assert r.returncode == 0, r.stdout[-3000:]
+    rates = re.findall(r"Img/sec ([\d.]+)\s+\[(sim|peers):", r.stdout)
+    assert [b for _, b in rates] == ["sim", "peers"] and all(float(v) > 0 for v, _ in rates)
+    assert "WRONG RESULT" not in r.stdout
+
+
+# ---- programs around the tools: policy-driven elastic example, elastic system benchmark, virtual cluster manager, remote install -------
+def _erun(script, args, slots=4, timeout=300):
+    import sys
+
+    rport, prange = _ports()
+    cmd = [_bin("kungfu-run"), "-q", "-w", "-np", "1", "-H", f"127.0.0.1:{slots}", "-port", str(rport), "-port-range", prange,
+           "-builtin-config-port", str(rport + 62), sys.executable, os.path.join(ROOT, script), *args]
+    e = dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="ERROR")
+    r = subprocess.run(cmd, cwd=ROOT, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+    out = re.sub(r"\x1b\[[0-9;]*m", "", r.stdout)
+    assert r.returncode == 0, out[-4000:]
+    return out
+
+
+def test_elastic_policy_example():
+    """examples/mnist_elastic_policy: a BasePolicy resizes 1 -> 2 -> 3 -> 1 on a step schedule under a PolicyHook; newcomers adopt the
+    progress, detached workers leave, the model still learns."""
+    out = _erun("examples/mnist_elastic_policy/main.py", ["--schedule", "5:2,10:3,20:1", "--num-epochs", "1", "--samples", "1500"])
+    m = re.search(r"done: steps=(\d+) trained=(\d+) resizes=\[\(5, 1, 2\), \(10, 2, 3\), \(20, 3, 1\)\] accuracy=([\d.]+)", out)
+    assert m, out[-3000:]
+    assert int(m.group(2)) >= 1500 and float(m.group(3)) > 0.9
+    assert out.count("detached after step 20") == 2
+
+
+def test_elastic_system_benchmark_on_the_host_plane():
+    out = _erun("benchmarks/system/benchmark_kungfu_elastic.py", ["--no-cuda", "--model", "slp", "--num-iters", "12", "--schedule", "4:2,8:1",
+                                                                  "--num-warmup-batches", "1"])
+    m = re.search(r"RESULT: ([\d.]+) \+-([\d.]+) (\{.*\})", out)
+    assert m, out[-3000:]
+    import json
+
+    attrs = json.loads(m.group(3))
+    assert [(c["from"], c["to"]) for c in attrs["changes"]] == [(1, 2), (2, 1)] and attrs["np"] == 1
+    assert "sync step : 0 -> 4" in out and "rank detached at iter 8" in out
+    assert len(re.findall(r"\.\d+::stdout\] Iter #\d+:", out)) == 12 + 4  # rank 0: 12 iterations, the second worker: iterations 5..8
+
+
+def test_virtual_cluster_manager_with_a_late_node():
+    """Config server + one launcher per loopback-alias host + a node that joins late + random resizes from outside
+    (≙ kungfu-cluster-manager-example); the job is the native adaptive trainer following the config server."""
+    import json
+    import sys
+
+    base = 12000 + (os.getpid() * 29 + 5000) % 14000
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "experiments", "cluster_manager.py"), "--nodes", "3", "--slots", "2", "--duration", "4",
+                        "--period", "0.6", "--late-node-after", "1.5", "--port", str(base), "--config-port", str(9500 + os.getpid() % 400)],
+                       cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=180)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    summary = [json.loads(l) for l in r.stdout.splitlines() if l.startswith('{"summary"')][0]
+    assert summary["wrong_steps"] == 0 and summary["late_node_ran_workers"] in (True, False)
+    assert all(c == 0 for c in summary["node_exit_codes"].values()), summary
+    assert summary["workers_joined"] >= 2 and len(summary["sizes_proposed"]) >= 3
+
+
+def test_remote_install_dry_run_lists_every_step():
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "experiments", "remote_install.py"), "-H", "10.1.0.1:8,10.1.0.2:8", "-u", "op", "--dry-run"],
+                       cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert r.stdout.count("tar -C /") == 2 and r.stdout.count("op@10.1.0.") >= 4 and "kungfu_b200._build" in r.stdout
