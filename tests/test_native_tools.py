@@ -167,4 +167,4 @@ def test_remote_install_dry_run_lists_every_step():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "experiments", "remote_install.py"), "-H", "10.1.0.1:8,10.1.0.2:8", "-u", "op", "--dry-run"],
                        cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
     assert r.returncode == 0, r.stdout[-2000:]
-    assert r.stdout.count("tar -C /") == 2 and r.stdout.count("op@10.1.0.") >= 4 and "kungfu_b200._build" in r.stdout
+    assert r.stdout.count("-cf - --exclude") == 2 and r.stdout.count("-xf -") == 2 and r.stdout.count("op@10.1.0.") >= 4 and "kungfu_b200._build" in r.stdout
