@@ -474,6 +474,21 @@ def broadcast_(x: torch.Tensor, root: int = 0, name: str = "") -> torch.Tensor:
     return x
 
 
+def broadcast_async_(x: torch.Tensor, name: str = "", root: int = 0) -> Handle:
+    """Asynchronous in-place broadcast (reference: torch/ops/collective.py `inplace_broadcast_async_op`, used by
+    `broadcast_parameters` to keep every tensor of a state dict in flight). Host tensors go through the same FIFO executor as the
+    asynchronous all-reduce (named in program order); device tensors are already stream-ordered — `broadcast_` enqueues on the comm
+    stream and makes the current stream wait, the host never blocks — so their handle is complete on return."""
+    rt = get_runtime()
+    if rt.size == 1:
+        return Handle()
+    if x.is_cuda or getattr(rt.control, "kind", "") != "native" or os.environ.get("KUNGFU_CPU_ASYNC", "1") == "0":
+        broadcast_(x, root, name)
+        return Handle()
+    fut = _cpu_executor().submit(broadcast_, x, root, name or _async_name(rt).replace("allreduce", "broadcast"))
+    return Handle(post=fut.result)
+
+
 def all_gather(x: torch.Tensor, name: str = "") -> torch.Tensor:
     """Returns a tensor of shape [np, *x.shape] (reference: torch/ops/collective.py:50-55)."""
     rt = get_runtime()

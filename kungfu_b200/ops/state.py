@@ -46,6 +46,10 @@ class ExponentialMovingAverage:
     def get(self) -> float:
         return 0.0 if self.value is None else self.value
 
+    def reset(self) -> None:
+        """Forget the history: the next sample is taken as it is (reference: utils/ema.py `reset`)."""
+        self.value = None
+
 
 def exponential_moving_average(alpha: float = 0.9) -> ExponentialMovingAverage:
     return ExponentialMovingAverage(alpha)

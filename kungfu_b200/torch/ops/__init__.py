@@ -27,6 +27,11 @@ def inplace_broadcast_op(x: torch.Tensor, root: int = 0) -> None:
     _c.broadcast_(x, root)
 
 
+def inplace_broadcast_async_op(x: torch.Tensor, name: str = "", root: int = 0) -> Handle:
+    """Asynchronous in-place broadcast from `root`; returns a handle (reference: torch/ops/collective.py:29-31)."""
+    return _c.broadcast_async_(x, name, root)
+
+
 def broadcast_parameters(state_dict, root: int = 0) -> None:
     """Broadcast every tensor of `state_dict` from `root` (reference: torch/ops/collective.py:42-47)."""
     for name, value in state_dict.items():
@@ -35,4 +40,4 @@ def broadcast_parameters(state_dict, root: int = 0) -> None:
 
 
 __all__ = ["all_reduce_fn", "broadcast_parameters", "inplace_all_reduce_async_op", "inplace_all_reduce_op",
-           "inplace_broadcast_op", "wait_handle", "wait_all_handles", "all_gather", "barrier", "consensus", "Handle"]
+           "inplace_broadcast_op", "inplace_broadcast_async_op", "wait_handle", "wait_all_handles", "all_gather", "barrier", "consensus", "Handle"]

@@ -691,6 +691,48 @@ def cmd_initializer(args):
     print(json.dumps({"ok": True, "traced": trace.ENABLED}), flush=True)
 
 
+def cmd_compat(args):
+    """A program written against the reference's module paths (`kungfu.torch.ops.clib` tables, `kungfu.tensorflow.*` names,
+    `kungfu.utils.ema`, the ctypes loader) runs unchanged on torch tensors."""
+    import kungfu  # noqa: F401
+    import kungfu.torch as kft
+    from kungfu.python import current_cluster_size, current_rank
+    from kungfu.tensorflow.initializer import BroadcastGlobalVariablesOp  # noqa: F401
+    from kungfu.tensorflow.ops import all_reduce as tf_all_reduce
+    from kungfu.tensorflow.optimizers import SynchronousSGDOptimizer
+    from kungfu.tensorflow.policy import BasePolicy, PolicyHook  # noqa: F401
+    from kungfu.torch.ops.clib import all_gather_op_map, all_reduce_async_op_map, all_reduce_op_map, broadcast_async_op_map, ops as clib_ops
+    from kungfu.torch.ops.collective import inplace_broadcast_async_op, wait_all_handles
+    from kungfu.utils.ema import EMA
+
+    n, r = current_cluster_size(), current_rank()
+    check(kft.current_cluster_size() == n and SynchronousSGDOptimizer is kf.optimizers.SynchronousSGDOptimizer, "aliases are the same objects")
+    x = torch.full((1000,), float(r + 1))
+    y = torch.empty_like(x)
+    all_reduce_op_map[x.type()](x, y, x.type(), "sum")  # the reference's call shape: (input, output, type, op)
+    check(y[0].item() == n * (n + 1) / 2 and x[0].item() == r + 1, "table all-reduce, out of place")
+    xi = torch.full((7,), r, dtype=torch.int64)
+    all_reduce_op_map[xi.type()](xi, xi, xi.type(), "max")
+    check(xi[0].item() == n - 1, "table all-reduce, in place, int64 max")
+    g = torch.empty((n, 5))
+    all_gather_op_map[x.type()](torch.full((5,), float(r)), g, x.type())
+    check([g[q, 0].item() for q in range(n)] == [float(q) for q in range(n)], "table all-gather")
+    hs = [all_reduce_async_op_map[x.type()](t, t, t.type(), "sum", f"a{i}") for i, t in enumerate(torch.ones(6, 300).unbind(0))]
+    clib_ops.wait_all_handles(hs)
+    ts = [torch.full((50 + i,), float(r * 10 + i)) for i in range(5)]
+    hs = [broadcast_async_op_map[t.type()](t, t, t.type(), f"b{i}") for i, t in enumerate(ts)]
+    hs += [inplace_broadcast_async_op(t, f"c{i}") for i, t in enumerate(ts)]
+    wait_all_handles(hs)
+    check(all(t[0].item() == float(i) and t[-1].item() == float(i) for i, t in enumerate(ts)), "asynchronous broadcasts deliver rank 0's values")
+    check(float(tf_all_reduce(torch.ones(3))[0]) == n, "kungfu.tensorflow.ops.all_reduce on a torch tensor")
+    e = EMA(0.5, scale_cap=2.0)
+    check(e.update(4.0) == 4.0 and e.update(100.0) == 6.0, "EMA clamps a jump to value * scale_cap before blending")
+    e.reset()
+    check(e.update(1.0) == 1.0, "EMA reset")
+    kf.run_barrier()
+    print(json.dumps({"ok": True, "compat": True, "rank": r, "np": n}), flush=True)
+
+
 def cmd_mismatch(args):
     """Workers that disagree on a tensor's size must get an error quickly, not wait for each other forever."""
     rt = get_runtime()

@@ -4,6 +4,7 @@ import subprocess
 import sys
 import time
 
+import pytest
 import torch
 
 from test_runtime_multiproc import ROOT, kungfu_run, launch, ports
@@ -172,3 +173,53 @@ def test_monitoring_benchmark_reports_overhead_and_values():
     rows = summary["rows"]
     assert [r_["arm"] for r_ in rows] == ["sync-sgd", "variance", "variance", "noise-scale", "noise-scale"] and summary["np"] == 2
     assert all(r_["img_per_sec"] > 0 for r_ in rows) and rows[1]["value"] > 0 and rows[3]["value"] != 0
+
+
+# ---- the reference's module paths and foreign-binding entry points ------------------------------------------------------------------
+def test_reference_module_paths_resolve_to_one_implementation():
+    """`kungfu.X[.Y]` maps onto `kungfu_b200` by a meta-path finder: the SAME module objects (no second copy of a class), including the
+    `kungfu.tensorflow.*` paths, submodules the alias list never named, and `python -m` of aliased packages."""
+    import importlib
+
+    import kungfu
+    import kungfu_b200
+
+    assert kungfu.__version__ == kungfu_b200.__version__
+    pairs = {"kungfu.torch.optimizers.sync_sgd": "kungfu_b200.torch.optimizers.sync_sgd", "kungfu.torch.ops.collective": "kungfu_b200.torch.ops.collective",
+             "kungfu.torch.ops.clib": "kungfu_b200.torch.ops.clib", "kungfu.utils.ema": "kungfu_b200.utils.ema", "kungfu.loader": "kungfu_b200.loader",
+             "kungfu._utils": "kungfu_b200.utils", "kungfu.tensorflow.ops": "kungfu_b200.ops", "kungfu.tensorflow.ops.adapt": "kungfu_b200.ops.adapt",
+             "kungfu.tensorflow.optimizers.async_sgd": "kungfu_b200.torch.optimizers.async_sgd", "kungfu.tensorflow.optimizers.keras": "kungfu_b200.torch.optimizers",
+             "kungfu.tensorflow.initializer.keras": "kungfu_b200.initializer", "kungfu.tensorflow.policy.policy_hook": "kungfu_b200.elastic.policy",
+             "kungfu.tensorflow.hooks.elastic": "kungfu_b200.elastic.hooks", "kungfu.tensorflow.variables": "kungfu_b200.variables",
+             "kungfu.tensorflow.v1.helpers.mnist": "kungfu_b200.helpers.mnist", "kungfu.tensorflow.v1.datasets.adaptor": "kungfu_b200.elastic.datasets",
+             "kungfu.tensorflow.v1.benchmarks.model_sizes": "kungfu_b200.benchmarks.model_sizes", "kungfu.parallel.engine": "kungfu_b200.parallel.engine"}
+    for alias, real in pairs.items():
+        assert importlib.import_module(alias) is importlib.import_module(real), alias
+    with pytest.raises(ModuleNotFoundError):
+        importlib.import_module("kungfu.no_such_module")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    for mod, want in (("kungfu.info", '"native_runtime": true'), ("kungfu.tensorflow.v1.examples", "examples ok")):
+        r = subprocess.run([sys.executable, "-m", mod], env=env, cwd="/tmp", stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=180)
+        assert r.returncode == 0 and want in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.parametrize("np", [1, 3])
+def test_program_written_against_reference_paths(np):
+    from test_runtime_multiproc import json_lines, launch
+
+    out = launch(np, "compat").stdout
+    assert len([j for j in json_lines(out) if j.get("compat")]) == np, out[-3000:]
+
+
+@pytest.mark.parametrize("np", [1, 2, 4])
+def test_c_abi_through_ctypes_without_torch(np):
+    """kungfu_b200/loader.py: the C ABI loaded with ctypes by a worker that never imports torch (sync and callback all-reduce, int max,
+    p2p save / request incl. the negative case)."""
+    from test_runtime_multiproc import json_lines, kungfu_run, ports
+
+    rport, prange = ports()
+    cmd = [kungfu_run(), "-q", "-np", str(np), "-H", f"127.0.0.1:{np}", "-port", str(rport), "-port-range", prange, sys.executable,
+           os.path.join(ROOT, "tests", "capi_ctypes_worker.py")]
+    r = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, KUNGFU_CONFIG_LOG_LEVEL="WARN"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert len([j for j in json_lines(r.stdout) if j.get("ctypes") and j.get("uid")]) == np
