@@ -11,20 +11,46 @@
 
 namespace kftools {
 
-inline std::vector<std::string> fake_model_names() { return {"resnet50", "vgg16", "bert", "slp"}; }
+inline std::vector<std::string> fake_model_names() { return {"resnet50", "resnet50-keras", "vgg16", "bert", "bert-base", "bert-large", "slp"}; }
+
+inline std::vector<size_t> fake_model_sizes(const std::string& name);
 
 inline std::vector<size_t> fake_model_sizes(const std::string& name) {
     if (name == "vgg16")
         return {1728, 64, 36864, 64, 73728, 128, 147456, 128, 294912, 256, 589824, 256, 589824, 256, 1179648, 512, 2359296, 512, 2359296, 512,
                 2359296, 512, 2359296, 512, 2359296, 512, 102760448, 4096, 16777216, 4096, 4096000, 1000};
     if (name == "slp") return {7840, 10};
-    if (name == "bert") {
-        // BERT-base: embeddings (word 30522, position 512, type 2) + LayerNorm, 12 encoder layers, pooler
-        const size_t h = 768, ff = 3072;
+    if (name == "bert" || name == "bert-base" || name == "bert-large") {
+        // embeddings (word 30522, position 512, type 2) + LayerNorm, L encoder layers, pooler. "bert" is the reference's list: BERT-base
+        // with the two Adam slots of every variable plus the optimizer's two scalars (599 tensors, 327.3 M elements); "bert-base" /
+        // "bert-large" are the bare gradients of the two model sizes (199 tensors / 109.1 M, 391 tensors / 334.1 M).
+        const bool large = name == "bert-large";
+        const size_t h = large ? 1024 : 768, ff = 4 * h;
+        const int layers = large ? 24 : 12;
         std::vector<size_t> v = {30522 * h, 512 * h, 2 * h, h, h};
-        for (int l = 0; l < 12; ++l)
+        for (int l = 0; l < layers; ++l)
             v.insert(v.end(), {h * h, h, h * h, h, h * h, h, h * h, h, h, h, h * ff, ff, ff * h, h, h, h});
         v.insert(v.end(), {h * h, h});
+        if (name == "bert") {
+            std::vector<size_t> with_slots;
+            for (size_t s : v) with_slots.insert(with_slots.end(), {s, s, s});
+            with_slots.insert(with_slots.end(), {1, 1});
+            return with_slots;
+        }
+        return v;
+    }
+    if (name == "resnet50-keras") {
+        // the reference's ResNet-50 list comes from tf.keras, whose convolutions carry a bias: 214 tensors / 25.58 M elements
+        std::vector<size_t> v = fake_model_sizes("resnet50");
+        std::vector<size_t> biases = {64};
+        const size_t mids[4] = {64, 128, 256, 512};
+        const int reps[4] = {3, 4, 6, 3};
+        for (int s = 0; s < 4; ++s)
+            for (int b = 0; b < reps[s]; ++b) {
+                biases.insert(biases.end(), {mids[s], mids[s], mids[s] * 4});
+                if (b == 0) biases.push_back(mids[s] * 4);
+            }
+        v.insert(v.end(), biases.begin(), biases.end());
         return v;
     }
     if (name != "resnet50") return {};

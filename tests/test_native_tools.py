@@ -53,10 +53,10 @@ def test_public_apis_with_monitoring_reads_its_own_metrics():
 
 
 @pytest.mark.parametrize("args", [("-model", "slp", "-mode", "seq"), ("-model", "resnet50", "-mode", "par", "-epochs", "3"),
-                                  ("-model", "bert", "-fuse", "-epochs", "2", "-versioned")])
+                                  ("-model", "resnet50-keras", "-fuse", "-epochs", "2", "-versioned")])
 def test_bench_p2p(args):
     _, out, _ = _run(3, "kungfu-bench-p2p", args)
-    m = re.search(r"Result: model: (\w+), (\d+) tensors, mode: (\w+), np: 3, rate: ([\d.]+) (\S+)", out)
+    m = re.search(r"Result: model: ([\w-]+), (\d+) tensors, mode: (\w+), np: 3, rate: ([\d.]+) (\S+)", out)
     assert m, out[-2000:]
     assert float(m.group(4)) > 0
     assert "VERIFICATION FAILED" not in out
