@@ -35,6 +35,13 @@ KUNGFU_TEST_REFILL=1 "$bin/kungfu-run" -q -w -shrink-on-failure -refill -standby
 # ... and a fully instrumented job (launcher AND workers): the C-ABI agent loses a worker and recovers
 "$bin/kungfu-run" -q -w -shrink-on-failure -np 3 -H 127.0.0.1:4 -port "$R" -port-range "$((R + 1))-$((R + 50))" \
     -builtin-config-port $((9200 + RANDOM % 90)) "$bin/kungfu-fake-agent" shrink 1@5
+# fully instrumented native tools: the public C++ API end to end (monitoring endpoint included), concurrent p2p pulls, an elastic job that
+# grows and shrinks 1 -> 2 -> 4 -> 2 -> 1 (resize protocol, runners starting / reaping workers), four peers as threads of one process
+KUNGFU_CONFIG_ENABLE_MONITORING=true "$bin/kungfu-run" -q -np 4 -H 127.0.0.1:4 -port "$R" -port-range "$((R + 1))-$((R + 50))" "$bin/kungfu-test-public-apis"
+"$bin/kungfu-run" -q -np 3 -H 127.0.0.1:3 -port "$R" -port-range "$((R + 1))-$((R + 50))" "$bin/kungfu-bench-p2p" -model slp -mode par -epochs 5
+"$bin/kungfu-run" -q -w -np 1 -H 127.0.0.1:4 -port "$R" -port-range "$((R + 1))-$((R + 50))" -builtin-config-port $((9200 + RANDOM % 90)) \
+    "$bin/kungfu-fake-adaptive-trainer" -max-step 14 -schedule 2:2,4:4,7:2,10:1 -slow-ms 20 -fast-ms 5
+"$bin/kungfu-fake-inproc-trainer" -np 4 -model slp -steps 20
 # the C++ unit tests under the same instrumentation: in-process multi-peer worlds (threads), the epoch fence, a world that loses a peer
 "$bin/kungfu-unit-tests"
 echo "sanitizer run ($mode) passed"
