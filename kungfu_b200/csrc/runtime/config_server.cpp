@@ -50,13 +50,31 @@ HttpResponse ConfigServer::handle(const HttpRequest& r) {
         resp.body = "stopping\n";
         return resp;
     }
-    if (r.path != path_) {
+    // The endpoints of the reference's older example server, which its elastic test script and compose generator still call
+    // (tests/go/cmd/kungfu-config-server-example/kungfu-config-server-example.go:36-44 `/get /put /clear /reset`;
+    // scripts/tests/run-elastic-test.sh:21, benchmarks/adaptation/gen-compose.py:84,102): same state, the verb is in the path.
+    std::string method = r.method;
+    bool legacy = true;
+    if (r.path == "/get") method = "GET";
+    else if (r.path == "/put") method = "PUT";
+    else if (r.path == "/reset") method = "POST";
+    else if (r.path == "/clear") method = "CLEAR";
+    else legacy = false;
+    if (!legacy && r.path != path_) {
         resp.status = 404;
         resp.body = "not found\n";
         return resp;
     }
     std::lock_guard<std::mutex> g(mu_);
-    if (r.method == "GET") {
+    if (method == "CLEAR") {
+        // an EMPTY cluster, not "no cluster": workers that follow the server all detach, and later updates are refused (403) until a reset
+        cluster_.workers = PeerList();
+        has_ = true;
+        ++version_;
+        KF_LOGW("config server: config cleared (every worker will leave)");
+        return resp;
+    }
+    if (method == "GET") {
         resp.content_type = "application/json";
         if (!has_) {
             resp.status = 404;
@@ -64,7 +82,7 @@ HttpResponse ConfigServer::handle(const HttpRequest& r) {
         } else {
             resp.body = cluster_.to_json() + "\n";
         }
-    } else if (r.method == "PUT") {
+    } else if (method == "PUT") {
         Cluster c;
         try {
             c = Cluster::from_json(r.body);
@@ -89,11 +107,11 @@ HttpResponse ConfigServer::handle(const HttpRequest& r) {
             resp.status = 403;
             resp.body = "config was cleared\n";
         }
-    } else if (r.method == "POST") {
+    } else if (method == "POST") {
         has_ = false;
         cluster_ = Cluster();
         KF_LOGI("config server: reset config");
-    } else if (r.method == "DELETE") {
+    } else if (method == "DELETE") {
         has_ = false;
         cluster_ = Cluster();
         KF_LOGW("config server: config deleted!");

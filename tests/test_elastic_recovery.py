@@ -46,6 +46,18 @@ def test_config_server_rest():
         assert rt.http_request("POST", url, "")[0] == 200 and rt.http_request("GET", url)[0] == 404
         assert rt.http_request("PUT", url, c1)[0] == 200
         assert rt.http_request("DELETE", url, "")[0] == 200 and srv.get() is None
+        # the older example server's endpoints (verb in the path), still called by the reference's scripts
+        base = f"http://127.0.0.1:{port}"
+        assert rt.http_request("GET", base + "/get")[0] == 404
+        assert rt.http_request("POST", base + "/put", c1)[0] == 200
+        st, body = rt.http_request("GET", base + "/get")
+        assert st == 200 and json.loads(body) == json.loads(c1)
+        assert rt.http_request("GET", base + "/clear")[0] == 200
+        st, body = rt.http_request("GET", url)
+        assert st == 200 and json.loads(body)["Workers"] == [] and len(json.loads(body)["Runners"]) == 1
+        assert rt.http_request("PUT", url, c1)[0] == 403  # cleared: updates refused until a reset
+        assert rt.http_request("GET", base + "/reset")[0] == 200 and rt.http_request("GET", url)[0] == 404
+        assert rt.http_request("PUT", base + "/put", c2)[0] == 200 and len(json.loads(rt.http_request("GET", url)[1])["Workers"]) == 3
     finally:
         srv.stop()
 
