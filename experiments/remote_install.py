@@ -19,7 +19,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-EXCLUDES = [".git", "gpurun_out", "baseline/_ref", "kungfu_b200/build", "kungfu_b200/bin", "*.so", "__pycache__", ".pytest_cache", "*.ncu-rep"]
+EXCLUDES = [".git", "gpurun_out", "baseline/_ref", "kungfu_b200/build", "kungfu_b200/bin", "kungfu_b200/lib", "*.so", "__pycache__", ".pytest_cache", "*.ncu-rep"]
 
 
 def ship(host, user, prefix, local, dry):

@@ -156,6 +156,15 @@ def build_runtime(verbose: bool = False, force: bool = False) -> Path | None:
     # launcher + tools: every launcher/*.cpp with a main() links against the runtime objects (minus bindings)
     BIN.mkdir(exist_ok=True)
     lib_objs = [str(o) for o in objs if o.stem != "bindings"]
+    # libkungfu-comm.so: the runtime with its C ABI (csrc/runtime/capi.h) and NO dependency on Python — what a C / C++ / foreign-language
+    # program links against (reference: the cgo c-archive libkungfu-comm + libkungfu.so, srcs/cmake/kungfu.cmake)
+    libdir = PKG / ("lib" if not _san else "lib-" + _san)
+    libdir.mkdir(exist_ok=True)
+    comm = libdir / "libkungfu-comm.so"
+    if changed or not comm.exists():
+        _run([CXX, "-shared", "-o", str(comm)] + lib_objs + LINK_FLAGS + ["-pthread", "-ldl"])
+        if verbose:
+            print(f"[kungfu_b200] linked lib/{comm.name}")
     tdir = CSRC / "tests"
     for cpp in sorted(ldir.glob("*.cpp")) + sorted(tdir.glob("*.cpp")):
         exe = BIN / cpp.stem.replace("_", "-")

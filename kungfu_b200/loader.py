@@ -97,10 +97,18 @@ _capi = None
 
 
 def load_capi() -> ctypes.CDLL:
-    """The runtime's C ABI (csrc/runtime/capi.h) as a ctypes library with argument / result types declared."""
+    """The runtime's C ABI (csrc/runtime/capi.h) as a ctypes library with argument / result types declared. Inside a process that
+    already runs the Python API the handle comes from the loaded `_kfrt` extension (ONE runtime instance per process); otherwise from
+    `lib/libkungfu-comm.so`, the same runtime without any dependency on Python."""
     global _capi
     if _capi is None:
-        lib = _load_clib("_kfrt")
+        import sys
+
+        standalone = os.path.join(_module_path(), "lib", "libkungfu-comm.so")
+        if "kungfu_b200._kfrt" in sys.modules or not os.path.exists(standalone):
+            lib = _load_clib("_kfrt")
+        else:
+            lib = ctypes.CDLL(standalone, mode=ctypes.RTLD_GLOBAL)
         for name, (args, res) in _SIGNATURES.items():
             fn = getattr(lib, name)
             fn.argtypes, fn.restype = args, res

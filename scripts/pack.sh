@@ -5,5 +5,5 @@ cd "$(dirname "$0")/.."
 name=$(basename "$(pwd)")
 out=${1:-../$name.tar.gz}
 tar --exclude='.git' --exclude='gpurun_out' --exclude='baseline/_ref' --exclude='*.so' --exclude='*.o' --exclude='__pycache__' \
-    --exclude='kungfu_b200/build*' --exclude='kungfu_b200/bin*' -czf "$out" -C .. "$name"
+    --exclude='kungfu_b200/build*' --exclude='kungfu_b200/bin*' --exclude='kungfu_b200/lib*' -czf "$out" -C .. "$name"
 du -h "$out"

@@ -21,7 +21,7 @@ setup(
     version="0.1.0",
     description="Blackwell-native adaptive distributed training for PyTorch (KungFu capabilities, B200-first design)",
     packages=find_packages(include=["kungfu_b200", "kungfu_b200.*", "kungfu", "kungfu.*"]),
-    package_data={"kungfu_b200": ["*.so", "bin/*", "csrc/**/*"]},
+    package_data={"kungfu_b200": ["*.so", "bin/*", "lib/*", "csrc/**/*"]},
     cmdclass={"build_py": BuildNative},
     entry_points={"console_scripts": ["kungfu-run=kungfu_b200.cmd:run", "kungfu-rrun=kungfu_b200.cmd.rrun:main",
                                       "kungfu-test-util=kungfu_b200.cmd.test_util:main",

@@ -223,3 +223,21 @@ def test_c_abi_through_ctypes_without_torch(np):
     r = subprocess.run(cmd, cwd=ROOT, env=dict(os.environ, KUNGFU_CONFIG_LOG_LEVEL="WARN"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
     assert r.returncode == 0, r.stdout[-3000:]
     assert len([j for j in json_lines(r.stdout) if j.get("ctypes") and j.get("uid")]) == np
+
+
+def test_c_program_links_against_libkungfu_comm(tmp_path):
+    """examples/c/allreduce.c compiled as C99 against capi.h and lib/libkungfu-comm.so (no Python in the link), run under the launcher."""
+    from kungfu_b200 import _build
+
+    _build.build_runtime()
+    lib = _build.PKG / "lib"
+    assert (lib / "libkungfu-comm.so").exists()
+    exe = tmp_path / "c_allreduce"
+    subprocess.run(["gcc", "-std=c99", "-D_DEFAULT_SOURCE", "-Wall", "-Werror", "-I", str(_build.CSRC / "runtime"), os.path.join(ROOT, "examples", "c", "allreduce.c"),
+                    "-L", str(lib), "-lkungfu-comm", f"-Wl,-rpath,{lib}", "-o", str(exe)], check=True)
+    deps = subprocess.run(["ldd", str(exe)], stdout=subprocess.PIPE, text=True).stdout
+    assert "libkungfu-comm.so" in deps and "python" not in deps.lower()
+    rport, prange = ports()
+    r = subprocess.run([kungfu_run(), "-q", "-np", "4", "-H", "127.0.0.1:4", "-port", str(rport), "-port-range", prange, "-strategy", "RING", str(exe)],
+                       env=dict(os.environ, KUNGFU_CONFIG_LOG_LEVEL="WARN"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0 and "c worker ok np=4" in r.stdout, r.stdout[-3000:]
