@@ -241,3 +241,73 @@ def test_c_program_links_against_libkungfu_comm(tmp_path):
     r = subprocess.run([kungfu_run(), "-q", "-np", "4", "-H", "127.0.0.1:4", "-port", str(rport), "-port-range", prange, "-strategy", "RING", str(exe)],
                        env=dict(os.environ, KUNGFU_CONFIG_LOG_LEVEL="WARN"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
     assert r.returncode == 0 and "c worker ok np=4" in r.stdout, r.stdout[-3000:]
+
+
+@pytest.mark.parametrize("np,strategy", [(1, "AUTO"), (3, "STAR"), (4, "BINARY_TREE_STAR")])
+def test_cpp_application_on_the_public_header(tmp_path, np, strategy):
+    """examples/cpp/adapt_tree.cpp on `kungfu.hpp` (header-only `kungfu::Peer` over the C ABI): latencies -> AllGatherTransform with a
+    minimum spanning tree -> consensus -> SetTree -> synchronous and callback all-reduces, p2p with a missing blob."""
+    from kungfu_b200 import _build
+
+    _build.build_runtime()
+    lib = _build.PKG / "lib"
+    exe = tmp_path / "adapt_tree"
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-I", str(_build.CSRC / "runtime"), os.path.join(ROOT, "examples", "cpp", "adapt_tree.cpp"),
+                    "-L", str(lib), "-lkungfu-comm", f"-Wl,-rpath,{lib}", "-pthread", "-o", str(exe)], check=True)
+    rport, prange = ports()
+    r = subprocess.run([kungfu_run(), "-q", "-np", str(np), "-H", f"127.0.0.1:{np}", "-port", str(rport), "-port-range", prange, "-strategy", strategy, str(exe)],
+                       env=dict(os.environ, KUNGFU_CONFIG_LOG_LEVEL="WARN"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0 and f"adapt_tree ok np={np} tree=[0" in r.stdout, r.stdout[-3000:]
+
+
+def test_minimum_spanning_tree_of_the_public_header(tmp_path):
+    """`kungfu::minimum_spanning_tree` against brute force on random dense graphs (reference: tests/cpp/unit/test_mst.cpp, n = 1..10)."""
+    src = tmp_path / "mst.cpp"
+    src.write_text(r'''
+#include <algorithm>
+#include <cstdio>
+#include <random>
+#include <vector>
+#include "kungfu.hpp"
+static double tree_cost(int n, const std::vector<double>& w, const std::vector<int32_t>& f) {
+    double c = 0;
+    for (int i = 0; i < n; ++i) if (f[i] != i) c += (w[i * n + f[i]] + w[f[i] * n + i]) / 2;
+    return c;
+}
+static bool is_tree(int n, const std::vector<int32_t>& f, int root) {
+    if (f[root] != root) return false;
+    for (int i = 0; i < n; ++i) { int v = i, hops = 0; while (v != root && hops++ <= n) v = f[v]; if (v != root) return false; }
+    return true;
+}
+int main() {
+    std::mt19937 rng(7);
+    for (int n = 1; n <= 7; ++n)
+        for (int rep = 0; rep < 20; ++rep) {
+            std::vector<double> w(n * n);
+            for (auto& x : w) x = 1 + rng() % 1000;
+            const int root = rng() % n;
+            auto f = kungfu::minimum_spanning_tree(n, w.data(), root);
+            if (!is_tree(n, f, root)) { std::printf("not a tree n=%d\n", n); return 1; }
+            // brute force: every father array that is a tree rooted at root
+            double best = 1e18;
+            std::vector<int32_t> g(n, 0);
+            long total = 1;
+            for (int i = 0; i < n; ++i) total *= n;
+            for (long code = 0; code < total; ++code) {
+                long c = code;
+                for (int i = 0; i < n; ++i) { g[i] = c % n; c /= n; }
+                if (is_tree(n, g, root)) best = std::min(best, tree_cost(n, w, g));
+            }
+            if (tree_cost(n, w, f) > best + 1e-9) { std::printf("n=%d cost %f > optimum %f\n", n, tree_cost(n, w, f), best); return 1; }
+        }
+    std::printf("mst ok\n");
+    return 0;
+}
+''')
+    from kungfu_b200 import _build
+
+    exe = tmp_path / "mst"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", str(_build.CSRC / "runtime"), str(src), "-L", str(_build.PKG / "lib"), "-lkungfu-comm",
+                    f"-Wl,-rpath,{_build.PKG / 'lib'}", "-pthread", "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode == 0 and "mst ok" in r.stdout, r.stdout
