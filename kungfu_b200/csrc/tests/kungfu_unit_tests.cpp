@@ -30,6 +30,8 @@
 #include "store.hpp"
 #include "transport.hpp"
 
+#include "runner_core.hpp"
+
 using namespace kfrt;
 
 static int g_fail = 0, g_checks = 0;
@@ -595,7 +597,193 @@ static void test_world_loses_a_peer() {
     on_all({0, 1}, [&](int r) { peers[r]->close(); });
 }
 
-int main() {
+// ---- launcher core: flags, worker environment, GPU slots (runner/flags_test.go, job/cuda_visible_device_test.go, proc/proc_test.go) ----
+static kfrun::Flags parse_cmd(std::vector<std::string> words) {
+    std::vector<char*> argv;
+    words.insert(words.begin(), "kungfu-run");
+    for (auto& w : words) argv.push_back(w.data());
+    return kfrun::parse_flags((int)argv.size(), argv.data());
+}
+
+static void test_launcher_core() {
+    using namespace kfrun;
+    { // defaults of the reference: np 1, all cores of this host, runner port 38080, BINARY_TREE_STAR, NVLink allowed
+        Flags f = parse_cmd({"python", "train.py", "--lr", "0.1"});
+        CHECK(f.np == 1 && f.port == kDefaultRunnerPort && f.strategy == "BINARY_TREE_STAR" && !f.watch && !f.keep && f.allow_nvlink);
+        CHECK(f.hosts.rfind("127.0.0.1:", 0) == 0 && f.prog == "python" && f.args.size() == 3 && f.args[2] == "0.1");
+    }
+    { // "-flag value", "-flag=value", "--flag", boolean flags without a value, "--" ends the launcher's flags
+        Flags f = parse_cmd({"-np", "4", "-H=10.0.0.1:4,10.0.0.2:4", "--strategy", "RING", "-w", "-k", "-port-range", "20000-20100", "-timeout", "90s",
+                             "-auto-recover=1m", "-delay", "500ms", "-q", "-init-version", "-1", "-builtin-config-port", "9100", "-standby", "2",
+                             "-shrink-on-failure", "-refill", "-allow-nvlink=false", "-logdir", "logs", "--", "-prog-that-starts-with-a-dash", "-x"});
+        CHECK(f.np == 4 && f.hosts == "10.0.0.1:4,10.0.0.2:4" && f.strategy == "RING" && f.watch && f.keep && f.quiet);
+        CHECK(f.port_range.begin == 20000 && f.port_range.end == 20100 && f.timeout_s == 90 && f.auto_recover_s == 60 && f.delay_s == 0.5);
+        CHECK(f.init_version == -1 && f.builtin_config_port == 9100 && f.standby == 2 && f.shrink_on_failure && f.refill && !f.allow_nvlink);
+        CHECK(f.logdir == "logs" && f.prog == "-prog-that-starts-with-a-dash" && f.args.size() == 1 && f.args[0] == "-x");
+    }
+    // the launcher's own flags stop at the program name: "-np" AFTER it belongs to the program
+    CHECK(parse_cmd({"-np", "2", "prog", "-np", "8"}).np == 2);
+    CHECK_THROWS(parse_cmd({"-np"}));                        // value missing
+    CHECK_THROWS(parse_cmd({"-no-such-flag", "1", "prog"})); // unknown flag
+    CHECK_THROWS(parse_cmd({"-np", "2"}));                   // no program
+    CHECK_THROWS(parse_cmd({"-strategy", "HYPERCUBE", "prog"}));
+    try {
+        parse_cmd({"-h"});
+        CHECK(false);
+    } catch (const UsageError& e) {
+        CHECK(std::string(e.what()).empty()); // a help request is not an error
+    }
+    CHECK(usage_text().find("-shrink-on-failure") != std::string::npos && usage_text().find("MULTI_BINARY_TREE_STAR") != std::string::npos);
+
+    { // smallest free GPU slot first, returned slots are reused, an exhausted pool says -1
+        GpuPool pool(3);
+        CHECK(pool.get() == 0 && pool.get() == 1 && pool.get() == 2 && pool.get() == -1);
+        pool.put(1);
+        CHECK(pool.get() == 1);
+        pool.put(7); // out of range: ignored
+        pool.put(0);
+        pool.put(2);
+        CHECK(pool.get() == 0 && pool.get() == 2);
+        CHECK(GpuPool(0).get() == -1 && GpuPool(-3).get() == -1);
+    }
+    { // a slot is an index INTO the launcher's CUDA_VISIBLE_DEVICES (ids or UUIDs), or the slot itself when the variable is unset
+        const char* old = getenv("CUDA_VISIBLE_DEVICES");
+        const std::string saved = old ? old : "";
+        unsetenv("CUDA_VISIBLE_DEVICES");
+        CHECK(Job::cuda_index(0) == "0" && Job::cuda_index(5) == "5");
+        setenv("CUDA_VISIBLE_DEVICES", "4,6,GPU-8f3c", 1);
+        CHECK(Job::cuda_index(0) == "4" && Job::cuda_index(1) == "6" && Job::cuda_index(2) == "GPU-8f3c" && Job::cuda_index(3) == "-1" && Job::cuda_index(-1) == "-1");
+        // the environment a worker is started with: the runner -> worker contract (env/envs.go)
+        Job job;
+        job.strategy = "RING";
+        job.prog = "python";
+        job.args = {"train.py"};
+        job.parent = PeerID{parse_ipv4("10.0.0.1"), 38080};
+        job.hosts = HostList::parse("10.0.0.1:2,10.0.0.2:2");
+        job.config_server = "http://10.0.0.1:9100/config";
+        job.start_time = 1234;
+        Cluster c;
+        c.runners = PeerList::parse("10.0.0.1:38080,10.0.0.2:38080");
+        c.workers = PeerList::parse("10.0.0.1:10000,10.0.0.1:10001,10.0.0.2:10000");
+        auto procs = job.create_procs(c, parse_ipv4("10.0.0.1"), 3);
+        CHECK(procs.size() == 2 && procs[0].name == "10.0.0.1.10000" && procs[1].name == "10.0.0.1.10001" && procs[1].log_prefix == "10.0.0.1.10001@3");
+        auto& e = procs[1].envs;
+        CHECK(e[envkeys::kSelfSpec] == "10.0.0.1:10001" && e[envkeys::kInitPeers] == "10.0.0.1:10000,10.0.0.1:10001,10.0.0.2:10000");
+        CHECK(e[envkeys::kInitRunners] == "10.0.0.1:38080,10.0.0.2:38080" && e[envkeys::kParentID] == "10.0.0.1:38080");
+        CHECK(e[envkeys::kInitClusterVersion] == "3" && e[envkeys::kAllReduceStrategy] == "RING" && e[envkeys::kJobStart] == "1234");
+        CHECK(e[envkeys::kConfigServer] == "http://10.0.0.1:9100/config" && e[envkeys::kCudaVisibleDevices] == "6" && e[envkeys::kAllowNvlink] == "1");
+        CHECK(e.count("CUDA_VISIBLE_DEVICES") == 0); // every GPU stays visible: peer-to-peer and multicast need it
+        job.allow_nvlink = false;
+        auto hidden = job.create_procs(c, parse_ipv4("10.0.0.1"), 3);
+        CHECK(hidden[0].envs["CUDA_VISIBLE_DEVICES"] == "4" && hidden[0].envs.count(envkeys::kAllowNvlink) == 0);
+        CHECK(job.create_procs(c, parse_ipv4("10.0.0.9"), 3).empty());
+        if (old) setenv("CUDA_VISIBLE_DEVICES", saved.c_str(), 1);
+        else unsetenv("CUDA_VISIBLE_DEVICES");
+    }
+    CHECK(infer_self_ipv4("127.0.0.7", "") == parse_ipv4("127.0.0.7") && infer_self_ipv4("", "") == parse_ipv4("127.0.0.1"));
+    CHECK(infer_self_ipv4("", "lo") == parse_ipv4("127.0.0.1"));
+    CHECK_THROWS(infer_self_ipv4("", "no-such-nic0"));
+}
+
+// ---- traffic counters and the metrics text (monitor/counters_test.go), duration / env helpers (utils/utils_test.go) --------------------
+static void test_counters_and_utils() {
+    NetMonitor& m = NetMonitor::get();
+    m.reset();
+    const PeerID a{parse_ipv4("10.1.0.1"), 10000}, b{parse_ipv4("10.1.0.2"), 10001};
+    m.egress(a, 1000);
+    m.egress(a, 24);
+    m.egress(b, 7);
+    m.ingress(b, 512);
+    auto tot = m.egress_totals();
+    CHECK(tot.size() == 2);
+    uint64_t sum = 0;
+    for (auto& kv : tot) sum += kv.second;
+    CHECK(sum == 1031);
+    PeerList pl;
+    pl.push_back(a);
+    pl.push_back(b);
+    (void)m.egress_rates(pl); // first query sets the reference point
+    sleep_ms(30);
+    m.egress(a, 3000);
+    auto rates = m.egress_rates(pl);
+    CHECK(rates.size() == 2 && rates[0] > 0 && rates[1] == 0);
+    m.set_gauge("kungfu_gradient_noise_scale", 12.5);
+    m.set_gauge("kungfu_gradient_noise_scale", 13.5); // overwritten
+    m.add_counter("gpu_collective_bytes_total{op=\"all_reduce\"}", 100);
+    m.add_counter("gpu_collective_bytes_total{op=\"all_reduce\"}", 28);
+    const std::string text = m.metrics_text();
+    CHECK(text.find("egress_total_bytes{peer=\"10.1.0.1:10000\"} 4024") != std::string::npos);
+    CHECK(text.find("ingress_total_bytes{peer=\"10.1.0.2:10001\"} 512") != std::string::npos);
+    CHECK(text.find("kungfu_gradient_noise_scale 13.5") != std::string::npos);
+    CHECK(text.find("gpu_collective_bytes_total{op=\"all_reduce\"} 128") != std::string::npos);
+    m.reset();
+    CHECK(m.egress_totals().empty());
+
+    CHECK(parse_duration_s("10s", 0) == 10 && parse_duration_s("500ms", 0) == 0.5 && parse_duration_s("2m", 0) == 120 && parse_duration_s("1.5", 0) == 1.5);
+    CHECK(parse_duration_s("", 7) == 7 && parse_duration_s("soon", 7) == 7);
+    setenv("KF_UNIT_BOOL", "true", 1);
+    CHECK(getenv_bool("KF_UNIT_BOOL", false) && !getenv_bool("KF_UNIT_UNSET_BOOL", false) && getenv_bool("KF_UNIT_UNSET_BOOL", true));
+    CHECK(getenv_str("KF_UNIT_UNSET", "dflt") == "dflt");
+    CHECK(merge_errors({"", ""}, "x").empty());
+    const std::string merged = merge_errors({"", "boom", "bang"}, "2 tasks");
+    CHECK(merged.find("boom") != std::string::npos && merged.find("bang") != std::string::npos);
+    const double t0 = now_s();
+    sleep_ms(20);
+    CHECK(now_s() - t0 >= 0.015 && unix_time_ns() > 1600000000ull * 1000000000ull);
+    CHECK(strprintf("%d-%s", 7, "x") == "7-x");
+}
+
+// ---- framed messages end to end (rchannel/connection/message_test.go: header / message round trips up to 16 MiB) ------------------------
+static void test_message_round_trip() {
+    const uint16_t port = (uint16_t)(45000 + getpid() % 2000);
+    const PeerID srv{parse_ipv4("127.0.0.1"), port}, cli{parse_ipv4("127.0.0.1"), (uint16_t)(port + 1)};
+    for (bool use_unix : {false, true}) {
+        CollectiveEndpoint coll;
+        Server server(srv, &coll, nullptr, use_unix);
+        std::vector<std::pair<std::string, size_t>> control;
+        std::mutex mu;
+        server.set_control_handler([&](const PeerID& src, const std::string& name, const Bytes& payload) {
+            std::lock_guard<std::mutex> g(mu);
+            if (src == cli) control.emplace_back(name, payload.size());
+        });
+        server.start();
+        Client c(cli);
+        CHECK(c.ping(srv) >= 0 && c.wait_peer(srv, 2.0));
+        std::mt19937 rng(11);
+        for (size_t len : {(size_t)0, (size_t)1, (size_t)4095, (size_t)(1 << 20) + 3, (size_t)16 << 20}) {
+            std::vector<uint8_t> msg(len);
+            for (size_t i = 0; i < len; i += 257) msg[i] = (uint8_t)rng();
+            if (len) msg[len - 1] = 0xA5;
+            const std::string name = "blob-" + std::to_string(len) + std::string(len % 7, 'n'); // names of different lengths
+            c.send(srv, name, msg.data(), len, kConnCollective, kNoFlag);
+            std::vector<uint8_t> got(len, 0xFF);
+            coll.recv_into(cli, name, got.data(), len); // straight into the receiver's buffer
+            CHECK(got == msg);
+        }
+        // a receive that expects another size than what was sent is an error, not a truncated copy
+        const char five[5] = {1, 2, 3, 4, 5};
+        c.send(srv, "five", five, 5, kConnCollective, kNoFlag);
+        char four[4];
+        CHECK_THROWS(coll.recv_into(cli, "five", four, 4));
+        c.send(srv, "update", "{}", 2, kConnControl, kNoFlag);
+        for (int i = 0; i < 200; ++i) {
+            {
+                std::lock_guard<std::mutex> g(mu);
+                if (!control.empty()) break;
+            }
+            sleep_ms(5);
+        }
+        {
+            std::lock_guard<std::mutex> g(mu);
+            CHECK(control.size() == 1 && control[0].first == "update" && control[0].second == 2);
+        }
+        c.close_all();
+        server.stop();
+        CHECK(c.ping(srv, 200) < 0); // nobody listens any more
+    }
+}
+
+int main(int argc, char** argv) {
     // read once, before any thread exists: a refused dial fails fast in these tests (50 x 20 ms instead of 500 x 200 ms)
     setenv("KUNGFU_CONFIG_CONN_RETRY_COUNT", "50", 1);
     setenv("KUNGFU_CONFIG_CONN_RETRY_PERIOD", "20ms", 1);
@@ -605,8 +793,12 @@ int main() {
     } tests[] = {{"dtypes_and_transform2", test_dtypes_and_transform2}, {"plan", test_plan}, {"topologies", test_topologies}, {"mst", test_mst},
                  {"placement", test_placement}, {"stores", test_stores}, {"single_process_peer", test_single_process_peer},
                  {"json_reader", test_json_reader}, {"epoch_fence", test_epoch_fence}, {"server_survives_garbage", test_server_survives_garbage}, {"world_all_strategies", test_world_all_strategies},
-                 {"world_loses_a_peer", test_world_loses_a_peer}};
+                 {"world_loses_a_peer", test_world_loses_a_peer}, {"launcher_core", test_launcher_core},
+                 {"counters_and_utils", test_counters_and_utils}, {"message_round_trip", test_message_round_trip}};
     for (auto& t : tests) {
+        bool wanted = argc <= 1; // `kungfu-unit-tests name…` runs the named tests only
+        for (int i = 1; i < argc; ++i) wanted = wanted || std::string(argv[i]) == t.name;
+        if (!wanted) continue;
         const int before = g_fail;
         try {
             t.fn();
