@@ -88,10 +88,19 @@ class _Alias(importlib.abc.MetaPathFinder, importlib.abc.InspectLoader):
         return importlib.util.spec_from_loader(fullname, self, is_package=True)
 
     def create_module(self, spec):
-        return importlib.import_module(_resolve(spec.name))  # the implementation module itself, under a second name
+        module = importlib.import_module(_resolve(spec.name))  # the implementation module itself, under a second name
+        self._real_spec[spec.name] = module.__spec__
+        return module
 
     def exec_module(self, module):
-        pass
+        # the import system has just stamped the alias spec on the module; the module keeps its own identity (`__spec__.parent` is what
+        # its relative imports resolve against)
+        for alias, real in list(self._real_spec.items()):
+            if real is not None and real.name == module.__name__:
+                module.__spec__ = real
+                del self._real_spec[alias]
+
+    _real_spec = {}
 
     # `python -m kungfu.info`, `python -m kungfu.tensorflow.v1.examples`: runpy asks the loader for the code of `<package>.__main__`
     def get_code(self, fullname):
