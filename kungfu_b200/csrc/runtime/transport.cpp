@@ -306,19 +306,33 @@ Socket Client::dial(const PeerID& to, ConnType type, bool retry) {
     const uint64_t gen = abort_gen_.load();
     for (int attempt = 0; attempt < tries; ++attempt) {
         if (abort_gen_.load() != gen) break; // interrupt(): the peer is known to be lost
-        Socket s;
-        if (cfg.use_unix_sock && to.colocated_with(self_)) s = Socket::connect_unix(to.sock_file());
-        if (!s.valid()) s = Socket::connect_tcp(to.ipv4, to.port, 2000);
-        if (s.valid()) {
-            ConnHeader h{(uint16_t)type, self_.port, self_.ipv4};
-            ConnAck ack{};
-            if (s.send_all(&h, sizeof(h)) && s.recv_all(&ack, sizeof(ack))) {
-                // stale-epoch fencing: collective traffic only flows between peers of the same cluster version
-                if (type != kConnCollective || ack.token == token_.load()) return s;
-                KF_LOGD("token mismatch dialing %s: mine %u theirs %u", to.str().c_str(), token_.load(), ack.token);
+        // One attempt = one retry period. A peer that ANSWERS but is still in another epoch (it has not adopted the new cluster version
+        // yet — after a resize the members switch within milliseconds of each other) is asked again after 1, 2, 4, ... ms inside the
+        // period instead of once per period: a shrink 8 -> 4 cost a full 200 ms whenever one survivor dialled before another had
+        // switched (measured, 2 runs in 3), now it costs the few ms the slowest member needs.
+        int waited = 0, step = 1;
+        for (;;) {
+            bool other_epoch = false;
+            Socket s;
+            if (cfg.use_unix_sock && to.colocated_with(self_)) s = Socket::connect_unix(to.sock_file());
+            if (!s.valid()) s = Socket::connect_tcp(to.ipv4, to.port, 2000);
+            if (s.valid()) {
+                ConnHeader h{(uint16_t)type, self_.port, self_.ipv4};
+                ConnAck ack{};
+                if (s.send_all(&h, sizeof(h)) && s.recv_all(&ack, sizeof(ack))) {
+                    // stale-epoch fencing: collective traffic only flows between peers of the same cluster version
+                    if (type != kConnCollective || ack.token == token_.load()) return s;
+                    KF_LOGD("token mismatch dialing %s: mine %u theirs %u", to.str().c_str(), token_.load(), ack.token);
+                    other_epoch = true;
+                }
             }
+            if (!other_epoch || !retry || waited >= cfg.conn_retry_period_ms || abort_gen_.load() != gen) break;
+            step = std::min(step, cfg.conn_retry_period_ms - waited);
+            sleep_ms(step);
+            waited += step;
+            step *= 2;
         }
-        if (attempt + 1 < tries) sleep_ms(cfg.conn_retry_period_ms);
+        if (attempt + 1 < tries && waited < cfg.conn_retry_period_ms) sleep_ms(cfg.conn_retry_period_ms - waited);
     }
     return Socket();
 }
