@@ -106,8 +106,10 @@ int main(int argc, char** argv) {
             const std::string name = "s" + std::to_string(step) + "v" + std::to_string(kungfu_cluster_version());
             if (kungfu_all_reduce(&one, &sum, 1, KungFu_F32, KungFu_SUM, name.c_str(), nullptr, nullptr) != 0) {
                 int changed = 0, detached = 0;
+                const double t0 = now();
                 CHECK(kungfu_recover(20.0, &changed, &detached) == 0);
                 CHECK(changed == 1 && detached == 0);
+                printf("fake-agent rank %d: recover took %.1f ms\n", kungfu_rank(), (now() - t0) * 1e3);
                 ++recovered;
                 --step; // repeat the interrupted step with the smaller cluster
                 continue;

@@ -760,7 +760,16 @@ void Server::start() {
     // not be a local interface.
     const bool loopback_alias = (self_.ipv4 >> 24) == 127;
     a.sin_addr.s_addr = htonl(loopback_alias ? self_.ipv4 : INADDR_ANY);
-    if (::bind(tcp_fd_, reinterpret_cast<sockaddr*>(&a), sizeof(a)) != 0 || ::listen(tcp_fd_, 256) != 0) {
+    // A port that is still held by a process on its way out (the previous owner of this slot in an elastic job, the metrics endpoint of a
+    // worker that is being reaped) frees itself within moments: wait for it briefly instead of failing the worker.
+    int bound = -1;
+    for (int attempt = 0; attempt < 30; ++attempt) {
+        bound = ::bind(tcp_fd_, reinterpret_cast<sockaddr*>(&a), sizeof(a));
+        if (bound == 0 || errno != EADDRINUSE) break;
+        if (attempt == 0) KF_LOGW("port %d is in use, waiting for it", (int)self_.port);
+        sleep_ms(100);
+    }
+    if (bound != 0 || ::listen(tcp_fd_, 256) != 0) {
         std::string e = strerror(errno);
         ::close(tcp_fd_);
         tcp_fd_ = -1;
