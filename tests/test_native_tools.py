@@ -67,6 +67,23 @@ def test_bench_p2p_rejects_unknown_model():
     assert rc != 0 and "invalid model name" in out
 
 
+@pytest.mark.parametrize("np,strategy,args", [(1, "AUTO", ("-model", "slp")), (3, "RING", ("-model", "resnet50", "-mode", "par", "-epochs", "2")),
+                                              (4, "BINARY_TREE_STAR", ("-model", "resnet50", "-fuse", "-epochs", "2", "-dtype", "bf16")),
+                                              (2, "STAR", ("-model", "slp", "-dtype", "i32", "-mode", "par"))])
+def test_bench_allreduce(np, strategy, args):
+    """≙ tests/go/cmd/kungfu-bench-allreduce: one all-reduce per tensor of a fake model, seq / par / fused, every result verified."""
+    _, out, _ = _run(np, "kungfu-bench-allreduce", args, flags=("-strategy", strategy))
+    m = re.search(rf"Result: model: ([\w-]+), (\d+) tensors, mode: (\w+)( \(fused\))?, np: {np}, rate: ([\d.]+) (\S+)", out)
+    assert m, out[-2000:]
+    assert "VERIFICATION FAILED" not in out
+
+
+def test_bench_allreduce_injected_startup_failure_fails_the_job():
+    """≙ -rand-nccl-failure: a worker that dies before it joins takes the job down (fail-fast), it does not hang the others."""
+    rc, out, _ = _run(3, "kungfu-bench-allreduce", ("-model", "slp", "-rand-failure", "1"), expect_rc=None, timeout=60)
+    assert rc != 0 and "injected start-up failure" in out
+
+
 def test_fake_adaptive_trainer_follows_its_schedule():
     """1 -> 2 -> 4 -> 8 -> 4 -> 1 inside one job, natively: step counters agree after every change, every step reduces to the size of
     the cluster of that step, detached workers leave, rank 0 finishes all steps."""
@@ -168,3 +185,93 @@ def test_remote_install_dry_run_lists_every_step():
                        cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
     assert r.returncode == 0, r.stdout[-2000:]
     assert r.stdout.count("-cf - --exclude") == 2 and r.stdout.count("-xf -") == 2 and r.stdout.count("op@10.1.0.") >= 4 and "kungfu_b200._build" in r.stdout
+
+
+def _tool(name, *args, timeout=60):
+    r = subprocess.run([_bin(name), *args], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+    return r.returncode, r.stdout
+
+
+def test_native_config_client_against_a_standalone_config_server(tmp_path):
+    """≙ tests/go/cmd/kungfu-config-client-example: read / resize / random proposals / clear, all through the REST endpoint."""
+    import json
+    import time
+
+    from kungfu_b200 import _kfrt as rt
+
+    init = tmp_path / "init.json"
+    init.write_text(rt.cluster_json("127.0.0.1:38080", "127.0.0.1:10000,127.0.0.1:10001"))
+    port = 9700 + (os.getpid() * 7 + next(_counter)) % 250
+    url = f"http://127.0.0.1:{port}/config"
+    p = subprocess.Popen([_bin("kungfu-config-server"), "-port", str(port), "-init", str(init), "-ttl", "60s"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    try:
+        for _ in range(100):
+            rc, out = _tool("kungfu-config-client", "-url", url)
+            if rc == 0:
+                break
+            time.sleep(0.1)
+        assert rc == 0 and json.loads(out) == {"size": 2, "runners": 1}, out
+        rc, out = _tool("kungfu-config-client", "-url", url, "-size", "5")
+        assert rc == 0 and json.loads(out) == {"resize_to": 5, "ok": True}
+        st, body = rt.http_request("GET", url)
+        ports_now = [w["Port"] for w in json.loads(body)["Workers"]]
+        assert len(ports_now) == 5 and len(set(ports_now)) == 5 and ports_now[:2] == [10000, 10001]
+        # a shuffled shrink keeps a subset in its old order
+        rc, out = _tool("kungfu-config-client", "-url", url, "-size", "3", "-shuffle", "-seed", "5")
+        assert rc == 0
+        st, body = rt.http_request("GET", url)
+        kept = [w["Port"] for w in json.loads(body)["Workers"]]
+        assert len(kept) == 3 and kept == sorted(kept) and set(kept) <= set(ports_now)
+        rc, out = _tool("kungfu-config-client", "-url", url, "-random", "-min", "1", "-max", "6", "-period", "50ms", "-duration", "600ms", "-final", "2",
+                        "-seed", "3")
+        lines = [json.loads(l) for l in out.strip().splitlines()]
+        assert rc == 0 and lines[-1]["final"] == 2 and lines[-1]["proposals"] >= 3 and all(1 <= l["resize_to"] <= 6 for l in lines[:-1])
+        rc, out = _tool("kungfu-config-client", "-url", url)
+        assert json.loads(out)["size"] == 2
+        rc, out = _tool("kungfu-config-client", "-url", url, "-clear")
+        assert rc == 0 and json.loads(out) == {"cleared": True}
+        rc, out = _tool("kungfu-config-client", "-url", url, "-size", "3")
+        assert rc != 0  # a cleared config takes no more updates: the job is over
+    finally:
+        rt.http_request("GET", f"http://127.0.0.1:{port}/stop")
+        try:
+            p.wait(timeout=10)
+        except subprocess.TimeoutExpired:
+            p.kill()
+
+
+def test_native_test_util_waits_pings_and_kills_a_worker():
+    """≙ tests/go/cmd/kungfu-test-util: -wait / -ping a worker of a running job, then -kill it: the `exit` control message ends that
+    worker (status 0) and its listener is gone."""
+    import json
+    import time
+
+    rport, prange = _ports()
+    base = int(prange.split("-")[0])
+    cmd = [_bin("kungfu-run"), "-q", "-np", "2", "-H", "127.0.0.1:2", "-port", str(rport), "-port-range", prange,
+           _bin("kungfu-bad-worker"), "-rank", "9", "-total", "60s"]  # nobody is "bad": both workers just keep all-reducing
+    p = subprocess.Popen(cmd, cwd=ROOT, env=dict(os.environ, KUNGFU_CONFIG_LOG_LEVEL="WARN"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    try:
+        target = f"127.0.0.1:{base + 1}"
+        rc, out = _tool("kungfu-test-util", "-wait", target, "-timeout", "20s")
+        assert rc == 0 and json.loads(out)["up"] is True, out
+        time.sleep(0.5)
+        rc, out = _tool("kungfu-test-util", "-ping", target, "-n", "3")
+        d = json.loads(out)
+        assert rc == 0 and d["pings"] == 3 and 0 <= d["rtt_s"] <= d["mean_rtt_s"] < 1.0
+        rc, out = _tool("kungfu-test-util", "-kill", target)
+        assert rc == 0 and json.loads(out) == {"killed": target}
+        t0 = time.time()
+        while time.time() - t0 < 10:  # the worker leaves with status 0 (its sibling then waits for it until its own dial budget ends)
+            rc, out = _tool("kungfu-test-util", "-wait", target, "-timeout", "300ms")
+            if rc == 1:
+                break
+            time.sleep(0.1)
+        assert rc == 1 and json.loads(out)["up"] is False
+        p.terminate()
+        p.wait(timeout=20)
+    finally:
+        if p.poll() is None:
+            p.kill()
+    rc, out = _tool("kungfu-test-util")
+    assert rc == 2 and "usage" in out
