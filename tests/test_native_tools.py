@@ -148,6 +148,49 @@ def test_elastic_policy_example():
     assert out.count("detached after step 20") == 2
 
 
+def test_elastic_eager_example():
+    """examples/mnist_elastic_eager: the loop itself keeps the job consistent with resize / all-reduce MAX / broadcast only."""
+    out = _erun("examples/mnist_elastic_eager/main.py", ["--samples", "3000", "--num-epochs", "2", "--schedule", "10:2,20:3,30:1", "--learning-rate", "0.1"])
+    m = re.search(r"done: steps=90 trained=6000 np=1 resizes=\[\(10, 1, 2\), \(20, 2, 3\), \(30, 3, 1\)\] accuracy=([\d.]+)", out)
+    assert m, out[-3000:]
+    assert float(m.group(1)) > 0.9 and out.count("detached after step 30") == 2
+
+
+def test_elastic_follow_example_with_an_external_resize():
+    """examples/mnist_elastic_docker: the program only follows the config server; the native config client resizes it from outside."""
+    import sys
+    import threading
+    import time
+
+    rport, prange = _ports()
+    url = f"http://127.0.0.1:{rport + 62}/config"
+    cmd = [_bin("kungfu-run"), "-q", "-w", "-np", "1", "-H", "127.0.0.1:3", "-port", str(rport), "-port-range", prange, "-builtin-config-port", str(rport + 62),
+           sys.executable, os.path.join(ROOT, "examples/mnist_elastic_docker/mnist_slp_elastic.py"), "--samples", "2000", "--num-epochs", "6", "--step-ms", "40"]
+    p = subprocess.Popen(cmd, cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT, KUNGFU_CONFIG_LOG_LEVEL="ERROR"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    done = {}
+
+    def resizer():
+        t0 = time.time()
+        while time.time() - t0 < 60 and p.poll() is None:  # wait until the job is up, then grow it once
+            rc, out = _tool("kungfu-config-client", "-url", url)
+            if rc == 0:
+                time.sleep(1.0)
+                done["rc"], done["out"] = _tool("kungfu-config-client", "-url", url, "-size", "3")
+                return
+            time.sleep(0.2)
+
+    th = threading.Thread(target=resizer)
+    th.start()
+    out, _ = p.communicate(timeout=240)
+    th.join()
+    out = re.sub(r"\x1b\[[0-9;]*m", "", out)
+    assert p.returncode == 0, out[-3000:]
+    assert done.get("rc") == 0, done
+    m = re.search(r"done: steps=(\d+) trained=(\d+) sizes_seen_by_rank0=\[1, 3\] accuracy=([\d.]+)", out)
+    assert m, out[-3000:]
+    assert int(m.group(2)) >= 12000 and float(m.group(3)) > 0.9
+
+
 def test_elastic_system_benchmark_on_the_host_plane():
     out = _erun("benchmarks/system/benchmark_kungfu_elastic.py", ["--no-cuda", "--model", "slp", "--num-iters", "12", "--schedule", "4:2,8:1",
                                                                   "--num-warmup-batches", "1"])
