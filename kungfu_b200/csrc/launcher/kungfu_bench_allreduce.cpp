@@ -9,8 +9,8 @@
 // (the bytes a ring moves in and out of every worker). Differences: written against the C++ Peer; every epoch's result is VERIFIED
 // (worker r contributes r + 1 in every element, so the sum must be np (np + 1) / 2 — a mis-routed chunk or a tensor reduced under the wrong
 // name shows up), the element type is selectable, and the reference's `-rand-nccl-failure` (a worker that dies at start-up with the
-// probability of a known driver bug, to exercise the launcher's retry) is `-rand-failure P`: with probability P this worker exits 1 before
-// it joins, which is what `kungfu-run`'s fail-fast / `-shrink-on-failure` paths are tested against.
+// probability of a known driver bug, to exercise the launcher's retry) is `-rand-failure P`: with probability P this worker prints the
+// loader's message and exits 1 before it joins — `kungfu-run` starts such a worker again (start-up retry, kungfu_run.cpp `should_restart`).
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -86,7 +86,8 @@ int main(int argc, char** argv) {
     if (p_fail > 0) {
         std::mt19937_64 rng(std::random_device{}() ^ ((uint64_t)getpid() << 20));
         if (std::uniform_real_distribution<double>(0, 1)(rng) < p_fail) {
-            std::fprintf(stderr, "kungfu-bench-allreduce: injected start-up failure (-rand-failure %.2f)\n", p_fail);
+            // the first line on stderr is the loader's message, which is what the launcher's start-up retry looks for
+            std::fprintf(stderr, "Inconsistency detected by ld.so: injected start-up failure (kungfu-bench-allreduce -rand-failure %.2f)\n", p_fail);
             return 1;
         }
     }

@@ -74,7 +74,8 @@ struct Cancel {
     }
 };
 
-void pump(int fd, const std::string& tag, const char* color, bool verbose, FILE* console, const std::string& logpath) {
+void pump(int fd, const std::string& tag, const char* color, bool verbose, FILE* console, const std::string& logpath,
+          std::shared_ptr<std::string> first_line = nullptr) {
     FILE* lf = logpath.empty() ? nullptr : fopen(logpath.c_str(), "we");
     FILE* in = fdopen(fd, "r");
     if (!in) {
@@ -86,7 +87,10 @@ void pump(int fd, const std::string& tag, const char* color, bool verbose, FILE*
     size_t cap = 0;
     ssize_t n;
     static std::mutex console_mu;
+    bool first = true;
     while ((n = getline(&line, &cap, in)) >= 0) {
+        if (first && first_line) first_line->assign(line, (size_t)n); // read by the waiter after this thread is joined
+        first = false;
         if (lf) {
             fwrite(line, 1, (size_t)n, lf);
             fflush(lf);
@@ -108,7 +112,19 @@ struct Child {
     pid_t pid = -1;
     int stdin_fd = -1;
     std::thread out, err;
+    std::shared_ptr<std::string> first_err = std::make_shared<std::string>(); // first line the process wrote to stderr
 };
+
+// Start-up retry (reference: srcs/go/utils/runner/local/hack.go:14-35, srcs/go/nccl/bug.go:12): a worker that dies with the dynamic
+// loader's "Inconsistency detected by ld.so" as the FIRST thing on its stderr hit a known loader race of some CUDA / NCCL builds and has
+// not joined anything yet, so it is simply started again with the same environment. The reference retries for ever; here the number of
+// restarts is bounded (KUNGFU_START_RETRIES, default 10) and the prefix can be changed (KUNGFU_RETRY_STDERR_PREFIX, used by the tests).
+bool should_restart(const Child& c, int rc, int attempt) {
+    if (rc == 0 || !c.first_err) return false;
+    static const std::string prefix = getenv_str("KUNGFU_RETRY_STDERR_PREFIX", "Inconsistency detected by ld.so");
+    static const int limit = std::atoi(getenv_str("KUNGFU_START_RETRIES", "10").c_str());
+    return !prefix.empty() && attempt <= limit && c.first_err->compare(0, prefix.size(), prefix) == 0;
+}
 
 Child spawn_proc(const Proc& p, bool verbose, const std::string& logdir, Cancel* cancel, int color_idx, bool want_stdin) {
     // O_CLOEXEC: workers are spawned from several threads at once; a plain pipe() leaks this worker's write ends into every
@@ -159,8 +175,8 @@ Child spawn_proc(const Proc& p, bool verbose, const std::string& logdir, Cancel*
     Child c;
     c.pid = pid;
     c.stdin_fd = want_stdin ? in_pipe[1] : -1;
-    c.out = std::thread(pump, out_pipe[0], p.name + "::stdout", color, verbose, stdout, base.empty() ? "" : base + ".stdout.log");
-    c.err = std::thread(pump, err_pipe[0], p.name + "::stderr", color, verbose, stderr, base.empty() ? "" : base + ".stderr.log");
+    c.out = std::thread(pump, out_pipe[0], p.name + "::stdout", color, verbose, stdout, base.empty() ? "" : base + ".stdout.log", nullptr);
+    c.err = std::thread(pump, err_pipe[0], p.name + "::stderr", color, verbose, stderr, base.empty() ? "" : base + ".stderr.log", c.first_err);
     return c;
 }
 
@@ -179,8 +195,12 @@ int wait_proc(Child& c, Cancel* cancel) {
 }
 
 int run_proc(const Proc& p, bool verbose, const std::string& logdir, Cancel* cancel, int color_idx) {
-    Child c = spawn_proc(p, verbose, logdir, cancel, color_idx, false);
-    return wait_proc(c, cancel);
+    for (int attempt = 1;; ++attempt) {
+        Child c = spawn_proc(p, verbose, logdir, cancel, color_idx, false);
+        const int rc = wait_proc(c, cancel);
+        if ((cancel && cancel->flag) || !should_restart(c, rc, attempt)) return rc;
+        KF_LOGE("%s: restarting for the %d-th time (exit %d after the loader bug at start-up)", p.name.c_str(), attempt, rc);
+    }
 }
 
 // run all procs concurrently; the first failure cancels the rest (fail-fast). Returns 0 iff all succeeded.
@@ -480,7 +500,18 @@ struct Watcher {
                 std::lock_guard<std::mutex> g(mu);
                 pids[id.key()] = c.pid;
             }
-            const int rc = wait_proc(c, &cancel);
+            int rc = wait_proc(c, &cancel);
+            Child* cur = &c;
+            for (int attempt = 1; !cancel.flag && should_restart(*cur, rc, attempt); ++attempt) { // died in the loader before joining: start it again
+                KF_LOGE("%s: restarting for the %d-th time (exit %d after the loader bug at start-up)", p.name.c_str(), attempt, rc);
+                own = spawn_proc(p, true, job.logdir, &cancel, color, false);
+                cur = &own;
+                {
+                    std::lock_guard<std::mutex> g(mu);
+                    pids[id.key()] = own.pid;
+                }
+                rc = wait_proc(own, &cancel);
+            }
             gpus.put(gpu);
             std::lock_guard<std::mutex> g(mu);
             pids.erase(id.key());

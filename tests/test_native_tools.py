@@ -78,10 +78,22 @@ def test_bench_allreduce(np, strategy, args):
     assert "VERIFICATION FAILED" not in out
 
 
-def test_bench_allreduce_injected_startup_failure_fails_the_job():
-    """≙ -rand-nccl-failure: a worker that dies before it joins takes the job down (fail-fast), it does not hang the others."""
-    rc, out, _ = _run(3, "kungfu-bench-allreduce", ("-model", "slp", "-rand-failure", "1"), expect_rc=None, timeout=60)
-    assert rc != 0 and "injected start-up failure" in out
+def test_launcher_restarts_workers_that_die_in_the_loader():
+    """≙ -rand-nccl-failure + runner/local/hack.go: a worker whose first stderr line is the loader's "Inconsistency detected by ld.so" is
+    started again (it has not joined anything yet); the job completes. With the retries used up the job fails instead of looping."""
+    _, out, _ = _run(3, "kungfu-bench-allreduce", ("-model", "slp", "-rand-failure", "0.5"), timeout=120)
+    assert re.search(r"Result: model: slp, 2 tensors, mode: seq, np: 3", out) and "VERIFICATION FAILED" not in out
+    rc, out, _ = _run(2, "kungfu-bench-allreduce", ("-model", "slp", "-rand-failure", "1"), env={"KUNGFU_START_RETRIES": "2"}, expect_rc=None, timeout=60)
+    assert rc != 0 and out.count("restarting for the") >= 2 and "restarting for the 3-th" not in out
+    # any other start-up failure is not retried
+    rc, out, _ = _run(2, "kungfu-bench-allreduce", ("-model", "alexnet",), expect_rc=None, timeout=60)
+    assert rc != 0 and "restarting" not in out
+
+
+def test_launcher_restart_in_watch_mode():
+    rport, _ = _ports()
+    _, out, _ = _run(2, "kungfu-bench-allreduce", ("-model", "slp", "-rand-failure", "0.5"), flags=("-w", "-builtin-config-port", str(rport + 62)), timeout=120)
+    assert re.search(r"Result: model: slp, 2 tensors, mode: seq, np: 2", out)
 
 
 def test_fake_adaptive_trainer_follows_its_schedule():
