@@ -42,6 +42,22 @@ KUNGFU_CONFIG_ENABLE_MONITORING=true "$bin/kungfu-run" -q -np 4 -H 127.0.0.1:4 -
 "$bin/kungfu-run" -q -w -np 1 -H 127.0.0.1:4 -port "$R" -port-range "$((R + 1))-$((R + 50))" -builtin-config-port $((9200 + RANDOM % 90)) \
     "$bin/kungfu-fake-adaptive-trainer" -max-step 14 -schedule 2:2,4:4,7:2,10:1 -slow-ms 20 -fast-ms 5
 "$bin/kungfu-fake-inproc-trainer" -np 4 -model slp -steps 20
+# every tensor of a model in flight at once over 32 threads; workers that die in the loader are restarted by the (instrumented) launcher;
+# the outside tools against a live job: ping a worker, resize through the config server, stop the last worker
+"$bin/kungfu-run" -q -np 3 -H 127.0.0.1:3 -port "$R" -port-range "$((R + 1))-$((R + 50))" -strategy BINARY_TREE_STAR "$bin/kungfu-bench-allreduce" -model resnet50 -mode par -epochs 2 -warmup 1
+"$bin/kungfu-run" -q -np 3 -H 127.0.0.1:3 -port "$R" -port-range "$((R + 1))-$((R + 50))" "$bin/kungfu-bench-allreduce" -model slp -rand-failure 0.5
+C=$((9200 + RANDOM % 90))
+"$bin/kungfu-run" -q -w -np 1 -H 127.0.0.1:3 -port "$R" -port-range "$((R + 1))-$((R + 50))" -builtin-config-port "$C" \
+    "$bin/kungfu-fake-adaptive-trainer" -max-step 100000 -slow-ms 20 -fast-ms 5 &
+job=$!
+"$bin/kungfu-test-util" -wait "127.0.0.1:$((R + 1))" -timeout 20s
+"$bin/kungfu-test-util" -ping "127.0.0.1:$((R + 1))" -n 3
+"$bin/kungfu-config-client" -url "http://127.0.0.1:$C/config" -size 3
+sleep 1
+"$bin/kungfu-config-client" -url "http://127.0.0.1:$C/config" -random -min 1 -max 3 -period 300ms -duration 2s -final 1
+sleep 1
+"$bin/kungfu-test-util" -kill "127.0.0.1:$((R + 1))"
+wait "$job"
 # the C++ unit tests under the same instrumentation: in-process multi-peer worlds (threads), the epoch fence, a world that loses a peer
 "$bin/kungfu-unit-tests"
 echo "sanitizer run ($mode) passed"
