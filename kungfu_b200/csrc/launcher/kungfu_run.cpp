@@ -115,15 +115,13 @@ struct Child {
     std::shared_ptr<std::string> first_err = std::make_shared<std::string>(); // first line the process wrote to stderr
 };
 
-// Start-up retry (reference: srcs/go/utils/runner/local/hack.go:14-35, srcs/go/nccl/bug.go:12): a worker that dies with the dynamic
-// loader's "Inconsistency detected by ld.so" as the FIRST thing on its stderr hit a known loader race of some CUDA / NCCL builds and has
-// not joined anything yet, so it is simply started again with the same environment. The reference retries for ever; here the number of
-// restarts is bounded (KUNGFU_START_RETRIES, default 10) and the prefix can be changed (KUNGFU_RETRY_STDERR_PREFIX, used by the tests).
+// Start-up retry (runner_core.hpp `restart_after_startup_failure`): bounded by KUNGFU_START_RETRIES (default 10); the prefix can be
+// changed with KUNGFU_RETRY_STDERR_PREFIX (empty = off).
 bool should_restart(const Child& c, int rc, int attempt) {
-    if (rc == 0 || !c.first_err) return false;
-    static const std::string prefix = getenv_str("KUNGFU_RETRY_STDERR_PREFIX", "Inconsistency detected by ld.so");
+    if (!c.first_err) return false;
+    static const std::string prefix = getenv_str("KUNGFU_RETRY_STDERR_PREFIX", kfrun::loader_bug_prefix());
     static const int limit = std::atoi(getenv_str("KUNGFU_START_RETRIES", "10").c_str());
-    return !prefix.empty() && attempt <= limit && c.first_err->compare(0, prefix.size(), prefix) == 0;
+    return kfrun::restart_after_startup_failure(*c.first_err, rc, attempt, prefix, limit);
 }
 
 Child spawn_proc(const Proc& p, bool verbose, const std::string& logdir, Cancel* cancel, int color_idx, bool want_stdin) {

@@ -271,4 +271,13 @@ struct Job {
     }
 };
 
+// Start-up retry (reference: srcs/go/utils/runner/local/hack.go:14-35, srcs/go/nccl/bug.go:12): a worker that exits non-zero with the
+// dynamic loader's "Inconsistency detected by ld.so" as the FIRST line on its stderr hit a known loader race of some CUDA / NCCL builds
+// before it joined anything, so it is simply started again with the same environment. The reference retries for ever; here `attempt`
+// (1 = first restart) is bounded by `limit`.
+inline const char* loader_bug_prefix() { return "Inconsistency detected by ld.so"; }
+inline bool restart_after_startup_failure(const std::string& first_stderr_line, int exit_code, int attempt, const std::string& prefix, int limit) {
+    return exit_code != 0 && !prefix.empty() && attempt >= 1 && attempt <= limit && first_stderr_line.compare(0, prefix.size(), prefix) == 0;
+}
+
 } // namespace kfrun

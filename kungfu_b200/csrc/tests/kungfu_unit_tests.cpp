@@ -30,6 +30,7 @@
 #include "store.hpp"
 #include "transport.hpp"
 
+#include "fake_model.hpp"
 #include "runner_core.hpp"
 
 using namespace kfrt;
@@ -685,6 +686,36 @@ static void test_launcher_core() {
     CHECK_THROWS(infer_self_ipv4("", "no-such-nic0"));
 }
 
+// ---- start-up retry rule (runner/local/hack.go), the "-flag value" grammar of the tools, fake model lists (tests/go/fakemodel) ------------
+static void test_tools_core() {
+    using namespace kfrun;
+    const std::string bug = loader_bug_prefix();
+    CHECK(restart_after_startup_failure(bug + ": dl-open.c: 4711\n", 127, 1, bug, 10));
+    CHECK(restart_after_startup_failure(bug, 1, 10, bug, 10));
+    CHECK(!restart_after_startup_failure(bug, 1, 11, bug, 10));                          // retries used up
+    CHECK(!restart_after_startup_failure(bug, 0, 1, bug, 10));                           // it finished fine: nothing to do
+    CHECK(!restart_after_startup_failure("Traceback (most recent call last):\n", 1, 1, bug, 10));
+    CHECK(!restart_after_startup_failure("note: " + bug, 1, 1, bug, 10));                // only as the FIRST thing on stderr
+    CHECK(!restart_after_startup_failure("", 1, 1, bug, 10) && !restart_after_startup_failure(bug, 1, 1, "", 10));
+    CHECK(!restart_after_startup_failure(bug, 1, 1, bug, 0));                            // switched off
+    {
+        const char* av[] = {"tool", "-model", "vgg16", "--mode=par", "-fuse", "-epochs", "7", "-rate=0.25", "-versioned=true", "-n"};
+        kftools::Flags fl{10, const_cast<char**>(av)};
+        CHECK(fl.str("model", "x") == "vgg16" && fl.str("mode", "seq") == "par" && fl.str("absent", "dflt") == "dflt");
+        CHECK(fl.num("epochs", 1) == 7 && fl.num("warmup", 2) == 2 && fl.str("rate", "") == "0.25");
+        CHECK(fl.flag("fuse") && fl.flag("versioned") && !fl.flag("shuffle"));
+        CHECK(fl.str("n", "none") == "none"); // a trailing flag without a value keeps its default
+    }
+    // the lists are derived from layer shapes: totals must be the architectures' parameter counts
+    CHECK(kftools::fake_model_sizes("resnet50").size() == 161 && kftools::total_elements(kftools::fake_model_sizes("resnet50")) == 25557032u);
+    CHECK(kftools::fake_model_sizes("vgg16").size() == 32 && kftools::total_elements(kftools::fake_model_sizes("vgg16")) == 138357544u);
+    CHECK(kftools::fake_model_sizes("slp").size() == 2 && kftools::total_elements(kftools::fake_model_sizes("slp")) == 7850u);
+    CHECK(kftools::fake_model_sizes("resnet50-keras").size() == 214 && kftools::fake_model_sizes("bert").size() == 599);
+    CHECK(kftools::fake_model_sizes("bert-base").size() == 199 && kftools::fake_model_sizes("bert-large").size() == 391);
+    CHECK(kftools::fake_model_sizes("alexnet").empty());
+    for (auto& n : kftools::fake_model_names()) CHECK(!kftools::fake_model_sizes(n).empty());
+}
+
 // ---- traffic counters and the metrics text (monitor/counters_test.go), duration / env helpers (utils/utils_test.go) --------------------
 static void test_counters_and_utils() {
     NetMonitor& m = NetMonitor::get();
@@ -793,7 +824,7 @@ int main(int argc, char** argv) {
     } tests[] = {{"dtypes_and_transform2", test_dtypes_and_transform2}, {"plan", test_plan}, {"topologies", test_topologies}, {"mst", test_mst},
                  {"placement", test_placement}, {"stores", test_stores}, {"single_process_peer", test_single_process_peer},
                  {"json_reader", test_json_reader}, {"epoch_fence", test_epoch_fence}, {"server_survives_garbage", test_server_survives_garbage}, {"world_all_strategies", test_world_all_strategies},
-                 {"world_loses_a_peer", test_world_loses_a_peer}, {"launcher_core", test_launcher_core},
+                 {"world_loses_a_peer", test_world_loses_a_peer}, {"launcher_core", test_launcher_core}, {"tools_core", test_tools_core},
                  {"counters_and_utils", test_counters_and_utils}, {"message_round_trip", test_message_round_trip}};
     for (auto& t : tests) {
         bool wanted = argc <= 1; // `kungfu-unit-tests name…` runs the named tests only
